@@ -1,0 +1,139 @@
+"""ctypes binding of the CPU oracle (oracle/liblamejs_oracle.so).  Test infrastructure only:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg -- never by the product."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liblamejs_oracle.so")
+TABLES_H = os.path.join(ORACLE_DIR, "lj_tables.h")
+
+SBMAX_l, SBMAX_s, SFBMAX = 22, 13, 39
+
+TRACE_DTYPE = np.dtype(
+    [
+        ("xr", np.float32, (2, 2, 576)),
+        ("en_l", np.float32, (2, 2, SBMAX_l)),
+        ("thm_l", np.float32, (2, 2, SBMAX_l)),
+        ("en_s", np.float32, (2, 2, SBMAX_s, 3)),
+        ("thm_s", np.float32, (2, 2, SBMAX_s, 3)),
+        ("blocktype", np.int32, (2, 2)),
+        ("ath_adjust", np.float64),
+        ("l3_enc", np.int32, (2, 2, 576)),
+        ("global_gain", np.int32, (2, 2)),
+        ("part2_3_length", np.int32, (2, 2)),
+        ("part2_length", np.int32, (2, 2)),
+        ("big_values", np.int32, (2, 2)),
+        ("count1", np.int32, (2, 2)),
+        ("scalefac", np.int32, (2, 2, SFBMAX)),
+        ("scalefac_compress", np.int32, (2, 2)),
+        ("table_select", np.int32, (2, 2, 3)),
+        ("region0", np.int32, (2, 2)),
+        ("region1", np.int32, (2, 2)),
+        ("preflag", np.int32, (2, 2)),
+        ("scalefac_scale", np.int32, (2, 2)),
+        ("count1table", np.int32, (2, 2)),
+        ("subblock_gain", np.int32, (2, 2, 3)),
+        ("scfsi", np.int32, (2, 4)),
+        ("frame_bytes", np.int32),
+        ("padding", np.int32),
+        ("old_value_in", np.int32, (2,)),
+        ("old_value_out", np.int32, (2,)),
+        ("cur_step_in", np.int32, (2,)),
+        ("cur_step_out", np.int32, (2,)),
+    ],
+    align=True,
+)
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        L = ctypes.CDLL(ORACLE_SO)
+        L.lj_create.restype = ctypes.c_void_p
+        L.lj_create.argtypes = [ctypes.c_int] * 3
+        L.lj_encode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.lj_flush.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.lj_destroy.argtypes = [ctypes.c_void_p]
+        L.lj_set_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.lj_trace_count.argtypes = [ctypes.c_void_p]
+        assert L.lj_trace_size() == TRACE_DTYPE.itemsize, (L.lj_trace_size(), TRACE_DTYPE.itemsize)
+        _lib = L
+    return _lib
+
+
+class OracleEncoder:
+    """Mirror of lamejs.Mp3Encoder (src/js/index.js:66-136) backed by the C++ restatement."""
+
+    def __init__(self, channels, samplerate, kbps, trace_frames=0):
+        self.L = lib()
+        self.h = self.L.lj_create(channels, samplerate, kbps)
+        if not self.h:
+            raise ValueError("unsupported configuration")
+        self.channels = channels
+        self.trace = None
+        if trace_frames:
+            self.trace = np.zeros(trace_frames, dtype=TRACE_DTYPE)
+            self.L.lj_set_trace(self.h, self.trace.ctypes.data, trace_frames)
+
+    def encode_buffer(self, left, right=None):
+        left = np.ascontiguousarray(left, dtype=np.int16)
+        right = left if (right is None or self.channels == 1) else np.ascontiguousarray(right, dtype=np.int16)
+        assert len(left) == len(right)
+        cap = int(1.25 * len(left) + 7200)
+        buf = np.empty(cap, dtype=np.uint8)
+        k = self.L.lj_encode(self.h, left.ctypes.data, right.ctypes.data, len(left), buf.ctypes.data, cap)
+        if k < 0:
+            raise RuntimeError("lj_encode error %d" % k)
+        return buf[:k].tobytes()
+
+    def flush(self):
+        cap = 7200 + 4 * 1440
+        buf = np.empty(cap, dtype=np.uint8)
+        k = self.L.lj_flush(self.h, buf.ctypes.data, cap)
+        if k < 0:
+            raise RuntimeError("lj_flush error %d" % k)
+        return buf[:k].tobytes()
+
+    def traces(self):
+        return self.trace[: self.L.lj_trace_count(self.h)]
+
+    def close(self):
+        if self.h:
+            self.L.lj_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def encode_stream(channels, samplerate, kbps, left, right=None, chunk=None, trace_frames=0):
+    """encodeBuffer(whole stream or chunks) + flush(); returns (bytes, per-call sizes, traces)."""
+    enc = OracleEncoder(channels, samplerate, kbps, trace_frames)
+    out, sizes = bytearray(), []
+    n = len(left)
+    step = chunk or max(n, 1)
+    for i in range(0, n, step):
+        b = enc.encode_buffer(left[i : i + step], None if right is None else right[i : i + step])
+        sizes.append(len(b))
+        out += b
+    b = enc.flush()
+    sizes.append(len(b))
+    out += b
+    tr = enc.traces().copy() if trace_frames else None
+    enc.close()
+    return bytes(out), sizes, tr
