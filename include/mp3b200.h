@@ -1,0 +1,95 @@
+/* mp3b200.h -- C ABI of the B200-native batch MP3 encoder (libmp3b200.so).
+ *
+ * Drop-in boundary for the lamejs `Mp3Encoder` hot path.  Each entry point names the reference
+ * interface it replaces (paths relative to zhuker/lamejs @ 582bbba).  Plain pointers and sizes only;
+ * no torch / CUDA types cross this boundary.  All work runs on the CUDA device selected with
+ * mp3b200_set_device() (default: device 0); there is NO CPU fallback -- every call fails with
+ * MP3B200_ERR_CUDA when no usable sm_100 device is present.
+ *
+ * Error codes mirror lamejs/LAME where one exists (src/js/Lame.js:1045-1061,1494; BitStream.js:916-919).
+ */
+#ifndef MP3B200_H
+#define MP3B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP3B200_OK 0
+#define MP3B200_ERR_CONFIG (-1)   /* unsupported channels/samplerate/bitrate: lame_init_params returns -1 */
+#define MP3B200_ERR_BUFFER (-1)   /* output buffer too small: copy_buffer returns -1 (BitStream.js:916-919) */
+#define MP3B200_ERR_HANDLE (-3)   /* bad handle: lame_encode_buffer returns -3 (Lame.js:1494) */
+#define MP3B200_ERR_CUDA (-100)   /* CUDA failure or no device (no reference equivalent) */
+
+typedef struct mp3b200_encoder mp3b200_encoder;
+
+/* Select the CUDA device used by subsequently created encoders / batch calls (one process per GPU). */
+int mp3b200_set_device(int device);
+
+/* Replaces `new lamejs.Mp3Encoder(channels, samplerate, kbps)` (src/js/index.js:66-115).
+ * channels 1|2; samplerate 32000|44100|48000 (MPEG-1, no resampling); kbps snapped to the nearest legal
+ * MPEG-1 rate like FindNearestBitrate (src/js/Lame.js:408-423).  Configurations for which lamejs would
+ * resample (out_samplerate != in_samplerate) return MP3B200_ERR_CONFIG. */
+int mp3b200_create(int channels, int samplerate, int kbps, mp3b200_encoder** out);
+
+/* Replaces `encodeBuffer(left, right)` (src/js/index.js:117-130 -> Lame.js:1490-1667).  `right` may be NULL
+ * for mono.  Writes the bytes of the frames completed by this call (possibly 0) into `out` and returns their
+ * count; lamejs sizes its buffer as trunc(1.25*n + 7200).  Buffers are borrowed for the call only. */
+int mp3b200_encode(mp3b200_encoder* h, const int16_t* left, const int16_t* right, int nsamples, uint8_t* out, int cap);
+
+/* Replaces `flush()` (src/js/index.js:132-135 -> Lame.js:1381-1488): encodes the buffered tail padded with
+ * zeros; a second flush returns 0; the encoder stays usable. */
+int mp3b200_flush(mp3b200_encoder* h, uint8_t* out, int cap);
+
+/* Replaces garbage collection of the Mp3Encoder object. */
+void mp3b200_destroy(mp3b200_encoder* h);
+
+/* ---- batch extension (same semantics, many independent streams per launch sequence) -------------------
+ * Equivalent to, for each stream s: e = new Mp3Encoder(ch, sr, kbps); bytes = e.encodeBuffer(L_s, R_s) ++
+ * e.flush().  This is the throughput path (a JS caller would loop over encoders, worker-example/worker.js). */
+
+/* Number of bytes / frames that stream of `nsamples` per channel produces (closed form: CBR, no reservoir). */
+int64_t mp3b200_stream_bytes(int channels, int samplerate, int kbps, int64_t nsamples);
+int64_t mp3b200_stream_frames(int64_t nsamples);
+
+/* Host buffers.  left[s]/right[s]: nsamples[s] Int16 each (right NULL or ignored for mono).  out[s] receives
+ * out_bytes[s] = mp3b200_stream_bytes(...) bytes (cap[s] must be >= that).  Returns 0 or a negative error. */
+int mp3b200_encode_streams(int channels, int samplerate, int kbps, int nstreams, const int16_t* const* left,
+                           const int16_t* const* right, const int64_t* nsamples, uint8_t* const* out,
+                           const int64_t* cap, int64_t* out_bytes);
+
+/* Device-resident variant for benchmarking kernel throughput: d_pcm is ONE device allocation holding, per
+ * stream s, nsamples[s] Int16 of the left channel at sample offset pcm_off[s] and (stereo) the right channel at
+ * pcm_off[s] + nsamples[s].  d_out is a device buffer; stream s is written at out_off[s].  `timings_ms`
+ * (optional, 8 floats) receives per-kernel CUDA-event times: [0] psy analysis, [1] scan, [2] masking,
+ * [3] filterbank+MDCT, [4] quantize+pack pass 1, [5] later passes, [6] total, [7] number of quantizer passes. */
+int mp3b200_encode_streams_device(int channels, int samplerate, int kbps, int nstreams, const int16_t* d_pcm,
+                                  const int64_t* pcm_off, const int64_t* nsamples, uint8_t* d_out,
+                                  const int64_t* out_off, float* timings_ms);
+
+/* ---- stage taps for parity tests (one stream, whole-stream semantics) -----------------------------------
+ * Run the pipeline for one stream given host PCM and copy intermediate results back.  Any output pointer may be
+ * NULL.  Shapes ([F] = mp3b200_stream_frames(n)):
+ *   xr          float [F][2 gr][nch][576]   MDCT spectrum (NewMDCT.js mdct_sub48 output)
+ *   blocktype   int32 [F][2][nch]           final block type per granule (PsyModel.js block_type_set)
+ *   en_l/thm_l  float [F][2][nch][22], en_s/thm_s float [F][2][nch][13][3]   masking handed to the quantizer
+ *   ath_adjust  double[F]                   ATH.adjust after adjust_ATH (Encoder.js:166-243)
+ *   l3_enc      int32 [F][2][nch][576], ginfo int32 [F][2][nch][16] (global_gain, part2_3_length, part2_length,
+ *               big_values, count1, scalefac_compress, table_select[3], region0, region1, preflag, scalefac_scale,
+ *               count1table, block_type, reserved)
+ * If `force_blocktype` is non-NULL (int32 [F][2][nch]) it overrides the psy model's block decision for the
+ * filterbank stage (used to test the MDCT in isolation). */
+int mp3b200_debug_stages(int channels, int samplerate, int kbps, const int16_t* left, const int16_t* right,
+                         int64_t nsamples, const int32_t* force_blocktype, float* xr, int32_t* blocktype,
+                         float* en_l, float* thm_l, float* en_s, float* thm_s, double* ath_adjust,
+                         int32_t* l3_enc, int32_t* ginfo, uint8_t* bytes_out, int64_t bytes_cap);
+
+const char* mp3b200_last_error(void);
+/* total number of kernel launches issued by this library since load (bench.py "gpu_launches") */
+int64_t mp3b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

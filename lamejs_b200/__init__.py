@@ -1,0 +1,11 @@
+"""lamejs_b200 -- host-side mirror of the lamejs `Mp3Encoder` API over the B200-native C-ABI library.
+
+    from lamejs_b200 import Mp3Encoder
+    enc = Mp3Encoder(2, 44100, 128)           # new lamejs.Mp3Encoder(channels, sampleRate, kbps)
+    mp3 = enc.encodeBuffer(left, right)        # Int16 arrays -> bytes (frames completed by this call)
+    mp3 += enc.flush()
+
+(reference: zhuker/lamejs src/js/index.js:66-136).  All computation happens in libmp3b200.so on the GPU; the
+module raises if the library or a CUDA device is missing -- there is no CPU fallback.
+"""
+from .encoder import Mp3Encoder, encode_streams, encode_streams_device, debug_stages, lib, stream_bytes, stream_frames, Mp3B200Error  # noqa: F401

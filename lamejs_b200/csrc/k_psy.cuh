@@ -1,0 +1,591 @@
+/* k_psy.cuh -- K2 / K3a / K3b: psycho-acoustic model (lamejs L3psycho_anal_ns) as four kernels.
+ *
+ * Reference: src/js/PsyModel.js L3psycho_anal_ns :1000-1383 with compute_ffts :251-324, mask_add :403-473,
+ * calc_interchannel_masking :525-543, convert_partition2scalefac_s/_l :644-734, compute_masking_s :736-782,
+ * block_type_set :784-826, calc_energy :906, calc_mask_index_l :930; src/js/FFT.js fht :31-115,
+ * fft_short :140-183, fft_long :185-224; src/js/Encoder.js adjust_ATH :166-243.
+ *
+ * lamejs runs one psy call per granule ("unit" c, analysing stream samples [576c-224, 576c+800)) and carries
+ * state from call to call.  Here the work is split by what it depends on:
+ *   k_psy_analysis   pure function of PCM: fs/4 HPF + 9 sub-block peaks, 1024-pt and 3x256-pt FHT, line
+ *                    energies, partition energies / tonality index, short-block spreading sums, loudness
+ *   k_attack_prepass pure function of two consecutive units: attack candidates (before the lastAttacks FSM)
+ *   k_stream_scan    the only sequential part: per stream, the attack / block-type FSM and the ATH-adjust IIR
+ *   k_psy_masking    long-block spreading with mask_add (needs ATH.adjust), short thresholds (need the previous
+ *                    block type), partition -> scalefactor-band conversion, inter-channel masking
+ * With the reservoir disabled pcfact == 0 (PsyModel.js:1036-1038), so every NS_INTERP pre-echo branch returns
+ * its second argument and nb_1/nb_2 are never read; PE (pecalc_*) feeds only dead values.
+ */
+#ifndef MP3B200_K_PSY_CUH
+#define MP3B200_K_PSY_CUH
+#include "mp3_device.cuh"
+#include "mp3_tables.h"
+
+#define PSY_THREADS 256
+#define MASK_THREADS 128
+
+struct PsyUnit {
+  double ecb_s[3][MP3_CBANDS];      /* short-block spreading sums (double; float32 of it is lamejs nb_s1) */
+  float eb_s[3][MP3_CBANDS];
+  float eb_l[MP3_CBANDS];
+  float peaks[9];                   /* en_subshort[3..11] */
+  float loudness;                   /* psycho_loudness_approx */
+  unsigned char mask_idx[MP3_CBANDS];
+  unsigned char attack[4];          /* pre-FSM ns_attacks[0..3] */
+};
+struct PsyRatioDev { float en_l[22], thm_l[22], en_s[13][3], thm_s[13][3]; };
+
+__constant__ unsigned char c_fft_rv[128];
+__constant__ double c_tab[9];
+__constant__ double c_table1[25];
+__constant__ double c_table2[10];
+__constant__ double c_table3[14];
+__constant__ double c_fircoef[10];
+
+static int psy_upload_constants() {
+  static const double tab[9] = {1.0, 0.79433, 0.63096, 0.63096, 0.63096, 0.63096, 0.63096, 0.25119, 0.11749};
+  static const double r1[25] = {3.3246, 3.23837, 3.15437, 3.00412, 2.86103, 2.65407, 2.46209, 2.284, 2.11879, 1.96552, 1.82335,
+    1.69146, 1.56911, 1.46658, 1.37074, 1.31036, 1.25264, 1.20648, 1.16203, 1.12765, 1.09428, 1.0659, 1.03826, 1.01895, 1};
+  static const double r2[10] = {1.33352, 1.35879, 1.38454, 1.39497, 1.40548, 1.3537, 1.30382, 1.22321, 1.14758, 1};
+  static const double r3[14] = {2.35364, 2.29259, 2.23313, 2.12675, 2.02545, 1.87894, 1.74303, 1.61695, 1.49999, 1.39148,
+    1.29083, 1.19746, 1.11084, 1.03826};
+  static const double fir_half[10] = {-8.65163e-18, -0.00851586, -6.74764e-18, 0.0209036, -3.36639e-17, -0.0438162,
+    -1.54175e-17, 0.0931738, -5.52212e-17, -0.313819};
+  double t1[25], t2[10], t3[14], fir[10];
+  for (int i = 0; i < 25; i++) t1[i] = r1[i] * r1[i];       /* PsyModel.js:378-398 spells them as x*x */
+  for (int i = 0; i < 10; i++) t2[i] = r2[i] * r2[i];
+  for (int i = 0; i < 14; i++) t3[i] = r3[i] * r3[i];
+  for (int i = 0; i < 10; i++) fir[i] = fir_half[i] * 2;     /* PsyModel.js:994-998 */
+  if (cudaMemcpyToSymbol(c_fft_rv, MP3_FFT_RV, 128) != cudaSuccess) return -100;
+  if (cudaMemcpyToSymbol(c_tab, tab, sizeof tab) != cudaSuccess) return -100;
+  if (cudaMemcpyToSymbol(c_table1, t1, sizeof t1) != cudaSuccess) return -100;
+  if (cudaMemcpyToSymbol(c_table2, t2, sizeof t2) != cudaSuccess) return -100;
+  if (cudaMemcpyToSymbol(c_table3, t3, sizeof t3) != cudaSuccess) return -100;
+  if (cudaMemcpyToSymbol(c_fircoef, fir, sizeof fir) != cudaSuccess) return -100;
+  return 0;
+}
+
+/* ---- one butterfly task of an FHT stage (FFT.js:31-115), fz float32 in shared memory ------------------- */
+__device__ __forceinline__ void fht_task(f32s* fz, int n, int stage, int task, const double* __restrict__ tw, const int* tw_off) {
+  const int k1 = 4 << (2 * stage);          /* 4,16,64,256 */
+  const int kx = k1 >> 1, k2 = k1 << 1, k3 = k2 + k1, k4 = k2 << 1;
+  const int groups = n / k4;
+  if (task < 2 * groups) {
+    const int g = task >> 1;
+    if ((task & 1) == 0) {
+      const int fi = g * k4;
+      double f0, f1, f2, f3;
+      f1 = fz[fi + 0] - fz[fi + k1];
+      f0 = fz[fi + 0] + fz[fi + k1];
+      f3 = fz[fi + k2] - fz[fi + k3];
+      f2 = fz[fi + k2] + fz[fi + k3];
+      fz[fi + k2] = f0 - f2;
+      fz[fi + 0] = f0 + f2;
+      fz[fi + k3] = f1 - f3;
+      fz[fi + k1] = f1 + f3;
+    } else {
+      const int gi = g * k4 + kx;
+      double f0, f1, f2, f3;
+      f1 = fz[gi + 0] - fz[gi + k1];
+      f0 = fz[gi + 0] + fz[gi + k1];
+      f3 = (SQRT2_D * fz[gi + k3]);
+      f2 = (SQRT2_D * fz[gi + k2]);
+      fz[gi + k2] = f0 - f2;
+      fz[gi + 0] = f0 + f2;
+      fz[gi + k3] = f1 - f3;
+      fz[gi + k1] = f1 + f3;
+    }
+    return;
+  }
+  const int q = task - 2 * groups;
+  const int g = q / (kx - 1), i = 1 + q - g * (kx - 1);
+  const double* e = tw + 4 * (tw_off[stage] + i);
+  const double c1 = e[0], s1 = e[1], c2 = e[2], s2 = e[3];
+  const int fi = g * k4 + i, gi = g * k4 + k1 - i;
+  double a, b, g0, f0, f1, g1, f2, g2, f3, g3;
+  b = s2 * fz[fi + k1] - c2 * fz[gi + k1];
+  a = c2 * fz[fi + k1] + s2 * fz[gi + k1];
+  f1 = fz[fi + 0] - a;
+  f0 = fz[fi + 0] + a;
+  g1 = fz[gi + 0] - b;
+  g0 = fz[gi + 0] + b;
+  b = s2 * fz[fi + k3] - c2 * fz[gi + k3];
+  a = c2 * fz[fi + k3] + s2 * fz[gi + k3];
+  f3 = fz[fi + k2] - a;
+  f2 = fz[fi + k2] + a;
+  g3 = fz[gi + k2] - b;
+  g2 = fz[gi + k2] + b;
+  b = s1 * f2 - c1 * g3;
+  a = c1 * f2 + s1 * g3;
+  fz[fi + k2] = f0 - a;
+  fz[fi + 0] = f0 + a;
+  fz[gi + k3] = g1 - b;
+  fz[gi + k1] = g1 + b;
+  b = c1 * g2 - s1 * f3;
+  a = s1 * g2 + c1 * f3;
+  fz[gi + k2] = g0 - a;
+  fz[gi + 0] = g0 + a;
+  fz[fi + k3] = f1 - b;
+  fz[fi + k1] = f1 + b;
+}
+__device__ __forceinline__ int fht_tasks(int n, int stage) {
+  const int k1 = 4 << (2 * stage), kx = k1 >> 1, k4 = k1 << 2;
+  return (n / k4) * (kx + 1);
+}
+
+/* psy row of (stream z, relative unit u >= -1): unit_base + z + u + 1 */
+__device__ __forceinline__ size_t psy_row(const StreamDesc& sd, int z, int u) { return (size_t)sd.unit_base + z + u + 1; }
+
+/* grid (max_units + 1, nch, nstreams) */
+__global__ void __launch_bounds__(PSY_THREADS)
+k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ out) {
+  const int z = blockIdx.z;
+  const StreamDesc sd = streams[z];
+  const int u = (int)blockIdx.x - 1;                 /* relative unit, -1 = halo */
+  if (u >= 2 * sd.nframes) return;
+  const int ch = blockIdx.y;
+  const int nch = T->nch;
+  const long long c = 2LL * sd.frame0 + u;           /* absolute psy call index */
+  PsyUnit* o = out + psy_row(sd, z, u) * nch + ch;
+  const int tid = threadIdx.x;
+
+  if (c < 0) {   /* before the first call: psymodel_init values (PsyModel.js:2573-2595) */
+    for (int i = tid; i < 3 * MP3_CBANDS; i += PSY_THREADS) { (&o->ecb_s[0][0])[i] = 1.0; (&o->eb_s[0][0])[i] = 0.0f; }
+    if (tid < MP3_CBANDS) { o->eb_l[tid] = 0.0f; o->mask_idx[tid] = 0; }
+    if (tid < 9) o->peaks[tid] = 10.0f;
+    if (tid == 0) o->loudness = 0.0f;
+    if (tid < 4) o->attack[tid] = 0;
+    return;
+  }
+
+  __shared__ float xs[1024];
+  __shared__ f32s wl[1024];
+  __shared__ f32s wsh[3][256];
+  __shared__ f32s hp[576];
+  __shared__ f32s fe[513];
+  __shared__ f32s fes[3][129];
+  __shared__ f32s s_max[MP3_CBANDS], s_avg[MP3_CBANDS];
+  __shared__ f32s s_ebs[3][MP3_CBANDS];
+
+  const int scale_applied = T->scale_applied;
+  const double scale = T->scale;
+  const long long x0 = 576 * c - 224;                /* stream sample of bufPos */
+  for (int j = tid; j < 1024; j += PSY_THREADS) xs[j] = load_pcm(sd, ch, x0 + j, scale_applied, scale);
+  __syncthreads();
+
+  /* fs/4 high-pass (PsyModel.js:1051-1069): firbuf index = bufPos + 397 + i + j */
+  for (int i = tid; i < 576; i += PSY_THREADS) {
+    const float* fb = xs + 397 + i;
+    double sum1 = (double)fb[10], sum2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 9; j += 2) {
+      sum1 += c_fircoef[j] * ((double)fb[j] + (double)fb[21 - j]);
+      sum2 += c_fircoef[j + 1] * ((double)fb[j + 1] + (double)fb[21 - j - 1]);
+    }
+    hp[i] = sum1 + sum2;
+  }
+  /* windowing + first radix-4 pass of fft_long (FFT.js:185-224): iteration jj writes y[4jj..4jj+3], y[512+4jj..] */
+  if (tid < 128) {
+    const int jj = tid, i = c_fft_rv[jj], x = 4 * jj;
+    const float* w = T->fft_window;
+    double f0, f1, f2, f3, wv;
+    f0 = (double)w[i] * (double)xs[i];
+    wv = (double)w[i + 0x200] * (double)xs[i + 0x200];
+    f1 = f0 - wv; f0 = f0 + wv;
+    f2 = (double)w[i + 0x100] * (double)xs[i + 0x100];
+    wv = (double)w[i + 0x300] * (double)xs[i + 0x300];
+    f3 = f2 - wv; f2 = f2 + wv;
+    wl[x + 0] = f0 + f2; wl[x + 2] = f0 - f2; wl[x + 1] = f1 + f3; wl[x + 3] = f1 - f3;
+    f0 = (double)w[i + 0x001] * (double)xs[i + 0x001];
+    wv = (double)w[i + 0x201] * (double)xs[i + 0x201];
+    f1 = f0 - wv; f0 = f0 + wv;
+    f2 = (double)w[i + 0x101] * (double)xs[i + 0x101];
+    wv = (double)w[i + 0x301] * (double)xs[i + 0x301];
+    f3 = f2 - wv; f2 = f2 + wv;
+    wl[x + 512 + 0] = f0 + f2; wl[x + 512 + 2] = f0 - f2; wl[x + 512 + 1] = f1 + f3; wl[x + 512 + 3] = f1 - f3;
+  } else if (tid < 128 + 96) {
+    /* fft_short (FFT.js:140-183): block b, iteration j writes x_real[b][4j..], [128+4j..] */
+    const int q = tid - 128, b = q >> 5, j = q & 31;
+    const int i = c_fft_rv[j << 2], x = 4 * j, k = 192 * (b + 1);
+    const float* w = T->fft_window_s;
+    const float* bx = xs + i + k;
+    double f0, f1, f2, f3, wv;
+    f0 = (double)w[i] * (double)bx[0];
+    wv = (double)w[0x7f - i] * (double)bx[0x80];
+    f1 = f0 - wv; f0 = f0 + wv;
+    f2 = (double)w[i + 0x40] * (double)bx[0x40];
+    wv = (double)w[0x3f - i] * (double)bx[0xc0];
+    f3 = f2 - wv; f2 = f2 + wv;
+    wsh[b][x + 0] = f0 + f2; wsh[b][x + 2] = f0 - f2; wsh[b][x + 1] = f1 + f3; wsh[b][x + 3] = f1 - f3;
+    f0 = (double)w[i + 0x01] * (double)bx[0x01];
+    wv = (double)w[0x7e - i] * (double)bx[0x81];
+    f1 = f0 - wv; f0 = f0 + wv;
+    f2 = (double)w[i + 0x41] * (double)bx[0x41];
+    wv = (double)w[0x3e - i] * (double)bx[0xc1];
+    f3 = f2 - wv; f2 = f2 + wv;
+    wsh[b][x + 128 + 0] = f0 + f2; wsh[b][x + 128 + 2] = f0 - f2; wsh[b][x + 128 + 1] = f1 + f3; wsh[b][x + 128 + 3] = f1 - f3;
+  }
+  __syncthreads();
+
+  /* 9 sub-block peaks of the high-passed signal (PsyModel.js:1125-1132) */
+  if (tid >= 224 && tid < 233) {
+    const int sbk = tid - 224;
+    double p = 1.;
+    for (int j = 0; j < 64; j++) { const double v = fabs((double)hp[sbk * 64 + j]); if (p < v) p = v; }
+    o->peaks[sbk] = (float)p;
+  }
+  /* FHT stages: long transform (4 stages) and the three short ones (3 stages) share the loop */
+  for (int stage = 0; stage < 4; stage++) {
+    const int tl = fht_tasks(1024, stage);
+    const int tsn = stage < 3 ? fht_tasks(256, stage) : 0;
+    for (int t = tid; t < tl + 3 * tsn; t += PSY_THREADS) {
+      if (t < tl) fht_task(wl, 1024, stage, t, T->tw, T->tw_off);
+      else { const int q = t - tl; fht_task(wsh[q / tsn], 256, stage, q % tsn, T->tw, T->tw_off); }
+    }
+    __syncthreads();
+  }
+
+  /* line energies (PsyModel.js:278-298) */
+  for (int j = tid; j < 512; j += PSY_THREADS) {
+    const double re = wl[512 - j], im = wl[512 + j];
+    fe[512 - j] = (re * re + im * im) * 0.5;
+  }
+  if (tid == 0) { f32s t0; t0 = (double)wl[0]; t0 *= (double)t0; fe[0] = (double)t0; }
+  for (int t = tid; t < 3 * 128; t += PSY_THREADS) {
+    const int b = t >> 7, j = t & 127;
+    const double re = wsh[b][128 - j], im = wsh[b][128 + j];
+    fes[b][128 - j] = (re * re + im * im) * 0.5;
+  }
+  if (tid < 3) { f32s t0; t0 = (double)wsh[tid][0]; t0 *= (double)t0; fes[tid][0] = (double)t0; }
+  __syncthreads();
+
+  const int npl = T->npart_l, nps = T->npart_s;
+  if (tid < npl) {                                   /* calc_energy (PsyModel.js:906-928) */
+    double ebb = 0, m = 0;
+    const int l0 = T->line0_l[tid], l1 = T->line0_l[tid + 1];
+    for (int j = l0; j < l1; j++) { const double el = fe[j]; ebb += el; if (m < el) m = el; }
+    o->eb_l[tid] = (float)ebb;
+    s_max[tid] = m;
+    s_avg[tid] = ebb * (double)T->rnumlines_l[tid];
+  } else if (tid >= 64 && tid < 64 + 3 * 64) {       /* short partition energies (compute_masking_s :740-750) */
+    const int q = tid - 64, sb = q >> 6, b = q & 63;
+    if (b < nps) {
+      double ebb = 0;
+      const int l0 = T->line0_s[b], l1 = T->line0_s[b + 1];
+      for (int j = l0; j < l1; j++) ebb += (double)fes[sb][j];
+      s_ebs[sb][b] = ebb;
+      o->eb_s[sb][b] = (float)ebb;
+    }
+  }
+  if (tid == PSY_THREADS - 1) {                      /* psycho_loudness_approx (PsyModel.js:241-249): ordered sum */
+    double lp = 0.0;
+    for (int i = 0; i < 512; ++i) lp += (double)fe[i] * (double)T->eql_w[i];
+    lp *= (1. / (14752. * 14752.) / 512);
+    o->loudness = (float)lp;
+  }
+  __syncthreads();
+
+  if (tid < npl) {                                   /* calc_mask_index_l (PsyModel.js:930-992) */
+    const int b = tid;
+    const int lo = b > 0 ? b - 1 : b, hi = b < npl - 1 ? b + 1 : b;
+    double a = 0; double m = 0; int lines = 0;
+    for (int q = lo; q <= hi; q++) {
+      if (q == lo) { a = (double)s_avg[q]; m = (double)s_max[q]; }
+      else { a = a + (double)s_avg[q]; if (m < (double)s_max[q]) m = (double)s_max[q]; }
+      lines += T->numlines_l[q];
+    }
+    int k = 0;
+    if (a > 0.0) {
+      const double cnt = (double)(hi - lo + 1);
+      a = 20.0 * (m * cnt - a) / (a * (lines - 1));
+      k = js_trunc(a);
+      if (k > 8) k = 8;
+    }
+    o->mask_idx[b] = (unsigned char)k;
+  } else if (tid >= 64 && tid < 64 + 3 * 64) {       /* short spreading sums (compute_masking_s :753-761) */
+    const int q = tid - 64, sb = q >> 6, b = q & 63;
+    if (b < nps) {
+      int kk = T->s3lo_s[b];
+      int j = T->s3off_s[b];
+      double ecb = (double)T->s3_ss[j++] * (double)s_ebs[sb][kk];
+      ++kk;
+      while (kk <= T->s3hi_s[b]) { ecb += (double)T->s3_ss[j] * (double)s_ebs[sb][kk]; ++j; ++kk; }
+      o->ecb_s[sb][b] = ecb;
+    }
+  }
+}
+
+/* ---- attack candidates: needs peaks of unit u and u-1 (PsyModel.js:1105-1181) -------------------------- */
+__global__ void k_attack_prepass(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ psy) {
+  const int z = blockIdx.z;
+  const StreamDesc sd = streams[z];
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= 2 * sd.nframes) return;
+  const int nch = T->nch;
+  const double thr = T->attack_threshold;
+  for (int ch = 0; ch < nch; ch++) {
+    PsyUnit* cur = psy + psy_row(sd, z, u) * nch + ch;
+    const PsyUnit* prev = psy + psy_row(sd, z, u - 1) * nch + ch;
+    f32s en_subshort[12], attack_intensity[12];
+    double en_short[4] = {0, 0, 0, 0};
+    int a[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 3; i++) {
+      en_subshort[i] = (double)prev->peaks[i + 6];
+      attack_intensity[i] = (double)en_subshort[i] / (double)prev->peaks[i + 4];
+      en_short[0] += (double)en_subshort[i];
+    }
+    for (int i = 0; i < 9; i++) {
+      double p = (double)cur->peaks[i];
+      en_subshort[i + 3] = p;
+      if (i % 3 == 0) en_short[1 + i / 3] += p;      /* fractional JS index: only i%3==0 lands */
+      if (p > (double)en_subshort[i + 3 - 2]) p = p / (double)en_subshort[i + 3 - 2];
+      else if ((double)en_subshort[i + 3 - 2] > p * 10.0) p = (double)en_subshort[i + 3 - 2] / (p * 10.0);
+      else p = 0.0;
+      attack_intensity[i + 3] = p;
+    }
+    for (int i = 0; i < 12; i += 3)
+      if ((double)attack_intensity[i] > thr) a[i / 3] = 1;
+    for (int i = 1; i < 4; i++) {
+      double ratio;
+      if (en_short[i - 1] > en_short[i]) ratio = en_short[i - 1] / en_short[i];
+      else ratio = en_short[i] / en_short[i - 1];
+      if (ratio < 1.7) { a[i] = 0; if (i == 1) a[0] = 0; }
+    }
+    for (int i = 0; i < 4; i++) cur->attack[i] = (unsigned char)a[i];
+  }
+}
+
+/* ---- sequential scans: thread (stream, role) ; role 0 = attack/block-type FSM, role 1 = ATH adjust -------- */
+__global__ void k_stream_scan(const Mp3Tables* __restrict__ T, StreamDesc* __restrict__ streams, int nstreams,
+                              const PsyUnit* __restrict__ psy, signed char* __restrict__ bt_final,
+                              signed char* __restrict__ bt_prev, double* __restrict__ ath_psy, double* __restrict__ ath_q) {
+  const int z = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int role = threadIdx.x >> 5;
+  if (z >= nstreams) return;
+  const StreamDesc sd = streams[z];
+  const int nch = T->nch;
+  if (role == 0) {
+    int old[2] = {sd.blocktype_old[0], sd.blocktype_old[1]};
+    int la[2] = {sd.last_attacks[0], sd.last_attacks[1]};
+    const int coupled = T->coupled_short_blocks;
+    for (int u = 0; u < 2 * sd.nframes; u++) {
+      int uselong[2] = {1, 1};
+      for (int ch = 0; ch < nch; ch++) {
+        const PsyUnit* p = psy + psy_row(sd, z, u) * nch + ch;
+        int a0 = p->attack[0], a1 = p->attack[1], a2 = p->attack[2], a3 = p->attack[3];
+        if (a0 != 0 && la[ch] != 0) a0 = 0;
+        if (la[ch] == 3 || (a0 + a1 + a2 + a3) != 0) {
+          uselong[ch] = 0;
+          if (a1 != 0 && a0 != 0) a1 = 0;
+          if (a2 != 0 && a1 != 0) a2 = 0;
+          if (a3 != 0 && a2 != 0) a3 = 0;
+        }
+        la[ch] = a2;
+      }
+      if (coupled && !(uselong[0] != 0 && uselong[1] != 0)) uselong[0] = uselong[1] = 0;
+      const size_t row = (size_t)(sd.unit_base + u) * 2;
+      for (int ch = 0; ch < nch; ch++) {
+        bt_prev[row + ch] = (signed char)old[ch];          /* what compute_masking_s of this call saw */
+        int bt = BT_NORM;
+        if (uselong[ch] != 0) {
+          if (old[ch] == BT_SHORT) bt = BT_STOP;
+        } else {
+          bt = BT_SHORT;
+          if (old[ch] == BT_NORM) old[ch] = BT_START;
+          if (old[ch] == BT_STOP) old[ch] = BT_SHORT;
+        }
+        bt_final[row + ch] = (signed char)old[ch];
+        old[ch] = bt;
+      }
+    }
+    streams[z].blocktype_old[0] = old[0]; streams[z].blocktype_old[1] = old[1];
+    streams[z].last_attacks[0] = la[0]; streams[z].last_attacks[1] = la[1];
+  } else {
+    double adjust = sd.ath_adjust, limit = sd.ath_adjust_limit;
+    const double sens = T->aa_sensitivity_p;
+    for (int f = 0; f < sd.nframes; f++) {
+      ath_psy[sd.frame_base + f] = adjust;
+      /* loudness_sq[gr][ch] is the loudness of the unit BEFORE call 2f+gr (one-call delay, PsyModel.js:321-322) */
+      const PsyUnit* r0 = psy + psy_row(sd, z, 2 * f - 1) * nch;
+      const PsyUnit* r1 = psy + psy_row(sd, z, 2 * f) * nch;
+      double max_pow = (double)r0[0].loudness, gr2_max = (double)r1[0].loudness;
+      if (nch == 2) { max_pow += (double)r0[1].loudness; gr2_max += (double)r1[1].loudness; }
+      else { max_pow += max_pow; gr2_max += gr2_max; }
+      max_pow = js_dmax(max_pow, gr2_max);
+      max_pow *= 0.5;
+      max_pow *= sens;
+      if (max_pow > 0.03125) {
+        if (adjust >= 1.0) adjust = 1.0;
+        else if (adjust < limit) adjust = limit;
+        limit = 1.0;
+      } else {
+        const double adj_lim_new = 31.98 * max_pow + 0.000625;
+        if (adjust >= adj_lim_new) {
+          adjust *= adj_lim_new * 0.075 + 0.925;
+          if (adjust < adj_lim_new) adjust = adj_lim_new;
+        } else {
+          if (limit >= adj_lim_new) adjust = adj_lim_new;
+          else if (adjust < limit) adjust = limit;
+        }
+        limit = adj_lim_new;
+      }
+      ath_q[sd.frame_base + f] = adjust;
+    }
+    streams[z].ath_adjust = adjust; streams[z].ath_adjust_limit = limit;
+  }
+}
+
+/* mask_add (PsyModel.js:403-473), long blocks only (shortblock == 0) */
+__device__ __forceinline__ double mask_add_dev(double m1, double m2, int kk, int b, const Mp3Tables* T, double ath_adjust) {
+  double ratio;
+  if (m2 > m1) {
+    if (m2 < (m1 * T->ma_max_i2)) ratio = m2 / m1;
+    else return (m1 + m2);
+  } else {
+    if (m1 >= (m2 * T->ma_max_i2)) return (m1 + m2);
+    ratio = m1 / m2;
+  }
+  m1 += m2;
+  if ((b + 3) <= 3 + 3) {                    /* sic: signed compare in lamejs */
+    if (ratio >= T->ma_max_i1) return m1;
+    const int i = js_trunc(m3_log10(ratio) * 16.0);
+    return m1 * c_table2[i];
+  }
+  const int i = js_trunc(m3_log10(ratio) * 16.0);
+  m2 = (double)T->ath_cb_l[kk] * ath_adjust;
+  if (m1 < T->ma_max_m * m2) {
+    if (m1 > m2) {
+      double f = 1.0, r;
+      if (i <= 13) f = c_table3[i];
+      r = m3_log10(m1 / m2) * (10.0 / 15.0);
+      return m1 * ((c_table1[i] - f) * r + f);
+    }
+    if (i > 13) return m1;
+    return m1 * c_table3[i];
+  }
+  return m1 * c_table1[i];
+}
+
+/* grid (max_units + 1, 1, nstreams); threads: 64 per channel */
+__global__ void __launch_bounds__(MASK_THREADS)
+k_psy_masking(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, const PsyUnit* __restrict__ psy,
+              const signed char* __restrict__ bt_prev, const double* __restrict__ ath_psy, PsyRatioDev* __restrict__ ratio) {
+  const int z = blockIdx.z;
+  const StreamDesc sd = streams[z];
+  const int u = (int)blockIdx.x - 1;
+  if (u >= 2 * sd.nframes) return;
+  const int nch = T->nch;
+  const long long c = 2LL * sd.frame0 + u;
+  const int tid = threadIdx.x, ch = tid >> 6, b = tid & 63;
+  PsyRatioDev* out = ratio + psy_row(sd, z, u) * nch;
+  if (u < 0) {
+    if (c < 0) {   /* en/thm start values 1e20 (PsyModel.js:2579-2587) */
+      const float big = (float)1e20;
+      for (int i = tid; i < nch * 122; i += MASK_THREADS) (&out[0].en_l[0])[i] = big;
+    }
+    return;        /* c >= 0: the streaming handle pre-fills this row from its carried state */
+  }
+  __shared__ f32s s_thr[2][MP3_CBANDS + 2], s_eb[2][MP3_CBANDS + 2];
+  __shared__ f32s s_thr_s[2][3][MP3_CBANDS + 2];
+  __shared__ PsyRatioDev s_out[2];
+  const int npl = T->npart_l, nps = T->npart_s;
+  const PsyUnit* pu = (ch < nch) ? psy + psy_row(sd, z, u) * nch + ch : nullptr;
+  const PsyUnit* pp = (ch < nch) ? psy + psy_row(sd, z, u - 1) * nch + ch : nullptr;
+  const double ath_adjust = ath_psy[sd.frame_base + (u >> 1)];
+
+  if (ch < nch) {
+    /* long-block spreading + mask_add (PsyModel.js:1274-1324); thr[b] = ecb because pcfact == 0 */
+    if (b < npl) {
+      int kk = T->s3lo_l[b];
+      int k = T->s3off_l[b];
+      double eb2 = (double)pu->eb_l[kk] * c_tab[pu->mask_idx[kk]];
+      double ecb = (double)T->s3_ll[k++] * eb2;
+      while (++kk <= T->s3hi_l[b]) {
+        eb2 = (double)pu->eb_l[kk] * c_tab[pu->mask_idx[kk]];
+        ecb = mask_add_dev(ecb, (double)T->s3_ll[k++] * eb2, kk, kk - b, T, ath_adjust);
+      }
+      ecb *= 0.158489319246111;
+      s_thr[ch][b] = ecb;
+      s_eb[ch][b] = (double)pu->eb_l[b];
+    } else { s_thr[ch][b] = 0.0; s_eb[ch][b] = 0.0; }
+    /* short-block thresholds (compute_masking_s :753-777); nb_s1/nb_s2 = float32 ecb of the two previous sub-blocks */
+    const int prev_short = bt_prev[(size_t)(sd.unit_base + u) * 2 + ch] == BT_SHORT;
+    for (int sb = 0; sb < 3; sb++) {
+      if (b < nps) {
+        const double ecb = pu->ecb_s[sb][b];
+        const float nb1 = sb >= 1 ? (float)pu->ecb_s[sb - 1][b] : (float)pp->ecb_s[2][b];
+        const float nb2 = sb == 2 ? (float)pu->ecb_s[0][b] : (sb == 1 ? (float)pp->ecb_s[2][b] : (float)pp->ecb_s[1][b]);
+        f32s t;
+        t = js_dmin(ecb, 2 * (double)nb1);
+        if (prev_short) { const double x = 16 * (double)nb2, y = (double)t; t = js_dmin(x, y); }
+        s_thr_s[ch][sb][b] = (double)t;
+      } else s_thr_s[ch][sb][b] = 0.0;
+    }
+  }
+  __syncthreads();
+
+  /* partition -> scalefactor band (convert_partition2scalefac_l/_s): ordered accumulation, one thread each */
+  if (ch < nch && b == 0) {
+    f32s* en = reinterpret_cast<f32s*>(s_out[ch].en_l);
+    f32s* thm = reinterpret_cast<f32s*>(s_out[ch].thm_l);
+    int sbi, p;
+    double enn = 0.0, thmm = 0.0;
+    for (sbi = p = 0; sbi < 22; ++p, ++sbi) {
+      const int bo = T->bo_l[sbi];
+      const int b_lim = bo < npl ? bo : npl;
+      while (p < b_lim) { enn += (double)s_eb[ch][p]; thmm += (double)s_thr[ch][p]; p++; }
+      en[sbi] = enn; thm[sbi] = thmm;
+      if (p >= npl) { ++sbi; break; }
+      const double w_curr = (double)T->bo_l_weight[sbi], w_next = 1.0 - w_curr;
+      enn = w_curr * (double)s_eb[ch][p];
+      thmm = w_curr * (double)s_thr[ch][p];
+      en[sbi] += enn; thm[sbi] += thmm;
+      enn = w_next * (double)s_eb[ch][p];
+      thmm = w_next * (double)s_thr[ch][p];
+    }
+    for (; sbi < 22; ++sbi) { en[sbi] = 0.0; thm[sbi] = 0.0; }
+  } else if (ch < nch && b >= 1 && b <= 3) {
+    const int sblock = b - 1;
+    int sbi, p;
+    double enn = 0.0, thmm = 0.0;
+    f32s(*en)[3] = reinterpret_cast<f32s(*)[3]>(s_out[ch].en_s);
+    f32s(*thm)[3] = reinterpret_cast<f32s(*)[3]>(s_out[ch].thm_s);
+    for (sbi = p = 0; sbi < 13; ++p, ++sbi) {
+      const int bo = T->bo_s[sbi];
+      const int b_lim = bo < nps ? bo : nps;
+      while (p < b_lim) { enn += (double)pu->eb_s[sblock][p]; thmm += (double)s_thr_s[ch][sblock][p]; p++; }
+      en[sbi][sblock] = enn; thm[sbi][sblock] = thmm;
+      if (p >= nps) { ++sbi; break; }
+      const double w_curr = (double)T->bo_s_weight[sbi], w_next = 1.0 - w_curr;
+      enn = w_curr * (double)pu->eb_s[sblock][p];
+      thmm = w_curr * (double)s_thr_s[ch][sblock][p];
+      en[sbi][sblock] += enn; thm[sbi][sblock] += thmm;
+      enn = w_next * (double)pu->eb_s[sblock][p];
+      thmm = w_next * (double)s_thr_s[ch][sblock][p];
+    }
+    for (; sbi < 13; ++sbi) { en[sbi][sblock] = 0.0; thm[sbi][sblock] = 0.0; }
+    /* pre-echo factor and pulse detection (PsyModel.js:1231-1266; NS_INTERP(.,thmm,0) == thmm) */
+    const double e3 = (double)pu->peaks[sblock * 3 + 0], e4 = (double)pu->peaks[sblock * 3 + 1], e5 = (double)pu->peaks[sblock * 3 + 2];
+    for (int s = 0; s < 13; s++) {
+      double t = (double)thm[s][sblock];
+      t *= 0.8;
+      const double enn2 = e3 + e4 + e5;
+      if (e5 * 6 < enn2) { t *= 0.5; if (e4 * 6 < enn2) t *= 0.5; }
+      thm[s][sblock] = t;
+    }
+  }
+  __syncthreads();
+  /* inter-channel masking (PsyModel.js:525-543), stereo with interChRatio > 0 */
+  if (nch == 2 && T->interch_ratio > 0.0 && tid < 22 + 39) {
+    const double r = T->interch_ratio;
+    f32s* t0 = reinterpret_cast<f32s*>(tid < 22 ? &s_out[0].thm_l[tid] : &s_out[0].thm_s[0][0] + (tid - 22));
+    f32s* t1 = reinterpret_cast<f32s*>(tid < 22 ? &s_out[1].thm_l[tid] : &s_out[1].thm_s[0][0] + (tid - 22));
+    const double l = (double)*t0, rr = (double)*t1;
+    *t0 += rr * r;
+    *t1 += l * r;
+  }
+  __syncthreads();
+  for (int i = tid; i < nch * 122; i += MASK_THREADS) (&out[0].en_l[0])[i] = (&s_out[0].en_l[0])[i];
+}
+
+#endif

@@ -1,0 +1,1403 @@
+/* k_quant.cuh -- K4/K5: bit allocation, noise-shaping loop, quantizer, Huffman bit counting, bit packing.
+ *
+ * Replaces lamejs CBRNewIterationLoop.iteration_loop (reference src/js/CBRNewIterationLoop.js:25-90) with
+ * everything it calls -- Reservoir.js (bit budget), QuantizePVT.js (on_pe :421, calc_xmin :569, calc_noise :725),
+ * Quantize.js (init_outer_loop :204, init_xrpow :105, bin_search_StepSize :322, outer_loop :871, balance_noise,
+ * amp_scalefac_bands, inc_scalefac_scale, inc_subblock_gain, iteration_finish_one :1059), Takehiro.js
+ * (quantize_xrpow :171, noquant_count_bits :521, choose_table :465, best_huffman_divide :727, best_scalefac_store
+ * :809, scale_bitcount :980) -- and BitStream.format_bitstream (src/js/BitStream.js:836-901).
+ *
+ * Mapping: one CUDA block per frame, one warp per channel (a granule-channel is "gc").  All control decisions are
+ * warp-uniform: scalars live in shared memory, lane 0 writes, __syncwarp publishes.  The 576 spectral lines are
+ * spread 18 per lane; Huffman bit counts, maxima and region scans are warp reductions over table look-ups
+ * (integer sums are order-free); floating-point sums whose order matters (calc_xmin energies, calc_noise) run one
+ * scalefactor band per lane in the reference's line order.  gr1 needs the bits both channels spent in gr0
+ * (Reservoir.ResvMaxBits), so the two warps meet at a block barrier between granules.
+ *
+ * Cross-frame recurrence: bin_search_StepSize starts from gfc.OldValue/CurrentStep left by the previous frame.
+ * Frames are encoded in parallel from a speculated in-state, the out-states are compared with the successor's
+ * assumption and mismatching frames are redone (host loop in quant_run) until a fixed point -- byte-identical to
+ * the sequential order.
+ */
+#ifndef MP3B200_K_QUANT_CUH
+#define MP3B200_K_QUANT_CUH
+#include "mp3_device.cuh"
+#include "mp3_tables.h"
+#include "k_psy.cuh"
+
+#define Q_LARGE_BITS 100000
+#define Q_IXMAX 8206
+#define Q_FULL 0xffffffffu
+
+struct GranuleInfoDev {
+  int global_gain, part2_3_length, part2_length, big_values, count1, scalefac_compress;
+  int table_select[3], region0_count, region1_count, preflag, scalefac_scale, count1table_select, block_type;
+  int subblock_gain[4];
+  int count1bits, sfbmax, sfbdivide, sfb_lmax, psymax, psy_lmax, sfb_smin, max_nonzero_coeff;
+  int scalefac[MP3_SFBMAX];
+  double xrpow_max;
+};
+struct QuantFrameState {
+  int stream, rel_frame;
+  int in_old[2], in_step[2];        /* assumed gfc.OldValue / CurrentStep at frame start */
+  int out_old[2], out_step[2];      /* state after the frame */
+  int bs_gain0[2], bs_step0[2];     /* gr0 bin-search result (re-validation shortcut) */
+  int valid;
+};
+
+__constant__ unsigned short c_huff_code[1666];
+__constant__ unsigned char c_huff_len[1666];
+__constant__ int c_huff_off[34];
+__constant__ int c_huff_xlen[34];
+__constant__ int c_huff_linmax[34];
+__constant__ unsigned int c_largetbl[256];
+__constant__ unsigned int c_table23[9];
+__constant__ unsigned int c_table56[16];
+__constant__ int c_pretab[22];
+__constant__ int c_t32l[16];
+__constant__ int c_t33l[16];
+__constant__ int c_slen1_n[16];
+__constant__ int c_slen2_n[16];
+__constant__ int c_slen1_tab[16];
+__constant__ int c_slen2_tab[16];
+__constant__ int c_scale_short[16];
+__constant__ int c_scale_long[16];
+__constant__ int c_huf_noesc[15];
+
+static int quant_upload_constants() {
+  static const int pretab[22] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2, 0};
+  static const int t32l[16] = {1, 5, 5, 7, 5, 8, 7, 9, 5, 7, 7, 9, 7, 9, 9, 10};
+  static const int t33l[16] = {4, 5, 5, 6, 5, 6, 6, 7, 5, 6, 6, 7, 6, 7, 7, 8};
+  static const int s1n[16] = {1, 1, 1, 1, 8, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 16};
+  static const int s2n[16] = {1, 2, 4, 8, 1, 2, 4, 8, 2, 4, 8, 2, 4, 8, 4, 8};
+  static const int s1t[16] = {0, 0, 0, 0, 3, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4};
+  static const int s2t[16] = {0, 1, 2, 3, 0, 1, 2, 3, 1, 2, 3, 1, 2, 3, 2, 3};
+  static const int ss[16] = {0, 18, 36, 54, 54, 36, 54, 72, 54, 72, 90, 72, 90, 108, 108, 126};
+  static const int sl[16] = {0, 10, 20, 30, 33, 21, 31, 41, 32, 42, 52, 43, 53, 63, 64, 74};
+  static const int hn[15] = {1, 2, 5, 7, 7, 10, 10, 13, 13, 13, 13, 13, 13, 13, 13};
+#define UP(sym, src) if (cudaMemcpyToSymbol(sym, src, sizeof(src)) != cudaSuccess) return -100
+  UP(c_huff_code, MP3_HUFF_CODE); UP(c_huff_len, MP3_HUFF_LEN); UP(c_huff_off, MP3_HUFF_OFF);
+  UP(c_huff_xlen, MP3_HUFF_XLEN); UP(c_huff_linmax, MP3_HUFF_LINMAX); UP(c_largetbl, MP3_HUFF_LARGETBL);
+  UP(c_table23, MP3_HUFF_TABLE23); UP(c_table56, MP3_HUFF_TABLE56);
+  UP(c_pretab, pretab); UP(c_t32l, t32l); UP(c_t33l, t33l); UP(c_slen1_n, s1n); UP(c_slen2_n, s2n);
+  UP(c_slen1_tab, s1t); UP(c_slen2_tab, s2t); UP(c_scale_short, ss); UP(c_scale_long, sl); UP(c_huf_noesc, hn);
+#undef UP
+  return 0;
+}
+
+/* ---- per-warp working set (shared memory) ---------------------------------------------------------------- */
+struct GcWork {
+  float xr[576];                 /* gi.xr after short-block reorder and analog-silence zeroing */
+  float xrpow[576];
+  short ixw[576];                /* cod_info_w.l3_enc */
+  short ixb[576];                /* cod_info.l3_enc (best so far) */
+  GranuleInfoDev w, b;           /* cod_info_w / cod_info */
+  int width[MP3_SFBMAX], window[MP3_SFBMAX];
+  unsigned char sfb_of_line[576];
+  float xmin[MP3_SFBMAX], distort[MP3_SFBMAX];
+  int pn_step[MP3_SFBMAX]; float pn_noise[MP3_SFBMAX], pn_noise_log[MP3_SFBMAX];
+  int pn_global_gain, pn_sfb_count1;
+  unsigned char mode[MP3_SFBMAX + 1];
+  int nstart[MP3_SFBMAX], nlen[MP3_SFBMAX];
+  int scratch[8];
+  double dscratch[4];
+};
+struct GcFinal {                  /* what the bit packer needs, kept for both granules */
+  short ix[576];
+  unsigned int neg[18];           /* sign bits of xr */
+  GranuleInfoDev gi;
+};
+struct FrameShared {
+  GcWork wk[2];
+  GcFinal fin[2][2];              /* [gr][ch] */
+  unsigned int bits[368];         /* frame bit buffer (<= 1441 bytes) */
+  int targ_bits[2];
+  int used_bits[2];               /* part2_3_length + part2_length of gr0, per channel */
+  int scfsi[2][4];
+  int old_value[2], current_step[2];
+  double ath21[6], ath12[6];
+  int flag;
+};
+
+#define LANE (threadIdx.x & 31)
+__device__ __forceinline__ int wmax(int v) { return __reduce_max_sync(Q_FULL, v); }
+__device__ __forceinline__ int wsum(int v) { return __reduce_add_sync(Q_FULL, v); }
+__device__ __forceinline__ unsigned wsumu(unsigned v) { return __reduce_add_sync(Q_FULL, v); }
+__device__ __forceinline__ int hlen(int t, int i) { return c_huff_len[c_huff_off[t] + i]; }
+
+/* ---- Huffman bit counting over ix[begin,end) (Takehiro.js:319-516), warp-parallel over pairs ---------------- */
+__device__ int choose_table_w(const short* ix, int begin, int end, int* bits) {
+  const int lane = LANE;
+  int mx = 0;
+  for (int p = begin + 2 * lane; p < end; p += 64) { mx = max(mx, max((int)ix[p], (int)ix[p + 1])); }
+  mx = wmax(mx);
+  if (mx == 0) return 0;
+  if (mx == 1) {
+    int s = 0;
+    for (int p = begin + 2 * lane; p < end; p += 64) s += hlen(1, ix[p] * 2 + ix[p + 1]);
+    *bits += wsum(s);
+    return 1;
+  }
+  if (mx <= 3) {
+    int t1 = c_huf_noesc[mx - 1];
+    const int xlen = c_huff_xlen[t1];
+    unsigned s = 0;
+    for (int p = begin + 2 * lane; p < end; p += 64) {
+      const int x = ix[p] * xlen + ix[p + 1];
+      s += (t1 == 2) ? c_table23[x] : c_table56[x];
+    }
+    s = wsumu(s);
+    int sum2 = (int)(s & 0xffff), sum = (int)(s >> 16);
+    if (sum > sum2) { sum = sum2; t1++; }
+    *bits += sum;
+    return t1;
+  }
+  if (mx <= 15) {
+    const int t1 = c_huf_noesc[mx - 1];
+    const int xlen = c_huff_xlen[t1];
+    int s1 = 0, s2 = 0, s3 = 0;
+    for (int p = begin + 2 * lane; p < end; p += 64) {
+      const int x = ix[p] * xlen + ix[p + 1];
+      s1 += hlen(t1, x); s2 += hlen(t1 + 1, x); s3 += hlen(t1 + 2, x);
+    }
+    s1 = wsum(s1); s2 = wsum(s2); s3 = wsum(s3);
+    int t = t1;
+    if (s1 > s2) { s1 = s2; t++; }
+    if (s1 > s3) { s1 = s3; t = t1 + 2; }
+    *bits += s1;
+    return t;
+  }
+  if (mx > Q_IXMAX) { *bits = Q_LARGE_BITS; return -1; }
+  mx -= 15;
+  int choice2, choice;
+  for (choice2 = 24; choice2 < 32; choice2++) if (c_huff_linmax[choice2] >= mx) break;
+  for (choice = choice2 - 8; choice < 24; choice++) if (c_huff_linmax[choice] >= mx) break;
+  const unsigned linbits = (unsigned)c_huff_xlen[choice] * 65536u + (unsigned)c_huff_xlen[choice2];
+  unsigned s = 0;
+  for (int p = begin + 2 * lane; p < end; p += 64) {
+    int x = ix[p], y = ix[p + 1];
+    if (x != 0) { if (x > 14) { x = 15; s += linbits; } x *= 16; }
+    if (y != 0) { if (y > 14) { y = 15; s += linbits; } x += y; }
+    s += c_largetbl[x];
+  }
+  s = wsumu(s);
+  int sum2 = (int)(s & 0xffff), sum = (int)(s >> 16);
+  int t1 = choice;
+  if (sum > sum2) { sum = sum2; t1 = choice2; }
+  *bits += sum;
+  return t1;
+}
+
+/* noquant_count_bits (Takehiro.js:521-628).  gi scalars are updated by lane 0. */
+__device__ int noquant_count_bits_w(const Mp3Tables* T, const short* ix, GranuleInfoDev* gi, GcWork* wk, bool use_prev) {
+  const int lane = LANE;
+  int i0 = ((gi->max_nonzero_coeff + 2) >> 1) << 1;
+  if (i0 > 576) i0 = 576;
+  /* count1 = end of the last non-zero pair below i0 */
+  int top = 0;
+  for (int p = 2 * lane; p < i0; p += 64) if ((ix[p] | ix[p + 1]) != 0) top = p + 2;
+  const int count1 = wmax(top);
+  /* quadruples of |x| <= 1 counted down from count1 */
+  int a1 = 0, a2 = 0, nq = 0;
+  const int qmax = count1 >> 2;
+  bool stop = false;
+  for (int q0 = 0; q0 < qmax && !stop; q0 += 32) {
+    const int q = q0 + lane;
+    int bad = 0, v1 = 0, v2 = 0;
+    if (q < qmax) {
+      const int i = count1 - 4 * q;
+      const int x0 = ix[i - 4], x1 = ix[i - 3], x2 = ix[i - 2], x3 = ix[i - 1];
+      if (((x0 | x1 | x2 | x3) & 0x7fffffff) > 1) bad = 1;
+      else { const int p = ((x0 * 2 + x1) * 2 + x2) * 2 + x3; v1 = c_t32l[p]; v2 = c_t33l[p]; }
+    } else bad = 1;
+    const unsigned m = __ballot_sync(Q_FULL, bad);
+    const int first_bad = m ? __ffs(m) - 1 : 32;
+    if (lane >= first_bad) { v1 = 0; v2 = 0; }
+    a1 += wsum(v1); a2 += wsum(v2);
+    nq += first_bad;
+    if (first_bad < 32) stop = true;
+  }
+  if (nq > qmax) nq = qmax;
+  const int bigv = count1 - 4 * nq;
+  int bits = a1, c1sel = 0;
+  if (a1 > a2) { bits = a2; c1sel = 1; }
+  const int count1bits = bits;
+  int r0 = gi->region0_count, r1 = gi->region1_count;
+  int ts0 = gi->table_select[0], ts1 = gi->table_select[1], ts2 = gi->table_select[2];
+  if (bigv != 0) {
+    int b1, b2;
+    const int bt = gi->block_type;
+    if (bt == BT_SHORT) {
+      b1 = 3 * T->sfb_s[3];
+      if (b1 > bigv) b1 = bigv;
+      b2 = bigv;
+    } else if (bt == BT_NORM) {
+      b1 = r0 = T->bv_scf[bigv - 2];
+      b2 = r1 = T->bv_scf[bigv - 1];
+      b2 = T->sfb_l[b1 + b2 + 2];
+      b1 = T->sfb_l[b1 + 1];
+      if (b2 < bigv) ts2 = choose_table_w(ix, b2, bigv, &bits);
+    } else {
+      r0 = 7; r1 = 22 - 1 - 7 - 1;
+      b1 = T->sfb_l[7 + 1];
+      b2 = bigv;
+      if (b1 > b2) b1 = b2;
+    }
+    b1 = min(b1, bigv);
+    b2 = min(b2, bigv);
+    if (0 < b1) ts0 = choose_table_w(ix, 0, b1, &bits);
+    if (b1 < b2) ts1 = choose_table_w(ix, b1, b2, &bits);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    gi->count1 = count1; gi->count1table_select = c1sel; gi->count1bits = count1bits; gi->big_values = bigv;
+    gi->region0_count = r0; gi->region1_count = r1;
+    gi->table_select[0] = ts0; gi->table_select[1] = ts1; gi->table_select[2] = ts2;
+    if (use_prev) {
+      int sc = 0;
+      if (bigv != 0 && gi->block_type == BT_NORM) { while (T->sfb_l[sc] < bigv) sc++; }
+      wk->pn_sfb_count1 = sc;
+    }
+  }
+  __syncwarp();
+  return bits;
+}
+
+/* step of scalefactor band sfb (Takehiro.js:205-209 / QuantizePVT.js:744-747) */
+__device__ __forceinline__ int sfb_step(const GranuleInfoDev* gi, const GcWork* wk, int sfb) {
+  return gi->global_gain - ((gi->scalefac[sfb] + (gi->preflag != 0 ? c_pretab[sfb < 22 ? sfb : 21] : 0)) << (gi->scalefac_scale + 1)) -
+         gi->subblock_gain[wk->window[sfb]] * 8;
+}
+
+/* count_bits (Takehiro.js:630-660) = range check + quantize_xrpow (:171-314) + noquant_count_bits */
+__device__ int count_bits_w(const Mp3Tables* T, GcWork* wk, GranuleInfoDev* gi, short* ix, bool use_prev) {
+  const int lane = LANE;
+  const double istep = (double)T->ipow20[gi->global_gain];
+  if (gi->xrpow_max > (double)Q_IXMAX / istep) return Q_LARGE_BITS;
+  const int sfbmax = gi->block_type == BT_SHORT ? 38 : 21;
+  const int mnz = gi->max_nonzero_coeff;
+  const bool prev_data_use = use_prev && (gi->global_gain == wk->pn_global_gain);
+  const bool calc_step = prev_data_use || gi->block_type == BT_NORM;
+  /* per-band decision: 0 skip (cached), 1 full quantizer, 2 zero/one quantizer; term = first non-cached band that
+   * crosses max_nonzero_coeff (the reference zero-fills the tail there and stops) */
+  int term = sfbmax + 1;
+  for (int s0 = 0; s0 <= sfbmax; s0 += 32) {
+    const int sfb = s0 + lane;
+    int md = 0, trunc_here = 0;
+    if (sfb <= sfbmax) {
+      int jst = 0;
+      for (int q = 0; q < sfb; q++) jst += wk->width[q];
+      const int step = calc_step ? sfb_step(gi, wk, sfb) : -1;
+      if (prev_data_use && wk->pn_step[sfb] == step) md = 0;
+      else {
+        if (jst + wk->width[sfb] > mnz) trunc_here = 1;
+        md = (use_prev && wk->pn_sfb_count1 > 0 && sfb >= wk->pn_sfb_count1 && wk->pn_step[sfb] > 0 && step >= wk->pn_step[sfb]) ? 2 : 1;
+      }
+      wk->mode[sfb] = (unsigned char)md;
+      wk->nstart[sfb] = jst;
+    }
+    const unsigned m = __ballot_sync(Q_FULL, trunc_here);
+    if (m && term == sfbmax + 1) term = s0 + __ffs(m) - 1;
+  }
+  __syncwarp();
+  int term_start = 576, term_len = 0;
+  if (term <= sfbmax) {
+    term_start = wk->nstart[term];
+    term_len = mnz - term_start + 1;
+    if (term_len < 0) term_len = 0;
+  }
+  const double compare01 = (1.0 - 0.4054) / istep;
+  for (int i = lane; i < 576; i += 32) {
+    const int sfb = wk->sfb_of_line[i];
+    int md;
+    if (sfb > sfbmax) continue;                 /* lines beyond the last band (sfb21 / sfb12 tail) */
+    if (sfb < term) md = wk->mode[sfb];
+    else if (sfb == term && i < term_start + (term_len & ~1)) md = 1;   /* truncated last piece: always full mode */
+    else {
+      if (term <= sfbmax && i >= mnz) ix[i] = 0;   /* Arrays.fill(pi, max_nonzero_coeff, 576, 0) */
+      continue;
+    }
+    if (term <= sfbmax && i >= mnz) { ix[i] = 0; if (!(sfb == term && i < term_start + (term_len & ~1))) continue; }
+    if (md == 0) continue;
+    const double xp = (double)wk->xrpow[i];
+    if (md == 2) ix[i] = (compare01 > xp) ? 0 : 1;
+    else {
+      double x = xp * istep;
+      const int rx = js_trunc(x);
+      x += (double)__ldg(&T->adj43[rx]);
+      ix[i] = (short)js_trunc(x);
+    }
+  }
+  __syncwarp();
+  return noquant_count_bits_w(T, ix, gi, wk, use_prev);
+}
+
+/* calc_noise (QuantizePVT.js:725-878) for quant_comp 9: over_count, over_SSD, max_noise (+ distort[]) */
+struct NoiseRes { int over_count; double over_SSD, max_noise; int bits; };
+__device__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const GranuleInfoDev* gi, const short* ix, NoiseRes* res) {
+  const int lane = LANE;
+  const int psymax = gi->psymax, mnz = gi->max_nonzero_coeff;
+  /* line cursor j is sequential (bands after the truncation point start where the previous one stopped) */
+  if (lane == 0) {
+    int j = 0;
+    for (int sfb = 0; sfb < psymax; sfb++) {
+      const int s = sfb_step(gi, wk, sfb);
+      if (wk->pn_step[sfb] == s) { wk->nlen[sfb] = -1; j += wk->width[sfb]; }
+      else {
+        int l = wk->width[sfb] >> 1;
+        if ((j + wk->width[sfb]) > mnz) { const int us = mnz - j + 1; l = us > 0 ? us >> 1 : 0; }
+        wk->nstart[sfb] = j; wk->nlen[sfb] = l;
+        j += 2 * l;
+      }
+    }
+  }
+  __syncwarp();
+  int over = 0; double ssd = 0, mxn = -20.0;
+  for (int s0 = 0; s0 < psymax; s0 += 32) {
+    const int sfb = s0 + lane;
+    if (sfb < psymax) {
+      const int s = sfb_step(gi, wk, sfb);
+      double noise;
+      if (wk->nlen[sfb] < 0) {
+        noise = (double)wk->pn_noise[sfb];
+        f32s d; d = noise / (double)wk->xmin[sfb];
+        wk->distort[sfb] = d.v;
+        noise = (double)wk->pn_noise_log[sfb];
+      } else {
+        const double step = (double)T->pow20[s + MP3_QMAX2];
+        int j = wk->nstart[sfb];
+        noise = 0;
+        for (int l = wk->nlen[sfb]; l > 0; l--) {
+          double temp;
+          temp = fabs((double)wk->xr[j]) - (double)__ldg(&T->pow43[ix[j]]) * step; j++; noise += temp * temp;
+          temp = fabs((double)wk->xr[j]) - (double)__ldg(&T->pow43[ix[j]]) * step; j++; noise += temp * temp;
+        }
+        wk->pn_step[sfb] = s;
+        { f32s t; t = noise; wk->pn_noise[sfb] = t.v; }
+        noise = noise / (double)wk->xmin[sfb];
+        { f32s t; t = noise; wk->distort[sfb] = t.v; }
+        noise = m3_log10(js_dmax(noise, 1E-20));
+        { f32s t; t = noise; wk->pn_noise_log[sfb] = t.v; }
+      }
+      if (noise > 0.0) {
+        int tmp = js_trunc(noise * 10 + .5);
+        if (tmp < 1) tmp = 1;
+        ssd += (double)tmp * (double)tmp;
+        over++;
+      }
+      mxn = js_dmax(mxn, noise);
+    }
+  }
+  /* integer-valued sums: order-free */
+  for (int o = 16; o > 0; o >>= 1) {
+    ssd += __shfl_xor_sync(Q_FULL, ssd, o);
+    const double other = __shfl_xor_sync(Q_FULL, mxn, o);
+    mxn = js_dmax(mxn, other);
+  }
+  over = wsum(over);
+  if (lane == 0) wk->pn_global_gain = gi->global_gain;
+  __syncwarp();
+  res->over_count = over; res->over_SSD = ssd; res->max_noise = mxn;
+}
+
+/* scale_bitcount (Takehiro.js:980-1030), lane 0 only; returns true when no legal scalefac_compress exists */
+__device__ bool scale_bitcount_l0(GranuleInfoDev* gi) {
+  int k, sfb, max_slen1 = 0, max_slen2 = 0;
+  const int* tab;
+  int* scalefac = gi->scalefac;
+  if (gi->block_type == BT_SHORT) tab = c_scale_short;
+  else {
+    tab = c_scale_long;
+    if (0 == gi->preflag) {
+      for (sfb = 11; sfb < 21; sfb++) if (scalefac[sfb] < c_pretab[sfb]) break;
+      if (sfb == 21) {
+        gi->preflag = 1;
+        for (sfb = 11; sfb < 21; sfb++) scalefac[sfb] -= c_pretab[sfb];
+      }
+    }
+  }
+  for (sfb = 0; sfb < gi->sfbdivide; sfb++) if (max_slen1 < scalefac[sfb]) max_slen1 = scalefac[sfb];
+  for (; sfb < gi->sfbmax; sfb++) if (max_slen2 < scalefac[sfb]) max_slen2 = scalefac[sfb];
+  gi->part2_length = Q_LARGE_BITS;
+  for (k = 0; k < 16; k++) {
+    if (max_slen1 < c_slen1_n[k] && max_slen2 < c_slen2_n[k] && gi->part2_length > tab[k]) {
+      gi->part2_length = tab[k];
+      gi->scalefac_compress = k;
+    }
+  }
+  return gi->part2_length == Q_LARGE_BITS;
+}
+
+__device__ bool loop_break_l0(const GranuleInfoDev* gi, const GcWork* wk) {
+  for (int sfb = 0; sfb < gi->sfbmax; sfb++)
+    if (gi->scalefac[sfb] + gi->subblock_gain[wk->window[sfb]] == 0) return false;
+  return true;
+}
+
+/* multiply xrpow of the bands flagged in wk->mode[] by `factor[band]` (amp_scalefac_bands / inc_scalefac_scale
+ * line loops, Quantize.js:650-655,690-695) and fold the new values into xrpow_max */
+__device__ void scale_xrpow_w(GcWork* wk, GranuleInfoDev* gi, double f34) {
+  const int lane = LANE;
+  float mx = 0.0f;
+  for (int i = lane; i < 576; i += 32) {
+    const int sfb = wk->sfb_of_line[i];
+    if (sfb < gi->sfbmax && wk->mode[sfb]) {
+      f32s v; v.v = wk->xrpow[i];
+      v *= f34;
+      wk->xrpow[i] = v.v;
+      mx = fmaxf(mx, v.v);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(Q_FULL, mx, o));
+  if (lane == 0 && (double)mx > gi->xrpow_max) gi->xrpow_max = (double)mx;
+  __syncwarp();
+}
+
+/* balance_noise (Quantize.js:783-846) on cod_info_w.  Returns true when a new scalefactor combination exists. */
+__device__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
+  const int lane = LANE;
+  GranuleInfoDev* gi = &wk->w;
+  /* ---- amp_scalefac_bands, noise_shaping_amp == 1 (Quantize.js:597-660) ---- */
+  const double ifq = gi->scalefac_scale == 0 ? 1.29683955465100964055 : 1.68179283050742922612;
+  if (lane == 0) {
+    double trigger = 0;
+    for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (trigger < (double)wk->distort[sfb]) trigger = (double)wk->distort[sfb];
+    if (trigger > 1.0) trigger = sqrt(trigger);     /* Math.pow(trigger, .5): fdlibm returns sqrt(x) for y == 0.5 */
+    else trigger *= .95;
+    for (int sfb = 0; sfb < gi->sfbmax; sfb++) {
+      const int amp = !((double)wk->distort[sfb] < trigger);
+      wk->mode[sfb] = (unsigned char)amp;
+      if (amp) gi->scalefac[sfb]++;
+    }
+  }
+  __syncwarp();
+  scale_xrpow_w(wk, gi, ifq);
+  /* ---- rest of balance_noise ---- */
+  int* flag = &wk->scratch[0];
+  if (lane == 0) {
+    int ret;
+    bool status = loop_break_l0(gi, wk);
+    if (status) ret = 0;                         /* all bands amplified */
+    else {
+      status = scale_bitcount_l0(gi);
+      if (!status) ret = 1;
+      else ret = 2;                              /* scalefactors too large: try scalefac_scale / subblock_gain */
+    }
+    *flag = ret;
+  }
+  __syncwarp();
+  int r = *flag;
+  __syncwarp();
+  if (r == 0) return false;
+  if (r == 1) return true;
+  bool status = true;
+  if (T->noise_shaping > 1) {
+    if (0 == gi->scalefac_scale) {
+      /* inc_scalefac_scale (Quantize.js:676-699) */
+      if (lane == 0) {
+        for (int sfb = 0; sfb < gi->sfbmax; sfb++) {
+          int s = gi->scalefac[sfb];
+          if (gi->preflag != 0) s += c_pretab[sfb < 22 ? sfb : 21];
+          const int odd = (s & 1) != 0;
+          if (odd) s++;
+          wk->mode[sfb] = (unsigned char)odd;
+          gi->scalefac[sfb] = s >> 1;
+        }
+        gi->preflag = 0;
+        gi->scalefac_scale = 1;
+      }
+      __syncwarp();
+      scale_xrpow_w(wk, gi, 1.29683955465100964055);
+      status = false;
+    } else if (gi->block_type == BT_SHORT) {      /* gfc.subblock_gain == 1 */
+      /* inc_subblock_gain (Quantize.js:705-781): lane 0 decides, all lanes rescale the touched windows */
+      if (lane == 0) {
+        int ret = 0;
+        int* scalefac = gi->scalefac;
+        for (int i = 0; i < MP3_SFBMAX; i++) wk->nlen[i] = -1;      /* per-band amp index: -1 none, else ipow20 index */
+        for (int window = 0; window < 3 && !ret; window++) {
+          int s1 = 0, s2 = 0, sfb;
+          for (sfb = gi->sfb_lmax + window; sfb < gi->sfbdivide; sfb += 3) if (s1 < scalefac[sfb]) s1 = scalefac[sfb];
+          for (; sfb < gi->sfbmax; sfb += 3) if (s2 < scalefac[sfb]) s2 = scalefac[sfb];
+          if (s1 < 16 && s2 < 8) continue;
+          if (gi->subblock_gain[window] >= 7) { ret = 1; break; }
+          gi->subblock_gain[window]++;
+          for (sfb = gi->sfb_lmax + window; sfb < gi->sfbmax; sfb += 3) {
+            int s = scalefac[sfb];
+            s = s - (4 >> gi->scalefac_scale);
+            if (s >= 0) { scalefac[sfb] = s; continue; }
+            scalefac[sfb] = 0;
+            wk->nlen[sfb] = 210 + s * (1 << (gi->scalefac_scale + 1));
+          }
+          wk->nlen[sfb] = 202;                      /* sfb12 window `window`: sfb == sfbmax + window */
+        }
+        *flag = ret;
+      }
+      __syncwarp();
+      /* NOTE: when inc_subblock_gain bails out with `true` mid-way the windows already processed stay modified,
+       * exactly like the reference (it returns without undoing). */
+      {
+        float mx = 0.0f;
+        for (int i = lane; i < 576; i += 32) {
+          const int sfb = wk->sfb_of_line[i];
+          if (sfb < MP3_SFBMAX && wk->nlen[sfb] >= 0) {
+            f32s v; v.v = wk->xrpow[i];
+            v *= (double)T->ipow20[wk->nlen[sfb]];
+            wk->xrpow[i] = v.v;
+            mx = fmaxf(mx, v.v);
+          }
+        }
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(Q_FULL, mx, o));
+        if (lane == 0 && (double)mx > gi->xrpow_max) gi->xrpow_max = (double)mx;
+        __syncwarp();
+      }
+      if (lane == 0) *flag = (*flag || loop_break_l0(gi, wk)) ? 1 : 0;
+      __syncwarp();
+      status = *flag != 0;
+      __syncwarp();
+    }
+  }
+  if (!status) {
+    if (lane == 0) *flag = scale_bitcount_l0(gi) ? 1 : 0;
+    __syncwarp();
+    status = *flag != 0;
+    __syncwarp();
+  }
+  return !status;
+}
+
+__device__ __forceinline__ void copy_gi_w(GranuleInfoDev* dst, const GranuleInfoDev* src) {
+  const int n = sizeof(GranuleInfoDev) / 4;
+  const int* s = reinterpret_cast<const int*>(src);
+  int* d = reinterpret_cast<int*>(dst);
+  for (int i = LANE; i < n; i += 32) d[i] = s[i];
+  __syncwarp();
+}
+__device__ __forceinline__ void copy_ix_w(short* dst, const short* src) {
+  const int* s = reinterpret_cast<const int*>(src);
+  int* d = reinterpret_cast<int*>(dst);
+  for (int i = LANE; i < 288; i += 32) d[i] = s[i];
+  __syncwarp();
+}
+
+/* bin_search_StepSize (Quantize.js:322-381) on cod_info (wk->b / ixb) */
+__device__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int desired_rate, int* old_value, int* current_step) {
+  GranuleInfoDev* gi = &wk->b;
+  int nBits;
+  int CurrentStep = *current_step;
+  bool flagGoneOver = false;
+  const int start = *old_value;
+  int Direction = 0;
+  int gain = start;
+  desired_rate -= gi->part2_length;
+  for (;;) {
+    int step;
+    if (LANE == 0) gi->global_gain = gain;
+    __syncwarp();
+    nBits = count_bits_w(T, wk, gi, wk->ixb, false);
+    if (CurrentStep == 1 || nBits == desired_rate) break;
+    if (nBits > desired_rate) {
+      if (Direction == 2) flagGoneOver = true;
+      if (flagGoneOver) CurrentStep /= 2;
+      Direction = 1;
+      step = CurrentStep;
+    } else {
+      if (Direction == 1) flagGoneOver = true;
+      if (flagGoneOver) CurrentStep /= 2;
+      Direction = 2;
+      step = -CurrentStep;
+    }
+    gain += step;
+    if (gain < 0) { gain = 0; flagGoneOver = true; }
+    if (gain > 255) { gain = 255; flagGoneOver = true; }
+  }
+  while (nBits > desired_rate && gain < 255) {
+    gain++;
+    if (LANE == 0) gi->global_gain = gain;
+    __syncwarp();
+    nBits = count_bits_w(T, wk, gi, wk->ixb, false);
+  }
+  *current_step = (start - gain >= 4) ? 4 : 2;
+  *old_value = gain;
+  if (LANE == 0) gi->part2_3_length = nBits;
+  __syncwarp();
+  return nBits;
+}
+
+/* outer_loop (Quantize.js:871-1052) for noise_shaping_amp 1, full_outer_loop 0, substep_shaping 0 */
+__device__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int targ_bits, int* old_value, int* current_step) {
+  const int lane = LANE;
+  NoiseRes best, cur;
+  int best_part2_3_length = 9999999;
+  for (int i = lane; i < MP3_SFBMAX; i += 32) { wk->pn_step[i] = 0; wk->pn_noise[i] = 0.0f; wk->pn_noise_log[i] = 0.0f; }
+  if (lane == 0) { wk->pn_global_gain = 0; wk->pn_sfb_count1 = 0; }
+  __syncwarp();
+  bin_search_w(T, wk, targ_bits, old_value, current_step);
+  calc_noise_w(T, wk, &wk->b, wk->ixb, &best);
+  best.bits = wk->b.part2_3_length;
+  copy_gi_w(&wk->w, &wk->b);
+  copy_ix_w(wk->ixw, wk->ixb);
+  int age = 0;
+  const int quant_comp = T->quant_comp;   /* 9 for long and short */
+  (void)quant_comp;
+  do {
+    const int search_limit = 3;
+    int maxggain = 255;
+    if (!balance_noise_w(T, wk)) break;
+    GranuleInfoDev* w = &wk->w;
+    if (w->scalefac_scale != 0) maxggain = 254;
+    const int huff_bits = targ_bits - w->part2_length;
+    if (huff_bits <= 0) break;
+    int p23;
+    while ((p23 = count_bits_w(T, wk, w, wk->ixw, true)) > huff_bits && w->global_gain <= maxggain) {
+      if (lane == 0) w->global_gain++;
+      __syncwarp();
+    }
+    if (lane == 0) w->part2_3_length = p23;
+    __syncwarp();
+    if (w->global_gain > maxggain) break;
+    if (best.over_count == 0) {
+      while ((p23 = count_bits_w(T, wk, w, wk->ixw, true)) > best_part2_3_length && w->global_gain <= maxggain) {
+        if (lane == 0) w->global_gain++;
+        __syncwarp();
+      }
+      if (lane == 0) w->part2_3_length = p23;
+      __syncwarp();
+      if (w->global_gain > maxggain) break;
+    }
+    calc_noise_w(T, wk, w, wk->ixw, &cur);
+    cur.bits = w->part2_3_length;
+    /* quant_compare, case 9 (Quantize.js:493-505,560-567) */
+    bool better;
+    if (best.over_count > 0) {
+      better = cur.over_SSD <= best.over_SSD;
+      if (cur.over_SSD == best.over_SSD) better = cur.bits < best.bits;
+    } else {
+      better = ((cur.max_noise < 0) && ((cur.max_noise * 10 + cur.bits) <= (best.max_noise * 10 + best.bits)));
+    }
+    if (best.over_count == 0) better = better && cur.bits < best.bits;
+    if (better) {
+      best_part2_3_length = wk->b.part2_3_length;   /* sic: read before the assign (Quantize.js:996-998) */
+      best = cur;
+      copy_gi_w(&wk->b, &wk->w);
+      copy_ix_w(wk->ixb, wk->ixw);
+      age = 0;
+    } else {
+      if (++age > search_limit && best.over_count == 0) break;
+    }
+  } while ((wk->w.global_gain + wk->w.scalefac_scale) < 255);
+}
+
+/* athAdjust (QuantizePVT.js:541-561) */
+__device__ double ath_adjust_dev(double a, double x, double athFloor) {
+  const double o = 90.30873362, p = 94.82444863;
+  double u = m3_log10(x) * 10.0;
+  const double v = a * a;
+  double w = 0.0;
+  u -= athFloor;
+  if (v > 1E-20) w = 1. + m3_log10(v) * (10.0 / o);
+  if (w < 0) w = 0.;
+  u *= w;
+  u += athFloor + o - p;
+  return m3_pow(10., 0.1 * u);
+}
+
+/* init_outer_loop + psfb21_analogsilence + init_xrpow + calc_xmin for one gc (Quantize.js:204-306,147-202,105-138;
+ * QuantizePVT.js:569-719).  Returns false when the granule is digital silence (all l3_enc = 0). */
+__device__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameShared* fs, const float* __restrict__ xr_g, int block_type,
+                             const PsyRatioDev* __restrict__ ratio, double ath_adjust) {
+  const int lane = LANE;
+  GranuleInfoDev* gi = &wk->b;
+  const bool is_short = block_type == BT_SHORT;
+  if (lane == 0) {
+    gi->part2_3_length = 0; gi->big_values = 0; gi->count1 = 0; gi->global_gain = 210; gi->scalefac_compress = 0;
+    gi->table_select[0] = gi->table_select[1] = gi->table_select[2] = 0;
+    gi->subblock_gain[0] = gi->subblock_gain[1] = gi->subblock_gain[2] = gi->subblock_gain[3] = 0;
+    gi->region0_count = 0; gi->region1_count = 0; gi->preflag = 0; gi->scalefac_scale = 0; gi->count1table_select = 0;
+    gi->part2_length = 0; gi->block_type = block_type; gi->count1bits = 0;
+    gi->sfb_lmax = is_short ? 0 : 21; gi->sfb_smin = is_short ? 0 : 12;
+    gi->psy_lmax = is_short ? 0 : 21;
+    gi->psymax = is_short ? 36 : 21; gi->sfbmax = is_short ? 36 : 21; gi->sfbdivide = is_short ? 18 : 11;
+    gi->max_nonzero_coeff = 575;
+    for (int i = 0; i < MP3_SFBMAX; i++) gi->scalefac[i] = 0;
+    gi->xrpow_max = 0;
+  }
+  /* band geometry */
+  if (!is_short) {
+    for (int sfb = lane; sfb < MP3_SFBMAX; sfb += 32) {
+      wk->width[sfb] = sfb < 22 ? T->sfb_l[sfb + 1] - T->sfb_l[sfb] : 0;
+      wk->window[sfb] = 3;
+    }
+    for (int i = lane; i < 576; i += 32) { int s = 0; while (T->sfb_l[s + 1] <= i) s++; wk->sfb_of_line[i] = (unsigned char)s; }
+    for (int i = lane; i < 576; i += 32) wk->xr[i] = xr_g[i];
+  } else {
+    for (int j = lane; j < MP3_SFBMAX; j += 32) {
+      const int sfb = j / 3;
+      wk->width[j] = T->sfb_s[sfb + 1] - T->sfb_s[sfb];
+      wk->window[j] = j - 3 * sfb;
+    }
+    /* reorder (Quantize.js:262-278): band sfb, window w, line l  ->  3*start + w*width + (l-start) */
+    for (int i = lane; i < 576; i += 32) {
+      const int l = i / 3, w = i - 3 * l;
+      int sfb = 0;
+      while (T->sfb_s[sfb + 1] <= l) sfb++;
+      const int start = T->sfb_s[sfb], wd = T->sfb_s[sfb + 1] - start;
+      const int dst = 3 * start + w * wd + (l - start);
+      wk->xr[dst] = xr_g[i];
+      wk->sfb_of_line[dst] = (unsigned char)(3 * sfb + w);
+    }
+  }
+  __syncwarp();
+  /* analog silence in the pseudo bands above sfb21 / sfb12 (sequential from the top; lane 0) */
+  if (lane == 0) {
+    if (!is_short) {
+      bool stop = false;
+      for (int g = 5; g >= 0 && !stop; g--) {
+        const int start = T->psfb21[g], end = T->psfb21[g + 1];
+        double ath21 = fs->ath21[g];
+        if ((double)T->longfact[21] > 1e-12) ath21 *= (double)T->longfact[21];
+        for (int j = end - 1; j >= start; j--) {
+          if (fabs((double)wk->xr[j]) < ath21) wk->xr[j] = 0.0f;
+          else { stop = true; break; }
+        }
+      }
+    } else {
+      for (int block = 0; block < 3; block++) {
+        bool stop = false;
+        for (int g = 5; g >= 0 && !stop; g--) {
+          const int start = T->sfb_s[12] * 3 + (T->sfb_s[13] - T->sfb_s[12]) * block + (T->psfb12[g] - T->psfb12[0]);
+          const int end = start + (T->psfb12[g + 1] - T->psfb12[g]);
+          double ath12 = fs->ath12[g];
+          if ((double)T->shortfact[12] > 1e-12) ath12 *= (double)T->shortfact[12];
+          for (int j = end - 1; j >= start; j--) {
+            if (fabs((double)wk->xr[j]) < ath12) wk->xr[j] = 0.0f;
+            else { stop = true; break; }
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  /* ---- init_xrpow: max_nonzero_coeff is still 575 here (set by init_outer_loop) ---- */
+  {
+    float mx = 0.0f, amax = 0.0f;
+    for (int i = lane; i < 576; i += 32) {
+      const double tmp = fabs((double)wk->xr[i]);
+      f32s p; p = sqrt(tmp * sqrt(tmp));
+      wk->xrpow[i] = p.v;
+      mx = fmaxf(mx, p.v);
+      amax = fmaxf(amax, (float)tmp);
+    }
+    for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(Q_FULL, mx, o)); amax = fmaxf(amax, __shfl_xor_sync(Q_FULL, amax, o)); }
+    /* sum > 1e-20 ? (Quantize.js:129): a running sum of non-negative terms is >= its largest term */
+    bool energy;
+    if ((double)amax > 1E-20) energy = true;
+    else {
+      if (lane == 0) { double sum = 0; for (int i = 0; i <= 575; ++i) sum += fabs((double)wk->xr[i]); wk->scratch[1] = sum > 1E-20; }
+      __syncwarp();
+      energy = wk->scratch[1] != 0;
+      __syncwarp();
+    }
+    if (lane == 0) gi->xrpow_max = (double)mx;
+    __syncwarp();
+    if (!energy) {
+      for (int i = lane; i < 576; i += 32) wk->ixb[i] = 0;
+      __syncwarp();
+      return false;
+    }
+  }
+  /* ---- calc_xmin ---- */
+  const double masking_lower = is_short ? T->masking_lower_short : T->masking_lower_long;
+  if (!is_short) {
+    if (lane < 21) {
+      const int gsfb = lane;
+      int j = T->sfb_l[gsfb];
+      const int width = wk->width[gsfb];
+      double xmin = ath_adjust * (double)T->ath_l[gsfb];
+      double en0 = 0.0;
+      for (int l = width >> 1; l > 0; l--) {
+        double xa = (double)wk->xr[j] * (double)wk->xr[j]; en0 += xa; j++;
+        double xb = (double)wk->xr[j] * (double)wk->xr[j]; en0 += xb; j++;
+      }
+      const double e = (double)ratio->en_l[gsfb];
+      if (e > 0.0) {
+        const double x = en0 * (double)ratio->thm_l[gsfb] * masking_lower / e;
+        if (xmin < x) xmin = x;
+      }
+      f32s o; o = xmin * (double)T->longfact[gsfb];
+      wk->xmin[gsfb] = o.v;
+    }
+    /* highest non-zero coefficient (QuantizePVT.js:645-653) */
+    int last = -1;
+    for (int i = lane; i < 576; i += 32) if (wk->xr[i] != 0.0f) last = i;
+    last = wmax(last);
+    int mnz = last + 1;
+    if (mnz > 575) mnz = 575;
+    if (lane == 0) gi->max_nonzero_coeff = mnz;
+  } else {
+    for (int t = lane; t < 36; t += 32) {
+      const int sfb = t / 3, b = t - 3 * sfb;
+      const int width = wk->width[t];
+      int j = 3 * T->sfb_s[sfb] + b * width;
+      const double tmpATH = ath_adjust * (double)T->ath_s[sfb];
+      double en0 = 0.0;
+      for (int l = width >> 1; l > 0; l--) {
+        double xa = (double)wk->xr[j] * (double)wk->xr[j]; en0 += xa; j++;
+        double xb = (double)wk->xr[j] * (double)wk->xr[j]; en0 += xb; j++;
+      }
+      double xmin = tmpATH;
+      const double e = (double)ratio->en_s[sfb][b];
+      if (e > 0.0) {
+        const double x = en0 * (double)ratio->thm_s[sfb][b] * masking_lower / e;
+        if (xmin < x) xmin = x;
+      }
+      f32s o; o = xmin * (double)T->shortfact[sfb];
+      wk->xmin[t] = o.v;
+    }
+    __syncwarp();
+    if (lane < 12) {   /* temporal smoothing across the three windows (useTemporal, QuantizePVT.js:707-714) */
+      f32s* p = reinterpret_cast<f32s*>(&wk->xmin[3 * lane]);
+      if ((double)p[0] > (double)p[1]) p[1] += ((double)p[0] - (double)p[1]) * T->decay;
+      if ((double)p[1] > (double)p[2]) p[2] += ((double)p[1] - (double)p[2]) * T->decay;
+    }
+    if (lane == 0) gi->max_nonzero_coeff = 575;
+  }
+  __syncwarp();
+  return true;
+}
+
+/* best_scalefac_store without the scfsi part (Takehiro.js:809-875), then scfsi_calc for gr1 (lane 0 logic) */
+__device__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, int gr, int ch) {
+  const int lane = LANE;
+  GranuleInfoDev* gi = &wk->b;
+  /* bands whose quantised lines are all zero */
+  for (int s0 = 0; s0 < gi->sfbmax; s0 += 32) {
+    const int sfb = s0 + lane;
+    if (sfb < gi->sfbmax) {
+      int j = 0;
+      for (int q = 0; q < sfb; q++) j += wk->width[q];
+      bool any = false;
+      for (int l = 0; l < wk->width[sfb]; l++) if (wk->ixb[j + l] != 0) { any = true; break; }
+      wk->mode[sfb] = any ? 1 : 0;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    int recalc = 0;
+    for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (!wk->mode[sfb]) gi->scalefac[sfb] = recalc = -2;
+    if (0 == gi->scalefac_scale && 0 == gi->preflag) {
+      int s = 0;
+      for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] > 0) s |= gi->scalefac[sfb];
+      if (0 == (s & 1) && s != 0) {
+        for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] > 0) gi->scalefac[sfb] >>= 1;
+        gi->scalefac_scale = recalc = 1;
+      }
+    }
+    if (0 == gi->preflag && gi->block_type != BT_SHORT) {
+      int sfb;
+      for (sfb = 11; sfb < 21; sfb++) if (gi->scalefac[sfb] < c_pretab[sfb] && gi->scalefac[sfb] != -2) break;
+      if (sfb == 21) {
+        for (sfb = 11; sfb < 21; sfb++) if (gi->scalefac[sfb] > 0) gi->scalefac[sfb] -= c_pretab[sfb];
+        gi->preflag = recalc = 1;
+      }
+    }
+    for (int i = 0; i < 4; i++) fs->scfsi[ch][i] = 0;
+    if (gr == 1 && fs->fin[0][ch].gi.block_type != BT_SHORT && gi->block_type != BT_SHORT) {
+      /* scfsi_calc (Takehiro.js:877-943) */
+      const int* g0sf = fs->fin[0][ch].gi.scalefac;
+      const int band[5] = {0, 6, 11, 16, 21};
+      int sfb;
+      for (int i = 0; i < 4; i++) {
+        for (sfb = band[i]; sfb < band[i + 1]; sfb++)
+          if (g0sf[sfb] != gi->scalefac[sfb] && gi->scalefac[sfb] >= 0) break;
+        if (sfb == band[i + 1]) {
+          for (sfb = band[i]; sfb < band[i + 1]; sfb++) gi->scalefac[sfb] = -1;
+          fs->scfsi[ch][i] = 1;
+        }
+      }
+      int s1 = 0, c1 = 0;
+      for (sfb = 0; sfb < 11; sfb++) {
+        if (gi->scalefac[sfb] == -1) continue;
+        c1++;
+        if (s1 < gi->scalefac[sfb]) s1 = gi->scalefac[sfb];
+      }
+      int s2 = 0, c2 = 0;
+      for (; sfb < 21; sfb++) {
+        if (gi->scalefac[sfb] == -1) continue;
+        c2++;
+        if (s2 < gi->scalefac[sfb]) s2 = gi->scalefac[sfb];
+      }
+      for (int i = 0; i < 16; i++) {
+        if (s1 < c_slen1_n[i] && s2 < c_slen2_n[i]) {
+          const int c = c_slen1_tab[i] * c1 + c_slen2_tab[i] * c2;
+          if (gi->part2_length > c) { gi->part2_length = c; gi->scalefac_compress = i; }
+        }
+      }
+      recalc = 0;
+    }
+    for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] == -2) gi->scalefac[sfb] = 0;
+    if (recalc != 0) scale_bitcount_l0(gi);
+  }
+  __syncwarp();
+}
+
+/* best_huffman_divide (Takehiro.js:727-800) on cod_info (wk->b / ixb); wk->w is free to use as cod_info2 */
+__device__ void recalc_divide_sub_w(const Mp3Tables* T, GcWork* wk, const GranuleInfoDev* cod_info2, const int* r01_bits,
+                                    const int* r01_div, const int* r0_tbl, const int* r1_tbl) {
+  GranuleInfoDev* gi = &wk->b;
+  const int bigv = cod_info2->big_values;
+  for (int r2 = 2; r2 < 22 + 1; r2++) {
+    const int a2 = T->sfb_l[r2];
+    if (a2 >= bigv) break;
+    int bits = r01_bits[r2 - 2] + cod_info2->count1bits;
+    if (gi->part2_3_length <= bits) break;
+    const int r2t = choose_table_w(wk->ixb, a2, bigv, &bits);
+    if (gi->part2_3_length <= bits) continue;
+    __syncwarp();
+    if (cod_info2 != gi) copy_gi_w(gi, cod_info2);
+    if (LANE == 0) {
+      gi->part2_3_length = bits;
+      gi->region0_count = r01_div[r2 - 2];
+      gi->region1_count = r2 - 2 - r01_div[r2 - 2];
+      gi->table_select[0] = r0_tbl[r2 - 2];
+      gi->table_select[1] = r1_tbl[r2 - 2];
+      gi->table_select[2] = r2t;
+    }
+    __syncwarp();
+  }
+}
+
+__device__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* wk) {
+  const int lane = LANE;
+  GranuleInfoDev* gi = &wk->b;
+  GranuleInfoDev* c2 = &wk->w;
+  const short* ix = wk->ixb;
+  int* r01_bits = wk->nstart;          /* 23 entries each; reuse per-band scratch */
+  int* r01_div = wk->nlen;
+  int* r0_tbl = wk->pn_step;
+  int* r1_tbl = reinterpret_cast<int*>(wk->pn_noise);
+  copy_gi_w(c2, gi);
+  if (gi->block_type == BT_NORM) {
+    /* recalc_divide_init (Takehiro.js:666-700) */
+    const int bigv = gi->big_values;
+    for (int i = lane; i < 23; i += 32) r01_bits[i] = Q_LARGE_BITS;
+    __syncwarp();
+    for (int r0 = 0; r0 < 16; r0++) {
+      const int a1 = T->sfb_l[r0 + 1];
+      if (a1 >= bigv) break;
+      int r0bits = 0;
+      const int r0t = choose_table_w(ix, 0, a1, &r0bits);
+      for (int r1 = 0; r1 < 8; r1++) {
+        const int a2 = T->sfb_l[r0 + r1 + 2];
+        if (a2 >= bigv) break;
+        int bits = r0bits;
+        const int r1t = choose_table_w(ix, a1, a2, &bits);
+        if (r01_bits[r0 + r1] > bits) {
+          __syncwarp();
+          if (lane == 0) { r01_bits[r0 + r1] = bits; r01_div[r0 + r1] = r0; r0_tbl[r0 + r1] = r0t; r1_tbl[r0 + r1] = r1t; }
+          __syncwarp();
+        }
+      }
+    }
+    recalc_divide_sub_w(T, wk, c2, r01_bits, r01_div, r0_tbl, r1_tbl);
+  }
+  int i = c2->big_values;
+  if (i == 0 || (ix[i - 2] | ix[i - 1]) > 1) return;
+  i = gi->count1 + 2;
+  if (i > 576) return;
+  copy_gi_w(c2, gi);
+  int a1 = 0, a2 = 0;
+  {
+    /* quadruples from count1+2 down to the old big_values; integer sums, any order */
+    const int top = i, bv = c2->big_values;
+    int v1 = 0, v2 = 0, n = 0;
+    for (int q = lane; top - 4 * q > bv; q += 32) {
+      const int e = top - 4 * q;
+      const int p = ((ix[e - 4] * 2 + ix[e - 3]) * 2 + ix[e - 2]) * 2 + ix[e - 1];
+      v1 += c_t32l[p]; v2 += c_t33l[p]; n++;
+    }
+    a1 = wsum(v1); a2 = wsum(v2);
+    i = top - 4 * wsum(n);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    c2->count1 = gi->count1 + 2;
+    c2->big_values = i;
+    c2->count1table_select = 0;
+    int a = a1;
+    if (a1 > a2) { a = a2; c2->count1table_select = 1; }
+    c2->count1bits = a;
+  }
+  __syncwarp();
+  if (a1 > a2) a1 = a2;
+  if (c2->block_type == BT_NORM) recalc_divide_sub_w(T, wk, c2, r01_bits, r01_div, r0_tbl, r1_tbl);
+  else {
+    int p23 = a1;
+    int b1 = T->sfb_l[7 + 1];
+    if (b1 > i) b1 = i;
+    int t0 = c2->table_select[0], t1 = c2->table_select[1];
+    if (b1 > 0) t0 = choose_table_w(ix, 0, b1, &p23);
+    if (i > b1) t1 = choose_table_w(ix, b1, i, &p23);
+    __syncwarp();
+    if (lane == 0) { c2->part2_3_length = p23; c2->table_select[0] = t0; c2->table_select[1] = t1; }
+    __syncwarp();
+    if (gi->part2_3_length > c2->part2_3_length) copy_gi_w(gi, c2);
+  }
+}
+
+/* ---- bit packing (BitStream.js:110-138,428-689) --------------------------------------------------------- */
+__device__ __forceinline__ void put_bits(unsigned int* buf, int pos, unsigned int val, int n) {
+  if (n <= 0) return;
+  val &= (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
+  const int w = pos >> 5, off = pos & 31;
+  const int room = 32 - off;
+  if (n <= room) atomicOr(&buf[w], val << (room - n));
+  else {
+    atomicOr(&buf[w], val >> (n - room));
+    atomicOr(&buf[w + 1], val << (32 - (n - room)));
+  }
+}
+
+/* main data of one gc, starting at bit `pos` of the frame buffer; returns nothing (lengths are already known) */
+__device__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, const GcFinal* f, int pos) {
+  const int lane = LANE;
+  const GranuleInfoDev* gi = &f->gi;
+  unsigned int* buf = fs->bits;
+  /* scalefactors (writeMainData, BitStream.js:609-625): serial, <= 36 values */
+  if (lane == 0) {
+    const int slen1 = c_slen1_tab[gi->scalefac_compress], slen2 = c_slen2_tab[gi->scalefac_compress];
+    int p = pos;
+    for (int sfb = 0; sfb < gi->sfbmax; sfb++) {
+      if (gi->scalefac[sfb] == -1) continue;
+      const int sl = sfb < gi->sfbdivide ? slen1 : slen2;
+      put_bits(buf, p, (unsigned)gi->scalefac[sfb], sl);
+      p += sl;
+    }
+  }
+  pos += gi->part2_length;
+  const int bigv = gi->big_values;
+  int r1s, r2s;
+  if (gi->block_type == BT_SHORT) {
+    r1s = 3 * T->sfb_s[3];
+    if (r1s > bigv) r1s = bigv;
+    r2s = bigv;
+  } else {
+    r1s = T->sfb_l[gi->region0_count + 1];
+    r2s = T->sfb_l[gi->region0_count + 1 + gi->region1_count + 1];
+    if (r1s > bigv) r1s = bigv;
+    if (r2s > bigv) r2s = bigv;
+  }
+  /* big_values pairs: lane handles a contiguous run of pairs so that one prefix sum gives every bit position */
+  const int npairs = bigv >> 1;
+  const int per = (npairs + 31) >> 5;
+  const int p0 = lane * per, p1 = min(npairs, p0 + per);
+  int mybits = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    int at = 0;
+    if (pass == 1) {
+      int incl = mybits;
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(Q_FULL, incl, o); if (lane >= o) incl += v; }
+      at = pos + incl - mybits;
+    }
+    for (int pr = p0; pr < p1; pr++) {
+      const int i = 2 * pr;
+      const int tb = i < r1s ? gi->table_select[0] : (i < r2s ? gi->table_select[1] : gi->table_select[2]);
+      if (tb == 0) continue;
+      const int hx = c_huff_xlen[tb];
+      int linbits = hx, xlen = hx;
+      int cbits = 0, xbits = 0;
+      unsigned ext = 0;
+      int x1 = f->ix[i], x2 = f->ix[i + 1];
+      if (x1 != 0) { if ((f->neg[i >> 5] >> (i & 31)) & 1) ext++; cbits--; }
+      if (tb > 15) {
+        if (x1 > 14) { ext |= (unsigned)(x1 - 15) << 1; xbits = linbits; x1 = 15; }
+        if (x2 > 14) { ext <<= linbits; ext |= (unsigned)(x2 - 15); xbits += linbits; x2 = 15; }
+        xlen = 16;
+      }
+      if (x2 != 0) { ext <<= 1; if ((f->neg[(i + 1) >> 5] >> ((i + 1) & 31)) & 1) ext++; cbits--; }
+      const int idx = x1 * xlen + x2;
+      xbits -= cbits;
+      cbits += c_huff_len[c_huff_off[tb] + idx];
+      if (pass == 0) mybits += cbits + xbits;
+      else {
+        put_bits(buf, at, c_huff_code[c_huff_off[tb] + idx], cbits);
+        put_bits(buf, at + cbits, ext, xbits);
+        at += cbits + xbits;
+      }
+    }
+  }
+  const int big_bits = wsum(mybits);
+  pos += big_bits;
+  /* count1 quadruples */
+  const int nquads = (gi->count1 - bigv) >> 2;
+  const int perq = (nquads + 31) >> 5;
+  const int q0 = lane * perq, q1 = min(nquads, q0 + perq);
+  const int tb = gi->count1table_select + 32;
+  mybits = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    int at = 0;
+    if (pass == 1) {
+      int incl = mybits;
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(Q_FULL, incl, o); if (lane >= o) incl += v; }
+      at = pos + incl - mybits;
+    }
+    for (int q = q0; q < q1; q++) {
+      const int i = bigv + 4 * q;
+      int huffbits = 0, p = 0;
+      if (f->ix[i] != 0) { p += 8; if ((f->neg[i >> 5] >> (i & 31)) & 1) huffbits++; }
+      if (f->ix[i + 1] != 0) { p += 4; huffbits *= 2; if ((f->neg[(i + 1) >> 5] >> ((i + 1) & 31)) & 1) huffbits++; }
+      if (f->ix[i + 2] != 0) { p += 2; huffbits *= 2; if ((f->neg[(i + 2) >> 5] >> ((i + 2) & 31)) & 1) huffbits++; }
+      if (f->ix[i + 3] != 0) { p++; huffbits *= 2; if ((f->neg[(i + 3) >> 5] >> ((i + 3) & 31)) & 1) huffbits++; }
+      const int len = c_huff_len[c_huff_off[tb] + p];
+      if (pass == 0) mybits += len;
+      else { put_bits(buf, at, (unsigned)huffbits + c_huff_code[c_huff_off[tb] + p], len); at += len; }
+    }
+  }
+  __syncwarp();
+}
+
+/* header + side info (encodeSideInfo2, BitStream.js:259-426, MPEG-1) by one thread */
+__device__ void pack_sideinfo(const Mp3Tables* T, FrameShared* fs, int padding) {
+  unsigned int* buf = fs->bits;
+  int p = 0;
+#define WH(v, n) do { put_bits(buf, p, (unsigned)(v), (n)); p += (n); } while (0)
+  const int nch = T->nch;
+  WH(0xfff, 12); WH(1, 1); WH(4 - 3, 2); WH(1, 1);
+  WH(T->bitrate_index, 4); WH(T->samplerate_index, 2); WH(padding, 1); WH(0, 1);
+  WH(T->mono ? 3 : 0, 2); WH(0, 2); WH(0, 1); WH(1, 1); WH(0, 2);
+  WH(0, 9);
+  WH(0, nch == 2 ? 3 : 5);
+  for (int ch = 0; ch < nch; ch++) for (int b = 0; b < 4; b++) WH(fs->scfsi[ch][b], 1);
+  for (int gr = 0; gr < 2; gr++) for (int ch = 0; ch < nch; ch++) {
+    GranuleInfoDev* gi = &fs->fin[gr][ch].gi;
+    WH(gi->part2_3_length + gi->part2_length, 12);
+    WH(gi->big_values / 2, 9);
+    WH(gi->global_gain, 8);
+    WH(gi->scalefac_compress, 4);
+    if (gi->table_select[0] == 14) gi->table_select[0] = 16;
+    if (gi->table_select[1] == 14) gi->table_select[1] = 16;
+    if (gi->block_type != BT_NORM) {
+      WH(1, 1); WH(gi->block_type, 2); WH(0, 1);
+      WH(gi->table_select[0], 5); WH(gi->table_select[1], 5);
+      WH(gi->subblock_gain[0], 3); WH(gi->subblock_gain[1], 3); WH(gi->subblock_gain[2], 3);
+    } else {
+      WH(0, 1);
+      if (gi->table_select[2] == 14) gi->table_select[2] = 16;
+      WH(gi->table_select[0], 5); WH(gi->table_select[1], 5); WH(gi->table_select[2], 5);
+      WH(gi->region0_count, 4); WH(gi->region1_count, 3);
+    }
+    WH(gi->preflag, 1); WH(gi->scalefac_scale, 1); WH(gi->count1table_select, 1);
+  }
+#undef WH
+}
+
+/* ---- the frame kernel ------------------------------------------------------------------------------------ */
+/* grid-stride over a work list of frame rows.  block = 32 * nch threads. */
+__global__ void __launch_bounds__(64)
+k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, const float* __restrict__ xr,
+                const PsyRatioDev* __restrict__ ratio, const signed char* __restrict__ bt_final,
+                const double* __restrict__ ath_q, QuantFrameState* __restrict__ qs, GranuleInfoDev* __restrict__ ginfo_out,
+                short* __restrict__ l3enc_out, const int* __restrict__ list, const int* __restrict__ count_ptr, int count_direct,
+                int revalidate, uint8_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FrameShared* fs = reinterpret_cast<FrameShared*>(smem_raw);
+  const int nch = T->nch;
+  const int ch = threadIdx.x >> 5, lane = LANE;
+  GcWork* wk = &fs->wk[ch];
+  const int nwork = count_ptr ? *count_ptr : count_direct;
+  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const int frow = list ? list[wi] : wi;
+    QuantFrameState* q = qs + frow;
+    const int z = q->stream;
+    const StreamDesc& sd = streams[z];
+    const int f = q->rel_frame;
+    const long long kabs = (long long)sd.frame0 + f;
+    const double ath_adjust = ath_q[frow];
+    __syncthreads();
+    /* prologue: frame buffer, analog-silence thresholds, in-state */
+    for (int i = threadIdx.x; i < 368; i += blockDim.x) fs->bits[i] = 0;
+    if (threadIdx.x < 12) {
+      const int g = threadIdx.x % 6;
+      if (threadIdx.x < 6) fs->ath21[g] = ath_adjust_dev(ath_adjust, (double)T->ath_psfb21[g], T->ath_floor);
+      else fs->ath12[g] = ath_adjust_dev(ath_adjust, (double)T->ath_psfb12[g], T->ath_floor);
+    }
+    if (threadIdx.x < 2) { fs->old_value[threadIdx.x] = q->in_old[threadIdx.x]; fs->current_step[threadIdx.x] = q->in_step[threadIdx.x]; fs->used_bits[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) fs->flag = 0;
+    __syncthreads();
+
+    const int padding = (int)(pad_count(kabs, T->frac_SpF, T->samplerate) - pad_count(kabs - 1, T->frac_SpF, T->samplerate));
+    const int frame_bytes = T->frame_bytes_nopad + padding;
+    const int frame_bits = 8 * frame_bytes;
+    const int mean_bits = (frame_bits - T->sideinfo_len * 8) / 2;      /* Reservoir.js:83 (exact: multiple of 4) */
+    int old_value = fs->old_value[ch], current_step = fs->current_step[ch];
+
+    for (int gr = 0; gr < 2; gr++) {
+      /* on_pe with the reservoir disabled (QuantizePVT.js:421-484 + Reservoir.js:190-229): gr0 gets mean_bits, gr1
+       * additionally what gr0 left over; per channel trunc(tbits / nch), capped at 4095; PE never matters */
+      if (threadIdx.x == 0) {
+        int tbits = mean_bits;
+        if (gr == 1) {
+          const int resv = -(fs->used_bits[0] + (nch == 2 ? fs->used_bits[1] : 0)) + mean_bits;   /* ResvSize + mean_bits */
+          if (resv * 10 > 0) tbits += resv;
+        }
+        for (int c = 0; c < nch; c++) {
+          double t = (double)tbits / nch;
+          if (t > 4095) t = 4095;
+          fs->targ_bits[c] = (int)t;
+        }
+        int bits = 0;
+        for (int c = 0; c < nch; c++) bits += fs->targ_bits[c];
+        if (bits > 7680) for (int c = 0; c < nch; c++) { fs->targ_bits[c] = fs->targ_bits[c] * 7680; fs->targ_bits[c] = (int)((double)fs->targ_bits[c] / bits); }
+      }
+      __syncthreads();
+      const size_t urow = (size_t)sd.unit_base + 2 * f + gr;
+      const int bt = bt_final[urow * 2 + ch];
+      /* masking of psy unit (2f+gr-1): halo-shifted row = unit_base + z + (2f+gr-1) + 1 */
+      const PsyRatioDev* rt = ratio + ((size_t)sd.unit_base + z + 2 * f + gr) * nch + ch;
+      const bool have = gc_prepare_w(T, wk, fs, xr + (urow * nch + ch) * 576, bt, rt, ath_adjust);
+      if (have) {
+        outer_loop_w(T, wk, fs->targ_bits[ch], &old_value, &current_step);
+        if (gr == 0 && lane == 0) { q->bs_gain0[ch] = old_value; q->bs_step0[ch] = current_step; }
+      }
+      /* iteration_finish_one (Quantize.js:1059-1078) */
+      best_scalefac_store_w(wk, fs, gr, ch);
+      best_huffman_divide_w(T, wk);
+      /* keep what the packer needs */
+      GcFinal* fin = &fs->fin[gr][ch];
+      copy_gi_w(&fin->gi, &wk->b);
+      copy_ix_w(fin->ix, wk->ixb);
+      for (int w = lane; w < 18; w += 32) {
+        unsigned m = 0;
+        for (int b = 0; b < 32; b++) if (wk->xr[32 * w + b] < 0.0f) m |= 1u << b;
+        fin->neg[w] = m;
+      }
+      if (lane == 0) fs->used_bits[ch] = wk->b.part2_3_length + wk->b.part2_length;
+      if (ginfo_out) copy_gi_w(&ginfo_out[urow * nch + ch], &wk->b);
+      if (l3enc_out) copy_ix_w(l3enc_out + (urow * nch + ch) * 576, wk->ixb);
+      __syncthreads();
+    }
+    if (lane == 0) { q->out_old[ch] = old_value; q->out_step[ch] = current_step; }
+    /* ---- format_bitstream: side info, main data, ancillary stuffing ---- */
+    if (threadIdx.x == 0) pack_sideinfo(T, fs, padding);
+    __syncthreads();
+    {
+      int pos = 8 * T->sideinfo_len;
+      int my_pos[2] = {0, 0};
+      for (int gr = 0; gr < 2; gr++) for (int c = 0; c < nch; c++) {
+        if (c == ch) my_pos[gr] = pos;
+        pos += fs->fin[gr][c].gi.part2_3_length + fs->fin[gr][c].gi.part2_length;
+      }
+      pack_gc_w(T, fs, &fs->fin[0][ch], my_pos[0]);
+      pack_gc_w(T, fs, &fs->fin[1][ch], my_pos[1]);
+      /* drain_into_ancillary (BitStream.js:175-213): "LAME" + the version string pushed through `>>` as numbers */
+      if (threadIdx.x == 0) {
+        int remaining = frame_bits - pos;
+        const unsigned char tag[10] = {0x4c, 0x41, 0x4d, 0x45, 3, 0, 9, 8, 0, 4};
+        int k = 0;
+        for (; k < 4 && remaining >= 8; k++) { put_bits(fs->bits, pos, tag[k], 8); pos += 8; remaining -= 8; }
+        if (remaining >= 32) for (; k < 10 && remaining >= 8; k++) { put_bits(fs->bits, pos, tag[k], 8); pos += 8; remaining -= 8; }
+      }
+    }
+    __syncthreads();
+    /* store the frame (big-endian bit order -> bytes) */
+    {
+      const long long off = sd.out_base + (long long)f * T->frame_bytes_nopad +
+                            (pad_count(kabs - 1, T->frac_SpF, T->samplerate) - pad_count((long long)sd.frame0 - 1, T->frac_SpF, T->samplerate));
+      uint8_t* dst = out + off;
+      for (int i = threadIdx.x; i < frame_bytes; i += blockDim.x) dst[i] = (uint8_t)(fs->bits[i >> 2] >> (24 - 8 * (i & 3)));
+    }
+    if (threadIdx.x == 0) q->valid = 1;
+    (void)revalidate;
+  }
+}
+
+/* qstate init: one thread per frame row */
+__global__ void k_qstate_init(const StreamDesc* __restrict__ streams, int nstreams, QuantFrameState* __restrict__ qs) {
+  const int z = blockIdx.y;
+  const StreamDesc sd = streams[z];
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= sd.nframes) return;
+  QuantFrameState* q = qs + sd.frame_base + f;
+  q->stream = z; q->rel_frame = f; q->valid = 0;
+  for (int c = 0; c < 2; c++) {
+    /* first frame: the stream's true state; others: speculation (re-validated afterwards) */
+    q->in_old[c] = f == 0 ? sd.old_value[c] : 180;
+    q->in_step[c] = f == 0 ? sd.current_step[c] : 2;
+    q->out_old[c] = q->out_step[c] = 0;
+  }
+}
+
+/* compare each frame's assumed in-state with its predecessor's out-state; append mismatches to the work list */
+__global__ void k_qstate_verify(const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs, long long nframes,
+                                int* __restrict__ list, int* __restrict__ counter) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nframes) return;
+  QuantFrameState* q = qs + r;
+  if (q->rel_frame == 0) return;
+  const QuantFrameState* p = q - 1;
+  bool same = true;
+  for (int c = 0; c < 2; c++) if (q->in_old[c] != p->out_old[c] || q->in_step[c] != p->out_step[c]) same = false;
+  if (!same) {
+    for (int c = 0; c < 2; c++) { q->in_old[c] = p->out_old[c]; q->in_step[c] = p->out_step[c]; }
+    list[atomicAdd(counter, 1)] = (int)r;
+  }
+}
+
+/* after the fixed point: hand the last frame's out-state back to the stream descriptor (streaming handles) */
+__global__ void k_qstate_commit(StreamDesc* __restrict__ streams, int nstreams, const QuantFrameState* __restrict__ qs) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= nstreams) return;
+  StreamDesc& sd = streams[z];
+  if (sd.nframes <= 0) return;
+  const QuantFrameState* q = qs + sd.frame_base + sd.nframes - 1;
+  for (int c = 0; c < 2; c++) { sd.old_value[c] = q->out_old[c]; sd.current_step[c] = q->out_step[c]; }
+}
+
+static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_streams, int S, int max_frames, long long F,
+                     const float* d_xr, const PsyRatioDev* d_ratio, const signed char* d_bt, const double* d_ath_q,
+                     QuantFrameState* d_qs, GranuleInfoDev* d_ginfo, short* d_l3enc, int* d_list, int* d_counter, uint8_t* d_out,
+                     cudaStream_t st, cudaEvent_t ev_pass1, int* passes_out, long long* launches) {
+  static bool attr_set = false;
+  const size_t smem = sizeof(FrameShared);
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_quantize_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
+    attr_set = true;
+  }
+  const int threads = 32 * hT.nch;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  {
+    dim3 g((max_frames + 127) / 128, S);
+    k_qstate_init<<<g, 128, 0, st>>>(d_streams, S, d_qs);
+    (*launches)++;
+  }
+  long long nblk = F < (long long)sms * 16 ? F : (long long)sms * 16;
+  if (nblk < 1) nblk = 1;
+  k_quantize_pack<<<(int)nblk, threads, smem, st>>>(dT, d_streams, d_xr, d_ratio, d_bt, d_ath_q, d_qs, d_ginfo, d_l3enc, nullptr, nullptr,
+                                                    (int)F, 0, d_out);
+  (*launches)++;
+  if (cudaEventRecord(ev_pass1, st) != cudaSuccess) return -100;
+  int passes = 1;
+  for (;;) {
+    if (cudaMemsetAsync(d_counter, 0, sizeof(int), st) != cudaSuccess) return -100;
+    k_qstate_verify<<<(int)((F + 255) / 256), 256, 0, st>>>(d_streams, d_qs, F, d_list, d_counter);
+    (*launches)++;
+    int h_count = 0;
+    if (cudaMemcpyAsync(&h_count, d_counter, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -100;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -100;
+    if (h_count == 0) break;
+    long long nb = h_count < sms * 16 ? h_count : sms * 16;
+    k_quantize_pack<<<(int)nb, threads, smem, st>>>(dT, d_streams, d_xr, d_ratio, d_bt, d_ath_q, d_qs, d_ginfo, d_l3enc, d_list, nullptr,
+                                                    h_count, 1, d_out);
+    (*launches)++;
+    passes++;
+    if (passes > max_frames + 2) return -100;   /* cannot happen: each pass fixes at least the first dirty frame */
+  }
+  k_qstate_commit<<<(S + 63) / 64, 64, 0, st>>>(d_streams, S, d_qs);
+  (*launches)++;
+  *passes_out = passes;
+  return 0;
+}
+
+#endif

@@ -1,0 +1,72 @@
+/* mp3_config.h -- per-(channels, samplerate, kbps) constants of the B200 MP3 encoder.
+ *
+ * Everything lamejs derives once in `new Mp3Encoder(ch, sr, kbps)` (reference src/js/index.js:66-115 ->
+ * src/js/Lame.js:747-1371 lame_init_params, src/js/Presets.js:246-358, src/js/QuantizePVT.js:229-414
+ * iteration_init, src/js/PsyModel.js:2537-2822 psymodel_init, src/js/FFT.js:226-242 init_fft) is
+ * computed on the host into one flat, trivially-copyable block (`Mp3Tables`) that is uploaded to HBM
+ * once per configuration and read by every kernel through a single pointer.
+ */
+#ifndef MP3B200_CONFIG_H
+#define MP3B200_CONFIG_H
+#include <stdint.h>
+
+#define MP3_CBANDS 64
+#define MP3_SBMAX_L 22
+#define MP3_SBMAX_S 13
+#define MP3_SFBMAX 39
+#define MP3_S3_MAX 2048     /* ragged spreading rows, flattened */
+#define MP3_PRECALC 8208
+#define MP3_QMAX 257
+#define MP3_QMAX2 116
+
+struct Mp3Tables {
+  /* ---- scalars ---- */
+  int nch, samplerate, kbps, mono;
+  int bitrate_index, samplerate_index, sideinfo_len, frac_SpF;
+  int frame_bytes_nopad;          /* floor(144000*kbps/sr) */
+  int noise_shaping;              /* 1 or 2 (sfscale) */
+  int quant_comp, quant_comp_short;
+  int coupled_short_blocks;
+  int npart_l, npart_s;
+  int scale_applied;              /* gfp.scale != 1 */
+  double scale;
+  double masking_lower_long, masking_lower_short;   /* 10^(mask_adjust*0.1), CBRNewIterationLoop.js:64 */
+  double interch_ratio;
+  double attack_threshold;
+  double aa_sensitivity_p, ath_floor, decay;
+  double ma_max_i1, ma_max_i2, ma_max_m;
+  /* ---- filterbank ---- */
+  float amp_filter[32];
+  /* ---- scalefactor bands ---- */
+  int sfb_l[MP3_SBMAX_L + 1], sfb_s[MP3_SBMAX_S + 1], psfb21[7], psfb12[7];
+  int bv_scf[576];
+  /* ---- psycho-acoustic partitions ---- */
+  int numlines_l[MP3_CBANDS], numlines_s[MP3_CBANDS];
+  int line0_l[MP3_CBANDS + 1], line0_s[MP3_CBANDS + 1];   /* prefix sums of numlines (ours) */
+  float rnumlines_l[MP3_CBANDS];
+  int s3lo_l[MP3_CBANDS], s3hi_l[MP3_CBANDS], s3off_l[MP3_CBANDS + 1];
+  int s3lo_s[MP3_CBANDS], s3hi_s[MP3_CBANDS], s3off_s[MP3_CBANDS + 1];
+  float s3_ll[MP3_S3_MAX], s3_ss[MP3_S3_MAX];
+  int bo_l[MP3_SBMAX_L], bo_s[MP3_SBMAX_S];
+  float bo_l_weight[MP3_SBMAX_L], bo_s_weight[MP3_SBMAX_S];
+  float ath_cb_l[MP3_CBANDS], ath_cb_s[MP3_CBANDS];
+  float eql_w[512];
+  /* ---- ATH per scalefactor band ---- */
+  float ath_l[MP3_SBMAX_L], ath_s[MP3_SBMAX_S], ath_psfb21[6], ath_psfb12[6];
+  float longfact[MP3_SBMAX_L], shortfact[MP3_SBMAX_S];
+  /* ---- FFT ---- */
+  float fft_window[1024], fft_window_s[128];
+  /* FHT twiddles per stage: entry i holds (c1, s1, c2, s2) for butterfly index i (1..kx-1);
+   * stage t has kx = 2*4^t entries starting at tw_off[t].  Produced by the same double recurrence
+   * the reference runs inside fht() (FFT.js:70-111). */
+  int tw_off[5];
+  double tw[4 * 176];
+  /* ---- quantizer ---- */
+  float pow20[MP3_QMAX + MP3_QMAX2 + 1], ipow20[MP3_QMAX], pow43[MP3_PRECALC], adj43[MP3_PRECALC];
+};
+
+/* returns 0, or -1 when lamejs itself would fail / needs the resampler or the MPEG-2 path
+ * (not built). */
+int mp3_build_tables(int channels, int samplerate, int kbps, Mp3Tables* t);
+
+#endif

@@ -1,0 +1,393 @@
+/* mp3_encoder.cu -- host orchestration + C ABI of libmp3b200.so (see include/mp3b200.h).
+ *
+ * One batch = S independent streams (lamejs Mp3Encoder instances) x their frames.  The pipeline is
+ *   K2 psy_analysis -> K3a sequential scans -> K3b masking -> K1 filterbank+MDCT -> K4/K5 quantize+pack
+ * launched on one CUDA stream; all intermediates live in HBM workspaces sized per batch.
+ * No CPU fallback exists: if CUDA is unavailable every entry point returns MP3B200_ERR_CUDA.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/mp3b200.h"
+#include "mp3_config.h"
+#include "mp3_device.cuh"
+#include "mp3_tables.h"
+#include "k_filterbank.cuh"
+#include "k_psy.cuh"
+#include "k_quant.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_mu;
+int g_device = 0;
+long long g_launches = 0;
+bool g_consts_ready = false;
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      char b_[512];                                                                               \
+      snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      g_err = b_;                                                                                 \
+      return MP3B200_ERR_CUDA;                                                                    \
+    }                                                                                             \
+  } while (0)
+
+struct Config { Mp3Tables host; Mp3Tables* dev; };
+std::map<std::tuple<int, int, int, int>, Config*> g_configs;   /* (device, ch, sr, kbps) */
+
+int ensure_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) { g_err = "no CUDA device available (libmp3b200 has no CPU fallback)"; return MP3B200_ERR_CUDA; }
+  CK(cudaSetDevice(g_device));
+  if (!g_consts_ready) {
+    CK(cudaMemcpyToSymbol(c_enwindow, MP3_ENWINDOW, sizeof(double) * 285));
+    CK(cudaMemcpyToSymbol(c_mdct_win, MP3_MDCT_WIN, sizeof(double) * 144));
+    CK(cudaMemcpyToSymbol(c_sb_order, MP3_SB_ORDER, sizeof(int) * 32));
+    int rc = psy_upload_constants();
+    if (rc) return rc;
+    rc = quant_upload_constants();
+    if (rc) return rc;
+    g_consts_ready = true;
+  }
+  return 0;
+}
+
+int get_config(int ch, int sr, int kbps, Config** out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = ensure_device();
+  if (rc) return rc;
+  auto key = std::make_tuple(g_device, ch, sr, kbps);
+  auto it = g_configs.find(key);
+  if (it != g_configs.end()) { *out = it->second; return 0; }
+  Config* c = new Config();
+  if (mp3_build_tables(ch, sr, kbps, &c->host) != 0) { delete c; g_err = "unsupported configuration"; return MP3B200_ERR_CONFIG; }
+  CK(cudaMalloc(&c->dev, sizeof(Mp3Tables)));
+  CK(cudaMemcpy(c->dev, &c->host, sizeof(Mp3Tables), cudaMemcpyHostToDevice));
+  g_configs[key] = c;
+  *out = c;
+  return 0;
+}
+
+/* frames produced by encodeBuffer(n samples) + flush()  (Lame.js:1592-1663 + :1393-1443 in closed form) */
+long long frames_for(long long n) {
+  const long long f_enc = n >= 1376 ? (n - 1376) / 1152 + 1 : 0;
+  const long long ste = 576 + n - 1152 * f_enc;
+  long long end_padding = 1152 - (ste % 1152);
+  if (end_padding < 576) end_padding += 1152;
+  return f_enc + (ste + end_padding) / 1152;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Per-batch device workspace.                                                                         */
+struct Workspace {
+  int nstreams = 0, nch = 0;
+  long long units = 0, frames = 0;        /* granule rows / frame rows */
+  StreamDesc* d_streams = nullptr;
+  signed char* d_bt_final = nullptr;      /* [units][2] final block type used by MDCT + quantizer */
+  signed char* d_bt_prev = nullptr;       /* [units][2] blocktype_old seen by the masking of this granule */
+  float* d_xr = nullptr;                  /* [units][nch][576] */
+  PsyUnit* d_psy = nullptr;               /* [units + nstreams][nch]  (one halo unit per stream in front) */
+  PsyRatioDev* d_ratio = nullptr;         /* [units + nstreams][nch]  masking of unit c (used by granule c+1) */
+  double* d_ath_psy = nullptr;            /* [frames] ATH.adjust seen by the psy calls of the frame */
+  double* d_ath_q = nullptr;              /* [frames] ATH.adjust after adjust_ATH (quantizer) */
+  QuantFrameState* d_qstate = nullptr;    /* [frames] speculation bookkeeping */
+  GranuleInfoDev* d_ginfo = nullptr;      /* [units][nch] side info of the final quantization */
+  short* d_l3enc = nullptr;               /* [units][nch][576] (debug tap) */
+  int* d_dirty = nullptr;                 /* [frames] work list for re-quantization passes */
+  int* d_counter = nullptr;               /* [4] */
+  ~Workspace() { release(); }
+  void release() {
+    cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_psy);
+    cudaFree(d_ratio); cudaFree(d_ath_psy); cudaFree(d_ath_q); cudaFree(d_qstate); cudaFree(d_ginfo);
+    cudaFree(d_l3enc); cudaFree(d_dirty); cudaFree(d_counter);
+    d_streams = nullptr; d_bt_final = d_bt_prev = nullptr; d_xr = nullptr; d_psy = nullptr; d_ratio = nullptr;
+    d_ath_psy = d_ath_q = nullptr; d_qstate = nullptr; d_ginfo = nullptr; d_l3enc = nullptr; d_dirty = nullptr; d_counter = nullptr;
+  }
+  int alloc(int S, int nch_, long long U, long long F, bool want_l3enc) {
+    release();
+    nstreams = S; nch = nch_; units = U; frames = F;
+    CK(cudaMalloc(&d_streams, sizeof(StreamDesc) * S));
+    CK(cudaMalloc(&d_bt_final, (size_t)U * 2 + 16));
+    CK(cudaMalloc(&d_bt_prev, (size_t)U * 2 + 16));
+    CK(cudaMalloc(&d_xr, sizeof(float) * (size_t)U * nch * 576));
+    CK(cudaMalloc(&d_psy, sizeof(PsyUnit) * (size_t)(U + S) * nch));
+    CK(cudaMalloc(&d_ratio, sizeof(PsyRatioDev) * (size_t)(U + S) * nch));
+    CK(cudaMalloc(&d_ath_psy, sizeof(double) * (size_t)(F + 1)));
+    CK(cudaMalloc(&d_ath_q, sizeof(double) * (size_t)(F + 1)));
+    CK(cudaMalloc(&d_qstate, sizeof(QuantFrameState) * (size_t)(F + 1)));
+    CK(cudaMalloc(&d_ginfo, sizeof(GranuleInfoDev) * (size_t)U * nch));
+    if (want_l3enc) CK(cudaMalloc(&d_l3enc, sizeof(short) * (size_t)U * nch * 576));
+    CK(cudaMalloc(&d_dirty, sizeof(int) * (size_t)(F + 1)));
+    CK(cudaMalloc(&d_counter, sizeof(int) * 4));
+    return 0;
+  }
+};
+
+struct Timings { float psy = 0, scan = 0, mask = 0, fb = 0, q1 = 0, qn = 0, total = 0; int passes = 0; };
+
+/* Runs the whole pipeline for the streams described in `h_streams` (device pointers already set).
+ * d_out: device output buffer.  force_bt: optional host array [units][nch] of block types (debug). */
+int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams, uint8_t* d_out, const int32_t* force_bt,
+                 bool stop_after_mdct, Timings* tm, cudaStream_t st) {
+  const int S = (int)h_streams.size();
+  const int nch = cfg->host.nch;
+  int max_frames = 0;
+  for (auto& s : h_streams) max_frames = s.nframes > max_frames ? s.nframes : max_frames;
+  CK(cudaMemcpyAsync(ws.d_streams, h_streams.data(), sizeof(StreamDesc) * S, cudaMemcpyHostToDevice, st));
+  cudaEvent_t ev[8];
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(ev[0], st));
+
+  /* K2: psy analysis, one block per (granule incl. 1 halo, channel, stream) */
+  {
+    dim3 grid(2 * max_frames + 1, nch, S);
+    k_psy_analysis<<<grid, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy);
+    g_launches++;
+  }
+  CK(cudaEventRecord(ev[1], st));
+  /* K3a: attack pre-pass (parallel) + sequential per-stream scans */
+  {
+    dim3 grid((2 * max_frames + 127) / 128, 1, S);
+    k_attack_prepass<<<grid, 128, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy);
+    k_stream_scan<<<(S + 31) / 32, 64, 0, st>>>(cfg->dev, ws.d_streams, S, ws.d_psy, ws.d_bt_final, ws.d_bt_prev, ws.d_ath_psy, ws.d_ath_q);
+    g_launches += 2;
+  }
+  CK(cudaEventRecord(ev[2], st));
+  /* K3b: masking thresholds */
+  {
+    dim3 grid(2 * max_frames + 1, 1, S);
+    k_psy_masking<<<grid, MASK_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_bt_prev, ws.d_ath_psy, ws.d_ratio);
+    g_launches++;
+  }
+  CK(cudaEventRecord(ev[3], st));
+  if (force_bt) {   /* debug: override block decision for the filterbank */
+    std::vector<signed char> bt((size_t)ws.units * 2, 0);
+    for (long long u = 0; u < ws.units; u++)
+      for (int c = 0; c < nch; c++) bt[u * 2 + c] = (signed char)force_bt[u * nch + c];
+    CK(cudaMemcpyAsync(ws.d_bt_final, bt.data(), bt.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  /* K1: filterbank + MDCT */
+  {
+    dim3 grid((2 * max_frames + FB_G - 1) / FB_G, nch, S);
+    const size_t smem = sizeof(float) * (FB_PCM_WORDS + (FB_G + 1) * 18 * FB_SLAB_STRIDE);
+    k_filterbank_mdct<<<grid, FB_THREADS, smem, st>>>(cfg->dev, ws.d_streams, ws.d_bt_final, ws.d_xr);
+    g_launches++;
+  }
+  CK(cudaEventRecord(ev[4], st));
+  int passes = 0;
+  if (!stop_after_mdct) {
+    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, max_frames, ws.frames, ws.d_xr, ws.d_ratio, ws.d_bt_final, ws.d_ath_q,
+                       ws.d_qstate, ws.d_ginfo, ws.d_l3enc, ws.d_dirty, ws.d_counter, d_out, st, ev[5], &passes, &g_launches);
+    if (rc) { g_err = "quantizer stage failed: " + std::string(cudaGetErrorString(cudaGetLastError())); return rc; }
+  } else {
+    CK(cudaEventRecord(ev[5], st));
+  }
+  CK(cudaEventRecord(ev[6], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (tm) {
+    cudaEventElapsedTime(&tm->psy, ev[0], ev[1]);
+    cudaEventElapsedTime(&tm->scan, ev[1], ev[2]);
+    cudaEventElapsedTime(&tm->mask, ev[2], ev[3]);
+    cudaEventElapsedTime(&tm->fb, ev[3], ev[4]);
+    cudaEventElapsedTime(&tm->q1, ev[4], ev[5]);
+    cudaEventElapsedTime(&tm->qn, ev[5], ev[6]);
+    cudaEventElapsedTime(&tm->total, ev[0], ev[6]);
+    tm->passes = passes;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+void init_stream_state(StreamDesc& sd) {   /* lame_init_old + psymodel_init start values */
+  sd.ath_adjust = 0.01; sd.ath_adjust_limit = 1.0;
+  sd.blocktype_old[0] = sd.blocktype_old[1] = BT_NORM;
+  sd.last_attacks[0] = sd.last_attacks[1] = 0;
+  sd.old_value[0] = sd.old_value[1] = 180;
+  sd.current_step[0] = sd.current_step[1] = 4;
+}
+
+long long bytes_for(const Mp3Tables& t, long long frames) {
+  return frames * t.frame_bytes_nopad + pad_count(frames - 1, t.frac_SpF, t.samplerate);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mp3b200_last_error(void) { return g_err.c_str(); }
+int64_t mp3b200_launch_count(void) { return g_launches; }
+
+int mp3b200_set_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { g_err = "invalid CUDA device"; return MP3B200_ERR_CUDA; }
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (device != g_device) { g_device = device; g_consts_ready = false; }
+  return 0;
+}
+
+int64_t mp3b200_stream_frames(int64_t nsamples) { return frames_for(nsamples); }
+
+int64_t mp3b200_stream_bytes(int channels, int samplerate, int kbps, int64_t nsamples) {
+  Mp3Tables* t = new Mp3Tables();
+  int64_t r = -1;
+  if (mp3_build_tables(channels, samplerate, kbps, t) == 0) r = bytes_for(*t, frames_for(nsamples));
+  delete t;
+  return r;
+}
+
+int mp3b200_encode_streams_device(int channels, int samplerate, int kbps, int nstreams, const int16_t* d_pcm,
+                                  const int64_t* pcm_off, const int64_t* nsamples, uint8_t* d_out,
+                                  const int64_t* out_off, float* timings_ms) {
+  Config* cfg;
+  int rc = get_config(channels, samplerate, kbps, &cfg);
+  if (rc) return rc;
+  std::vector<StreamDesc> sds(nstreams);
+  long long U = 0, F = 0;
+  for (int s = 0; s < nstreams; s++) {
+    StreamDesc& sd = sds[s];
+    memset(&sd, 0, sizeof sd);
+    sd.pcm[0] = d_pcm + pcm_off[s];
+    sd.pcm[1] = channels == 2 ? d_pcm + pcm_off[s] + nsamples[s] : sd.pcm[0];
+    sd.pcm_base = 0; sd.pcm_end = nsamples[s];
+    sd.frame0 = 0; sd.nframes = (int)frames_for(nsamples[s]);
+    sd.unit_base = (int)U; sd.frame_base = (int)F;
+    sd.out_base = out_off[s];
+    init_stream_state(sd);
+    U += 2LL * sd.nframes; F += sd.nframes;
+  }
+  static thread_local Workspace ws;
+  if (ws.units < U || ws.frames < F || ws.nstreams < nstreams || ws.nch != cfg->host.nch) {
+    rc = ws.alloc(nstreams, cfg->host.nch, U, F, false);
+    if (rc) return rc;
+  }
+  Timings tm;
+  rc = run_pipeline(cfg, ws, sds, d_out, nullptr, false, &tm, 0);
+  if (rc) return rc;
+  if (timings_ms) {
+    timings_ms[0] = tm.psy; timings_ms[1] = tm.scan; timings_ms[2] = tm.mask; timings_ms[3] = tm.fb;
+    timings_ms[4] = tm.q1; timings_ms[5] = tm.qn; timings_ms[6] = tm.total; timings_ms[7] = (float)tm.passes;
+  }
+  return 0;
+}
+
+int mp3b200_encode_streams(int channels, int samplerate, int kbps, int nstreams, const int16_t* const* left,
+                           const int16_t* const* right, const int64_t* nsamples, uint8_t* const* out,
+                           const int64_t* cap, int64_t* out_bytes) {
+  Config* cfg;
+  int rc = get_config(channels, samplerate, kbps, &cfg);
+  if (rc) return rc;
+  std::vector<int64_t> pcm_off(nstreams), out_off(nstreams);
+  long long tot_samples = 0, tot_bytes = 0;
+  for (int s = 0; s < nstreams; s++) {
+    pcm_off[s] = tot_samples;
+    tot_samples += nsamples[s] * channels;
+    out_off[s] = tot_bytes;
+    const long long b = bytes_for(cfg->host, frames_for(nsamples[s]));
+    if (cap[s] < b) { g_err = "output buffer too small"; return MP3B200_ERR_BUFFER; }
+    out_bytes[s] = b;
+    tot_bytes += b;
+  }
+  int16_t* d_pcm = nullptr; uint8_t* d_out = nullptr;
+  CK(cudaMalloc(&d_pcm, sizeof(int16_t) * (size_t)(tot_samples + 8)));
+  CK(cudaMalloc(&d_out, (size_t)tot_bytes + 8));
+  for (int s = 0; s < nstreams; s++) {
+    CK(cudaMemcpy(d_pcm + pcm_off[s], left[s], sizeof(int16_t) * nsamples[s], cudaMemcpyHostToDevice));
+    if (channels == 2) CK(cudaMemcpy(d_pcm + pcm_off[s] + nsamples[s], right[s], sizeof(int16_t) * nsamples[s], cudaMemcpyHostToDevice));
+  }
+  rc = mp3b200_encode_streams_device(channels, samplerate, kbps, nstreams, d_pcm, pcm_off.data(), nsamples, d_out, out_off.data(), nullptr);
+  if (rc == 0) {
+    for (int s = 0; s < nstreams; s++)
+      if (cudaMemcpy(out[s], d_out + out_off[s], (size_t)out_bytes[s], cudaMemcpyDeviceToHost) != cudaSuccess) rc = MP3B200_ERR_CUDA;
+  }
+  cudaFree(d_pcm); cudaFree(d_out);
+  return rc;
+}
+
+int mp3b200_debug_stages(int channels, int samplerate, int kbps, const int16_t* left, const int16_t* right,
+                         int64_t nsamples, const int32_t* force_blocktype, float* xr, int32_t* blocktype,
+                         float* en_l, float* thm_l, float* en_s, float* thm_s, double* ath_adjust,
+                         int32_t* l3_enc, int32_t* ginfo, uint8_t* bytes_out, int64_t bytes_cap) {
+  Config* cfg;
+  int rc = get_config(channels, samplerate, kbps, &cfg);
+  if (rc) return rc;
+  const int nch = cfg->host.nch;
+  const long long F = frames_for(nsamples), U = 2 * F;
+  int16_t* d_pcm = nullptr; uint8_t* d_out = nullptr;
+  CK(cudaMalloc(&d_pcm, sizeof(int16_t) * (size_t)(nsamples * nch + 8)));
+  CK(cudaMemcpy(d_pcm, left, sizeof(int16_t) * nsamples, cudaMemcpyHostToDevice));
+  if (nch == 2) CK(cudaMemcpy(d_pcm + nsamples, right, sizeof(int16_t) * nsamples, cudaMemcpyHostToDevice));
+  const long long nbytes = bytes_for(cfg->host, F);
+  CK(cudaMalloc(&d_out, (size_t)nbytes + 8));
+  CK(cudaMemset(d_out, 0, (size_t)nbytes + 8));
+  std::vector<StreamDesc> sds(1);
+  StreamDesc& sd = sds[0];
+  memset(&sd, 0, sizeof sd);
+  sd.pcm[0] = d_pcm; sd.pcm[1] = nch == 2 ? d_pcm + nsamples : d_pcm;
+  sd.pcm_end = nsamples; sd.nframes = (int)F;
+  init_stream_state(sd);
+  Workspace ws;
+  rc = ws.alloc(1, nch, U, F, true);
+  if (rc) { cudaFree(d_pcm); cudaFree(d_out); return rc; }
+  const bool only_mdct = (l3_enc == nullptr && ginfo == nullptr && bytes_out == nullptr);
+  rc = run_pipeline(cfg, ws, sds, d_out, force_blocktype, only_mdct, nullptr, 0);
+  if (rc == 0) {
+    if (xr) CK(cudaMemcpy(xr, ws.d_xr, sizeof(float) * (size_t)U * nch * 576, cudaMemcpyDeviceToHost));
+    if (blocktype) {
+      std::vector<signed char> bt((size_t)U * 2);
+      CK(cudaMemcpy(bt.data(), ws.d_bt_final, bt.size(), cudaMemcpyDeviceToHost));
+      for (long long u = 0; u < U; u++) for (int c = 0; c < nch; c++) blocktype[u * nch + c] = bt[u * 2 + c];
+    }
+    if (en_l || thm_l || en_s || thm_s) {
+      /* masking used by granule u is the ratio of psy unit u-1: row (u + 1 - 1) of the halo-shifted array */
+      std::vector<PsyRatioDev> r((size_t)(U + 1) * nch);
+      CK(cudaMemcpy(r.data(), ws.d_ratio, sizeof(PsyRatioDev) * r.size(), cudaMemcpyDeviceToHost));
+      for (long long u = 0; u < U; u++) for (int c = 0; c < nch; c++) {
+        const PsyRatioDev& q = r[(size_t)u * nch + c];
+        if (en_l) memcpy(en_l + (u * nch + c) * 22, q.en_l, sizeof q.en_l);
+        if (thm_l) memcpy(thm_l + (u * nch + c) * 22, q.thm_l, sizeof q.thm_l);
+        if (en_s) memcpy(en_s + (u * nch + c) * 39, q.en_s, sizeof q.en_s);
+        if (thm_s) memcpy(thm_s + (u * nch + c) * 39, q.thm_s, sizeof q.thm_s);
+      }
+    }
+    if (ath_adjust) CK(cudaMemcpy(ath_adjust, ws.d_ath_q, sizeof(double) * (size_t)F, cudaMemcpyDeviceToHost));
+    if (l3_enc) {
+      std::vector<short> t((size_t)U * nch * 576);
+      CK(cudaMemcpy(t.data(), ws.d_l3enc, sizeof(short) * t.size(), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < t.size(); i++) l3_enc[i] = t[i];
+    }
+    if (ginfo) {
+      std::vector<GranuleInfoDev> g((size_t)U * nch);
+      CK(cudaMemcpy(g.data(), ws.d_ginfo, sizeof(GranuleInfoDev) * g.size(), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < g.size(); i++) {
+        int32_t* o = ginfo + i * 16;
+        o[0] = g[i].global_gain; o[1] = g[i].part2_3_length; o[2] = g[i].part2_length; o[3] = g[i].big_values;
+        o[4] = g[i].count1; o[5] = g[i].scalefac_compress; o[6] = g[i].table_select[0]; o[7] = g[i].table_select[1];
+        o[8] = g[i].table_select[2]; o[9] = g[i].region0_count; o[10] = g[i].region1_count; o[11] = g[i].preflag;
+        o[12] = g[i].scalefac_scale; o[13] = g[i].count1table_select; o[14] = g[i].block_type; o[15] = 0;
+      }
+    }
+    if (bytes_out) {
+      if (bytes_cap < nbytes) { g_err = "output buffer too small"; rc = MP3B200_ERR_BUFFER; }
+      else CK(cudaMemcpy(bytes_out, d_out, (size_t)nbytes, cudaMemcpyDeviceToHost));
+    }
+  }
+  cudaFree(d_pcm); cudaFree(d_out);
+  return rc;
+}
+
+}  // extern "C"
+
+#include "mp3_handle.inc"

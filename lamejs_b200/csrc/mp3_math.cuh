@@ -1,0 +1,346 @@
+/* mp3_math.cuh -- engine-side Math.* functions used on the MP3 hot path, host + device.
+ *
+ * lamejs calls Math.log10 / Math.pow per frame (reference: src/js/PsyModel.js:433,444,461 mask_add;
+ * src/js/QuantizePVT.js:541-561 athAdjust, :842 calc_noise) and Math.exp/log/pow at init.  CUDA's
+ * libdevice versions are not bit-identical to any JS engine, so the published fdlibm 5.3 algorithms
+ * (what V8's base/ieee754 ports) are written out here in plain IEEE double arithmetic, usable from both
+ * host and device.  Compile with -fmad=false (device) / -ffp-contract=off (host): no FMA contraction.
+ */
+#ifndef MP3B200_MATH_CUH
+#define MP3B200_MATH_CUH
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define MP3M_FN static __host__ __device__ __forceinline__
+#else
+#define MP3M_FN static inline
+#endif
+
+MP3M_FN uint64_t m3m_bits(double x) {
+#ifdef __CUDA_ARCH__
+  return (uint64_t)__double_as_longlong(x);
+#else
+  uint64_t u; memcpy(&u, &x, 8); return u;
+#endif
+}
+MP3M_FN double m3m_from_bits(uint64_t u) {
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)u);
+#else
+  double x; memcpy(&x, &u, 8); return x;
+#endif
+}
+MP3M_FN int32_t m3m_hi(double x) { return (int32_t)(m3m_bits(x) >> 32); }
+MP3M_FN uint32_t m3m_lo(double x) { return (uint32_t)m3m_bits(x); }
+MP3M_FN double m3m_set_hi(double x, int32_t hi) {
+  uint64_t u = m3m_bits(x); u = (u & 0xffffffffull) | ((uint64_t)(uint32_t)hi << 32);
+  return m3m_from_bits(u);
+}
+MP3M_FN double m3m_set_lo(double x, uint32_t lo) {
+  uint64_t u = m3m_bits(x); u = (u & 0xffffffff00000000ull) | lo;
+  return m3m_from_bits(u);
+}
+MP3M_FN double m3m_from_words(int32_t hi, uint32_t lo) {
+  return m3m_from_bits(((uint64_t)(uint32_t)hi << 32) | lo);
+}
+
+/* ---- log (fdlibm e_log.c) ---- */
+MP3M_FN double m3_log(double x) {
+  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+               two54 = 1.80143985094819840000e+16,
+               Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
+               Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+               Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+               Lg7 = 1.479819860511658591e-01;
+  double hfsq, f, s, z, R, w, t1, t2, dk;
+  int32_t k, hx, i, j;
+  uint32_t lx;
+  hx = m3m_hi(x); lx = m3m_lo(x);
+  k = 0;
+  if (hx < 0x00100000) {
+    if (((hx & 0x7fffffff) | lx) == 0) return (-m3m_from_bits(0x7ff0000000000000ull));
+    if (hx < 0) return m3m_from_bits(0x7ff8000000000000ull);
+    k -= 54; x *= two54; hx = m3m_hi(x);
+  }
+  if (hx >= 0x7ff00000) return x + x;
+  k += (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  i = (hx + 0x95f64) & 0x100000;
+  x = m3m_set_hi(x, hx | (i ^ 0x3ff00000));
+  k += (i >> 20);
+  f = x - 1.0;
+  if ((0x000fffff & (2 + hx)) < 3) {
+    if (f == 0.0) {
+      if (k == 0) return 0.0;
+      dk = (double)k; return dk * ln2_hi + dk * ln2_lo;
+    }
+    R = f * f * (0.5 - 0.33333333333333333 * f);
+    if (k == 0) return f - R;
+    dk = (double)k; return dk * ln2_hi - ((R - dk * ln2_lo) - f);
+  }
+  s = f / (2.0 + f);
+  dk = (double)k;
+  z = s * s;
+  i = hx - 0x6147a;
+  w = z * z;
+  j = 0x6b851 - hx;
+  t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+  t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+  i |= j;
+  R = t2 + t1;
+  if (i > 0) {
+    hfsq = 0.5 * f * f;
+    if (k == 0) return f - (hfsq - s * (hfsq + R));
+    return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+  } else {
+    if (k == 0) return f - s * (f - R);
+    return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+  }
+}
+
+/* ---- log10 (fdlibm e_log10.c, as ported in V8 base/ieee754) ---- */
+MP3M_FN double m3_log10(double x) {
+  const double two54 = 1.80143985094819840000e+16, ivln10 = 4.34294481903251816668e-01,
+               log10_2hi = 3.01029995663611771306e-01, log10_2lo = 3.69423907715893078616e-13;
+  double y, z;
+  int32_t i, k, hx;
+  uint32_t lx;
+  hx = m3m_hi(x); lx = m3m_lo(x);
+  k = 0;
+  if (hx < 0x00100000) {
+    if (((hx & 0x7fffffff) | lx) == 0) return (-m3m_from_bits(0x7ff0000000000000ull));
+    if (hx < 0) return m3m_from_bits(0x7ff8000000000000ull);
+    k -= 54; x *= two54; hx = m3m_hi(x); lx = m3m_lo(x);
+  }
+  if (hx >= 0x7ff00000) return x + x;
+  k += (hx >> 20) - 1023;
+  i = (int32_t)(((uint32_t)k & 0x80000000u) >> 31);
+  hx = (hx & 0x000fffff) | ((0x3ff - i) << 20);
+  y = (double)(k + i);
+  x = m3m_from_words(hx, lx);
+  z = y * log10_2lo + ivln10 * m3_log(x);
+  return z + y * log10_2hi;
+}
+
+/* ---- exp (fdlibm e_exp.c) ---- */
+MP3M_FN double m3_exp(double x) {
+  const double huge = 1.0e+300, twom1000 = 9.33263618503218878990e-302,
+               o_threshold = 7.09782712893383973096e+02, u_threshold = -7.45133219101941108420e+02,
+               ln2HI0 = 6.93147180369123816490e-01, ln2LO0 = 1.90821492927058770002e-10,
+               invln2 = 1.44269504088896338700e+00,
+               P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
+               P3 = 6.61375632143793436117e-05, P4 = -1.65339022054652515390e-06,
+               P5 = 4.13813679705723846039e-08;
+  double y, hi = 0, lo = 0, c, t;
+  int32_t k = 0, xsb;
+  uint32_t hx;
+  hx = (uint32_t)m3m_hi(x);
+  xsb = (hx >> 31) & 1;
+  hx &= 0x7fffffff;
+  if (hx >= 0x40862E42) {
+    if (hx >= 0x7ff00000) {
+      if (((hx & 0xfffff) | m3m_lo(x)) != 0) return x + x;
+      return (xsb == 0) ? x : 0.0;
+    }
+    if (x > o_threshold) return huge * huge;
+    if (x < u_threshold) return twom1000 * twom1000;
+  }
+  if (hx > 0x3fd62e42) {
+    if (hx < 0x3FF0A2B2) {
+      hi = x - (xsb ? -ln2HI0 : ln2HI0); lo = (xsb ? -ln2LO0 : ln2LO0); k = 1 - xsb - xsb;
+    } else {
+      k = (int32_t)(invln2 * x + (xsb ? -0.5 : 0.5));
+      t = k;
+      hi = x - t * ln2HI0;
+      lo = t * ln2LO0;
+    }
+    x = hi - lo;
+  } else if (hx < 0x3e300000) {
+    if (huge + x > 1.0) return 1.0 + x;
+  } else k = 0;
+  t = x * x;
+  c = x - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  if (k == 0) return 1.0 - ((x * c) / (c - 2.0) - x);
+  y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
+  if (k >= -1021) {
+    return m3m_set_hi(y, m3m_hi(y) + (k << 20));
+  } else {
+    y = m3m_set_hi(y, m3m_hi(y) + ((k + 1000) << 20));
+    return y * twom1000;
+  }
+}
+
+/* ---- pow (fdlibm e_pow.c) ---- */
+MP3M_FN double m3_pow(double x, double y) {
+  const double dp_h1 = 5.84962487220764160156e-01, dp_l1 = 1.35003920212974897128e-08,
+               two53 = 9007199254740992.0, huge = 1.0e300, tiny = 1.0e-300,
+               L1 = 5.99999999999994648725e-01, L2 = 4.28571428578550184252e-01,
+               L3 = 3.33333329818377432918e-01, L4 = 2.72728123808534006489e-01,
+               L5 = 2.30660745775561754067e-01, L6 = 2.06975017800338417784e-01,
+               P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
+               P3 = 6.61375632143793436117e-05, P4 = -1.65339022054652515390e-06,
+               P5 = 4.13813679705723846039e-08,
+               lg2 = 6.93147180559945286227e-01, lg2_h = 6.93147182464599609375e-01,
+               lg2_l = -1.90465429995776804525e-09, ovt = 8.0085662595372944372e-0017,
+               cp = 9.61796693925975554329e-01, cp_h = 9.61796700954437255859e-01,
+               cp_l = -7.02846165095275826516e-09, ivln2 = 1.44269504088896338700e+00,
+               ivln2_h = 1.44269502162933349609e+00, ivln2_l = 1.92596299112661746887e-08;
+  double z, ax, z_h, z_l, p_h, p_l;
+  double y1, t1, t2, r, s, t, u, v, w;
+  int32_t i, j, k, yisint, n;
+  int32_t hx, hy, ix, iy;
+  uint32_t lx, ly;
+
+  hx = m3m_hi(x); lx = m3m_lo(x);
+  hy = m3m_hi(y); ly = m3m_lo(y);
+  ix = hx & 0x7fffffff; iy = hy & 0x7fffffff;
+
+  if ((iy | ly) == 0) return 1.0;
+  if (ix > 0x7ff00000 || ((ix == 0x7ff00000) && (lx != 0)) ||
+      iy > 0x7ff00000 || ((iy == 0x7ff00000) && (ly != 0)))
+    return x + y;
+
+  yisint = 0;
+  if (hx < 0) {
+    if (iy >= 0x43400000) yisint = 2;
+    else if (iy >= 0x3ff00000) {
+      k = (iy >> 20) - 0x3ff;
+      if (k > 20) {
+        j = (int32_t)(ly >> (52 - k));
+        if (((uint32_t)j << (52 - k)) == ly) yisint = 2 - (j & 1);
+      } else if (ly == 0) {
+        j = iy >> (20 - k);
+        if ((j << (20 - k)) == iy) yisint = 2 - (j & 1);
+      }
+    }
+  }
+
+  if (ly == 0) {
+    if (iy == 0x7ff00000) {
+      if (((ix - 0x3ff00000) | lx) == 0) return m3m_from_bits(0x7ff8000000000000ull); /* ES: (+-1)**+-inf is NaN */
+      else if (ix >= 0x3ff00000) return (hy >= 0) ? y : 0.0;
+      else return (hy < 0) ? -y : 0.0;
+    }
+    if (iy == 0x3ff00000) { if (hy < 0) return 1.0 / x; else return x; }
+    if (hy == 0x40000000) return x * x;
+    if (hy == 0x3fe00000) { if (hx >= 0) return sqrt(x); }
+  }
+
+  ax = fabs(x);
+  if (lx == 0) {
+    if (ix == 0x7ff00000 || ix == 0 || ix == 0x3ff00000) {
+      z = ax;
+      if (hy < 0) z = 1.0 / z;
+      if (hx < 0) {
+        if (((ix - 0x3ff00000) | yisint) == 0) z = m3m_from_bits(0x7ff8000000000000ull);
+        else if (yisint == 1) z = -z;
+      }
+      return z;
+    }
+  }
+
+  n = (hx < 0) ? 0 : 1; /* fdlibm: (hx>>31)+1 */
+  if ((n | yisint) == 0) return m3m_from_bits(0x7ff8000000000000ull);
+  s = 1.0;
+  if ((n | (yisint - 1)) == 0) s = -1.0;
+
+  if (iy > 0x41e00000) {
+    if (iy > 0x43f00000) {
+      if (ix <= 0x3fefffff) return (hy < 0) ? huge * huge : tiny * tiny;
+      if (ix >= 0x3ff00000) return (hy > 0) ? huge * huge : tiny * tiny;
+    }
+    if (ix < 0x3fefffff) return (hy < 0) ? s * huge * huge : s * tiny * tiny;
+    if (ix > 0x3ff00000) return (hy > 0) ? s * huge * huge : s * tiny * tiny;
+    t = ax - 1.0;
+    w = (t * t) * (0.5 - t * (0.3333333333333333333333 - t * 0.25));
+    u = ivln2_h * t;
+    v = t * ivln2_l - w * ivln2;
+    t1 = u + v;
+    t1 = m3m_set_lo(t1, 0);
+    t2 = v - (t1 - u);
+  } else {
+    double ss, s2, s_h, s_l, t_h, t_l;
+    n = 0;
+    if (ix < 0x00100000) { ax *= two53; n -= 53; ix = m3m_hi(ax); }
+    n += ((ix) >> 20) - 0x3ff;
+    j = ix & 0x000fffff;
+    ix = j | 0x3ff00000;
+    if (j <= 0x3988E) k = 0;
+    else if (j < 0xBB67A) k = 1;
+    else { k = 0; n += 1; ix -= 0x00100000; }
+    ax = m3m_set_hi(ax, ix);
+
+    u = ax - (k ? 1.5 : 1.0);
+    v = 1.0 / (ax + (k ? 1.5 : 1.0));
+    ss = u * v;
+    s_h = ss;
+    s_h = m3m_set_lo(s_h, 0);
+    t_h = m3m_from_words(((ix >> 1) | 0x20000000) + 0x00080000 + (k << 18), 0);
+    t_l = ax - (t_h - (k ? 1.5 : 1.0));
+    s_l = v * ((u - s_h * t_h) - s_h * t_l);
+    s2 = ss * ss;
+    r = s2 * s2 * (L1 + s2 * (L2 + s2 * (L3 + s2 * (L4 + s2 * (L5 + s2 * L6)))));
+    r += s_l * (s_h + ss);
+    s2 = s_h * s_h;
+    t_h = 3.0 + s2 + r;
+    t_h = m3m_set_lo(t_h, 0);
+    t_l = r - ((t_h - 3.0) - s2);
+    u = s_h * t_h;
+    v = s_l * t_h + t_l * ss;
+    p_h = u + v;
+    p_h = m3m_set_lo(p_h, 0);
+    p_l = v - (p_h - u);
+    z_h = cp_h * p_h;
+    z_l = cp_l * p_h + p_l * cp + (k ? dp_l1 : 0.0);
+    t = (double)n;
+    t1 = (((z_h + z_l) + (k ? dp_h1 : 0.0)) + t);
+    t1 = m3m_set_lo(t1, 0);
+    t2 = z_l - (((t1 - t) - (k ? dp_h1 : 0.0)) - z_h);
+  }
+
+  y1 = y;
+  y1 = m3m_set_lo(y1, 0);
+  p_l = (y - y1) * t1 + y * t2;
+  p_h = y1 * t1;
+  z = p_l + p_h;
+  j = m3m_hi(z);
+  i = (int32_t)m3m_lo(z);
+  if (j >= 0x40900000) {
+    if (((j - 0x40900000) | i) != 0) return s * huge * huge;
+    else { if (p_l + ovt > z - p_h) return s * huge * huge; }
+  } else if ((j & 0x7fffffff) >= 0x4090cc00) {
+    if (((j - (int32_t)0xc090cc00) | i) != 0) return s * tiny * tiny;
+    else { if (p_l <= z - p_h) return s * tiny * tiny; }
+  }
+  i = j & 0x7fffffff;
+  k = (i >> 20) - 0x3ff;
+  n = 0;
+  if (i > 0x3fe00000) {
+    n = j + (0x00100000 >> (k + 1));
+    k = ((n & 0x7fffffff) >> 20) - 0x3ff;
+    t = m3m_from_words(n & ~(0x000fffff >> k), 0);
+    n = ((n & 0x000fffff) | 0x00100000) >> (20 - k);
+    if (j < 0) n = -n;
+    p_h -= t;
+  }
+  t = p_l + p_h;
+  t = m3m_set_lo(t, 0);
+  u = t * lg2_h;
+  v = (p_l - (t - p_h)) * lg2 + t * lg2_l;
+  z = u + v;
+  w = v - (z - u);
+  t = z * z;
+  t1 = z - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  r = (z * t1) / (t1 - 2.0) - (w + z * w);
+  z = 1.0 - (r - z);
+  j = m3m_hi(z);
+  j += (n << 20);
+  if ((j >> 20) <= 0) z = ldexp(z, n);
+  else z = m3m_set_hi(z, m3m_hi(z) + (n << 20));
+  return s * z;
+}
+
+#endif /* MP3B200_MATH_CUH */

@@ -1,0 +1,166 @@
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+class Mp3B200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (building if needed) libmp3b200.so and declare the C-ABI of include/mp3b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        _build.build()
+    L = ctypes.CDLL(path)
+    c_int, c_i64, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
+    L.mp3b200_last_error.restype = ctypes.c_char_p
+    L.mp3b200_launch_count.restype = c_i64
+    L.mp3b200_set_device.argtypes = [c_int]
+    L.mp3b200_create.argtypes = [c_int, c_int, c_int, ctypes.POINTER(vp)]
+    L.mp3b200_encode.argtypes = [vp, vp, vp, c_int, vp, c_int]
+    L.mp3b200_flush.argtypes = [vp, vp, c_int]
+    L.mp3b200_destroy.argtypes = [vp]
+    L.mp3b200_destroy.restype = None
+    L.mp3b200_stream_bytes.restype = c_i64
+    L.mp3b200_stream_bytes.argtypes = [c_int, c_int, c_int, c_i64]
+    L.mp3b200_stream_frames.restype = c_i64
+    L.mp3b200_stream_frames.argtypes = [c_i64]
+    L.mp3b200_encode_streams.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    L.mp3b200_encode_streams_device.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    L.mp3b200_debug_stages.argtypes = [c_int, c_int, c_int, vp, vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_i64]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        raise Mp3B200Error("libmp3b200 error %d: %s" % (rc, lib().mp3b200_last_error().decode()))
+    return rc
+
+
+def stream_frames(nsamples):
+    return int(lib().mp3b200_stream_frames(int(nsamples)))
+
+
+def stream_bytes(channels, samplerate, kbps, nsamples):
+    return int(lib().mp3b200_stream_bytes(channels, samplerate, kbps, int(nsamples)))
+
+
+class Mp3Encoder:
+    """Drop-in for lamejs.Mp3Encoder(channels, samplerate, kbps) (src/js/index.js:66-136)."""
+
+    def __init__(self, channels=1, samplerate=44100, kbps=128):
+        self._L = lib()
+        self._h = ctypes.c_void_p()
+        self.channels = channels
+        rc = self._L.mp3b200_create(channels, samplerate, kbps, ctypes.byref(self._h))
+        _check(rc)
+
+    def encodeBuffer(self, left, right=None):
+        left = np.ascontiguousarray(left, dtype=np.int16)
+        if self.channels == 1 or right is None:
+            right = left
+        right = np.ascontiguousarray(right, dtype=np.int16)
+        assert len(left) == len(right)
+        cap = int(1.25 * len(left) + 7200)     # index.js:114,124
+        buf = np.empty(cap, dtype=np.uint8)
+        n = _check(self._L.mp3b200_encode(self._h, left.ctypes.data, right.ctypes.data, len(left), buf.ctypes.data, cap))
+        return buf[:n].tobytes()
+
+    def flush(self):
+        cap = 7200 + 8 * 1441
+        buf = np.empty(cap, dtype=np.uint8)
+        n = _check(self._L.mp3b200_flush(self._h, buf.ctypes.data, cap))
+        return buf[:n].tobytes()
+
+    # pythonic aliases
+    encode_buffer = encodeBuffer
+
+    def close(self):
+        if self._h:
+            self._L.mp3b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def encode_streams(channels, samplerate, kbps, lefts, rights=None):
+    """Batch extension: encodeBuffer(whole stream) + flush() for many independent streams in one launch sequence.
+    Host buffers in, list of bytes out."""
+    L = lib()
+    S = len(lefts)
+    lefts = [np.ascontiguousarray(x, dtype=np.int16) for x in lefts]
+    rights = lefts if (rights is None or channels == 1) else [np.ascontiguousarray(x, dtype=np.int16) for x in rights]
+    ns = np.array([len(x) for x in lefts], dtype=np.int64)
+    nb = [stream_bytes(channels, samplerate, kbps, int(n)) for n in ns]
+    outs = [np.empty(b, dtype=np.uint8) for b in nb]
+    lp = (ctypes.c_void_p * S)(*[x.ctypes.data for x in lefts])
+    rp = (ctypes.c_void_p * S)(*[x.ctypes.data for x in rights])
+    op = (ctypes.c_void_p * S)(*[x.ctypes.data for x in outs])
+    caps = np.array(nb, dtype=np.int64)
+    got = np.zeros(S, dtype=np.int64)
+    _check(L.mp3b200_encode_streams(channels, samplerate, kbps, S, lp, rp, ns.ctypes.data, op, caps.ctypes.data, got.ctypes.data))
+    return [o[: int(g)].tobytes() for o, g in zip(outs, got)]
+
+
+def encode_streams_device(channels, samplerate, kbps, d_pcm_ptr, pcm_off, nsamples, d_out_ptr, out_off):
+    """Device-resident batch (raw device pointers as ints).  Returns the 8 kernel timings (ms)."""
+    L = lib()
+    pcm_off = np.ascontiguousarray(pcm_off, dtype=np.int64)
+    nsamples = np.ascontiguousarray(nsamples, dtype=np.int64)
+    out_off = np.ascontiguousarray(out_off, dtype=np.int64)
+    tm = np.zeros(8, dtype=np.float32)
+    _check(L.mp3b200_encode_streams_device(channels, samplerate, kbps, len(nsamples), d_pcm_ptr, pcm_off.ctypes.data,
+                                           nsamples.ctypes.data, d_out_ptr, out_off.ctypes.data, tm.ctypes.data))
+    return tm
+
+
+def debug_stages(channels, samplerate, kbps, left, right=None, force_blocktype=None, want=("xr",)):
+    """Stage taps for parity tests: returns a dict of numpy arrays (see include/mp3b200.h)."""
+    L = lib()
+    left = np.ascontiguousarray(left, dtype=np.int16)
+    right = left if (right is None or channels == 1) else np.ascontiguousarray(right, dtype=np.int16)
+    n = len(left)
+    F = stream_frames(n)
+    nch = channels
+    res = {}
+
+    def alloc(name, shape, dt):
+        if name in want:
+            res[name] = np.zeros(shape, dtype=dt)
+            return res[name].ctypes.data
+        return None
+
+    fb = None
+    if force_blocktype is not None:
+        fb = np.ascontiguousarray(force_blocktype, dtype=np.int32)
+        assert fb.shape == (F, 2, nch)
+    p_xr = alloc("xr", (F, 2, nch, 576), np.float32)
+    p_bt = alloc("blocktype", (F, 2, nch), np.int32)
+    p_enl = alloc("en_l", (F, 2, nch, 22), np.float32)
+    p_thl = alloc("thm_l", (F, 2, nch, 22), np.float32)
+    p_ens = alloc("en_s", (F, 2, nch, 13, 3), np.float32)
+    p_ths = alloc("thm_s", (F, 2, nch, 13, 3), np.float32)
+    p_ath = alloc("ath_adjust", (F,), np.float64)
+    p_l3 = alloc("l3_enc", (F, 2, nch, 576), np.int32)
+    p_gi = alloc("ginfo", (F, 2, nch, 16), np.int32)
+    nb = stream_bytes(channels, samplerate, kbps, n)
+    p_by = alloc("bytes", (nb,), np.uint8)
+    _check(L.mp3b200_debug_stages(channels, samplerate, kbps, left.ctypes.data, right.ctypes.data, n,
+                                  fb.ctypes.data if fb is not None else None, p_xr, p_bt, p_enl, p_thl, p_ens, p_ths, p_ath,
+                                  p_l3, p_gi, p_by, nb))
+    return res

@@ -1,0 +1,66 @@
+"""C-ABI library: builds for sm_100a without a GPU, loads, exports every symbol include/mp3b200.h declares; the
+closed-form stream geometry (no compute) matches the oracle; host-side logic fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def M():
+    import lamejs_b200
+
+    lamejs_b200.lib()
+    return lamejs_b200
+
+
+def test_exports_every_declared_symbol(M):
+    hdr = open(os.path.join(ROOT, "include", "mp3b200.h")).read()
+    names = set(re.findall(r"\b(mp3b200_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 12
+    L = ctypes.CDLL(os.path.join(ROOT, "lamejs_b200", "libmp3b200.so"))
+    for n in sorted(names):
+        assert hasattr(L, n), n
+
+
+@pytest.mark.parametrize("n", [0, 1, 1151, 1152, 1375, 1376, 1377, 2304, 44100, 11520000])
+def test_stream_geometry_matches_oracle(M, oracle, n):
+    F = M.stream_frames(n)
+    if n <= 50000:
+        x = np.zeros(n, dtype=np.int16)
+        data, _, tr = oracle.encode_stream(2, 44100, 128, x, x, trace_frames=F + 4)
+        assert len(tr) == F
+        assert len(data) == M.stream_bytes(2, 44100, 128, n)
+    else:
+        assert F == (n - 1376) // 1152 + 1 + 2 or F == (n - 1376) // 1152 + 1 + 1
+
+
+def test_config_errors(M):
+    assert M.stream_bytes(2, 44100, 64, 1000) == -1       # lamejs would resample to 32 kHz: not built
+    assert M.stream_bytes(2, 22050, 64, 1000) == -1       # MPEG-2
+    assert M.stream_bytes(3, 44100, 128, 1000) == -1
+    assert M.stream_bytes(2, 44100, 123, 44100) == M.stream_bytes(2, 44100, 128, 44100)   # FindNearestBitrate
+
+
+def test_no_cpu_fallback(M):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(M.Mp3B200Error):
+        M.Mp3Encoder(2, 44100, 128)
+    with pytest.raises(M.Mp3B200Error):
+        M.encode_streams(1, 44100, 128, [np.zeros(5000, dtype=np.int16)])
+
+
+def test_product_does_not_reference_oracle():
+    """The shipped path must not import, link or execute anything under oracle/."""
+    for d, _, files in os.walk(os.path.join(ROOT, "lamejs_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inc")):
+                s = open(os.path.join(d, f)).read()
+                assert "oracle_lib" not in s and "liblamejs_oracle" not in s and "oracle/" not in s.replace("the oracle/", ""), f
