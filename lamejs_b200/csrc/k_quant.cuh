@@ -491,8 +491,10 @@ __device__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
   if (r == 0) return false;
   if (r == 1) return true;
   bool status = true;
+  const int scale_now = gi->scalefac_scale, is_short_blk = gi->block_type == BT_SHORT;
+  __syncwarp();                                    /* all lanes hold the decision inputs before lane 0 edits gi */
   if (T->noise_shaping > 1) {
-    if (0 == gi->scalefac_scale) {
+    if (0 == scale_now) {
       /* inc_scalefac_scale (Quantize.js:676-699) */
       if (lane == 0) {
         for (int sfb = 0; sfb < gi->sfbmax; sfb++) {
@@ -509,7 +511,7 @@ __device__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
       __syncwarp();
       scale_xrpow_w(wk, gi, 1.29683955465100964055);
       status = false;
-    } else if (gi->block_type == BT_SHORT) {      /* gfc.subblock_gain == 1 */
+    } else if (is_short_blk) {                    /* gfc.subblock_gain == 1 */
       /* inc_subblock_gain (Quantize.js:705-781): lane 0 decides, all lanes rescale the touched windows */
       if (lane == 0) {
         int ret = 0;
@@ -570,12 +572,14 @@ __device__ __forceinline__ void copy_gi_w(GranuleInfoDev* dst, const GranuleInfo
   const int n = sizeof(GranuleInfoDev) / 4;
   const int* s = reinterpret_cast<const int*>(src);
   int* d = reinterpret_cast<int*>(dst);
+  __syncwarp();                                   /* earlier readers of *dst are done */
   for (int i = LANE; i < n; i += 32) d[i] = s[i];
   __syncwarp();
 }
 __device__ __forceinline__ void copy_ix_w(short* dst, const short* src) {
   const int* s = reinterpret_cast<const int*>(src);
   int* d = reinterpret_cast<int*>(dst);
+  __syncwarp();
   for (int i = LANE; i < 288; i += 32) d[i] = s[i];
   __syncwarp();
 }
@@ -590,6 +594,7 @@ __device__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int desired_rate, in
   int Direction = 0;
   int gain = start;
   desired_rate -= gi->part2_length;
+  __syncwarp();
   for (;;) {
     int step;
     if (LANE == 0) gi->global_gain = gain;
@@ -626,6 +631,7 @@ __device__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int desired_rate, in
 
 /* outer_loop (Quantize.js:871-1052) for noise_shaping_amp 1, full_outer_loop 0, substep_shaping 0 */
 __device__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int targ_bits, int* old_value, int* current_step) {
+  /* note: *old_value / *current_step are final right after bin_search_w below (outer_loop never touches them again) */
   const int lane = LANE;
   NoiseRes best, cur;
   int best_part2_3_length = 9999999;
@@ -648,22 +654,30 @@ __device__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int targ_bits, int*
     if (w->scalefac_scale != 0) maxggain = 254;
     const int huff_bits = targ_bits - w->part2_length;
     if (huff_bits <= 0) break;
-    int p23;
-    while ((p23 = count_bits_w(T, wk, w, wk->ixw, true)) > huff_bits && w->global_gain <= maxggain) {
-      if (lane == 0) w->global_gain++;
+    int p23, gg;
+    for (;;) {                                     /* while (count_bits > huff_bits && global_gain <= maxggain) global_gain++ */
+      p23 = count_bits_w(T, wk, w, wk->ixw, true);
+      gg = w->global_gain;
+      __syncwarp();                                /* every lane has read the gain before lane 0 bumps it */
+      if (!(p23 > huff_bits && gg <= maxggain)) break;
+      if (lane == 0) w->global_gain = gg + 1;
       __syncwarp();
     }
     if (lane == 0) w->part2_3_length = p23;
     __syncwarp();
-    if (w->global_gain > maxggain) break;
+    if (gg > maxggain) break;
     if (best.over_count == 0) {
-      while ((p23 = count_bits_w(T, wk, w, wk->ixw, true)) > best_part2_3_length && w->global_gain <= maxggain) {
-        if (lane == 0) w->global_gain++;
+      for (;;) {
+        p23 = count_bits_w(T, wk, w, wk->ixw, true);
+        gg = w->global_gain;
+        __syncwarp();
+        if (!(p23 > best_part2_3_length && gg <= maxggain)) break;
+        if (lane == 0) w->global_gain = gg + 1;
         __syncwarp();
       }
       if (lane == 0) w->part2_3_length = p23;
       __syncwarp();
-      if (w->global_gain > maxggain) break;
+      if (gg > maxggain) break;
     }
     calc_noise_w(T, wk, w, wk->ixw, &cur);
     cur.bits = w->part2_3_length;
@@ -685,7 +699,10 @@ __device__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int targ_bits, int*
     } else {
       if (++age > search_limit && best.over_count == 0) break;
     }
-  } while ((wk->w.global_gain + wk->w.scalefac_scale) < 255);
+    const int cont = (wk->w.global_gain + wk->w.scalefac_scale) < 255;
+    __syncwarp();
+    if (!cont) break;
+  } while (true);
 }
 
 /* athAdjust (QuantizePVT.js:541-561) */
@@ -1231,6 +1248,33 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
     const int mean_bits = (frame_bits - T->sideinfo_len * 8) / 2;      /* Reservoir.js:83 (exact: multiple of 4) */
     int old_value = fs->old_value[ch], current_step = fs->current_step[ch];
 
+    if (revalidate) {
+      /* Re-validation of an already encoded frame under a corrected in-state: the only place the in-state enters is
+       * the gr0 bin search.  If it lands on the same gain and CurrentStep as the recorded full run (both channels),
+       * everything downstream -- both granules, the bytes and the out-state -- is unchanged. */
+      if (threadIdx.x == 0) {
+        double t = (double)mean_bits / nch;
+        if (t > 4095) t = 4095;
+        fs->targ_bits[0] = fs->targ_bits[1] = (int)t;
+      }
+      __syncthreads();
+      const size_t urow0 = (size_t)sd.unit_base + 2 * f;
+      const PsyRatioDev* rt0 = ratio + ((size_t)sd.unit_base + z + 2 * f) * nch + ch;
+      int ov = old_value, cs = current_step;
+      const bool have0 = gc_prepare_w(T, wk, fs, xr + (urow0 * nch + ch) * 576, bt_final[urow0 * 2 + ch], rt0, ath_adjust);
+      if (have0) {
+        for (int i = lane; i < MP3_SFBMAX; i += 32) wk->pn_step[i] = 0;
+        if (lane == 0) { wk->pn_global_gain = 0; wk->pn_sfb_count1 = 0; }
+        __syncwarp();
+        bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs);
+      }
+      if (lane == 0 && (ov != q->bs_gain0[ch] || cs != q->bs_step0[ch])) atomicOr(&fs->flag, 1);
+      __syncthreads();
+      const int changed = fs->flag;
+      __syncthreads();
+      if (!changed) continue;
+    }
+
     for (int gr = 0; gr < 2; gr++) {
       /* on_pe with the reservoir disabled (QuantizePVT.js:421-484 + Reservoir.js:190-229): gr0 gets mean_bits, gr1
        * additionally what gr0 left over; per channel trunc(tbits / nch), capped at 4095; PE never matters */
@@ -1257,8 +1301,9 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       const bool have = gc_prepare_w(T, wk, fs, xr + (urow * nch + ch) * 576, bt, rt, ath_adjust);
       if (have) {
         outer_loop_w(T, wk, fs->targ_bits[ch], &old_value, &current_step);
-        if (gr == 0 && lane == 0) { q->bs_gain0[ch] = old_value; q->bs_step0[ch] = current_step; }
       }
+      /* state right after gr0's bin search (pass-through when the granule is silent): re-validation key */
+      if (gr == 0 && lane == 0) { q->bs_gain0[ch] = old_value; q->bs_step0[ch] = current_step; }
       /* iteration_finish_one (Quantize.js:1059-1078) */
       best_scalefac_store_w(wk, fs, gr, ch);
       best_huffman_divide_w(T, wk);
@@ -1307,7 +1352,6 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       for (int i = threadIdx.x; i < frame_bytes; i += blockDim.x) dst[i] = (uint8_t)(fs->bits[i >> 2] >> (24 - 8 * (i & 3)));
     }
     if (threadIdx.x == 0) q->valid = 1;
-    (void)revalidate;
   }
 }
 

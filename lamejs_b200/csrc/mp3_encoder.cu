@@ -134,6 +134,17 @@ struct Workspace {
   }
 };
 
+/* MP3B200_DEBUG_SYNC=1: synchronise after every launch and name the failing kernel */
+bool debug_sync() { static int v = -1; if (v < 0) { const char* e = getenv("MP3B200_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; } return v == 1; }
+#define DBG(name)                                                                           \
+  do {                                                                                      \
+    if (debug_sync()) {                                                                     \
+      cudaError_t e_ = cudaStreamSynchronize(st);                                           \
+      if (e_ == cudaSuccess) e_ = cudaGetLastError();                                       \
+      if (e_ != cudaSuccess) { g_err = std::string(name) + ": " + cudaGetErrorString(e_); return MP3B200_ERR_CUDA; } \
+    }                                                                                       \
+  } while (0)
+
 struct Timings { float psy = 0, scan = 0, mask = 0, fb = 0, q1 = 0, qn = 0, total = 0; int passes = 0; };
 
 /* Runs the whole pipeline for the streams described in `h_streams` (device pointers already set).
@@ -143,7 +154,8 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   const int S = (int)h_streams.size();
   const int nch = cfg->host.nch;
   int max_frames = 0;
-  for (auto& s : h_streams) max_frames = s.nframes > max_frames ? s.nframes : max_frames;
+  long long total_frames = 0;          /* rows actually used this launch (the workspace may be larger) */
+  for (auto& s : h_streams) { max_frames = s.nframes > max_frames ? s.nframes : max_frames; total_frames += s.nframes; }
   CK(cudaMemcpyAsync(ws.d_streams, h_streams.data(), sizeof(StreamDesc) * S, cudaMemcpyHostToDevice, st));
   cudaEvent_t ev[8];
   for (auto& e : ev) CK(cudaEventCreate(&e));
@@ -154,14 +166,17 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     dim3 grid(2 * max_frames + 1, nch, S);
     k_psy_analysis<<<grid, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy);
     g_launches++;
+    DBG("k_psy_analysis");
   }
   CK(cudaEventRecord(ev[1], st));
   /* K3a: attack pre-pass (parallel) + sequential per-stream scans */
   {
     dim3 grid((2 * max_frames + 127) / 128, 1, S);
     k_attack_prepass<<<grid, 128, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy);
+    DBG("k_attack_prepass");
     k_stream_scan<<<(S + 31) / 32, 64, 0, st>>>(cfg->dev, ws.d_streams, S, ws.d_psy, ws.d_bt_final, ws.d_bt_prev, ws.d_ath_psy, ws.d_ath_q);
     g_launches += 2;
+    DBG("k_stream_scan");
   }
   CK(cudaEventRecord(ev[2], st));
   /* K3b: masking thresholds */
@@ -169,6 +184,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     dim3 grid(2 * max_frames + 1, 1, S);
     k_psy_masking<<<grid, MASK_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_bt_prev, ws.d_ath_psy, ws.d_ratio);
     g_launches++;
+    DBG("k_psy_masking");
   }
   CK(cudaEventRecord(ev[3], st));
   if (force_bt) {   /* debug: override block decision for the filterbank */
@@ -184,11 +200,12 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     const size_t smem = sizeof(float) * (FB_PCM_WORDS + (FB_G + 1) * 18 * FB_SLAB_STRIDE);
     k_filterbank_mdct<<<grid, FB_THREADS, smem, st>>>(cfg->dev, ws.d_streams, ws.d_bt_final, ws.d_xr);
     g_launches++;
+    DBG("k_filterbank_mdct");
   }
   CK(cudaEventRecord(ev[4], st));
   int passes = 0;
   if (!stop_after_mdct) {
-    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, max_frames, ws.frames, ws.d_xr, ws.d_ratio, ws.d_bt_final, ws.d_ath_q,
+    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, max_frames, total_frames, ws.d_xr, ws.d_ratio, ws.d_bt_final, ws.d_ath_q,
                        ws.d_qstate, ws.d_ginfo, ws.d_l3enc, ws.d_dirty, ws.d_counter, d_out, st, ev[5], &passes, &g_launches);
     if (rc) { g_err = "quantizer stage failed: " + std::string(cudaGetErrorString(cudaGetLastError())); return rc; }
   } else {
