@@ -36,10 +36,11 @@ struct PsyUnit {
 struct PsyRatioDev { float en_l[22], thm_l[22], en_s[13][3], thm_s[13][3]; };
 
 __constant__ unsigned char c_fft_rv[128];
-__constant__ double c_tab[9];
-__constant__ double c_table1[25];
-__constant__ double c_table2[10];
-__constant__ double c_table3[14];
+/* indexed per lane by data: global + read-only cache instead of __constant__ (divergent constant reads serialise) */
+__device__ double c_tab[9];
+__device__ double c_table1[25];
+__device__ double c_table2[10];
+__device__ double c_table3[14];
 __constant__ double c_fircoef[10];
 
 static int psy_upload_constants() {
@@ -355,85 +356,140 @@ __global__ void k_attack_prepass(const Mp3Tables* __restrict__ T, const StreamDe
   }
 }
 
-/* ---- sequential scans: thread (stream, role) ; role 0 = attack/block-type FSM, role 1 = ATH adjust -------- */
-__global__ void k_stream_scan(const Mp3Tables* __restrict__ T, StreamDesc* __restrict__ streams, int nstreams,
-                              const PsyUnit* __restrict__ psy, signed char* __restrict__ bt_final,
-                              signed char* __restrict__ bt_prev, double* __restrict__ ath_psy, double* __restrict__ ath_q) {
-  const int z = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int role = threadIdx.x >> 5;
+/* ---- sequential scans, parallelised by speculation ---------------------------------------------------------
+ * Two recurrences run through a stream: the attack / block-type FSM (PsyModel.js:1183-1204, 784-826; state =
+ * lastAttacks and blocktype_old of both channels) and the ATH auto-adjust IIR (Encoder.js:166-243; state = adjust,
+ * adjustLimit).  Both forget their past quickly (two attack-free granules reset the FSM to (0, NORM); two loud frames
+ * reset the ATH state to (1, 1)), so each 32-frame chunk is run from a guessed in-state by its own thread, the
+ * guesses are checked against the predecessor's out-state, and only wrong chunks are redone until nothing changes.
+ * The result equals the sequential scan exactly; the worst case degenerates to it.  One block per stream. */
+#define SCAN_FRAMES 32
+#define SCAN_THREADS 256
+struct ScanChunk { int fsm_in, fsm_out, dirty_fsm, dirty_ath; double ath_in[2], ath_out[2]; };
+
+__device__ __forceinline__ int fsm_pack(int la0, int la1, int o0, int o1) { return la0 | (la1 << 2) | (o0 << 4) | (o1 << 6); }
+
+__device__ void scan_fsm_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, const PsyUnit* psy, signed char* bt_final,
+                               signed char* bt_prev, int f0, int f1, ScanChunk* ck) {
+  const int nch = T->nch, coupled = T->coupled_short_blocks;
+  int la[2] = {ck->fsm_in & 3, (ck->fsm_in >> 2) & 3};
+  int old[2] = {(ck->fsm_in >> 4) & 3, (ck->fsm_in >> 6) & 3};
+  for (int u = 2 * f0; u < 2 * f1; u++) {
+    int uselong[2] = {1, 1};
+    for (int ch = 0; ch < nch; ch++) {
+      const PsyUnit* p = psy + psy_row(sd, z, u) * nch + ch;
+      const unsigned av = *reinterpret_cast<const unsigned*>(p->attack);
+      int a0 = av & 0xff, a1 = (av >> 8) & 0xff, a2 = (av >> 16) & 0xff, a3 = (av >> 24) & 0xff;
+      if (a0 != 0 && la[ch] != 0) a0 = 0;
+      if (la[ch] == 3 || (a0 + a1 + a2 + a3) != 0) {
+        uselong[ch] = 0;
+        if (a1 != 0 && a0 != 0) a1 = 0;
+        if (a2 != 0 && a1 != 0) a2 = 0;
+        if (a3 != 0 && a2 != 0) a3 = 0;
+      }
+      la[ch] = a2;
+    }
+    if (coupled && !(uselong[0] != 0 && uselong[1] != 0)) uselong[0] = uselong[1] = 0;
+    const size_t row = (size_t)(sd.unit_base + u) * 2;
+    for (int ch = 0; ch < nch; ch++) {
+      bt_prev[row + ch] = (signed char)old[ch];          /* what compute_masking_s of this call saw */
+      int bt = BT_NORM;
+      if (uselong[ch] != 0) {
+        if (old[ch] == BT_SHORT) bt = BT_STOP;
+      } else {
+        bt = BT_SHORT;
+        if (old[ch] == BT_NORM) old[ch] = BT_START;
+        if (old[ch] == BT_STOP) old[ch] = BT_SHORT;
+      }
+      bt_final[row + ch] = (signed char)old[ch];
+      old[ch] = bt;
+    }
+  }
+  ck->fsm_out = fsm_pack(la[0], la[1], old[0], old[1]);
+}
+
+__device__ void scan_ath_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, const PsyUnit* psy, double* ath_psy,
+                               double* ath_q, int f0, int f1, ScanChunk* ck) {
+  const int nch = T->nch;
+  double adjust = ck->ath_in[0], limit = ck->ath_in[1];
+  const double sens = T->aa_sensitivity_p;
+  for (int f = f0; f < f1; f++) {
+    ath_psy[sd.frame_base + f] = adjust;
+    /* loudness_sq[gr][ch] is the loudness of the unit BEFORE call 2f+gr (one-call delay, PsyModel.js:321-322) */
+    const PsyUnit* r0 = psy + psy_row(sd, z, 2 * f - 1) * nch;
+    const PsyUnit* r1 = psy + psy_row(sd, z, 2 * f) * nch;
+    double max_pow = (double)r0[0].loudness, gr2_max = (double)r1[0].loudness;
+    if (nch == 2) { max_pow += (double)r0[1].loudness; gr2_max += (double)r1[1].loudness; }
+    else { max_pow += max_pow; gr2_max += gr2_max; }
+    max_pow = js_dmax(max_pow, gr2_max);
+    max_pow *= 0.5;
+    max_pow *= sens;
+    if (max_pow > 0.03125) {
+      if (adjust >= 1.0) adjust = 1.0;
+      else if (adjust < limit) adjust = limit;
+      limit = 1.0;
+    } else {
+      const double adj_lim_new = 31.98 * max_pow + 0.000625;
+      if (adjust >= adj_lim_new) {
+        adjust *= adj_lim_new * 0.075 + 0.925;
+        if (adjust < adj_lim_new) adjust = adj_lim_new;
+      } else {
+        if (limit >= adj_lim_new) adjust = adj_lim_new;
+        else if (adjust < limit) adjust = limit;
+      }
+      limit = adj_lim_new;
+    }
+    ath_q[sd.frame_base + f] = adjust;
+  }
+  ck->ath_out[0] = adjust; ck->ath_out[1] = limit;
+}
+
+/* grid: nstreams blocks x SCAN_THREADS.  chunks: scratch rows [sd.scan_base, sd.scan_base + nchunks) */
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_stream_scan(const Mp3Tables* __restrict__ T, StreamDesc* __restrict__ streams, int nstreams,
+              const PsyUnit* __restrict__ psy, signed char* __restrict__ bt_final,
+              signed char* __restrict__ bt_prev, double* __restrict__ ath_psy, double* __restrict__ ath_q,
+              ScanChunk* __restrict__ scratch) {
+  const int z = blockIdx.x;
   if (z >= nstreams) return;
   const StreamDesc sd = streams[z];
-  const int nch = T->nch;
-  if (role == 0) {
-    int old[2] = {sd.blocktype_old[0], sd.blocktype_old[1]};
-    int la[2] = {sd.last_attacks[0], sd.last_attacks[1]};
-    const int coupled = T->coupled_short_blocks;
-    for (int u = 0; u < 2 * sd.nframes; u++) {
-      int uselong[2] = {1, 1};
-      for (int ch = 0; ch < nch; ch++) {
-        const PsyUnit* p = psy + psy_row(sd, z, u) * nch + ch;
-        int a0 = p->attack[0], a1 = p->attack[1], a2 = p->attack[2], a3 = p->attack[3];
-        if (a0 != 0 && la[ch] != 0) a0 = 0;
-        if (la[ch] == 3 || (a0 + a1 + a2 + a3) != 0) {
-          uselong[ch] = 0;
-          if (a1 != 0 && a0 != 0) a1 = 0;
-          if (a2 != 0 && a1 != 0) a2 = 0;
-          if (a3 != 0 && a2 != 0) a3 = 0;
-        }
-        la[ch] = a2;
-      }
-      if (coupled && !(uselong[0] != 0 && uselong[1] != 0)) uselong[0] = uselong[1] = 0;
-      const size_t row = (size_t)(sd.unit_base + u) * 2;
-      for (int ch = 0; ch < nch; ch++) {
-        bt_prev[row + ch] = (signed char)old[ch];          /* what compute_masking_s of this call saw */
-        int bt = BT_NORM;
-        if (uselong[ch] != 0) {
-          if (old[ch] == BT_SHORT) bt = BT_STOP;
-        } else {
-          bt = BT_SHORT;
-          if (old[ch] == BT_NORM) old[ch] = BT_START;
-          if (old[ch] == BT_STOP) old[ch] = BT_SHORT;
-        }
-        bt_final[row + ch] = (signed char)old[ch];
-        old[ch] = bt;
+  const int nchunks = (sd.nframes + SCAN_FRAMES - 1) / SCAN_FRAMES;
+  ScanChunk* ck = scratch + sd.scan_base;
+  const int tid = threadIdx.x;
+  for (int c = tid; c < nchunks; c += SCAN_THREADS) {
+    ck[c].fsm_in = c == 0 ? fsm_pack(sd.last_attacks[0], sd.last_attacks[1], sd.blocktype_old[0], sd.blocktype_old[1])
+                          : fsm_pack(0, 0, BT_NORM, BT_NORM);
+    ck[c].ath_in[0] = c == 0 ? sd.ath_adjust : 1.0;
+    ck[c].ath_in[1] = c == 0 ? sd.ath_adjust_limit : 1.0;
+    ck[c].dirty_fsm = ck[c].dirty_ath = 1;
+  }
+  for (;;) {
+    for (int c = tid; c < nchunks; c += SCAN_THREADS) {
+      const int f0 = c * SCAN_FRAMES, f1 = min(sd.nframes, f0 + SCAN_FRAMES);
+      if (ck[c].dirty_fsm) scan_fsm_chunk(T, sd, z, psy, bt_final, bt_prev, f0, f1, &ck[c]);
+      if (ck[c].dirty_ath) scan_ath_chunk(T, sd, z, psy, ath_psy, ath_q, f0, f1, &ck[c]);
+    }
+    __syncthreads();
+    int any = 0;
+    for (int c = tid; c < nchunks; c += SCAN_THREADS) {
+      ck[c].dirty_fsm = ck[c].dirty_ath = 0;
+      if (c == 0) continue;
+      if (ck[c].fsm_in != ck[c - 1].fsm_out) { ck[c].fsm_in = ck[c - 1].fsm_out; ck[c].dirty_fsm = 1; any = 1; }
+      if (ck[c].ath_in[0] != ck[c - 1].ath_out[0] || ck[c].ath_in[1] != ck[c - 1].ath_out[1]) {
+        ck[c].ath_in[0] = ck[c - 1].ath_out[0]; ck[c].ath_in[1] = ck[c - 1].ath_out[1]; ck[c].dirty_ath = 1; any = 1;
       }
     }
-    streams[z].blocktype_old[0] = old[0]; streams[z].blocktype_old[1] = old[1];
-    streams[z].last_attacks[0] = la[0]; streams[z].last_attacks[1] = la[1];
-  } else {
-    double adjust = sd.ath_adjust, limit = sd.ath_adjust_limit;
-    const double sens = T->aa_sensitivity_p;
-    for (int f = 0; f < sd.nframes; f++) {
-      ath_psy[sd.frame_base + f] = adjust;
-      /* loudness_sq[gr][ch] is the loudness of the unit BEFORE call 2f+gr (one-call delay, PsyModel.js:321-322) */
-      const PsyUnit* r0 = psy + psy_row(sd, z, 2 * f - 1) * nch;
-      const PsyUnit* r1 = psy + psy_row(sd, z, 2 * f) * nch;
-      double max_pow = (double)r0[0].loudness, gr2_max = (double)r1[0].loudness;
-      if (nch == 2) { max_pow += (double)r0[1].loudness; gr2_max += (double)r1[1].loudness; }
-      else { max_pow += max_pow; gr2_max += gr2_max; }
-      max_pow = js_dmax(max_pow, gr2_max);
-      max_pow *= 0.5;
-      max_pow *= sens;
-      if (max_pow > 0.03125) {
-        if (adjust >= 1.0) adjust = 1.0;
-        else if (adjust < limit) adjust = limit;
-        limit = 1.0;
-      } else {
-        const double adj_lim_new = 31.98 * max_pow + 0.000625;
-        if (adjust >= adj_lim_new) {
-          adjust *= adj_lim_new * 0.075 + 0.925;
-          if (adjust < adj_lim_new) adjust = adj_lim_new;
-        } else {
-          if (limit >= adj_lim_new) adjust = adj_lim_new;
-          else if (adjust < limit) adjust = limit;
-        }
-        limit = adj_lim_new;
-      }
-      ath_q[sd.frame_base + f] = adjust;
-    }
-    streams[z].ath_adjust = adjust; streams[z].ath_adjust_limit = limit;
+    if (!__syncthreads_or(any)) break;
+  }
+  if (tid == 0 && nchunks > 0) {
+    const ScanChunk& l = ck[nchunks - 1];
+    streams[z].last_attacks[0] = l.fsm_out & 3; streams[z].last_attacks[1] = (l.fsm_out >> 2) & 3;
+    streams[z].blocktype_old[0] = (l.fsm_out >> 4) & 3; streams[z].blocktype_old[1] = (l.fsm_out >> 6) & 3;
+    streams[z].ath_adjust = l.ath_out[0]; streams[z].ath_adjust_limit = l.ath_out[1];
   }
 }
+
+__device__ __noinline__ double psy_log10(double x) { return m3_log10(x); }
 
 /* mask_add (PsyModel.js:403-473), long blocks only (shortblock == 0) */
 __device__ __forceinline__ double mask_add_dev(double m1, double m2, int kk, int b, const Mp3Tables* T, double ath_adjust) {
@@ -448,16 +504,16 @@ __device__ __forceinline__ double mask_add_dev(double m1, double m2, int kk, int
   m1 += m2;
   if ((b + 3) <= 3 + 3) {                    /* sic: signed compare in lamejs */
     if (ratio >= T->ma_max_i1) return m1;
-    const int i = js_trunc(m3_log10(ratio) * 16.0);
+    const int i = js_trunc(psy_log10(ratio) * 16.0);
     return m1 * c_table2[i];
   }
-  const int i = js_trunc(m3_log10(ratio) * 16.0);
+  const int i = js_trunc(psy_log10(ratio) * 16.0);
   m2 = (double)T->ath_cb_l[kk] * ath_adjust;
   if (m1 < T->ma_max_m * m2) {
     if (m1 > m2) {
       double f = 1.0, r;
       if (i <= 13) f = c_table3[i];
-      r = m3_log10(m1 / m2) * (10.0 / 15.0);
+      r = psy_log10(m1 / m2) * (10.0 / 15.0);
       return m1 * ((c_table1[i] - f) * r + f);
     }
     if (i > 13) return m1;

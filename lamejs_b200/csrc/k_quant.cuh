@@ -41,21 +41,26 @@ struct QuantFrameState {
   int stream, rel_frame;
   int in_old[2], in_step[2];        /* assumed gfc.OldValue / CurrentStep at frame start */
   int out_old[2], out_step[2];      /* state after the frame */
-  int bs_gain0[2], bs_step0[2];     /* gr0 bin-search result (re-validation shortcut) */
+  int bs_gain0[2], bs_step0[2];     /* state right after gr0's bin search (re-validation shortcut) */
+  int used0[2];                     /* bits gr0 spent per channel (part2_3_length + part2_length) */
+  unsigned long long bs_hash[2][2]; /* [gr][ch] fingerprint of cod_info right after the bin search: stale fields such as
+                                       table_select[] of an empty region depend on the gains the search visited */
   int valid;
 };
 
-__constant__ unsigned short c_huff_code[1666];
-__constant__ unsigned char c_huff_len[1666];
+/* tables indexed by data (different index per lane) live in global memory and are read through the read-only
+ * cache (__ldg): divergent __constant__ reads would serialise 32-fold */
+__device__ unsigned short g_huff_code[1666];
+__device__ unsigned char g_huff_len[1666];
 __constant__ int c_huff_off[34];
 __constant__ int c_huff_xlen[34];
 __constant__ int c_huff_linmax[34];
-__constant__ unsigned int c_largetbl[256];
-__constant__ unsigned int c_table23[9];
-__constant__ unsigned int c_table56[16];
+__device__ unsigned int g_largetbl[256];
+__device__ unsigned int g_table23[9];
+__device__ unsigned int g_table56[16];
 __constant__ int c_pretab[22];
-__constant__ int c_t32l[16];
-__constant__ int c_t33l[16];
+__device__ int g_t32l[16];
+__device__ int g_t33l[16];
 __constant__ int c_slen1_n[16];
 __constant__ int c_slen2_n[16];
 __constant__ int c_slen1_tab[16];
@@ -76,10 +81,10 @@ static int quant_upload_constants() {
   static const int sl[16] = {0, 10, 20, 30, 33, 21, 31, 41, 32, 42, 52, 43, 53, 63, 64, 74};
   static const int hn[15] = {1, 2, 5, 7, 7, 10, 10, 13, 13, 13, 13, 13, 13, 13, 13};
 #define UP(sym, src) if (cudaMemcpyToSymbol(sym, src, sizeof(src)) != cudaSuccess) return -100
-  UP(c_huff_code, MP3_HUFF_CODE); UP(c_huff_len, MP3_HUFF_LEN); UP(c_huff_off, MP3_HUFF_OFF);
-  UP(c_huff_xlen, MP3_HUFF_XLEN); UP(c_huff_linmax, MP3_HUFF_LINMAX); UP(c_largetbl, MP3_HUFF_LARGETBL);
-  UP(c_table23, MP3_HUFF_TABLE23); UP(c_table56, MP3_HUFF_TABLE56);
-  UP(c_pretab, pretab); UP(c_t32l, t32l); UP(c_t33l, t33l); UP(c_slen1_n, s1n); UP(c_slen2_n, s2n);
+  UP(g_huff_code, MP3_HUFF_CODE); UP(g_huff_len, MP3_HUFF_LEN); UP(c_huff_off, MP3_HUFF_OFF);
+  UP(c_huff_xlen, MP3_HUFF_XLEN); UP(c_huff_linmax, MP3_HUFF_LINMAX); UP(g_largetbl, MP3_HUFF_LARGETBL);
+  UP(g_table23, MP3_HUFF_TABLE23); UP(g_table56, MP3_HUFF_TABLE56);
+  UP(c_pretab, pretab); UP(g_t32l, t32l); UP(g_t33l, t33l); UP(c_slen1_n, s1n); UP(c_slen2_n, s2n);
   UP(c_slen1_tab, s1t); UP(c_slen2_tab, s2t); UP(c_scale_short, ss); UP(c_scale_long, sl); UP(c_huf_noesc, hn);
 #undef UP
   return 0;
@@ -92,7 +97,7 @@ struct GcWork {
   short ixw[576];                /* cod_info_w.l3_enc */
   short ixb[576];                /* cod_info.l3_enc (best so far) */
   GranuleInfoDev w, b;           /* cod_info_w / cod_info */
-  int width[MP3_SFBMAX], window[MP3_SFBMAX];
+  int width[MP3_SFBMAX], window[MP3_SFBMAX], start[MP3_SFBMAX + 1];
   unsigned char sfb_of_line[576];
   float xmin[MP3_SFBMAX], distort[MP3_SFBMAX];
   int pn_step[MP3_SFBMAX]; float pn_noise[MP3_SFBMAX], pn_noise_log[MP3_SFBMAX];
@@ -120,13 +125,16 @@ struct FrameShared {
 };
 
 #define LANE (threadIdx.x & 31)
+/* one copy of the fdlibm routines per kernel instead of one per call site (instruction-cache footprint) */
+__device__ __noinline__ double q_log10(double x) { return m3_log10(x); }
+__device__ __noinline__ double q_pow(double x, double y) { return m3_pow(x, y); }
 __device__ __forceinline__ int wmax(int v) { return __reduce_max_sync(Q_FULL, v); }
 __device__ __forceinline__ int wsum(int v) { return __reduce_add_sync(Q_FULL, v); }
 __device__ __forceinline__ unsigned wsumu(unsigned v) { return __reduce_add_sync(Q_FULL, v); }
-__device__ __forceinline__ int hlen(int t, int i) { return c_huff_len[c_huff_off[t] + i]; }
+__device__ __forceinline__ int hlen(int t, int i) { return __ldg(&g_huff_len[c_huff_off[t] + i]); }
 
 /* ---- Huffman bit counting over ix[begin,end) (Takehiro.js:319-516), warp-parallel over pairs ---------------- */
-__device__ int choose_table_w(const short* ix, int begin, int end, int* bits) {
+__device__ __noinline__ int choose_table_w(const short* ix, int begin, int end, int* bits) {
   const int lane = LANE;
   int mx = 0;
   for (int p = begin + 2 * lane; p < end; p += 64) { mx = max(mx, max((int)ix[p], (int)ix[p + 1])); }
@@ -144,7 +152,7 @@ __device__ int choose_table_w(const short* ix, int begin, int end, int* bits) {
     unsigned s = 0;
     for (int p = begin + 2 * lane; p < end; p += 64) {
       const int x = ix[p] * xlen + ix[p + 1];
-      s += (t1 == 2) ? c_table23[x] : c_table56[x];
+      s += (t1 == 2) ? __ldg(&g_table23[x]) : __ldg(&g_table56[x]);
     }
     s = wsumu(s);
     int sum2 = (int)(s & 0xffff), sum = (int)(s >> 16);
@@ -178,7 +186,7 @@ __device__ int choose_table_w(const short* ix, int begin, int end, int* bits) {
     int x = ix[p], y = ix[p + 1];
     if (x != 0) { if (x > 14) { x = 15; s += linbits; } x *= 16; }
     if (y != 0) { if (y > 14) { y = 15; s += linbits; } x += y; }
-    s += c_largetbl[x];
+    s += __ldg(&g_largetbl[x]);
   }
   s = wsumu(s);
   int sum2 = (int)(s & 0xffff), sum = (int)(s >> 16);
@@ -189,7 +197,7 @@ __device__ int choose_table_w(const short* ix, int begin, int end, int* bits) {
 }
 
 /* noquant_count_bits (Takehiro.js:521-628).  gi scalars are updated by lane 0. */
-__device__ int noquant_count_bits_w(const Mp3Tables* T, const short* ix, GranuleInfoDev* gi, GcWork* wk, bool use_prev) {
+__device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short* ix, GranuleInfoDev* gi, GcWork* wk, bool use_prev) {
   const int lane = LANE;
   int i0 = ((gi->max_nonzero_coeff + 2) >> 1) << 1;
   if (i0 > 576) i0 = 576;
@@ -208,7 +216,7 @@ __device__ int noquant_count_bits_w(const Mp3Tables* T, const short* ix, Granule
       const int i = count1 - 4 * q;
       const int x0 = ix[i - 4], x1 = ix[i - 3], x2 = ix[i - 2], x3 = ix[i - 1];
       if (((x0 | x1 | x2 | x3) & 0x7fffffff) > 1) bad = 1;
-      else { const int p = ((x0 * 2 + x1) * 2 + x2) * 2 + x3; v1 = c_t32l[p]; v2 = c_t33l[p]; }
+      else { const int p = ((x0 * 2 + x1) * 2 + x2) * 2 + x3; v1 = __ldg(&g_t32l[p]); v2 = __ldg(&g_t33l[p]); }
     } else bad = 1;
     const unsigned m = __ballot_sync(Q_FULL, bad);
     const int first_bad = m ? __ffs(m) - 1 : 32;
@@ -270,7 +278,7 @@ __device__ __forceinline__ int sfb_step(const GranuleInfoDev* gi, const GcWork* 
 }
 
 /* count_bits (Takehiro.js:630-660) = range check + quantize_xrpow (:171-314) + noquant_count_bits */
-__device__ int count_bits_w(const Mp3Tables* T, GcWork* wk, GranuleInfoDev* gi, short* ix, bool use_prev) {
+__device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, GranuleInfoDev* gi, short* ix, bool use_prev) {
   const int lane = LANE;
   const double istep = (double)T->ipow20[gi->global_gain];
   if (gi->xrpow_max > (double)Q_IXMAX / istep) return Q_LARGE_BITS;
@@ -285,8 +293,7 @@ __device__ int count_bits_w(const Mp3Tables* T, GcWork* wk, GranuleInfoDev* gi, 
     const int sfb = s0 + lane;
     int md = 0, trunc_here = 0;
     if (sfb <= sfbmax) {
-      int jst = 0;
-      for (int q = 0; q < sfb; q++) jst += wk->width[q];
+      const int jst = wk->start[sfb];
       const int step = calc_step ? sfb_step(gi, wk, sfb) : -1;
       if (prev_data_use && wk->pn_step[sfb] == step) md = 0;
       else {
@@ -334,7 +341,7 @@ __device__ int count_bits_w(const Mp3Tables* T, GcWork* wk, GranuleInfoDev* gi, 
 
 /* calc_noise (QuantizePVT.js:725-878) for quant_comp 9: over_count, over_SSD, max_noise (+ distort[]) */
 struct NoiseRes { int over_count; double over_SSD, max_noise; int bits; };
-__device__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const GranuleInfoDev* gi, const short* ix, NoiseRes* res) {
+__device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const GranuleInfoDev* gi, const short* ix, NoiseRes* res) {
   const int lane = LANE;
   const int psymax = gi->psymax, mnz = gi->max_nonzero_coeff;
   /* line cursor j is sequential (bands after the truncation point start where the previous one stopped) */
@@ -376,7 +383,7 @@ __device__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const GranuleInfoDe
         { f32s t; t = noise; wk->pn_noise[sfb] = t.v; }
         noise = noise / (double)wk->xmin[sfb];
         { f32s t; t = noise; wk->distort[sfb] = t.v; }
-        noise = m3_log10(js_dmax(noise, 1E-20));
+        noise = q_log10(js_dmax(noise, 1E-20));
         { f32s t; t = noise; wk->pn_noise_log[sfb] = t.v; }
       }
       if (noise > 0.0) {
@@ -401,7 +408,7 @@ __device__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const GranuleInfoDe
 }
 
 /* scale_bitcount (Takehiro.js:980-1030), lane 0 only; returns true when no legal scalefac_compress exists */
-__device__ bool scale_bitcount_l0(GranuleInfoDev* gi) {
+__device__ __noinline__ bool scale_bitcount_l0(GranuleInfoDev* gi) {
   int k, sfb, max_slen1 = 0, max_slen2 = 0;
   const int* tab;
   int* scalefac = gi->scalefac;
@@ -428,7 +435,7 @@ __device__ bool scale_bitcount_l0(GranuleInfoDev* gi) {
   return gi->part2_length == Q_LARGE_BITS;
 }
 
-__device__ bool loop_break_l0(const GranuleInfoDev* gi, const GcWork* wk) {
+__device__ __noinline__ bool loop_break_l0(const GranuleInfoDev* gi, const GcWork* wk) {
   for (int sfb = 0; sfb < gi->sfbmax; sfb++)
     if (gi->scalefac[sfb] + gi->subblock_gain[wk->window[sfb]] == 0) return false;
   return true;
@@ -436,7 +443,7 @@ __device__ bool loop_break_l0(const GranuleInfoDev* gi, const GcWork* wk) {
 
 /* multiply xrpow of the bands flagged in wk->mode[] by `factor[band]` (amp_scalefac_bands / inc_scalefac_scale
  * line loops, Quantize.js:650-655,690-695) and fold the new values into xrpow_max */
-__device__ void scale_xrpow_w(GcWork* wk, GranuleInfoDev* gi, double f34) {
+__device__ __noinline__ void scale_xrpow_w(GcWork* wk, GranuleInfoDev* gi, double f34) {
   const int lane = LANE;
   float mx = 0.0f;
   for (int i = lane; i < 576; i += 32) {
@@ -454,7 +461,7 @@ __device__ void scale_xrpow_w(GcWork* wk, GranuleInfoDev* gi, double f34) {
 }
 
 /* balance_noise (Quantize.js:783-846) on cod_info_w.  Returns true when a new scalefactor combination exists. */
-__device__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
+__device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
   const int lane = LANE;
   GranuleInfoDev* gi = &wk->w;
   /* ---- amp_scalefac_bands, noise_shaping_amp == 1 (Quantize.js:597-660) ---- */
@@ -585,7 +592,7 @@ __device__ __forceinline__ void copy_ix_w(short* dst, const short* src) {
 }
 
 /* bin_search_StepSize (Quantize.js:322-381) on cod_info (wk->b / ixb) */
-__device__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int desired_rate, int* old_value, int* current_step) {
+__device__ __noinline__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int desired_rate, int* old_value, int* current_step) {
   GranuleInfoDev* gi = &wk->b;
   int nBits;
   int CurrentStep = *current_step;
@@ -629,8 +636,17 @@ __device__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int desired_rate, in
   return nBits;
 }
 
+/* fingerprint of a GranuleInfoDev (all lanes compute the same value) */
+__device__ __noinline__ unsigned long long gi_hash(const GranuleInfoDev* gi) {
+  const unsigned* w = reinterpret_cast<const unsigned*>(gi);
+  unsigned long long h = 1469598103934665603ull;
+  for (int i = 0; i < (int)(sizeof(GranuleInfoDev) / 4); i++) { h ^= w[i]; h *= 1099511628211ull; }
+  return h;
+}
+
 /* outer_loop (Quantize.js:871-1052) for noise_shaping_amp 1, full_outer_loop 0, substep_shaping 0 */
-__device__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int targ_bits, int* old_value, int* current_step) {
+__device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int targ_bits, int* old_value, int* current_step,
+                                          unsigned long long* bs_hash) {
   /* note: *old_value / *current_step are final right after bin_search_w below (outer_loop never touches them again) */
   const int lane = LANE;
   NoiseRes best, cur;
@@ -639,6 +655,7 @@ __device__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int targ_bits, int*
   if (lane == 0) { wk->pn_global_gain = 0; wk->pn_sfb_count1 = 0; }
   __syncwarp();
   bin_search_w(T, wk, targ_bits, old_value, current_step);
+  *bs_hash = gi_hash(&wk->b);
   calc_noise_w(T, wk, &wk->b, wk->ixb, &best);
   best.bits = wk->b.part2_3_length;
   copy_gi_w(&wk->w, &wk->b);
@@ -706,22 +723,22 @@ __device__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int targ_bits, int*
 }
 
 /* athAdjust (QuantizePVT.js:541-561) */
-__device__ double ath_adjust_dev(double a, double x, double athFloor) {
+__device__ __noinline__ double ath_adjust_dev(double a, double x, double athFloor) {
   const double o = 90.30873362, p = 94.82444863;
-  double u = m3_log10(x) * 10.0;
+  double u = q_log10(x) * 10.0;
   const double v = a * a;
   double w = 0.0;
   u -= athFloor;
-  if (v > 1E-20) w = 1. + m3_log10(v) * (10.0 / o);
+  if (v > 1E-20) w = 1. + q_log10(v) * (10.0 / o);
   if (w < 0) w = 0.;
   u *= w;
   u += athFloor + o - p;
-  return m3_pow(10., 0.1 * u);
+  return q_pow(10., 0.1 * u);
 }
 
 /* init_outer_loop + psfb21_analogsilence + init_xrpow + calc_xmin for one gc (Quantize.js:204-306,147-202,105-138;
  * QuantizePVT.js:569-719).  Returns false when the granule is digital silence (all l3_enc = 0). */
-__device__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameShared* fs, const float* __restrict__ xr_g, int block_type,
+__device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameShared* fs, const float* __restrict__ xr_g, int block_type,
                              const PsyRatioDev* __restrict__ ratio, double ath_adjust) {
   const int lane = LANE;
   GranuleInfoDev* gi = &wk->b;
@@ -765,6 +782,11 @@ __device__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameShared* fs, co
     }
   }
   __syncwarp();
+  for (int sfb = lane; sfb <= MP3_SFBMAX; sfb += 32) {
+    int j = 0;
+    for (int q = 0; q < sfb; q++) j += wk->width[q];
+    wk->start[sfb] = j;
+  }
   /* analog silence in the pseudo bands above sfb21 / sfb12 (sequential from the top; lane 0) */
   if (lane == 0) {
     if (!is_short) {
@@ -884,15 +906,14 @@ __device__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameShared* fs, co
 }
 
 /* best_scalefac_store without the scfsi part (Takehiro.js:809-875), then scfsi_calc for gr1 (lane 0 logic) */
-__device__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, int gr, int ch) {
+__device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, int gr, int ch) {
   const int lane = LANE;
   GranuleInfoDev* gi = &wk->b;
   /* bands whose quantised lines are all zero */
   for (int s0 = 0; s0 < gi->sfbmax; s0 += 32) {
     const int sfb = s0 + lane;
     if (sfb < gi->sfbmax) {
-      int j = 0;
-      for (int q = 0; q < sfb; q++) j += wk->width[q];
+      const int j = wk->start[sfb];
       bool any = false;
       for (int l = 0; l < wk->width[sfb]; l++) if (wk->ixb[j + l] != 0) { any = true; break; }
       wk->mode[sfb] = any ? 1 : 0;
@@ -959,7 +980,7 @@ __device__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, int gr, int c
 }
 
 /* best_huffman_divide (Takehiro.js:727-800) on cod_info (wk->b / ixb); wk->w is free to use as cod_info2 */
-__device__ void recalc_divide_sub_w(const Mp3Tables* T, GcWork* wk, const GranuleInfoDev* cod_info2, const int* r01_bits,
+__device__ __noinline__ void recalc_divide_sub_w(const Mp3Tables* T, GcWork* wk, const GranuleInfoDev* cod_info2, const int* r01_bits,
                                     const int* r01_div, const int* r0_tbl, const int* r1_tbl) {
   GranuleInfoDev* gi = &wk->b;
   const int bigv = cod_info2->big_values;
@@ -984,7 +1005,7 @@ __device__ void recalc_divide_sub_w(const Mp3Tables* T, GcWork* wk, const Granul
   }
 }
 
-__device__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* wk) {
+__device__ __noinline__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* wk) {
   const int lane = LANE;
   GranuleInfoDev* gi = &wk->b;
   GranuleInfoDev* c2 = &wk->w;
@@ -1031,7 +1052,7 @@ __device__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* wk) {
     for (int q = lane; top - 4 * q > bv; q += 32) {
       const int e = top - 4 * q;
       const int p = ((ix[e - 4] * 2 + ix[e - 3]) * 2 + ix[e - 2]) * 2 + ix[e - 1];
-      v1 += c_t32l[p]; v2 += c_t33l[p]; n++;
+      v1 += __ldg(&g_t32l[p]); v2 += __ldg(&g_t33l[p]); n++;
     }
     a1 = wsum(v1); a2 = wsum(v2);
     i = top - 4 * wsum(n);
@@ -1076,7 +1097,7 @@ __device__ __forceinline__ void put_bits(unsigned int* buf, int pos, unsigned in
 }
 
 /* main data of one gc, starting at bit `pos` of the frame buffer; returns nothing (lengths are already known) */
-__device__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, const GcFinal* f, int pos) {
+__device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, const GcFinal* f, int pos) {
   const int lane = LANE;
   const GranuleInfoDev* gi = &f->gi;
   unsigned int* buf = fs->bits;
@@ -1134,10 +1155,10 @@ __device__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, const GcFinal* f,
       if (x2 != 0) { ext <<= 1; if ((f->neg[(i + 1) >> 5] >> ((i + 1) & 31)) & 1) ext++; cbits--; }
       const int idx = x1 * xlen + x2;
       xbits -= cbits;
-      cbits += c_huff_len[c_huff_off[tb] + idx];
+      cbits += __ldg(&g_huff_len[c_huff_off[tb] + idx]);
       if (pass == 0) mybits += cbits + xbits;
       else {
-        put_bits(buf, at, c_huff_code[c_huff_off[tb] + idx], cbits);
+        put_bits(buf, at, __ldg(&g_huff_code[c_huff_off[tb] + idx]), cbits);
         put_bits(buf, at + cbits, ext, xbits);
         at += cbits + xbits;
       }
@@ -1165,16 +1186,16 @@ __device__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, const GcFinal* f,
       if (f->ix[i + 1] != 0) { p += 4; huffbits *= 2; if ((f->neg[(i + 1) >> 5] >> ((i + 1) & 31)) & 1) huffbits++; }
       if (f->ix[i + 2] != 0) { p += 2; huffbits *= 2; if ((f->neg[(i + 2) >> 5] >> ((i + 2) & 31)) & 1) huffbits++; }
       if (f->ix[i + 3] != 0) { p++; huffbits *= 2; if ((f->neg[(i + 3) >> 5] >> ((i + 3) & 31)) & 1) huffbits++; }
-      const int len = c_huff_len[c_huff_off[tb] + p];
+      const int len = __ldg(&g_huff_len[c_huff_off[tb] + p]);
       if (pass == 0) mybits += len;
-      else { put_bits(buf, at, (unsigned)huffbits + c_huff_code[c_huff_off[tb] + p], len); at += len; }
+      else { put_bits(buf, at, (unsigned)huffbits + __ldg(&g_huff_code[c_huff_off[tb] + p]), len); at += len; }
     }
   }
   __syncwarp();
 }
 
 /* header + side info (encodeSideInfo2, BitStream.js:259-426, MPEG-1) by one thread */
-__device__ void pack_sideinfo(const Mp3Tables* T, FrameShared* fs, int padding) {
+__device__ __noinline__ void pack_sideinfo(const Mp3Tables* T, FrameShared* fs, int padding) {
   unsigned int* buf = fs->bits;
   int p = 0;
 #define WH(v, n) do { put_bits(buf, p, (unsigned)(v), (n)); p += (n); } while (0)
@@ -1206,6 +1227,25 @@ __device__ void pack_sideinfo(const Mp3Tables* T, FrameShared* fs, int padding) 
     WH(gi->preflag, 1); WH(gi->scalefac_scale, 1); WH(gi->count1table_select, 1);
   }
 #undef WH
+}
+
+/* on_pe with the reservoir disabled (QuantizePVT.js:421-484 + Reservoir.js:190-229): gr0 gets mean_bits, gr1 additionally
+ * what gr0 left over; per channel trunc(tbits / nch), capped at 4095, rescaled if the pair exceeds 7680; PE never matters
+ * because extra_bits == 0 */
+__device__ __noinline__ void granule_budget(FrameShared* fs, int nch, int mean_bits, int gr, int used0, int used1) {
+  int tbits = mean_bits;
+  if (gr == 1) {
+    const int resv = -(used0 + (nch == 2 ? used1 : 0)) + mean_bits;   /* ResvSize + mean_bits */
+    if (resv * 10 > 0) tbits += resv;
+  }
+  for (int c = 0; c < nch; c++) {
+    double t = (double)tbits / nch;
+    if (t > 4095) t = 4095;
+    fs->targ_bits[c] = (int)t;
+  }
+  int bits = 0;
+  for (int c = 0; c < nch; c++) bits += fs->targ_bits[c];
+  if (bits > 7680) for (int c = 0; c < nch; c++) { fs->targ_bits[c] = fs->targ_bits[c] * 7680; fs->targ_bits[c] = (int)((double)fs->targ_bits[c] / bits); }
 }
 
 /* ---- the frame kernel ------------------------------------------------------------------------------------ */
@@ -1249,59 +1289,58 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
     int old_value = fs->old_value[ch], current_step = fs->current_step[ch];
 
     if (revalidate) {
-      /* Re-validation of an already encoded frame under a corrected in-state: the only place the in-state enters is
-       * the gr0 bin search.  If it lands on the same gain and CurrentStep as the recorded full run (both channels),
-       * everything downstream -- both granules, the bytes and the out-state -- is unchanged. */
-      if (threadIdx.x == 0) {
-        double t = (double)mean_bits / nch;
-        if (t > 4095) t = 4095;
-        fs->targ_bits[0] = fs->targ_bits[1] = (int)t;
-      }
+      /* Re-validation of an already encoded frame under a corrected in-state.  The in-state enters only through the
+       * bin searches: gr0 starts at (OldValue, CurrentStep); gr1 starts at gr0's gain with CurrentStep derived from
+       * where gr0 started.  If gr0 lands on the recorded gain, gr0's bytes and the bits it spent are unchanged; if then
+       * gr1's search (re-run only when its CurrentStep changed) lands on the recorded gain too, the whole frame and
+       * its out-state are unchanged.  Otherwise fall through to a full re-encode. */
+      if (threadIdx.x == 0) granule_budget(fs, nch, mean_bits, 0, 0, 0);
       __syncthreads();
       const size_t urow0 = (size_t)sd.unit_base + 2 * f;
-      const PsyRatioDev* rt0 = ratio + ((size_t)sd.unit_base + z + 2 * f) * nch + ch;
       int ov = old_value, cs = current_step;
-      const bool have0 = gc_prepare_w(T, wk, fs, xr + (urow0 * nch + ch) * 576, bt_final[urow0 * 2 + ch], rt0, ath_adjust);
-      if (have0) {
-        for (int i = lane; i < MP3_SFBMAX; i += 32) wk->pn_step[i] = 0;
-        if (lane == 0) { wk->pn_global_gain = 0; wk->pn_sfb_count1 = 0; }
-        __syncwarp();
-        bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs);
+      const bool have0 = gc_prepare_w(T, wk, fs, xr + (urow0 * nch + ch) * 576, bt_final[urow0 * 2 + ch],
+                                      ratio + ((size_t)sd.unit_base + z + 2 * f) * nch + ch, ath_adjust);
+      unsigned long long h0 = 0;
+      if (have0) { bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs); h0 = gi_hash(&wk->b); }
+      if (lane == 0) {
+        if (ov != q->bs_gain0[ch] || h0 != q->bs_hash[0][ch]) atomicOr(&fs->flag, 1);
+        else if (cs != q->bs_step0[ch]) atomicOr(&fs->flag, 2);
       }
-      if (lane == 0 && (ov != q->bs_gain0[ch] || cs != q->bs_step0[ch])) atomicOr(&fs->flag, 1);
       __syncthreads();
-      const int changed = fs->flag;
+      int verdict = fs->flag;
       __syncthreads();
-      if (!changed) continue;
+      if (!(verdict & 1) && (verdict & 2)) {
+        if (threadIdx.x == 0) { fs->flag = 0; granule_budget(fs, nch, mean_bits, 1, q->used0[0], q->used0[1]); }
+        __syncthreads();
+        const bool have1 = gc_prepare_w(T, wk, fs, xr + ((urow0 + 1) * nch + ch) * 576, bt_final[(urow0 + 1) * 2 + ch],
+                                        ratio + ((size_t)sd.unit_base + z + 2 * f + 1) * nch + ch, ath_adjust);
+        const int step0 = cs;
+        if (have1) {
+          bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs);
+          const unsigned long long h1 = gi_hash(&wk->b);
+          if (lane == 0 && (ov != q->out_old[ch] || h1 != q->bs_hash[1][ch])) atomicOr(&fs->flag, 1);
+        }
+        __syncthreads();
+        verdict = fs->flag;
+        __syncthreads();
+        if (!(verdict & 1) && lane == 0) { q->bs_step0[ch] = step0; q->out_old[ch] = ov; q->out_step[ch] = cs; }
+      }
+      if (!(verdict & 1)) continue;
+      if (threadIdx.x == 0) fs->flag = 0;
+      __syncthreads();
     }
 
     for (int gr = 0; gr < 2; gr++) {
-      /* on_pe with the reservoir disabled (QuantizePVT.js:421-484 + Reservoir.js:190-229): gr0 gets mean_bits, gr1
-       * additionally what gr0 left over; per channel trunc(tbits / nch), capped at 4095; PE never matters */
-      if (threadIdx.x == 0) {
-        int tbits = mean_bits;
-        if (gr == 1) {
-          const int resv = -(fs->used_bits[0] + (nch == 2 ? fs->used_bits[1] : 0)) + mean_bits;   /* ResvSize + mean_bits */
-          if (resv * 10 > 0) tbits += resv;
-        }
-        for (int c = 0; c < nch; c++) {
-          double t = (double)tbits / nch;
-          if (t > 4095) t = 4095;
-          fs->targ_bits[c] = (int)t;
-        }
-        int bits = 0;
-        for (int c = 0; c < nch; c++) bits += fs->targ_bits[c];
-        if (bits > 7680) for (int c = 0; c < nch; c++) { fs->targ_bits[c] = fs->targ_bits[c] * 7680; fs->targ_bits[c] = (int)((double)fs->targ_bits[c] / bits); }
-      }
+      if (threadIdx.x == 0) granule_budget(fs, nch, mean_bits, gr, fs->used_bits[0], fs->used_bits[1]);
       __syncthreads();
       const size_t urow = (size_t)sd.unit_base + 2 * f + gr;
       const int bt = bt_final[urow * 2 + ch];
       /* masking of psy unit (2f+gr-1): halo-shifted row = unit_base + z + (2f+gr-1) + 1 */
       const PsyRatioDev* rt = ratio + ((size_t)sd.unit_base + z + 2 * f + gr) * nch + ch;
       const bool have = gc_prepare_w(T, wk, fs, xr + (urow * nch + ch) * 576, bt, rt, ath_adjust);
-      if (have) {
-        outer_loop_w(T, wk, fs->targ_bits[ch], &old_value, &current_step);
-      }
+      unsigned long long bsh = 0;
+      if (have) outer_loop_w(T, wk, fs->targ_bits[ch], &old_value, &current_step, &bsh);
+      if (lane == 0) q->bs_hash[gr][ch] = bsh;
       /* state right after gr0's bin search (pass-through when the granule is silent): re-validation key */
       if (gr == 0 && lane == 0) { q->bs_gain0[ch] = old_value; q->bs_step0[ch] = current_step; }
       /* iteration_finish_one (Quantize.js:1059-1078) */
@@ -1316,7 +1355,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
         for (int b = 0; b < 32; b++) if (wk->xr[32 * w + b] < 0.0f) m |= 1u << b;
         fin->neg[w] = m;
       }
-      if (lane == 0) fs->used_bits[ch] = wk->b.part2_3_length + wk->b.part2_length;
+      if (lane == 0) { fs->used_bits[ch] = wk->b.part2_3_length + wk->b.part2_length; if (gr == 0) q->used0[ch] = fs->used_bits[ch]; }
       if (ginfo_out) copy_gi_w(&ginfo_out[urow * nch + ch], &wk->b);
       if (l3enc_out) copy_ix_w(l3enc_out + (urow * nch + ch) * 576, wk->ixb);
       __syncthreads();

@@ -40,6 +40,8 @@ struct StreamDesc {
   int unit_base;           /* row of frame0's granule 0 in the per-granule arrays */
   int frame_base;          /* row of frame0 in the per-frame arrays */
   long long out_base;      /* byte offset of frame0 in the output buffer */
+  int scan_base;           /* first row of this stream in the scan-chunk scratch */
+  int pad_;
   /* sequential state at the start of frame0 (lamejs gfc.* carried across frames) */
   double ath_adjust, ath_adjust_limit;
   int blocktype_old[2], last_attacks[2];

@@ -106,11 +106,12 @@ struct Workspace {
   short* d_l3enc = nullptr;               /* [units][nch][576] (debug tap) */
   int* d_dirty = nullptr;                 /* [frames] work list for re-quantization passes */
   int* d_counter = nullptr;               /* [4] */
+  ScanChunk* d_scan = nullptr;            /* [frames / SCAN_FRAMES + nstreams] */
   ~Workspace() { release(); }
   void release() {
     cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_psy);
     cudaFree(d_ratio); cudaFree(d_ath_psy); cudaFree(d_ath_q); cudaFree(d_qstate); cudaFree(d_ginfo);
-    cudaFree(d_l3enc); cudaFree(d_dirty); cudaFree(d_counter);
+    cudaFree(d_l3enc); cudaFree(d_dirty); cudaFree(d_counter); cudaFree(d_scan); d_scan = nullptr;
     d_streams = nullptr; d_bt_final = d_bt_prev = nullptr; d_xr = nullptr; d_psy = nullptr; d_ratio = nullptr;
     d_ath_psy = d_ath_q = nullptr; d_qstate = nullptr; d_ginfo = nullptr; d_l3enc = nullptr; d_dirty = nullptr; d_counter = nullptr;
   }
@@ -130,6 +131,7 @@ struct Workspace {
     if (want_l3enc) CK(cudaMalloc(&d_l3enc, sizeof(short) * (size_t)U * nch * 576));
     CK(cudaMalloc(&d_dirty, sizeof(int) * (size_t)(F + 1)));
     CK(cudaMalloc(&d_counter, sizeof(int) * 4));
+    CK(cudaMalloc(&d_scan, sizeof(ScanChunk) * (size_t)(F / SCAN_FRAMES + S + 1)));
     return 0;
   }
 };
@@ -155,7 +157,13 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   const int nch = cfg->host.nch;
   int max_frames = 0;
   long long total_frames = 0;          /* rows actually used this launch (the workspace may be larger) */
-  for (auto& s : h_streams) { max_frames = s.nframes > max_frames ? s.nframes : max_frames; total_frames += s.nframes; }
+  int scan_rows = 0;
+  for (auto& s : h_streams) {
+    max_frames = s.nframes > max_frames ? s.nframes : max_frames;
+    total_frames += s.nframes;
+    s.scan_base = scan_rows;
+    scan_rows += (s.nframes + SCAN_FRAMES - 1) / SCAN_FRAMES;
+  }
   CK(cudaMemcpyAsync(ws.d_streams, h_streams.data(), sizeof(StreamDesc) * S, cudaMemcpyHostToDevice, st));
   cudaEvent_t ev[8];
   for (auto& e : ev) CK(cudaEventCreate(&e));
@@ -174,7 +182,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     dim3 grid((2 * max_frames + 127) / 128, 1, S);
     k_attack_prepass<<<grid, 128, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy);
     DBG("k_attack_prepass");
-    k_stream_scan<<<(S + 31) / 32, 64, 0, st>>>(cfg->dev, ws.d_streams, S, ws.d_psy, ws.d_bt_final, ws.d_bt_prev, ws.d_ath_psy, ws.d_ath_q);
+    k_stream_scan<<<S, SCAN_THREADS, 0, st>>>(cfg->dev, ws.d_streams, S, ws.d_psy, ws.d_bt_final, ws.d_bt_prev, ws.d_ath_psy, ws.d_ath_q, ws.d_scan);
     g_launches += 2;
     DBG("k_stream_scan");
   }
