@@ -4,8 +4,10 @@
  * window_subband (:534-914), mdct_long (:981-1051), mdct_short (:927-979).
  *
  * Parallel decomposition:
- *   phase 0  stage the block's PCM span as scaled float32 in shared memory (coalesced Int16 loads,
- *            one pad word per 32 samples so that the stride-32 window taps hit distinct banks)
+ *   phase 0  stage the block's PCM span in shared memory as double holding the scaled float32 value (coalesced
+ *            Int16 loads; the f32->f64 widening each of the 16 taps per sample would need is paid once -- the
+ *            first profile showed the conversion (XU) pipe, not FP64, as the busiest unit; one pad word per 32
+ *            samples so that the stride-32 window taps hit distinct banks)
  *   phase 1  one thread per (granule slab, time slot): a full window_subband -- 512-tap folded window in
  *            double, 32-point butterfly network in registers -- writes 32 subband samples
  *   phase 2  one thread per (granule, subband): block-type windowing + 36->18 / 3x(12->6) MDCT
@@ -20,9 +22,9 @@
 
 #define FB_G 8                                   /* granules per block */
 #define FB_SPAN (576 * FB_G + 1055)              /* PCM samples a block touches */
-#define FB_PCM_WORDS (FB_SPAN + (FB_SPAN >> 5) + 2)
+#define FB_PCM_WORDS (FB_SPAN + (FB_SPAN >> 5) + 2)   /* doubles: Int16 -> scaled float32 -> double is converted ONCE */
 #define FB_SLAB_STRIDE 33
-#define FB_THREADS 256
+#define FB_THREADS 192
 
 __constant__ double c_enwindow[285];
 __constant__ double c_mdct_win[4 * 36];
@@ -36,9 +38,9 @@ __constant__ int c_sb_order[32];
 __device__ __forceinline__ int fb_pad(int i) { return i + (i >> 5); }
 
 /* x: padded shared PCM; p0 = index (unpadded) of the reference's x1[x1Pos]. a[] = 32 float32 results. */
-__device__ __forceinline__ void window_subband_dev(const float* __restrict__ x, int p0, f32s* a) {
-#define X1(o) ((double)x[fb_pad(x1p + (o))])
-#define X2(o) ((double)x[fb_pad(x2p + (o))])
+__device__ __forceinline__ void window_subband_dev(const double* __restrict__ x, int p0, f32s* a) {
+#define X1(o) (x[fb_pad(x1p + (o))])
+#define X2(o) (x[fb_pad(x2p + (o))])
   int x1p = p0, x2p = p0 + 238 - 14 - 286;
 #pragma unroll
   for (int i = -15; i < 0; i++) {
@@ -292,7 +294,7 @@ __device__ __forceinline__ void mdct_short_dev(f32s* io) {
 
 /* grid: (ceil(max_granules / FB_G), nch, nstreams); block: FB_THREADS.
  * blocktype: int8 [granule row][2]; xr_out: float [granule row][nch][576]. */
-__global__ void __launch_bounds__(FB_THREADS)
+__global__ void __launch_bounds__(FB_THREADS, 2)
 k_filterbank_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams,
                   const signed char* __restrict__ blocktype, float* __restrict__ xr_out) {
   const StreamDesc sd = streams[blockIdx.z];
@@ -304,9 +306,9 @@ k_filterbank_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict_
   const long long c0 = 2LL * sd.frame0 + g0;        /* absolute granule index */
   const int nch = T->nch;
 
-  extern __shared__ float smem[];
-  float* pcm = smem;                                /* FB_PCM_WORDS, later reused as xr[FB_G][576] */
-  f32s* slab = reinterpret_cast<f32s*>(smem + FB_PCM_WORDS);   /* [FB_G+1][18][33] */
+  extern __shared__ double smem_d[];
+  double* pcm = smem_d;                             /* FB_PCM_WORDS doubles, later reused as xr[FB_G][576] float32 */
+  f32s* slab = reinterpret_cast<f32s*>(smem_d + FB_PCM_WORDS);   /* [FB_G+1][18][33] */
   __shared__ float s_amp[32];                       /* amp_filter by subband-array position */
   __shared__ int s_bt[FB_G];
 
@@ -316,7 +318,7 @@ k_filterbank_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict_
   const int scale_applied = T->scale_applied;
   const double scale = T->scale;
   const int span = 576 * gcount + 1055;
-  for (int j = tid; j < span; j += FB_THREADS) pcm[fb_pad(j)] = load_pcm(sd, ch, lo + j, scale_applied, scale);
+  for (int j = tid; j < span; j += FB_THREADS) pcm[fb_pad(j)] = (double)load_pcm(sd, ch, lo + j, scale_applied, scale);
   if (tid < 32) s_amp[c_sb_order[tid]] = T->amp_filter[tid];
   if (tid < gcount) s_bt[tid] = blocktype[(size_t)(sd.unit_base + g0 + tid) * 2 + ch];
   __syncthreads();

@@ -67,6 +67,8 @@ static int psy_upload_constants() {
 }
 
 /* ---- one butterfly task of an FHT stage (FFT.js:31-115), fz float32 in shared memory ------------------- */
+/* one pad word per 16 floats: the stage-0/1 butterflies stride 16 / 64 floats across lanes (first profile: 116 M bank conflicts) */
+#define FHT_PAD(i) ((i) + ((i) >> 4))
 __device__ __forceinline__ void fht_task(f32s* fz, int n, int stage, int task, const double* __restrict__ tw, const int* tw_off) {
   const int k1 = 4 << (2 * stage);          /* 4,16,64,256 */
   const int kx = k1 >> 1, k2 = k1 << 1, k3 = k2 + k1, k4 = k2 << 1;
@@ -76,25 +78,25 @@ __device__ __forceinline__ void fht_task(f32s* fz, int n, int stage, int task, c
     if ((task & 1) == 0) {
       const int fi = g * k4;
       double f0, f1, f2, f3;
-      f1 = fz[fi + 0] - fz[fi + k1];
-      f0 = fz[fi + 0] + fz[fi + k1];
-      f3 = fz[fi + k2] - fz[fi + k3];
-      f2 = fz[fi + k2] + fz[fi + k3];
-      fz[fi + k2] = f0 - f2;
-      fz[fi + 0] = f0 + f2;
-      fz[fi + k3] = f1 - f3;
-      fz[fi + k1] = f1 + f3;
+      f1 = fz[FHT_PAD(fi + 0)] - fz[FHT_PAD(fi + k1)];
+      f0 = fz[FHT_PAD(fi + 0)] + fz[FHT_PAD(fi + k1)];
+      f3 = fz[FHT_PAD(fi + k2)] - fz[FHT_PAD(fi + k3)];
+      f2 = fz[FHT_PAD(fi + k2)] + fz[FHT_PAD(fi + k3)];
+      fz[FHT_PAD(fi + k2)] = f0 - f2;
+      fz[FHT_PAD(fi + 0)] = f0 + f2;
+      fz[FHT_PAD(fi + k3)] = f1 - f3;
+      fz[FHT_PAD(fi + k1)] = f1 + f3;
     } else {
       const int gi = g * k4 + kx;
       double f0, f1, f2, f3;
-      f1 = fz[gi + 0] - fz[gi + k1];
-      f0 = fz[gi + 0] + fz[gi + k1];
-      f3 = (SQRT2_D * fz[gi + k3]);
-      f2 = (SQRT2_D * fz[gi + k2]);
-      fz[gi + k2] = f0 - f2;
-      fz[gi + 0] = f0 + f2;
-      fz[gi + k3] = f1 - f3;
-      fz[gi + k1] = f1 + f3;
+      f1 = fz[FHT_PAD(gi + 0)] - fz[FHT_PAD(gi + k1)];
+      f0 = fz[FHT_PAD(gi + 0)] + fz[FHT_PAD(gi + k1)];
+      f3 = (SQRT2_D * fz[FHT_PAD(gi + k3)]);
+      f2 = (SQRT2_D * fz[FHT_PAD(gi + k2)]);
+      fz[FHT_PAD(gi + k2)] = f0 - f2;
+      fz[FHT_PAD(gi + 0)] = f0 + f2;
+      fz[FHT_PAD(gi + k3)] = f1 - f3;
+      fz[FHT_PAD(gi + k1)] = f1 + f3;
     }
     return;
   }
@@ -104,30 +106,30 @@ __device__ __forceinline__ void fht_task(f32s* fz, int n, int stage, int task, c
   const double c1 = e[0], s1 = e[1], c2 = e[2], s2 = e[3];
   const int fi = g * k4 + i, gi = g * k4 + k1 - i;
   double a, b, g0, f0, f1, g1, f2, g2, f3, g3;
-  b = s2 * fz[fi + k1] - c2 * fz[gi + k1];
-  a = c2 * fz[fi + k1] + s2 * fz[gi + k1];
-  f1 = fz[fi + 0] - a;
-  f0 = fz[fi + 0] + a;
-  g1 = fz[gi + 0] - b;
-  g0 = fz[gi + 0] + b;
-  b = s2 * fz[fi + k3] - c2 * fz[gi + k3];
-  a = c2 * fz[fi + k3] + s2 * fz[gi + k3];
-  f3 = fz[fi + k2] - a;
-  f2 = fz[fi + k2] + a;
-  g3 = fz[gi + k2] - b;
-  g2 = fz[gi + k2] + b;
+  b = s2 * fz[FHT_PAD(fi + k1)] - c2 * fz[FHT_PAD(gi + k1)];
+  a = c2 * fz[FHT_PAD(fi + k1)] + s2 * fz[FHT_PAD(gi + k1)];
+  f1 = fz[FHT_PAD(fi + 0)] - a;
+  f0 = fz[FHT_PAD(fi + 0)] + a;
+  g1 = fz[FHT_PAD(gi + 0)] - b;
+  g0 = fz[FHT_PAD(gi + 0)] + b;
+  b = s2 * fz[FHT_PAD(fi + k3)] - c2 * fz[FHT_PAD(gi + k3)];
+  a = c2 * fz[FHT_PAD(fi + k3)] + s2 * fz[FHT_PAD(gi + k3)];
+  f3 = fz[FHT_PAD(fi + k2)] - a;
+  f2 = fz[FHT_PAD(fi + k2)] + a;
+  g3 = fz[FHT_PAD(gi + k2)] - b;
+  g2 = fz[FHT_PAD(gi + k2)] + b;
   b = s1 * f2 - c1 * g3;
   a = c1 * f2 + s1 * g3;
-  fz[fi + k2] = f0 - a;
-  fz[fi + 0] = f0 + a;
-  fz[gi + k3] = g1 - b;
-  fz[gi + k1] = g1 + b;
+  fz[FHT_PAD(fi + k2)] = f0 - a;
+  fz[FHT_PAD(fi + 0)] = f0 + a;
+  fz[FHT_PAD(gi + k3)] = g1 - b;
+  fz[FHT_PAD(gi + k1)] = g1 + b;
   b = c1 * g2 - s1 * f3;
   a = s1 * g2 + c1 * f3;
-  fz[gi + k2] = g0 - a;
-  fz[gi + 0] = g0 + a;
-  fz[fi + k3] = f1 - b;
-  fz[fi + k1] = f1 + b;
+  fz[FHT_PAD(gi + k2)] = g0 - a;
+  fz[FHT_PAD(gi + 0)] = g0 + a;
+  fz[FHT_PAD(fi + k3)] = f1 - b;
+  fz[FHT_PAD(fi + k1)] = f1 + b;
 }
 __device__ __forceinline__ int fht_tasks(int n, int stage) {
   const int k1 = 4 << (2 * stage), kx = k1 >> 1, k4 = k1 << 2;
@@ -160,8 +162,8 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   }
 
   __shared__ float xs[1024];
-  __shared__ f32s wl[1024];
-  __shared__ f32s wsh[3][256];
+  __shared__ f32s wl[1024 + 64];
+  __shared__ f32s wsh[3][256 + 16];
   __shared__ f32s hp[576];
   __shared__ f32s fe[513];
   __shared__ f32s fes[3][129];
@@ -196,14 +198,14 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     f2 = (double)w[i + 0x100] * (double)xs[i + 0x100];
     wv = (double)w[i + 0x300] * (double)xs[i + 0x300];
     f3 = f2 - wv; f2 = f2 + wv;
-    wl[x + 0] = f0 + f2; wl[x + 2] = f0 - f2; wl[x + 1] = f1 + f3; wl[x + 3] = f1 - f3;
+    wl[FHT_PAD(x + 0)] = f0 + f2; wl[FHT_PAD(x + 2)] = f0 - f2; wl[FHT_PAD(x + 1)] = f1 + f3; wl[FHT_PAD(x + 3)] = f1 - f3;
     f0 = (double)w[i + 0x001] * (double)xs[i + 0x001];
     wv = (double)w[i + 0x201] * (double)xs[i + 0x201];
     f1 = f0 - wv; f0 = f0 + wv;
     f2 = (double)w[i + 0x101] * (double)xs[i + 0x101];
     wv = (double)w[i + 0x301] * (double)xs[i + 0x301];
     f3 = f2 - wv; f2 = f2 + wv;
-    wl[x + 512 + 0] = f0 + f2; wl[x + 512 + 2] = f0 - f2; wl[x + 512 + 1] = f1 + f3; wl[x + 512 + 3] = f1 - f3;
+    wl[FHT_PAD(x + 512 + 0)] = f0 + f2; wl[FHT_PAD(x + 512 + 2)] = f0 - f2; wl[FHT_PAD(x + 512 + 1)] = f1 + f3; wl[FHT_PAD(x + 512 + 3)] = f1 - f3;
   } else if (tid < 128 + 96) {
     /* fft_short (FFT.js:140-183): block b, iteration j writes x_real[b][4j..], [128+4j..] */
     const int q = tid - 128, b = q >> 5, j = q & 31;
@@ -217,14 +219,14 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     f2 = (double)w[i + 0x40] * (double)bx[0x40];
     wv = (double)w[0x3f - i] * (double)bx[0xc0];
     f3 = f2 - wv; f2 = f2 + wv;
-    wsh[b][x + 0] = f0 + f2; wsh[b][x + 2] = f0 - f2; wsh[b][x + 1] = f1 + f3; wsh[b][x + 3] = f1 - f3;
+    wsh[b][FHT_PAD(x + 0)] = f0 + f2; wsh[b][FHT_PAD(x + 2)] = f0 - f2; wsh[b][FHT_PAD(x + 1)] = f1 + f3; wsh[b][FHT_PAD(x + 3)] = f1 - f3;
     f0 = (double)w[i + 0x01] * (double)bx[0x01];
     wv = (double)w[0x7e - i] * (double)bx[0x81];
     f1 = f0 - wv; f0 = f0 + wv;
     f2 = (double)w[i + 0x41] * (double)bx[0x41];
     wv = (double)w[0x3e - i] * (double)bx[0xc1];
     f3 = f2 - wv; f2 = f2 + wv;
-    wsh[b][x + 128 + 0] = f0 + f2; wsh[b][x + 128 + 2] = f0 - f2; wsh[b][x + 128 + 1] = f1 + f3; wsh[b][x + 128 + 3] = f1 - f3;
+    wsh[b][FHT_PAD(x + 128 + 0)] = f0 + f2; wsh[b][FHT_PAD(x + 128 + 2)] = f0 - f2; wsh[b][FHT_PAD(x + 128 + 1)] = f1 + f3; wsh[b][FHT_PAD(x + 128 + 3)] = f1 - f3;
   }
   __syncthreads();
 
@@ -248,13 +250,13 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
 
   /* line energies (PsyModel.js:278-298) */
   for (int j = tid; j < 512; j += PSY_THREADS) {
-    const double re = wl[512 - j], im = wl[512 + j];
+    const double re = wl[FHT_PAD(512 - j)], im = wl[FHT_PAD(512 + j)];
     fe[512 - j] = (re * re + im * im) * 0.5;
   }
   if (tid == 0) { f32s t0; t0 = (double)wl[0]; t0 *= (double)t0; fe[0] = (double)t0; }
   for (int t = tid; t < 3 * 128; t += PSY_THREADS) {
     const int b = t >> 7, j = t & 127;
-    const double re = wsh[b][128 - j], im = wsh[b][128 + j];
+    const double re = wsh[b][FHT_PAD(128 - j)], im = wsh[b][FHT_PAD(128 + j)];
     fes[b][128 - j] = (re * re + im * im) * 0.5;
   }
   if (tid < 3) { f32s t0; t0 = (double)wsh[tid][0]; t0 *= (double)t0; fes[tid][0] = (double)t0; }

@@ -137,11 +137,13 @@ __device__ __forceinline__ int hlen(int t, int i) { return __ldg(&g_huff_len[c_h
 __device__ __noinline__ int choose_table_w(const short* ix, int begin, int end, int* bits) {
   const int lane = LANE;
   int mx = 0;
+#pragma unroll 1
   for (int p = begin + 2 * lane; p < end; p += 64) { mx = max(mx, max((int)ix[p], (int)ix[p + 1])); }
   mx = wmax(mx);
   if (mx == 0) return 0;
   if (mx == 1) {
     int s = 0;
+#pragma unroll 1
     for (int p = begin + 2 * lane; p < end; p += 64) s += hlen(1, ix[p] * 2 + ix[p + 1]);
     *bits += wsum(s);
     return 1;
@@ -150,6 +152,7 @@ __device__ __noinline__ int choose_table_w(const short* ix, int begin, int end, 
     int t1 = c_huf_noesc[mx - 1];
     const int xlen = c_huff_xlen[t1];
     unsigned s = 0;
+#pragma unroll 1
     for (int p = begin + 2 * lane; p < end; p += 64) {
       const int x = ix[p] * xlen + ix[p + 1];
       s += (t1 == 2) ? __ldg(&g_table23[x]) : __ldg(&g_table56[x]);
@@ -164,6 +167,7 @@ __device__ __noinline__ int choose_table_w(const short* ix, int begin, int end, 
     const int t1 = c_huf_noesc[mx - 1];
     const int xlen = c_huff_xlen[t1];
     int s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 1
     for (int p = begin + 2 * lane; p < end; p += 64) {
       const int x = ix[p] * xlen + ix[p + 1];
       s1 += hlen(t1, x); s2 += hlen(t1 + 1, x); s3 += hlen(t1 + 2, x);
@@ -178,10 +182,13 @@ __device__ __noinline__ int choose_table_w(const short* ix, int begin, int end, 
   if (mx > Q_IXMAX) { *bits = Q_LARGE_BITS; return -1; }
   mx -= 15;
   int choice2, choice;
+#pragma unroll 1
   for (choice2 = 24; choice2 < 32; choice2++) if (c_huff_linmax[choice2] >= mx) break;
+#pragma unroll 1
   for (choice = choice2 - 8; choice < 24; choice++) if (c_huff_linmax[choice] >= mx) break;
   const unsigned linbits = (unsigned)c_huff_xlen[choice] * 65536u + (unsigned)c_huff_xlen[choice2];
   unsigned s = 0;
+#pragma unroll 1
   for (int p = begin + 2 * lane; p < end; p += 64) {
     int x = ix[p], y = ix[p + 1];
     if (x != 0) { if (x > 14) { x = 15; s += linbits; } x *= 16; }
@@ -203,12 +210,14 @@ __device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short
   if (i0 > 576) i0 = 576;
   /* count1 = end of the last non-zero pair below i0 */
   int top = 0;
+#pragma unroll 1
   for (int p = 2 * lane; p < i0; p += 64) if ((ix[p] | ix[p + 1]) != 0) top = p + 2;
   const int count1 = wmax(top);
   /* quadruples of |x| <= 1 counted down from count1 */
   int a1 = 0, a2 = 0, nq = 0;
   const int qmax = count1 >> 2;
   bool stop = false;
+#pragma unroll 1
   for (int q0 = 0; q0 < qmax && !stop; q0 += 32) {
     const int q = q0 + lane;
     int bad = 0, v1 = 0, v2 = 0;
@@ -289,6 +298,7 @@ __device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, Granule
   /* per-band decision: 0 skip (cached), 1 full quantizer, 2 zero/one quantizer; term = first non-cached band that
    * crosses max_nonzero_coeff (the reference zero-fills the tail there and stops) */
   int term = sfbmax + 1;
+#pragma unroll 1
   for (int s0 = 0; s0 <= sfbmax; s0 += 32) {
     const int sfb = s0 + lane;
     int md = 0, trunc_here = 0;
@@ -314,6 +324,7 @@ __device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, Granule
     if (term_len < 0) term_len = 0;
   }
   const double compare01 = (1.0 - 0.4054) / istep;
+#pragma unroll 1
   for (int i = lane; i < 576; i += 32) {
     const int sfb = wk->sfb_of_line[i];
     int md;
@@ -347,6 +358,7 @@ __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const 
   /* line cursor j is sequential (bands after the truncation point start where the previous one stopped) */
   if (lane == 0) {
     int j = 0;
+#pragma unroll 1
     for (int sfb = 0; sfb < psymax; sfb++) {
       const int s = sfb_step(gi, wk, sfb);
       if (wk->pn_step[sfb] == s) { wk->nlen[sfb] = -1; j += wk->width[sfb]; }
@@ -360,6 +372,7 @@ __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const 
   }
   __syncwarp();
   int over = 0; double ssd = 0, mxn = -20.0;
+#pragma unroll 1
   for (int s0 = 0; s0 < psymax; s0 += 32) {
     const int sfb = s0 + lane;
     if (sfb < psymax) {
@@ -374,6 +387,7 @@ __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const 
         const double step = (double)T->pow20[s + MP3_QMAX2];
         int j = wk->nstart[sfb];
         noise = 0;
+#pragma unroll 1
         for (int l = wk->nlen[sfb]; l > 0; l--) {
           double temp;
           temp = fabs((double)wk->xr[j]) - (double)__ldg(&T->pow43[ix[j]]) * step; j++; noise += temp * temp;
@@ -416,16 +430,21 @@ __device__ __noinline__ bool scale_bitcount_l0(GranuleInfoDev* gi) {
   else {
     tab = c_scale_long;
     if (0 == gi->preflag) {
+#pragma unroll 1
       for (sfb = 11; sfb < 21; sfb++) if (scalefac[sfb] < c_pretab[sfb]) break;
       if (sfb == 21) {
         gi->preflag = 1;
+#pragma unroll 1
         for (sfb = 11; sfb < 21; sfb++) scalefac[sfb] -= c_pretab[sfb];
       }
     }
   }
+#pragma unroll 1
   for (sfb = 0; sfb < gi->sfbdivide; sfb++) if (max_slen1 < scalefac[sfb]) max_slen1 = scalefac[sfb];
+#pragma unroll 1
   for (; sfb < gi->sfbmax; sfb++) if (max_slen2 < scalefac[sfb]) max_slen2 = scalefac[sfb];
   gi->part2_length = Q_LARGE_BITS;
+#pragma unroll 1
   for (k = 0; k < 16; k++) {
     if (max_slen1 < c_slen1_n[k] && max_slen2 < c_slen2_n[k] && gi->part2_length > tab[k]) {
       gi->part2_length = tab[k];
@@ -436,6 +455,7 @@ __device__ __noinline__ bool scale_bitcount_l0(GranuleInfoDev* gi) {
 }
 
 __device__ __noinline__ bool loop_break_l0(const GranuleInfoDev* gi, const GcWork* wk) {
+#pragma unroll 1
   for (int sfb = 0; sfb < gi->sfbmax; sfb++)
     if (gi->scalefac[sfb] + gi->subblock_gain[wk->window[sfb]] == 0) return false;
   return true;
@@ -446,6 +466,7 @@ __device__ __noinline__ bool loop_break_l0(const GranuleInfoDev* gi, const GcWor
 __device__ __noinline__ void scale_xrpow_w(GcWork* wk, GranuleInfoDev* gi, double f34) {
   const int lane = LANE;
   float mx = 0.0f;
+#pragma unroll 1
   for (int i = lane; i < 576; i += 32) {
     const int sfb = wk->sfb_of_line[i];
     if (sfb < gi->sfbmax && wk->mode[sfb]) {
@@ -468,9 +489,11 @@ __device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
   const double ifq = gi->scalefac_scale == 0 ? 1.29683955465100964055 : 1.68179283050742922612;
   if (lane == 0) {
     double trigger = 0;
+#pragma unroll 1
     for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (trigger < (double)wk->distort[sfb]) trigger = (double)wk->distort[sfb];
     if (trigger > 1.0) trigger = sqrt(trigger);     /* Math.pow(trigger, .5): fdlibm returns sqrt(x) for y == 0.5 */
     else trigger *= .95;
+#pragma unroll 1
     for (int sfb = 0; sfb < gi->sfbmax; sfb++) {
       const int amp = !((double)wk->distort[sfb] < trigger);
       wk->mode[sfb] = (unsigned char)amp;
@@ -504,6 +527,7 @@ __device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
     if (0 == scale_now) {
       /* inc_scalefac_scale (Quantize.js:676-699) */
       if (lane == 0) {
+#pragma unroll 1
         for (int sfb = 0; sfb < gi->sfbmax; sfb++) {
           int s = gi->scalefac[sfb];
           if (gi->preflag != 0) s += c_pretab[sfb < 22 ? sfb : 21];
@@ -523,14 +547,19 @@ __device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
       if (lane == 0) {
         int ret = 0;
         int* scalefac = gi->scalefac;
+#pragma unroll 1
         for (int i = 0; i < MP3_SFBMAX; i++) wk->nlen[i] = -1;      /* per-band amp index: -1 none, else ipow20 index */
+#pragma unroll 1
         for (int window = 0; window < 3 && !ret; window++) {
           int s1 = 0, s2 = 0, sfb;
+#pragma unroll 1
           for (sfb = gi->sfb_lmax + window; sfb < gi->sfbdivide; sfb += 3) if (s1 < scalefac[sfb]) s1 = scalefac[sfb];
+#pragma unroll 1
           for (; sfb < gi->sfbmax; sfb += 3) if (s2 < scalefac[sfb]) s2 = scalefac[sfb];
           if (s1 < 16 && s2 < 8) continue;
           if (gi->subblock_gain[window] >= 7) { ret = 1; break; }
           gi->subblock_gain[window]++;
+#pragma unroll 1
           for (sfb = gi->sfb_lmax + window; sfb < gi->sfbmax; sfb += 3) {
             int s = scalefac[sfb];
             s = s - (4 >> gi->scalefac_scale);
@@ -547,6 +576,7 @@ __device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
        * exactly like the reference (it returns without undoing). */
       {
         float mx = 0.0f;
+#pragma unroll 1
         for (int i = lane; i < 576; i += 32) {
           const int sfb = wk->sfb_of_line[i];
           if (sfb < MP3_SFBMAX && wk->nlen[sfb] >= 0) {
@@ -580,6 +610,7 @@ __device__ __forceinline__ void copy_gi_w(GranuleInfoDev* dst, const GranuleInfo
   const int* s = reinterpret_cast<const int*>(src);
   int* d = reinterpret_cast<int*>(dst);
   __syncwarp();                                   /* earlier readers of *dst are done */
+#pragma unroll 1
   for (int i = LANE; i < n; i += 32) d[i] = s[i];
   __syncwarp();
 }
@@ -587,6 +618,7 @@ __device__ __forceinline__ void copy_ix_w(short* dst, const short* src) {
   const int* s = reinterpret_cast<const int*>(src);
   int* d = reinterpret_cast<int*>(dst);
   __syncwarp();
+#pragma unroll 1
   for (int i = LANE; i < 288; i += 32) d[i] = s[i];
   __syncwarp();
 }
@@ -640,6 +672,7 @@ __device__ __noinline__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int des
 __device__ __noinline__ unsigned long long gi_hash(const GranuleInfoDev* gi) {
   const unsigned* w = reinterpret_cast<const unsigned*>(gi);
   unsigned long long h = 1469598103934665603ull;
+#pragma unroll 1
   for (int i = 0; i < (int)(sizeof(GranuleInfoDev) / 4); i++) { h ^= w[i]; h *= 1099511628211ull; }
   return h;
 }
@@ -651,6 +684,7 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
   const int lane = LANE;
   NoiseRes best, cur;
   int best_part2_3_length = 9999999;
+#pragma unroll 1
   for (int i = lane; i < MP3_SFBMAX; i += 32) { wk->pn_step[i] = 0; wk->pn_noise[i] = 0.0f; wk->pn_noise_log[i] = 0.0f; }
   if (lane == 0) { wk->pn_global_gain = 0; wk->pn_sfb_count1 = 0; }
   __syncwarp();
@@ -753,24 +787,30 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
     gi->psy_lmax = is_short ? 0 : 21;
     gi->psymax = is_short ? 36 : 21; gi->sfbmax = is_short ? 36 : 21; gi->sfbdivide = is_short ? 18 : 11;
     gi->max_nonzero_coeff = 575;
+#pragma unroll 1
     for (int i = 0; i < MP3_SFBMAX; i++) gi->scalefac[i] = 0;
     gi->xrpow_max = 0;
   }
   /* band geometry */
   if (!is_short) {
+#pragma unroll 1
     for (int sfb = lane; sfb < MP3_SFBMAX; sfb += 32) {
       wk->width[sfb] = sfb < 22 ? T->sfb_l[sfb + 1] - T->sfb_l[sfb] : 0;
       wk->window[sfb] = 3;
     }
+#pragma unroll 1
     for (int i = lane; i < 576; i += 32) { int s = 0; while (T->sfb_l[s + 1] <= i) s++; wk->sfb_of_line[i] = (unsigned char)s; }
+#pragma unroll 1
     for (int i = lane; i < 576; i += 32) wk->xr[i] = xr_g[i];
   } else {
+#pragma unroll 1
     for (int j = lane; j < MP3_SFBMAX; j += 32) {
       const int sfb = j / 3;
       wk->width[j] = T->sfb_s[sfb + 1] - T->sfb_s[sfb];
       wk->window[j] = j - 3 * sfb;
     }
     /* reorder (Quantize.js:262-278): band sfb, window w, line l  ->  3*start + w*width + (l-start) */
+#pragma unroll 1
     for (int i = lane; i < 576; i += 32) {
       const int l = i / 3, w = i - 3 * l;
       int sfb = 0;
@@ -782,8 +822,10 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
     }
   }
   __syncwarp();
+#pragma unroll 1
   for (int sfb = lane; sfb <= MP3_SFBMAX; sfb += 32) {
     int j = 0;
+#pragma unroll 1
     for (int q = 0; q < sfb; q++) j += wk->width[q];
     wk->start[sfb] = j;
   }
@@ -791,23 +833,28 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
   if (lane == 0) {
     if (!is_short) {
       bool stop = false;
+#pragma unroll 1
       for (int g = 5; g >= 0 && !stop; g--) {
         const int start = T->psfb21[g], end = T->psfb21[g + 1];
         double ath21 = fs->ath21[g];
         if ((double)T->longfact[21] > 1e-12) ath21 *= (double)T->longfact[21];
+#pragma unroll 1
         for (int j = end - 1; j >= start; j--) {
           if (fabs((double)wk->xr[j]) < ath21) wk->xr[j] = 0.0f;
           else { stop = true; break; }
         }
       }
     } else {
+#pragma unroll 1
       for (int block = 0; block < 3; block++) {
         bool stop = false;
+#pragma unroll 1
         for (int g = 5; g >= 0 && !stop; g--) {
           const int start = T->sfb_s[12] * 3 + (T->sfb_s[13] - T->sfb_s[12]) * block + (T->psfb12[g] - T->psfb12[0]);
           const int end = start + (T->psfb12[g + 1] - T->psfb12[g]);
           double ath12 = fs->ath12[g];
           if ((double)T->shortfact[12] > 1e-12) ath12 *= (double)T->shortfact[12];
+#pragma unroll 1
           for (int j = end - 1; j >= start; j--) {
             if (fabs((double)wk->xr[j]) < ath12) wk->xr[j] = 0.0f;
             else { stop = true; break; }
@@ -820,6 +867,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
   /* ---- init_xrpow: max_nonzero_coeff is still 575 here (set by init_outer_loop) ---- */
   {
     float mx = 0.0f, amax = 0.0f;
+#pragma unroll 1
     for (int i = lane; i < 576; i += 32) {
       const double tmp = fabs((double)wk->xr[i]);
       f32s p; p = sqrt(tmp * sqrt(tmp));
@@ -840,6 +888,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
     if (lane == 0) gi->xrpow_max = (double)mx;
     __syncwarp();
     if (!energy) {
+#pragma unroll 1
       for (int i = lane; i < 576; i += 32) wk->ixb[i] = 0;
       __syncwarp();
       return false;
@@ -854,6 +903,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
       const int width = wk->width[gsfb];
       double xmin = ath_adjust * (double)T->ath_l[gsfb];
       double en0 = 0.0;
+#pragma unroll 1
       for (int l = width >> 1; l > 0; l--) {
         double xa = (double)wk->xr[j] * (double)wk->xr[j]; en0 += xa; j++;
         double xb = (double)wk->xr[j] * (double)wk->xr[j]; en0 += xb; j++;
@@ -868,18 +918,21 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
     }
     /* highest non-zero coefficient (QuantizePVT.js:645-653) */
     int last = -1;
+#pragma unroll 1
     for (int i = lane; i < 576; i += 32) if (wk->xr[i] != 0.0f) last = i;
     last = wmax(last);
     int mnz = last + 1;
     if (mnz > 575) mnz = 575;
     if (lane == 0) gi->max_nonzero_coeff = mnz;
   } else {
+#pragma unroll 1
     for (int t = lane; t < 36; t += 32) {
       const int sfb = t / 3, b = t - 3 * sfb;
       const int width = wk->width[t];
       int j = 3 * T->sfb_s[sfb] + b * width;
       const double tmpATH = ath_adjust * (double)T->ath_s[sfb];
       double en0 = 0.0;
+#pragma unroll 1
       for (int l = width >> 1; l > 0; l--) {
         double xa = (double)wk->xr[j] * (double)wk->xr[j]; en0 += xa; j++;
         double xb = (double)wk->xr[j] * (double)wk->xr[j]; en0 += xb; j++;
@@ -910,11 +963,13 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
   const int lane = LANE;
   GranuleInfoDev* gi = &wk->b;
   /* bands whose quantised lines are all zero */
+#pragma unroll 1
   for (int s0 = 0; s0 < gi->sfbmax; s0 += 32) {
     const int sfb = s0 + lane;
     if (sfb < gi->sfbmax) {
       const int j = wk->start[sfb];
       bool any = false;
+#pragma unroll 1
       for (int l = 0; l < wk->width[sfb]; l++) if (wk->ixb[j + l] != 0) { any = true; break; }
       wk->mode[sfb] = any ? 1 : 0;
     }
@@ -922,49 +977,61 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
   __syncwarp();
   if (lane == 0) {
     int recalc = 0;
+#pragma unroll 1
     for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (!wk->mode[sfb]) gi->scalefac[sfb] = recalc = -2;
     if (0 == gi->scalefac_scale && 0 == gi->preflag) {
       int s = 0;
+#pragma unroll 1
       for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] > 0) s |= gi->scalefac[sfb];
       if (0 == (s & 1) && s != 0) {
+#pragma unroll 1
         for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] > 0) gi->scalefac[sfb] >>= 1;
         gi->scalefac_scale = recalc = 1;
       }
     }
     if (0 == gi->preflag && gi->block_type != BT_SHORT) {
       int sfb;
+#pragma unroll 1
       for (sfb = 11; sfb < 21; sfb++) if (gi->scalefac[sfb] < c_pretab[sfb] && gi->scalefac[sfb] != -2) break;
       if (sfb == 21) {
+#pragma unroll 1
         for (sfb = 11; sfb < 21; sfb++) if (gi->scalefac[sfb] > 0) gi->scalefac[sfb] -= c_pretab[sfb];
         gi->preflag = recalc = 1;
       }
     }
+#pragma unroll 1
     for (int i = 0; i < 4; i++) fs->scfsi[ch][i] = 0;
     if (gr == 1 && fs->fin[0][ch].gi.block_type != BT_SHORT && gi->block_type != BT_SHORT) {
       /* scfsi_calc (Takehiro.js:877-943) */
       const int* g0sf = fs->fin[0][ch].gi.scalefac;
       const int band[5] = {0, 6, 11, 16, 21};
       int sfb;
+#pragma unroll 1
       for (int i = 0; i < 4; i++) {
+#pragma unroll 1
         for (sfb = band[i]; sfb < band[i + 1]; sfb++)
           if (g0sf[sfb] != gi->scalefac[sfb] && gi->scalefac[sfb] >= 0) break;
         if (sfb == band[i + 1]) {
+#pragma unroll 1
           for (sfb = band[i]; sfb < band[i + 1]; sfb++) gi->scalefac[sfb] = -1;
           fs->scfsi[ch][i] = 1;
         }
       }
       int s1 = 0, c1 = 0;
+#pragma unroll 1
       for (sfb = 0; sfb < 11; sfb++) {
         if (gi->scalefac[sfb] == -1) continue;
         c1++;
         if (s1 < gi->scalefac[sfb]) s1 = gi->scalefac[sfb];
       }
       int s2 = 0, c2 = 0;
+#pragma unroll 1
       for (; sfb < 21; sfb++) {
         if (gi->scalefac[sfb] == -1) continue;
         c2++;
         if (s2 < gi->scalefac[sfb]) s2 = gi->scalefac[sfb];
       }
+#pragma unroll 1
       for (int i = 0; i < 16; i++) {
         if (s1 < c_slen1_n[i] && s2 < c_slen2_n[i]) {
           const int c = c_slen1_tab[i] * c1 + c_slen2_tab[i] * c2;
@@ -973,6 +1040,7 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
       }
       recalc = 0;
     }
+#pragma unroll 1
     for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] == -2) gi->scalefac[sfb] = 0;
     if (recalc != 0) scale_bitcount_l0(gi);
   }
@@ -984,6 +1052,7 @@ __device__ __noinline__ void recalc_divide_sub_w(const Mp3Tables* T, GcWork* wk,
                                     const int* r01_div, const int* r0_tbl, const int* r1_tbl) {
   GranuleInfoDev* gi = &wk->b;
   const int bigv = cod_info2->big_values;
+#pragma unroll 1
   for (int r2 = 2; r2 < 22 + 1; r2++) {
     const int a2 = T->sfb_l[r2];
     if (a2 >= bigv) break;
@@ -1018,13 +1087,16 @@ __device__ __noinline__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* w
   if (gi->block_type == BT_NORM) {
     /* recalc_divide_init (Takehiro.js:666-700) */
     const int bigv = gi->big_values;
+#pragma unroll 1
     for (int i = lane; i < 23; i += 32) r01_bits[i] = Q_LARGE_BITS;
     __syncwarp();
+#pragma unroll 1
     for (int r0 = 0; r0 < 16; r0++) {
       const int a1 = T->sfb_l[r0 + 1];
       if (a1 >= bigv) break;
       int r0bits = 0;
       const int r0t = choose_table_w(ix, 0, a1, &r0bits);
+#pragma unroll 1
       for (int r1 = 0; r1 < 8; r1++) {
         const int a2 = T->sfb_l[r0 + r1 + 2];
         if (a2 >= bigv) break;
@@ -1049,6 +1121,7 @@ __device__ __noinline__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* w
     /* quadruples from count1+2 down to the old big_values; integer sums, any order */
     const int top = i, bv = c2->big_values;
     int v1 = 0, v2 = 0, n = 0;
+#pragma unroll 1
     for (int q = lane; top - 4 * q > bv; q += 32) {
       const int e = top - 4 * q;
       const int p = ((ix[e - 4] * 2 + ix[e - 3]) * 2 + ix[e - 2]) * 2 + ix[e - 1];
@@ -1105,6 +1178,7 @@ __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, cons
   if (lane == 0) {
     const int slen1 = c_slen1_tab[gi->scalefac_compress], slen2 = c_slen2_tab[gi->scalefac_compress];
     int p = pos;
+#pragma unroll 1
     for (int sfb = 0; sfb < gi->sfbmax; sfb++) {
       if (gi->scalefac[sfb] == -1) continue;
       const int sl = sfb < gi->sfbdivide ? slen1 : slen2;
@@ -1130,6 +1204,7 @@ __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, cons
   const int per = (npairs + 31) >> 5;
   const int p0 = lane * per, p1 = min(npairs, p0 + per);
   int mybits = 0;
+#pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
     int at = 0;
     if (pass == 1) {
@@ -1137,6 +1212,7 @@ __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, cons
       for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(Q_FULL, incl, o); if (lane >= o) incl += v; }
       at = pos + incl - mybits;
     }
+#pragma unroll 1
     for (int pr = p0; pr < p1; pr++) {
       const int i = 2 * pr;
       const int tb = i < r1s ? gi->table_select[0] : (i < r2s ? gi->table_select[1] : gi->table_select[2]);
@@ -1172,6 +1248,7 @@ __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, cons
   const int q0 = lane * perq, q1 = min(nquads, q0 + perq);
   const int tb = gi->count1table_select + 32;
   mybits = 0;
+#pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
     int at = 0;
     if (pass == 1) {
@@ -1179,6 +1256,7 @@ __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, cons
       for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(Q_FULL, incl, o); if (lane >= o) incl += v; }
       at = pos + incl - mybits;
     }
+#pragma unroll 1
     for (int q = q0; q < q1; q++) {
       const int i = bigv + 4 * q;
       int huffbits = 0, p = 0;
@@ -1205,7 +1283,9 @@ __device__ __noinline__ void pack_sideinfo(const Mp3Tables* T, FrameShared* fs, 
   WH(T->mono ? 3 : 0, 2); WH(0, 2); WH(0, 1); WH(1, 1); WH(0, 2);
   WH(0, 9);
   WH(0, nch == 2 ? 3 : 5);
+#pragma unroll 1
   for (int ch = 0; ch < nch; ch++) for (int b = 0; b < 4; b++) WH(fs->scfsi[ch][b], 1);
+#pragma unroll 1
   for (int gr = 0; gr < 2; gr++) for (int ch = 0; ch < nch; ch++) {
     GranuleInfoDev* gi = &fs->fin[gr][ch].gi;
     WH(gi->part2_3_length + gi->part2_length, 12);
@@ -1238,12 +1318,14 @@ __device__ __noinline__ void granule_budget(FrameShared* fs, int nch, int mean_b
     const int resv = -(used0 + (nch == 2 ? used1 : 0)) + mean_bits;   /* ResvSize + mean_bits */
     if (resv * 10 > 0) tbits += resv;
   }
+#pragma unroll 1
   for (int c = 0; c < nch; c++) {
     double t = (double)tbits / nch;
     if (t > 4095) t = 4095;
     fs->targ_bits[c] = (int)t;
   }
   int bits = 0;
+#pragma unroll 1
   for (int c = 0; c < nch; c++) bits += fs->targ_bits[c];
   if (bits > 7680) for (int c = 0; c < nch; c++) { fs->targ_bits[c] = fs->targ_bits[c] * 7680; fs->targ_bits[c] = (int)((double)fs->targ_bits[c] / bits); }
 }
@@ -1262,6 +1344,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
   const int ch = threadIdx.x >> 5, lane = LANE;
   GcWork* wk = &fs->wk[ch];
   const int nwork = count_ptr ? *count_ptr : count_direct;
+#pragma unroll 1
   for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
     const int frow = list ? list[wi] : wi;
     QuantFrameState* q = qs + frow;
@@ -1272,6 +1355,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
     const double ath_adjust = ath_q[frow];
     __syncthreads();
     /* prologue: frame buffer, analog-silence thresholds, in-state */
+#pragma unroll 1
     for (int i = threadIdx.x; i < 368; i += blockDim.x) fs->bits[i] = 0;
     if (threadIdx.x < 12) {
       const int g = threadIdx.x % 6;
@@ -1330,6 +1414,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       __syncthreads();
     }
 
+#pragma unroll 1
     for (int gr = 0; gr < 2; gr++) {
       if (threadIdx.x == 0) granule_budget(fs, nch, mean_bits, gr, fs->used_bits[0], fs->used_bits[1]);
       __syncthreads();
@@ -1350,8 +1435,10 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       GcFinal* fin = &fs->fin[gr][ch];
       copy_gi_w(&fin->gi, &wk->b);
       copy_ix_w(fin->ix, wk->ixb);
+#pragma unroll 1
       for (int w = lane; w < 18; w += 32) {
         unsigned m = 0;
+#pragma unroll 1
         for (int b = 0; b < 32; b++) if (wk->xr[32 * w + b] < 0.0f) m |= 1u << b;
         fin->neg[w] = m;
       }
@@ -1367,6 +1454,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
     {
       int pos = 8 * T->sideinfo_len;
       int my_pos[2] = {0, 0};
+#pragma unroll 1
       for (int gr = 0; gr < 2; gr++) for (int c = 0; c < nch; c++) {
         if (c == ch) my_pos[gr] = pos;
         pos += fs->fin[gr][c].gi.part2_3_length + fs->fin[gr][c].gi.part2_length;
@@ -1378,6 +1466,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
         int remaining = frame_bits - pos;
         const unsigned char tag[10] = {0x4c, 0x41, 0x4d, 0x45, 3, 0, 9, 8, 0, 4};
         int k = 0;
+#pragma unroll 1
         for (; k < 4 && remaining >= 8; k++) { put_bits(fs->bits, pos, tag[k], 8); pos += 8; remaining -= 8; }
         if (remaining >= 32) for (; k < 10 && remaining >= 8; k++) { put_bits(fs->bits, pos, tag[k], 8); pos += 8; remaining -= 8; }
       }
@@ -1388,6 +1477,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       const long long off = sd.out_base + (long long)f * T->frame_bytes_nopad +
                             (pad_count(kabs - 1, T->frac_SpF, T->samplerate) - pad_count((long long)sd.frame0 - 1, T->frac_SpF, T->samplerate));
       uint8_t* dst = out + off;
+#pragma unroll 1
       for (int i = threadIdx.x; i < frame_bytes; i += blockDim.x) dst[i] = (uint8_t)(fs->bits[i >> 2] >> (24 - 8 * (i & 3)));
     }
     if (threadIdx.x == 0) q->valid = 1;
@@ -1402,6 +1492,7 @@ __global__ void k_qstate_init(const StreamDesc* __restrict__ streams, int nstrea
   if (f >= sd.nframes) return;
   QuantFrameState* q = qs + sd.frame_base + f;
   q->stream = z; q->rel_frame = f; q->valid = 0;
+#pragma unroll 1
   for (int c = 0; c < 2; c++) {
     /* first frame: the stream's true state; others: speculation (re-validated afterwards) */
     q->in_old[c] = f == 0 ? sd.old_value[c] : 180;
@@ -1419,8 +1510,10 @@ __global__ void k_qstate_verify(const StreamDesc* __restrict__ streams, QuantFra
   if (q->rel_frame == 0) return;
   const QuantFrameState* p = q - 1;
   bool same = true;
+#pragma unroll 1
   for (int c = 0; c < 2; c++) if (q->in_old[c] != p->out_old[c] || q->in_step[c] != p->out_step[c]) same = false;
   if (!same) {
+#pragma unroll 1
     for (int c = 0; c < 2; c++) { q->in_old[c] = p->out_old[c]; q->in_step[c] = p->out_step[c]; }
     list[atomicAdd(counter, 1)] = (int)r;
   }
@@ -1433,6 +1526,7 @@ __global__ void k_qstate_commit(StreamDesc* __restrict__ streams, int nstreams, 
   StreamDesc& sd = streams[z];
   if (sd.nframes <= 0) return;
   const QuantFrameState* q = qs + sd.frame_base + sd.nframes - 1;
+#pragma unroll 1
   for (int c = 0; c < 2; c++) { sd.old_value[c] = q->out_old[c]; sd.current_step[c] = q->out_step[c]; }
 }
 
