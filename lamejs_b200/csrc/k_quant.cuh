@@ -107,9 +107,7 @@ struct GcWork {
   int scratch[8];
   double dscratch[4];
 };
-struct GcFinal {                  /* what the bit packer needs, kept for both granules */
-  short ix[576];
-  unsigned int neg[18];           /* sign bits of xr */
+struct GcFinal {                  /* side info of a finished granule-channel (main data is packed right away) */
   GranuleInfoDev gi;
 };
 struct FrameShared {
@@ -253,7 +251,6 @@ __device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short
       b2 = r1 = T->bv_scf[bigv - 1];
       b2 = T->sfb_l[b1 + b2 + 2];
       b1 = T->sfb_l[b1 + 1];
-      if (b2 < bigv) ts2 = choose_table_w(ix, b2, bigv, &bits);
     } else {
       r0 = 7; r1 = 22 - 1 - 7 - 1;
       b1 = T->sfb_l[7 + 1];
@@ -262,8 +259,93 @@ __device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short
     }
     b1 = min(b1, bigv);
     b2 = min(b2, bigv);
-    if (0 < b1) ts0 = choose_table_w(ix, 0, b1, &bits);
-    if (b1 < b2) ts1 = choose_table_w(ix, b1, b2, &bits);
+    /* The three choose_table() calls of the reference ([0,b1), [b1,b2), [b2,bigv) for NORM) fused into two passes over
+     * the big-value pairs with every lane busy: pass 1 = per-region maximum, pass 2 = per-region code-length sums for
+     * the candidate books of that maximum.  Integer sums: any order gives the reference's totals. */
+    int m0 = 0, m1 = 0, m2 = 0;
+#pragma unroll 1
+    for (int p = 2 * lane; p < bigv; p += 64) {
+      const int v = max((int)ix[p], (int)ix[p + 1]);
+      if (p < b1) m0 = max(m0, v); else if (p < b2) m1 = max(m1, v); else m2 = max(m2, v);
+    }
+    m0 = wmax(m0); m1 = wmax(m1); m2 = wmax(m2);
+    int kind[3], tb1[3], xl[3]; unsigned lin[3];
+    const int mm[3] = {m0, m1, m2};
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int M = mm[r];
+      kind[r] = 0; tb1[r] = 0; xl[r] = 0; lin[r] = 0;
+      if (M == 0) kind[r] = 0;
+      else if (M == 1) { kind[r] = 1; tb1[r] = 1; }
+      else if (M <= 3) { kind[r] = 2; tb1[r] = c_huf_noesc[M - 1]; xl[r] = c_huff_xlen[tb1[r]]; }
+      else if (M <= 15) { kind[r] = 3; tb1[r] = c_huf_noesc[M - 1]; xl[r] = c_huff_xlen[tb1[r]]; }
+      else {
+        kind[r] = 4;
+        const int mx = M - 15;
+        int choice2, choice;
+        for (choice2 = 24; choice2 < 32; choice2++) if (c_huff_linmax[choice2] >= mx) break;
+        for (choice = choice2 - 8; choice < 24; choice++) if (c_huff_linmax[choice] >= mx) break;
+        tb1[r] = choice; xl[r] = choice2;
+        lin[r] = (unsigned)c_huff_xlen[choice] * 65536u + (unsigned)c_huff_xlen[choice2];
+      }
+    }
+    unsigned long long acc0 = 0, acc1 = 0, acc2 = 0;
+#pragma unroll 1
+    for (int p = 2 * lane; p < bigv; p += 64) {
+      const int r = p < b1 ? 0 : (p < b2 ? 1 : 2);
+      const int k = r == 0 ? kind[0] : (r == 1 ? kind[1] : kind[2]);
+      const int t1 = r == 0 ? tb1[0] : (r == 1 ? tb1[1] : tb1[2]);
+      const int xlen = r == 0 ? xl[0] : (r == 1 ? xl[1] : xl[2]);
+      int x = ix[p], y = ix[p + 1];
+      unsigned long long c = 0;
+      if (k == 1) c = (unsigned)hlen(1, x * 2 + y);
+      else if (k == 2) { const int q = x * xlen + y; c = (t1 == 2) ? __ldg(&g_table23[q]) : __ldg(&g_table56[q]); }
+      else if (k == 3) {
+        const int q = x * xlen + y;
+        c = (unsigned long long)hlen(t1, q) | ((unsigned long long)hlen(t1 + 1, q) << 21) | ((unsigned long long)hlen(t1 + 2, q) << 42);
+      } else if (k == 4) {
+        const unsigned linbits = r == 0 ? lin[0] : (r == 1 ? lin[1] : lin[2]);
+        unsigned sacc = 0;
+        if (x != 0) { if (x > 14) { x = 15; sacc += linbits; } x *= 16; }
+        if (y != 0) { if (y > 14) { y = 15; sacc += linbits; } x += y; }
+        sacc += __ldg(&g_largetbl[x]);
+        c = sacc;
+      }
+      if (r == 0) acc0 += c; else if (r == 1) acc1 += c; else acc2 += c;
+    }
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+      acc0 += __shfl_xor_sync(Q_FULL, acc0, o); acc1 += __shfl_xor_sync(Q_FULL, acc1, o); acc2 += __shfl_xor_sync(Q_FULL, acc2, o);
+    }
+    const unsigned long long accs[3] = {acc0, acc1, acc2};
+    int tsel[3] = {ts0, ts1, ts2};
+    const bool present[3] = {0 < b1, b1 < b2, bt == BT_NORM && b2 < bigv};
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      if (!present[r]) continue;                      /* table_select keeps its stale value, as in the reference */
+      const unsigned long long A = accs[r];
+      int t = 0;
+      if (kind[r] == 1) { t = 1; bits += (int)A; }
+      else if (kind[r] == 2) {
+        t = tb1[r];
+        int sum2 = (int)(A & 0xffff), sum = (int)((A >> 16) & 0xffff);
+        if (sum > sum2) { sum = sum2; t++; }
+        bits += sum;
+      } else if (kind[r] == 3) {
+        int s1 = (int)(A & 0x1fffff), s2 = (int)((A >> 21) & 0x1fffff), s3 = (int)((A >> 42) & 0x1fffff);
+        t = tb1[r];
+        if (s1 > s2) { s1 = s2; t++; }
+        if (s1 > s3) { s1 = s3; t = tb1[r] + 2; }
+        bits += s1;
+      } else if (kind[r] == 4) {
+        int sum2 = (int)(A & 0xffff), sum = (int)((A >> 16) & 0xffff);
+        t = tb1[r];
+        if (sum > sum2) { sum = sum2; t = xl[r]; }
+        bits += sum;
+      }
+      tsel[r] = t;
+    }
+    ts0 = tsel[0]; ts1 = tsel[1]; ts2 = tsel[2];
   }
   __syncwarp();
   if (lane == 0) {
@@ -1170,9 +1252,9 @@ __device__ __forceinline__ void put_bits(unsigned int* buf, int pos, unsigned in
 }
 
 /* main data of one gc, starting at bit `pos` of the frame buffer; returns nothing (lengths are already known) */
-__device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, const GcFinal* f, int pos) {
+__device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, const GranuleInfoDev* gi, const short* ixq,
+                                       const float* xrq, int pos) {
   const int lane = LANE;
-  const GranuleInfoDev* gi = &f->gi;
   unsigned int* buf = fs->bits;
   /* scalefactors (writeMainData, BitStream.js:609-625): serial, <= 36 values */
   if (lane == 0) {
@@ -1215,20 +1297,21 @@ __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, cons
 #pragma unroll 1
     for (int pr = p0; pr < p1; pr++) {
       const int i = 2 * pr;
-      const int tb = i < r1s ? gi->table_select[0] : (i < r2s ? gi->table_select[1] : gi->table_select[2]);
+      int tb = i < r1s ? gi->table_select[0] : (i < r2s ? gi->table_select[1] : gi->table_select[2]);
+      if (tb == 14) tb = 16;                      /* encodeSideInfo2 rewrites 14 -> 16 before the main data is coded */
       if (tb == 0) continue;
       const int hx = c_huff_xlen[tb];
       int linbits = hx, xlen = hx;
       int cbits = 0, xbits = 0;
       unsigned ext = 0;
-      int x1 = f->ix[i], x2 = f->ix[i + 1];
-      if (x1 != 0) { if ((f->neg[i >> 5] >> (i & 31)) & 1) ext++; cbits--; }
+      int x1 = ixq[i], x2 = ixq[i + 1];
+      if (x1 != 0) { if (xrq[i] < 0.0f) ext++; cbits--; }
       if (tb > 15) {
         if (x1 > 14) { ext |= (unsigned)(x1 - 15) << 1; xbits = linbits; x1 = 15; }
         if (x2 > 14) { ext <<= linbits; ext |= (unsigned)(x2 - 15); xbits += linbits; x2 = 15; }
         xlen = 16;
       }
-      if (x2 != 0) { ext <<= 1; if ((f->neg[(i + 1) >> 5] >> ((i + 1) & 31)) & 1) ext++; cbits--; }
+      if (x2 != 0) { ext <<= 1; if (xrq[i + 1] < 0.0f) ext++; cbits--; }
       const int idx = x1 * xlen + x2;
       xbits -= cbits;
       cbits += __ldg(&g_huff_len[c_huff_off[tb] + idx]);
@@ -1260,10 +1343,10 @@ __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, cons
     for (int q = q0; q < q1; q++) {
       const int i = bigv + 4 * q;
       int huffbits = 0, p = 0;
-      if (f->ix[i] != 0) { p += 8; if ((f->neg[i >> 5] >> (i & 31)) & 1) huffbits++; }
-      if (f->ix[i + 1] != 0) { p += 4; huffbits *= 2; if ((f->neg[(i + 1) >> 5] >> ((i + 1) & 31)) & 1) huffbits++; }
-      if (f->ix[i + 2] != 0) { p += 2; huffbits *= 2; if ((f->neg[(i + 2) >> 5] >> ((i + 2) & 31)) & 1) huffbits++; }
-      if (f->ix[i + 3] != 0) { p++; huffbits *= 2; if ((f->neg[(i + 3) >> 5] >> ((i + 3) & 31)) & 1) huffbits++; }
+      if (ixq[i] != 0) { p += 8; if (xrq[i] < 0.0f) huffbits++; }
+      if (ixq[i + 1] != 0) { p += 4; huffbits *= 2; if (xrq[i + 1] < 0.0f) huffbits++; }
+      if (ixq[i + 2] != 0) { p += 2; huffbits *= 2; if (xrq[i + 2] < 0.0f) huffbits++; }
+      if (ixq[i + 3] != 0) { p++; huffbits *= 2; if (xrq[i + 3] < 0.0f) huffbits++; }
       const int len = __ldg(&g_huff_len[c_huff_off[tb] + p]);
       if (pass == 0) mybits += len;
       else { put_bits(buf, at, (unsigned)huffbits + __ldg(&g_huff_code[c_huff_off[tb] + p]), len); at += len; }
@@ -1431,20 +1514,21 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       /* iteration_finish_one (Quantize.js:1059-1078) */
       best_scalefac_store_w(wk, fs, gr, ch);
       best_huffman_divide_w(T, wk);
-      /* keep what the packer needs */
+      /* side info persists; the main data of this granule is packed straight from the working set */
       GcFinal* fin = &fs->fin[gr][ch];
       copy_gi_w(&fin->gi, &wk->b);
-      copy_ix_w(fin->ix, wk->ixb);
-#pragma unroll 1
-      for (int w = lane; w < 18; w += 32) {
-        unsigned m = 0;
-#pragma unroll 1
-        for (int b = 0; b < 32; b++) if (wk->xr[32 * w + b] < 0.0f) m |= 1u << b;
-        fin->neg[w] = m;
-      }
       if (lane == 0) { fs->used_bits[ch] = wk->b.part2_3_length + wk->b.part2_length; if (gr == 0) q->used0[ch] = fs->used_bits[ch]; }
       if (ginfo_out) copy_gi_w(&ginfo_out[urow * nch + ch], &wk->b);
       if (l3enc_out) copy_ix_w(l3enc_out + (urow * nch + ch) * 576, wk->ixb);
+      __syncthreads();
+      {
+        /* bit position of this gc: side info, then gr0ch0, gr0ch1, gr1ch0, gr1ch1 back to back */
+        int pos = 8 * T->sideinfo_len;
+        for (int g2 = 0; g2 < gr; g2++)
+          for (int c = 0; c < nch; c++) pos += fs->fin[g2][c].gi.part2_3_length + fs->fin[g2][c].gi.part2_length;
+        for (int c = 0; c < ch; c++) pos += fs->fin[gr][c].gi.part2_3_length + fs->fin[gr][c].gi.part2_length;
+        pack_gc_w(T, fs, &wk->b, wk->ixb, wk->xr, pos);
+      }
       __syncthreads();
     }
     if (lane == 0) { q->out_old[ch] = old_value; q->out_step[ch] = current_step; }
@@ -1453,20 +1537,12 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
     __syncthreads();
     {
       int pos = 8 * T->sideinfo_len;
-      int my_pos[2] = {0, 0};
-#pragma unroll 1
-      for (int gr = 0; gr < 2; gr++) for (int c = 0; c < nch; c++) {
-        if (c == ch) my_pos[gr] = pos;
-        pos += fs->fin[gr][c].gi.part2_3_length + fs->fin[gr][c].gi.part2_length;
-      }
-      pack_gc_w(T, fs, &fs->fin[0][ch], my_pos[0]);
-      pack_gc_w(T, fs, &fs->fin[1][ch], my_pos[1]);
+      for (int gr = 0; gr < 2; gr++) for (int c = 0; c < nch; c++) pos += fs->fin[gr][c].gi.part2_3_length + fs->fin[gr][c].gi.part2_length;
       /* drain_into_ancillary (BitStream.js:175-213): "LAME" + the version string pushed through `>>` as numbers */
       if (threadIdx.x == 0) {
         int remaining = frame_bits - pos;
         const unsigned char tag[10] = {0x4c, 0x41, 0x4d, 0x45, 3, 0, 9, 8, 0, 4};
         int k = 0;
-#pragma unroll 1
         for (; k < 4 && remaining >= 8; k++) { put_bits(fs->bits, pos, tag[k], 8); pos += 8; remaining -= 8; }
         if (remaining >= 32) for (; k < 10 && remaining >= 8; k++) { put_bits(fs->bits, pos, tag[k], 8); pos += 8; remaining -= 8; }
       }
