@@ -161,7 +161,7 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     return;
   }
 
-  __shared__ float xs[1024];
+  __shared__ double xs[1024];                       /* scaled float32 PCM widened ONCE (HPF reads each sample 21x) */
   __shared__ f32s wl[1024 + 64];
   __shared__ f32s wsh[3][256 + 16];
   __shared__ f32s hp[576];
@@ -173,17 +173,17 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   const int scale_applied = T->scale_applied;
   const double scale = T->scale;
   const long long x0 = 576 * c - 224;                /* stream sample of bufPos */
-  for (int j = tid; j < 1024; j += PSY_THREADS) xs[j] = load_pcm(sd, ch, x0 + j, scale_applied, scale);
+  for (int j = tid; j < 1024; j += PSY_THREADS) xs[j] = (double)load_pcm(sd, ch, x0 + j, scale_applied, scale);
   __syncthreads();
 
   /* fs/4 high-pass (PsyModel.js:1051-1069): firbuf index = bufPos + 397 + i + j */
   for (int i = tid; i < 576; i += PSY_THREADS) {
-    const float* fb = xs + 397 + i;
-    double sum1 = (double)fb[10], sum2 = 0.0;
+    const double* fb = xs + 397 + i;
+    double sum1 = fb[10], sum2 = 0.0;
 #pragma unroll
     for (int j = 0; j < 9; j += 2) {
-      sum1 += c_fircoef[j] * ((double)fb[j] + (double)fb[21 - j]);
-      sum2 += c_fircoef[j + 1] * ((double)fb[j + 1] + (double)fb[21 - j - 1]);
+      sum1 += c_fircoef[j] * (fb[j] + fb[21 - j]);
+      sum2 += c_fircoef[j + 1] * (fb[j + 1] + fb[21 - j - 1]);
     }
     hp[i] = sum1 + sum2;
   }
@@ -211,7 +211,7 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     const int q = tid - 128, b = q >> 5, j = q & 31;
     const int i = c_fft_rv[j << 2], x = 4 * j, k = 192 * (b + 1);
     const float* w = T->fft_window_s;
-    const float* bx = xs + i + k;
+    const double* bx = xs + i + k;
     double f0, f1, f2, f3, wv;
     f0 = (double)w[i] * (double)bx[0];
     wv = (double)w[0x7f - i] * (double)bx[0x80];

@@ -131,30 +131,31 @@ __device__ __forceinline__ int wsum(int v) { return __reduce_add_sync(Q_FULL, v)
 __device__ __forceinline__ unsigned wsumu(unsigned v) { return __reduce_add_sync(Q_FULL, v); }
 __device__ __forceinline__ int hlen(int t, int i) { return __ldg(&g_huff_len[c_huff_off[t] + i]); }
 
-/* ---- Huffman bit counting over ix[begin,end) (Takehiro.js:319-516), warp-parallel over pairs ---------------- */
-__device__ __noinline__ int choose_table_w(const short* ix, int begin, int end, int* bits) {
+/* Huffman bits of the pairs [begin, end) (even bounds) -- choose_table (Takehiro.js:465-516) with its count_bit_*
+ * callees, as one max pass and one sum pass; a pair is one 32-bit shared-memory word (x | y << 16). */
+__device__ __noinline__ int region_table_w(const short* ix, int begin, int end, int* bits) {
   const int lane = LANE;
-  int mx = 0;
-#pragma unroll 1
-  for (int p = begin + 2 * lane; p < end; p += 64) { mx = max(mx, max((int)ix[p], (int)ix[p + 1])); }
-  mx = wmax(mx);
+  const unsigned* w32 = reinterpret_cast<const unsigned*>(ix);
+  const int p0 = (begin >> 1) + lane, p1 = end >> 1;
+  unsigned m = 0;
+#pragma unroll 3
+  for (int p = p0; p < p1; p += 32) { const unsigned w = w32[p]; m = max(m, max(w & 0xffffu, w >> 16)); }
+  const int mx = (int)__reduce_max_sync(Q_FULL, m);
   if (mx == 0) return 0;
   if (mx == 1) {
     int s = 0;
-#pragma unroll 1
-    for (int p = begin + 2 * lane; p < end; p += 64) s += hlen(1, ix[p] * 2 + ix[p + 1]);
+#pragma unroll 3
+    for (int p = p0; p < p1; p += 32) { const unsigned w = w32[p]; s += hlen(1, (int)((w & 0xffffu) * 2 + (w >> 16))); }
     *bits += wsum(s);
     return 1;
   }
   if (mx <= 3) {
     int t1 = c_huf_noesc[mx - 1];
-    const int xlen = c_huff_xlen[t1];
+    const unsigned xlen = (unsigned)c_huff_xlen[t1];
+    const unsigned* tab = (t1 == 2) ? g_table23 : g_table56;
     unsigned s = 0;
-#pragma unroll 1
-    for (int p = begin + 2 * lane; p < end; p += 64) {
-      const int x = ix[p] * xlen + ix[p + 1];
-      s += (t1 == 2) ? __ldg(&g_table23[x]) : __ldg(&g_table56[x]);
-    }
+#pragma unroll 3
+    for (int p = p0; p < p1; p += 32) { const unsigned w = w32[p]; s += __ldg(&tab[(w & 0xffffu) * xlen + (w >> 16)]); }
     s = wsumu(s);
     int sum2 = (int)(s & 0xffff), sum = (int)(s >> 16);
     if (sum > sum2) { sum = sum2; t1++; }
@@ -163,14 +164,19 @@ __device__ __noinline__ int choose_table_w(const short* ix, int begin, int end, 
   }
   if (mx <= 15) {
     const int t1 = c_huf_noesc[mx - 1];
-    const int xlen = c_huff_xlen[t1];
-    int s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll 1
-    for (int p = begin + 2 * lane; p < end; p += 64) {
-      const int x = ix[p] * xlen + ix[p + 1];
-      s1 += hlen(t1, x); s2 += hlen(t1 + 1, x); s3 += hlen(t1 + 2, x);
+    const unsigned xlen = (unsigned)c_huff_xlen[t1];
+    const unsigned char* h1 = g_huff_len + c_huff_off[t1];
+    const unsigned char* h2 = g_huff_len + c_huff_off[t1 + 1];
+    const unsigned char* h3 = g_huff_len + c_huff_off[t1 + 2];
+    unsigned s = 0;                                   /* three sums of < 2^10 each packed 10:11:11 -- no carries */
+#pragma unroll 3
+    for (int p = p0; p < p1; p += 32) {
+      const unsigned w = w32[p];
+      const unsigned q = (w & 0xffffu) * xlen + (w >> 16);
+      s += (unsigned)__ldg(&h1[q]) | ((unsigned)__ldg(&h2[q]) << 11) | ((unsigned)__ldg(&h3[q]) << 22);
     }
-    s1 = wsum(s1); s2 = wsum(s2); s3 = wsum(s3);
+    /* per-lane partial: <= 9 pairs x 19 bits = 171 < 2^11; warp total <= 288 x 19 = 5472 needs 13 bits -> reduce fields separately */
+    int s1 = wsum((int)(s & 0x7ff)), s2 = wsum((int)((s >> 11) & 0x7ff)), s3 = wsum((int)(s >> 22));
     int t = t1;
     if (s1 > s2) { s1 = s2; t++; }
     if (s1 > s3) { s1 = s3; t = t1 + 2; }
@@ -178,20 +184,20 @@ __device__ __noinline__ int choose_table_w(const short* ix, int begin, int end, 
     return t;
   }
   if (mx > Q_IXMAX) { *bits = Q_LARGE_BITS; return -1; }
-  mx -= 15;
   int choice2, choice;
 #pragma unroll 1
-  for (choice2 = 24; choice2 < 32; choice2++) if (c_huff_linmax[choice2] >= mx) break;
+  for (choice2 = 24; choice2 < 32; choice2++) if (c_huff_linmax[choice2] >= mx - 15) break;
 #pragma unroll 1
-  for (choice = choice2 - 8; choice < 24; choice++) if (c_huff_linmax[choice] >= mx) break;
+  for (choice = choice2 - 8; choice < 24; choice++) if (c_huff_linmax[choice] >= mx - 15) break;
   const unsigned linbits = (unsigned)c_huff_xlen[choice] * 65536u + (unsigned)c_huff_xlen[choice2];
   unsigned s = 0;
-#pragma unroll 1
-  for (int p = begin + 2 * lane; p < end; p += 64) {
-    int x = ix[p], y = ix[p + 1];
-    if (x != 0) { if (x > 14) { x = 15; s += linbits; } x *= 16; }
-    if (y != 0) { if (y > 14) { y = 15; s += linbits; } x += y; }
-    s += __ldg(&g_largetbl[x]);
+#pragma unroll 3
+  for (int p = p0; p < p1; p += 32) {
+    const unsigned w = w32[p];
+    unsigned x = w & 0xffffu, y = w >> 16;
+    if (x > 14) { x = 15; s += linbits; }
+    if (y > 14) { y = 15; s += linbits; }
+    s += __ldg(&g_largetbl[x * 16 + y]);
   }
   s = wsumu(s);
   int sum2 = (int)(s & 0xffff), sum = (int)(s >> 16);
@@ -204,27 +210,31 @@ __device__ __noinline__ int choose_table_w(const short* ix, int begin, int end, 
 /* noquant_count_bits (Takehiro.js:521-628).  gi scalars are updated by lane 0. */
 __device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short* ix, GranuleInfoDev* gi, GcWork* wk, bool use_prev) {
   const int lane = LANE;
+  const unsigned* w32 = reinterpret_cast<const unsigned*>(ix);
   int i0 = ((gi->max_nonzero_coeff + 2) >> 1) << 1;
   if (i0 > 576) i0 = 576;
   /* count1 = end of the last non-zero pair below i0 */
   int top = 0;
-#pragma unroll 1
-  for (int p = 2 * lane; p < i0; p += 64) if ((ix[p] | ix[p + 1]) != 0) top = p + 2;
+#pragma unroll 3
+  for (int p = lane; p < (i0 >> 1); p += 32) if (w32[p] != 0) top = 2 * p + 2;
   const int count1 = wmax(top);
-  /* quadruples of |x| <= 1 counted down from count1 */
+  /* quadruples of |x| <= 1 counted down from count1 (values are >= 0: "<= 1" == no bit above bit 0 in either half) */
   int a1 = 0, a2 = 0, nq = 0;
   const int qmax = count1 >> 2;
   bool stop = false;
 #pragma unroll 1
   for (int q0 = 0; q0 < qmax && !stop; q0 += 32) {
     const int q = q0 + lane;
-    int bad = 0, v1 = 0, v2 = 0;
+    int bad = 1, v1 = 0, v2 = 0;
     if (q < qmax) {
       const int i = count1 - 4 * q;
-      const int x0 = ix[i - 4], x1 = ix[i - 3], x2 = ix[i - 2], x3 = ix[i - 1];
-      if (((x0 | x1 | x2 | x3) & 0x7fffffff) > 1) bad = 1;
-      else { const int p = ((x0 * 2 + x1) * 2 + x2) * 2 + x3; v1 = __ldg(&g_t32l[p]); v2 = __ldg(&g_t33l[p]); }
-    } else bad = 1;
+      const unsigned wa = w32[(i - 4) >> 1], wb = w32[(i - 2) >> 1];
+      if (((wa | wb) & 0xfffefffeu) == 0) {
+        bad = 0;
+        const int p = (int)(((wa & 1u) << 3) | ((wa >> 16) << 2) | ((wb & 1u) << 1) | (wb >> 16));
+        v1 = __ldg(&g_t32l[p]); v2 = __ldg(&g_t33l[p]);
+      }
+    }
     const unsigned m = __ballot_sync(Q_FULL, bad);
     const int first_bad = m ? __ffs(m) - 1 : 32;
     if (lane >= first_bad) { v1 = 0; v2 = 0; }
@@ -251,6 +261,7 @@ __device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short
       b2 = r1 = T->bv_scf[bigv - 1];
       b2 = T->sfb_l[b1 + b2 + 2];
       b1 = T->sfb_l[b1 + 1];
+      if (b2 < bigv) ts2 = region_table_w(ix, b2, bigv, &bits);
     } else {
       r0 = 7; r1 = 22 - 1 - 7 - 1;
       b1 = T->sfb_l[7 + 1];
@@ -259,93 +270,8 @@ __device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short
     }
     b1 = min(b1, bigv);
     b2 = min(b2, bigv);
-    /* The three choose_table() calls of the reference ([0,b1), [b1,b2), [b2,bigv) for NORM) fused into two passes over
-     * the big-value pairs with every lane busy: pass 1 = per-region maximum, pass 2 = per-region code-length sums for
-     * the candidate books of that maximum.  Integer sums: any order gives the reference's totals. */
-    int m0 = 0, m1 = 0, m2 = 0;
-#pragma unroll 1
-    for (int p = 2 * lane; p < bigv; p += 64) {
-      const int v = max((int)ix[p], (int)ix[p + 1]);
-      if (p < b1) m0 = max(m0, v); else if (p < b2) m1 = max(m1, v); else m2 = max(m2, v);
-    }
-    m0 = wmax(m0); m1 = wmax(m1); m2 = wmax(m2);
-    int kind[3], tb1[3], xl[3]; unsigned lin[3];
-    const int mm[3] = {m0, m1, m2};
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-      const int M = mm[r];
-      kind[r] = 0; tb1[r] = 0; xl[r] = 0; lin[r] = 0;
-      if (M == 0) kind[r] = 0;
-      else if (M == 1) { kind[r] = 1; tb1[r] = 1; }
-      else if (M <= 3) { kind[r] = 2; tb1[r] = c_huf_noesc[M - 1]; xl[r] = c_huff_xlen[tb1[r]]; }
-      else if (M <= 15) { kind[r] = 3; tb1[r] = c_huf_noesc[M - 1]; xl[r] = c_huff_xlen[tb1[r]]; }
-      else {
-        kind[r] = 4;
-        const int mx = M - 15;
-        int choice2, choice;
-        for (choice2 = 24; choice2 < 32; choice2++) if (c_huff_linmax[choice2] >= mx) break;
-        for (choice = choice2 - 8; choice < 24; choice++) if (c_huff_linmax[choice] >= mx) break;
-        tb1[r] = choice; xl[r] = choice2;
-        lin[r] = (unsigned)c_huff_xlen[choice] * 65536u + (unsigned)c_huff_xlen[choice2];
-      }
-    }
-    unsigned long long acc0 = 0, acc1 = 0, acc2 = 0;
-#pragma unroll 1
-    for (int p = 2 * lane; p < bigv; p += 64) {
-      const int r = p < b1 ? 0 : (p < b2 ? 1 : 2);
-      const int k = r == 0 ? kind[0] : (r == 1 ? kind[1] : kind[2]);
-      const int t1 = r == 0 ? tb1[0] : (r == 1 ? tb1[1] : tb1[2]);
-      const int xlen = r == 0 ? xl[0] : (r == 1 ? xl[1] : xl[2]);
-      int x = ix[p], y = ix[p + 1];
-      unsigned long long c = 0;
-      if (k == 1) c = (unsigned)hlen(1, x * 2 + y);
-      else if (k == 2) { const int q = x * xlen + y; c = (t1 == 2) ? __ldg(&g_table23[q]) : __ldg(&g_table56[q]); }
-      else if (k == 3) {
-        const int q = x * xlen + y;
-        c = (unsigned long long)hlen(t1, q) | ((unsigned long long)hlen(t1 + 1, q) << 21) | ((unsigned long long)hlen(t1 + 2, q) << 42);
-      } else if (k == 4) {
-        const unsigned linbits = r == 0 ? lin[0] : (r == 1 ? lin[1] : lin[2]);
-        unsigned sacc = 0;
-        if (x != 0) { if (x > 14) { x = 15; sacc += linbits; } x *= 16; }
-        if (y != 0) { if (y > 14) { y = 15; sacc += linbits; } x += y; }
-        sacc += __ldg(&g_largetbl[x]);
-        c = sacc;
-      }
-      if (r == 0) acc0 += c; else if (r == 1) acc1 += c; else acc2 += c;
-    }
-#pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) {
-      acc0 += __shfl_xor_sync(Q_FULL, acc0, o); acc1 += __shfl_xor_sync(Q_FULL, acc1, o); acc2 += __shfl_xor_sync(Q_FULL, acc2, o);
-    }
-    const unsigned long long accs[3] = {acc0, acc1, acc2};
-    int tsel[3] = {ts0, ts1, ts2};
-    const bool present[3] = {0 < b1, b1 < b2, bt == BT_NORM && b2 < bigv};
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-      if (!present[r]) continue;                      /* table_select keeps its stale value, as in the reference */
-      const unsigned long long A = accs[r];
-      int t = 0;
-      if (kind[r] == 1) { t = 1; bits += (int)A; }
-      else if (kind[r] == 2) {
-        t = tb1[r];
-        int sum2 = (int)(A & 0xffff), sum = (int)((A >> 16) & 0xffff);
-        if (sum > sum2) { sum = sum2; t++; }
-        bits += sum;
-      } else if (kind[r] == 3) {
-        int s1 = (int)(A & 0x1fffff), s2 = (int)((A >> 21) & 0x1fffff), s3 = (int)((A >> 42) & 0x1fffff);
-        t = tb1[r];
-        if (s1 > s2) { s1 = s2; t++; }
-        if (s1 > s3) { s1 = s3; t = tb1[r] + 2; }
-        bits += s1;
-      } else if (kind[r] == 4) {
-        int sum2 = (int)(A & 0xffff), sum = (int)((A >> 16) & 0xffff);
-        t = tb1[r];
-        if (sum > sum2) { sum = sum2; t = xl[r]; }
-        bits += sum;
-      }
-      tsel[r] = t;
-    }
-    ts0 = tsel[0]; ts1 = tsel[1]; ts2 = tsel[2];
+    if (0 < b1) ts0 = region_table_w(ix, 0, b1, &bits);
+    if (b1 < b2) ts1 = region_table_w(ix, b1, b2, &bits);
   }
   __syncwarp();
   if (lane == 0) {
@@ -375,6 +301,25 @@ __device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, Granule
   if (gi->xrpow_max > (double)Q_IXMAX / istep) return Q_LARGE_BITS;
   const int sfbmax = gi->block_type == BT_SHORT ? 38 : 21;
   const int mnz = gi->max_nonzero_coeff;
+  if (!use_prev) {
+    /* bin_search_StepSize path (prevNoise == null): no band is cached and none uses the 0/1 quantizer, so the band
+     * walk of quantize_xrpow reduces to: full quantizer below the truncation point, zeros from max_nonzero_coeff on.
+     * Band starts are even, hence the quantised range ends at (mnz + 1) & ~1 (an odd tail length drops its last line). */
+    const int qend = (mnz + 1) & ~1;
+#pragma unroll 3
+    for (int i = lane; i < 576; i += 32) {
+      short v = 0;
+      if (i < qend) {
+        double x = (double)wk->xrpow[i] * istep;
+        const int rx = js_trunc(x);
+        x += (double)__ldg(&T->adj43[rx]);
+        v = (short)js_trunc(x);
+      }
+      ix[i] = v;
+    }
+    __syncwarp();
+    return noquant_count_bits_w(T, ix, gi, wk, false);
+  }
   const bool prev_data_use = use_prev && (gi->global_gain == wk->pn_global_gain);
   const bool calc_step = prev_data_use || gi->block_type == BT_NORM;
   /* per-band decision: 0 skip (cached), 1 full quantizer, 2 zero/one quantizer; term = first non-cached band that
@@ -399,25 +344,20 @@ __device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, Granule
     if (m && term == sfbmax + 1) term = s0 + __ffs(m) - 1;
   }
   __syncwarp();
-  int term_start = 576, term_len = 0;
+  /* lines >= zero_from are zero-filled (Arrays.fill(pi, max_nonzero_coeff, 576, 0) happens when the walk reaches the
+   * truncating band); the truncating band itself quantises an even number of lines in full mode */
+  int zero_from = 576;
   if (term <= sfbmax) {
-    term_start = wk->nstart[term];
-    term_len = mnz - term_start + 1;
-    if (term_len < 0) term_len = 0;
+    const int term_len = mnz - wk->nstart[term] + 1;
+    zero_from = term_len > 0 ? ((term_len & 1) ? mnz : mnz + 1) : mnz;
+    if (lane == 0) wk->mode[term] = 1;
   }
+  __syncwarp();
   const double compare01 = (1.0 - 0.4054) / istep;
-#pragma unroll 1
+#pragma unroll 3
   for (int i = lane; i < 576; i += 32) {
-    const int sfb = wk->sfb_of_line[i];
-    int md;
-    if (sfb > sfbmax) continue;                 /* lines beyond the last band (sfb21 / sfb12 tail) */
-    if (sfb < term) md = wk->mode[sfb];
-    else if (sfb == term && i < term_start + (term_len & ~1)) md = 1;   /* truncated last piece: always full mode */
-    else {
-      if (term <= sfbmax && i >= mnz) ix[i] = 0;   /* Arrays.fill(pi, max_nonzero_coeff, 576, 0) */
-      continue;
-    }
-    if (term <= sfbmax && i >= mnz) { ix[i] = 0; if (!(sfb == term && i < term_start + (term_len & ~1))) continue; }
+    if (i >= zero_from) { ix[i] = 0; continue; }
+    const int md = wk->mode[wk->sfb_of_line[i]];
     if (md == 0) continue;
     const double xp = (double)wk->xrpow[i];
     if (md == 2) ix[i] = (compare01 > xp) ? 0 : 1;
@@ -469,7 +409,7 @@ __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const 
         const double step = (double)T->pow20[s + MP3_QMAX2];
         int j = wk->nstart[sfb];
         noise = 0;
-#pragma unroll 1
+#pragma unroll 2
         for (int l = wk->nlen[sfb]; l > 0; l--) {
           double temp;
           temp = fabs((double)wk->xr[j]) - (double)__ldg(&T->pow43[ix[j]]) * step; j++; noise += temp * temp;
@@ -1140,7 +1080,7 @@ __device__ __noinline__ void recalc_divide_sub_w(const Mp3Tables* T, GcWork* wk,
     if (a2 >= bigv) break;
     int bits = r01_bits[r2 - 2] + cod_info2->count1bits;
     if (gi->part2_3_length <= bits) break;
-    const int r2t = choose_table_w(wk->ixb, a2, bigv, &bits);
+    const int r2t = region_table_w(wk->ixb, a2, bigv, &bits);
     if (gi->part2_3_length <= bits) continue;
     __syncwarp();
     if (cod_info2 != gi) copy_gi_w(gi, cod_info2);
@@ -1177,13 +1117,13 @@ __device__ __noinline__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* w
       const int a1 = T->sfb_l[r0 + 1];
       if (a1 >= bigv) break;
       int r0bits = 0;
-      const int r0t = choose_table_w(ix, 0, a1, &r0bits);
+      const int r0t = region_table_w(ix, 0, a1, &r0bits);
 #pragma unroll 1
       for (int r1 = 0; r1 < 8; r1++) {
         const int a2 = T->sfb_l[r0 + r1 + 2];
         if (a2 >= bigv) break;
         int bits = r0bits;
-        const int r1t = choose_table_w(ix, a1, a2, &bits);
+        const int r1t = region_table_w(ix, a1, a2, &bits);
         if (r01_bits[r0 + r1] > bits) {
           __syncwarp();
           if (lane == 0) { r01_bits[r0 + r1] = bits; r01_div[r0 + r1] = r0; r0_tbl[r0 + r1] = r0t; r1_tbl[r0 + r1] = r1t; }
@@ -1229,8 +1169,8 @@ __device__ __noinline__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* w
     int b1 = T->sfb_l[7 + 1];
     if (b1 > i) b1 = i;
     int t0 = c2->table_select[0], t1 = c2->table_select[1];
-    if (b1 > 0) t0 = choose_table_w(ix, 0, b1, &p23);
-    if (i > b1) t1 = choose_table_w(ix, b1, i, &p23);
+    if (b1 > 0) t0 = region_table_w(ix, 0, b1, &p23);
+    if (i > b1) t1 = region_table_w(ix, b1, i, &p23);
     __syncwarp();
     if (lane == 0) { c2->part2_3_length = p23; c2->table_select[0] = t0; c2->table_select[1] = t1; }
     __syncwarp();

@@ -327,19 +327,29 @@ int mp3b200_encode_streams(int channels, int samplerate, int kbps, int nstreams,
     out_bytes[s] = b;
     tot_bytes += b;
   }
-  int16_t* d_pcm = nullptr; uint8_t* d_out = nullptr;
-  CK(cudaMalloc(&d_pcm, sizeof(int16_t) * (size_t)(tot_samples + 8)));
-  CK(cudaMalloc(&d_out, (size_t)tot_bytes + 8));
+  /* grow-only staging buffers: a steady stream of batches does not pay cudaMalloc/cudaFree per call */
+  static thread_local int16_t* d_pcm = nullptr; static thread_local size_t pcm_cap = 0;
+  static thread_local uint8_t* d_out = nullptr; static thread_local size_t out_cap = 0;
+  if (pcm_cap < (size_t)tot_samples + 8) {
+    cudaFree(d_pcm); d_pcm = nullptr; pcm_cap = 0;
+    CK(cudaMalloc(&d_pcm, sizeof(int16_t) * ((size_t)tot_samples + 8)));
+    pcm_cap = (size_t)tot_samples + 8;
+  }
+  if (out_cap < (size_t)tot_bytes + 8) {
+    cudaFree(d_out); d_out = nullptr; out_cap = 0;
+    CK(cudaMalloc(&d_out, (size_t)tot_bytes + 8));
+    out_cap = (size_t)tot_bytes + 8;
+  }
   for (int s = 0; s < nstreams; s++) {
-    CK(cudaMemcpy(d_pcm + pcm_off[s], left[s], sizeof(int16_t) * nsamples[s], cudaMemcpyHostToDevice));
-    if (channels == 2) CK(cudaMemcpy(d_pcm + pcm_off[s] + nsamples[s], right[s], sizeof(int16_t) * nsamples[s], cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(d_pcm + pcm_off[s], left[s], sizeof(int16_t) * nsamples[s], cudaMemcpyHostToDevice, 0));
+    if (channels == 2) CK(cudaMemcpyAsync(d_pcm + pcm_off[s] + nsamples[s], right[s], sizeof(int16_t) * nsamples[s], cudaMemcpyHostToDevice, 0));
   }
   rc = mp3b200_encode_streams_device(channels, samplerate, kbps, nstreams, d_pcm, pcm_off.data(), nsamples, d_out, out_off.data(), nullptr);
   if (rc == 0) {
     for (int s = 0; s < nstreams; s++)
-      if (cudaMemcpy(out[s], d_out + out_off[s], (size_t)out_bytes[s], cudaMemcpyDeviceToHost) != cudaSuccess) rc = MP3B200_ERR_CUDA;
+      if (cudaMemcpyAsync(out[s], d_out + out_off[s], (size_t)out_bytes[s], cudaMemcpyDeviceToHost, 0) != cudaSuccess) rc = MP3B200_ERR_CUDA;
+    if (cudaStreamSynchronize(0) != cudaSuccess) rc = MP3B200_ERR_CUDA;
   }
-  cudaFree(d_pcm); cudaFree(d_out);
   return rc;
 }
 
