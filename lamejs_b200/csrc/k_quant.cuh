@@ -94,26 +94,24 @@ static int quant_upload_constants() {
 struct GcWork {
   float xr[576];                 /* gi.xr after short-block reorder and analog-silence zeroing */
   float xrpow[576];
-  short ixw[576];                /* cod_info_w.l3_enc */
-  short ixb[576];                /* cod_info.l3_enc (best so far) */
+  short ixw[576];                /* the one quantised-line buffer: cod_info_w.l3_enc; cod_info.l3_enc (best so far) is
+                                    either this buffer (best_here) or parked in global memory at ixg */
+  short* ixg;                    /* this gc's row of the l3_enc array in HBM */
   GranuleInfoDev w, b;           /* cod_info_w / cod_info */
-  int width[MP3_SFBMAX], window[MP3_SFBMAX], start[MP3_SFBMAX + 1];
-  unsigned char sfb_of_line[576];
+  const Mp3Geo* geo;             /* band geometry of this block type (constant table in HBM, L1-resident) */
   float xmin[MP3_SFBMAX], distort[MP3_SFBMAX];
   int pn_step[MP3_SFBMAX]; float pn_noise[MP3_SFBMAX], pn_noise_log[MP3_SFBMAX];
   int pn_global_gain, pn_sfb_count1;
   unsigned char mode[MP3_SFBMAX + 1];
-  int nstart[MP3_SFBMAX], nlen[MP3_SFBMAX];
+  short nstart[MP3_SFBMAX], nlen[MP3_SFBMAX];
   int scratch[8];
   double dscratch[4];
 };
-struct GcFinal {                  /* side info of a finished granule-channel (main data is packed right away) */
-  GranuleInfoDev gi;
-};
 struct FrameShared {
   GcWork wk[2];
-  GcFinal fin[2][2];              /* [gr][ch] */
-  unsigned int bits[368];         /* frame bit buffer (<= 1441 bytes) */
+  const GranuleInfoDev* fin;      /* finished side info of this frame in HBM: fin[gr * nch + ch] */
+  unsigned int* bits;             /* frame bit buffer in HBM (368 words, <= 1441 bytes), filled with atomic ORs */
+  int gc_bits[2][2];              /* part2_3_length + part2_length of the finished gcs [gr][ch] */
   int targ_bits[2];
   int used_bits[2];               /* part2_3_length + part2_length of gr0, per channel */
   int scfsi[2][4];
@@ -291,7 +289,7 @@ __device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short
 /* step of scalefactor band sfb (Takehiro.js:205-209 / QuantizePVT.js:744-747) */
 __device__ __forceinline__ int sfb_step(const GranuleInfoDev* gi, const GcWork* wk, int sfb) {
   return gi->global_gain - ((gi->scalefac[sfb] + (gi->preflag != 0 ? c_pretab[sfb < 22 ? sfb : 21] : 0)) << (gi->scalefac_scale + 1)) -
-         gi->subblock_gain[wk->window[sfb]] * 8;
+         gi->subblock_gain[wk->geo->window[sfb]] * 8;
 }
 
 /* count_bits (Takehiro.js:630-660) = range check + quantize_xrpow (:171-314) + noquant_count_bits */
@@ -330,11 +328,11 @@ __device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, Granule
     const int sfb = s0 + lane;
     int md = 0, trunc_here = 0;
     if (sfb <= sfbmax) {
-      const int jst = wk->start[sfb];
+      const int jst = wk->geo->start[sfb];
       const int step = calc_step ? sfb_step(gi, wk, sfb) : -1;
       if (prev_data_use && wk->pn_step[sfb] == step) md = 0;
       else {
-        if (jst + wk->width[sfb] > mnz) trunc_here = 1;
+        if (jst + wk->geo->width[sfb] > mnz) trunc_here = 1;
         md = (use_prev && wk->pn_sfb_count1 > 0 && sfb >= wk->pn_sfb_count1 && wk->pn_step[sfb] > 0 && step >= wk->pn_step[sfb]) ? 2 : 1;
       }
       wk->mode[sfb] = (unsigned char)md;
@@ -357,7 +355,7 @@ __device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, Granule
 #pragma unroll 3
   for (int i = lane; i < 576; i += 32) {
     if (i >= zero_from) { ix[i] = 0; continue; }
-    const int md = wk->mode[wk->sfb_of_line[i]];
+    const int md = wk->mode[wk->geo->sfb_of_line[i]];
     if (md == 0) continue;
     const double xp = (double)wk->xrpow[i];
     if (md == 2) ix[i] = (compare01 > xp) ? 0 : 1;
@@ -383,10 +381,10 @@ __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const 
 #pragma unroll 1
     for (int sfb = 0; sfb < psymax; sfb++) {
       const int s = sfb_step(gi, wk, sfb);
-      if (wk->pn_step[sfb] == s) { wk->nlen[sfb] = -1; j += wk->width[sfb]; }
+      if (wk->pn_step[sfb] == s) { wk->nlen[sfb] = -1; j += wk->geo->width[sfb]; }
       else {
-        int l = wk->width[sfb] >> 1;
-        if ((j + wk->width[sfb]) > mnz) { const int us = mnz - j + 1; l = us > 0 ? us >> 1 : 0; }
+        int l = wk->geo->width[sfb] >> 1;
+        if ((j + wk->geo->width[sfb]) > mnz) { const int us = mnz - j + 1; l = us > 0 ? us >> 1 : 0; }
         wk->nstart[sfb] = j; wk->nlen[sfb] = l;
         j += 2 * l;
       }
@@ -479,7 +477,7 @@ __device__ __noinline__ bool scale_bitcount_l0(GranuleInfoDev* gi) {
 __device__ __noinline__ bool loop_break_l0(const GranuleInfoDev* gi, const GcWork* wk) {
 #pragma unroll 1
   for (int sfb = 0; sfb < gi->sfbmax; sfb++)
-    if (gi->scalefac[sfb] + gi->subblock_gain[wk->window[sfb]] == 0) return false;
+    if (gi->scalefac[sfb] + gi->subblock_gain[wk->geo->window[sfb]] == 0) return false;
   return true;
 }
 
@@ -490,7 +488,7 @@ __device__ __noinline__ void scale_xrpow_w(GcWork* wk, GranuleInfoDev* gi, doubl
   float mx = 0.0f;
 #pragma unroll 1
   for (int i = lane; i < 576; i += 32) {
-    const int sfb = wk->sfb_of_line[i];
+    const int sfb = wk->geo->sfb_of_line[i];
     if (sfb < gi->sfbmax && wk->mode[sfb]) {
       f32s v; v.v = wk->xrpow[i];
       v *= f34;
@@ -600,7 +598,7 @@ __device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
         float mx = 0.0f;
 #pragma unroll 1
         for (int i = lane; i < 576; i += 32) {
-          const int sfb = wk->sfb_of_line[i];
+          const int sfb = wk->geo->sfb_of_line[i];
           if (sfb < MP3_SFBMAX && wk->nlen[sfb] >= 0) {
             f32s v; v.v = wk->xrpow[i];
             v *= (double)T->ipow20[wk->nlen[sfb]];
@@ -660,7 +658,7 @@ __device__ __noinline__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int des
     int step;
     if (LANE == 0) gi->global_gain = gain;
     __syncwarp();
-    nBits = count_bits_w(T, wk, gi, wk->ixb, false);
+    nBits = count_bits_w(T, wk, gi, wk->ixw, false);
     if (CurrentStep == 1 || nBits == desired_rate) break;
     if (nBits > desired_rate) {
       if (Direction == 2) flagGoneOver = true;
@@ -681,7 +679,7 @@ __device__ __noinline__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int des
     gain++;
     if (LANE == 0) gi->global_gain = gain;
     __syncwarp();
-    nBits = count_bits_w(T, wk, gi, wk->ixb, false);
+    nBits = count_bits_w(T, wk, gi, wk->ixw, false);
   }
   *current_step = (start - gain >= 4) ? 4 : 2;
   *old_value = gain;
@@ -712,10 +710,10 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
   __syncwarp();
   bin_search_w(T, wk, targ_bits, old_value, current_step);
   *bs_hash = gi_hash(&wk->b);
-  calc_noise_w(T, wk, &wk->b, wk->ixb, &best);
+  calc_noise_w(T, wk, &wk->b, wk->ixw, &best);
   best.bits = wk->b.part2_3_length;
   copy_gi_w(&wk->w, &wk->b);
-  copy_ix_w(wk->ixw, wk->ixb);
+  bool best_here = true;          /* cod_info.l3_enc == the shared-memory buffer (no copy parked in HBM yet) */
   int age = 0;
   const int quant_comp = T->quant_comp;   /* 9 for long and short */
   (void)quant_comp;
@@ -728,6 +726,7 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
     const int huff_bits = targ_bits - w->part2_length;
     if (huff_bits <= 0) break;
     int p23, gg;
+    if (best_here) { copy_ix_w(wk->ixg, wk->ixw); best_here = false; }   /* park the best lines before re-quantising */
     for (;;) {                                     /* while (count_bits > huff_bits && global_gain <= maxggain) global_gain++ */
       p23 = count_bits_w(T, wk, w, wk->ixw, true);
       gg = w->global_gain;
@@ -767,7 +766,7 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
       best_part2_3_length = wk->b.part2_3_length;   /* sic: read before the assign (Quantize.js:996-998) */
       best = cur;
       copy_gi_w(&wk->b, &wk->w);
-      copy_ix_w(wk->ixb, wk->ixw);
+      best_here = true;
       age = 0;
     } else {
       if (++age > search_limit && best.over_count == 0) break;
@@ -776,6 +775,7 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
     __syncwarp();
     if (!cont) break;
   } while (true);
+  if (!best_here) copy_ix_w(wk->ixw, wk->ixg);
 }
 
 /* athAdjust (QuantizePVT.js:541-561) */
@@ -813,44 +813,17 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
     for (int i = 0; i < MP3_SFBMAX; i++) gi->scalefac[i] = 0;
     gi->xrpow_max = 0;
   }
-  /* band geometry */
+  /* band geometry: constant per block type; short blocks are reordered band-major on the way in */
+  const Mp3Geo* geo = &T->geo[is_short ? 1 : 0];
+  if (lane == 0) wk->geo = geo;
   if (!is_short) {
-#pragma unroll 1
-    for (int sfb = lane; sfb < MP3_SFBMAX; sfb += 32) {
-      wk->width[sfb] = sfb < 22 ? T->sfb_l[sfb + 1] - T->sfb_l[sfb] : 0;
-      wk->window[sfb] = 3;
-    }
-#pragma unroll 1
-    for (int i = lane; i < 576; i += 32) { int s = 0; while (T->sfb_l[s + 1] <= i) s++; wk->sfb_of_line[i] = (unsigned char)s; }
-#pragma unroll 1
+#pragma unroll 3
     for (int i = lane; i < 576; i += 32) wk->xr[i] = xr_g[i];
   } else {
-#pragma unroll 1
-    for (int j = lane; j < MP3_SFBMAX; j += 32) {
-      const int sfb = j / 3;
-      wk->width[j] = T->sfb_s[sfb + 1] - T->sfb_s[sfb];
-      wk->window[j] = j - 3 * sfb;
-    }
-    /* reorder (Quantize.js:262-278): band sfb, window w, line l  ->  3*start + w*width + (l-start) */
-#pragma unroll 1
-    for (int i = lane; i < 576; i += 32) {
-      const int l = i / 3, w = i - 3 * l;
-      int sfb = 0;
-      while (T->sfb_s[sfb + 1] <= l) sfb++;
-      const int start = T->sfb_s[sfb], wd = T->sfb_s[sfb + 1] - start;
-      const int dst = 3 * start + w * wd + (l - start);
-      wk->xr[dst] = xr_g[i];
-      wk->sfb_of_line[dst] = (unsigned char)(3 * sfb + w);
-    }
+#pragma unroll 3
+    for (int i = lane; i < 576; i += 32) wk->xr[__ldg(&geo->reorder[i])] = xr_g[i];
   }
   __syncwarp();
-#pragma unroll 1
-  for (int sfb = lane; sfb <= MP3_SFBMAX; sfb += 32) {
-    int j = 0;
-#pragma unroll 1
-    for (int q = 0; q < sfb; q++) j += wk->width[q];
-    wk->start[sfb] = j;
-  }
   /* analog silence in the pseudo bands above sfb21 / sfb12 (sequential from the top; lane 0) */
   if (lane == 0) {
     if (!is_short) {
@@ -911,7 +884,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
     __syncwarp();
     if (!energy) {
 #pragma unroll 1
-      for (int i = lane; i < 576; i += 32) wk->ixb[i] = 0;
+      for (int i = lane; i < 576; i += 32) wk->ixw[i] = 0;
       __syncwarp();
       return false;
     }
@@ -922,7 +895,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
     if (lane < 21) {
       const int gsfb = lane;
       int j = T->sfb_l[gsfb];
-      const int width = wk->width[gsfb];
+      const int width = wk->geo->width[gsfb];
       double xmin = ath_adjust * (double)T->ath_l[gsfb];
       double en0 = 0.0;
 #pragma unroll 1
@@ -950,7 +923,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
 #pragma unroll 1
     for (int t = lane; t < 36; t += 32) {
       const int sfb = t / 3, b = t - 3 * sfb;
-      const int width = wk->width[t];
+      const int width = wk->geo->width[t];
       int j = 3 * T->sfb_s[sfb] + b * width;
       const double tmpATH = ath_adjust * (double)T->ath_s[sfb];
       double en0 = 0.0;
@@ -989,10 +962,10 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
   for (int s0 = 0; s0 < gi->sfbmax; s0 += 32) {
     const int sfb = s0 + lane;
     if (sfb < gi->sfbmax) {
-      const int j = wk->start[sfb];
+      const int j = wk->geo->start[sfb];
       bool any = false;
 #pragma unroll 1
-      for (int l = 0; l < wk->width[sfb]; l++) if (wk->ixb[j + l] != 0) { any = true; break; }
+      for (int l = 0; l < wk->geo->width[sfb]; l++) if (wk->ixw[j + l] != 0) { any = true; break; }
       wk->mode[sfb] = any ? 1 : 0;
     }
   }
@@ -1023,9 +996,9 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
     }
 #pragma unroll 1
     for (int i = 0; i < 4; i++) fs->scfsi[ch][i] = 0;
-    if (gr == 1 && fs->fin[0][ch].gi.block_type != BT_SHORT && gi->block_type != BT_SHORT) {
+    if (gr == 1 && fs->fin[ch].block_type != BT_SHORT && gi->block_type != BT_SHORT) {
       /* scfsi_calc (Takehiro.js:877-943) */
-      const int* g0sf = fs->fin[0][ch].gi.scalefac;
+      const int* g0sf = fs->fin[ch].scalefac;
       const int band[5] = {0, 6, 11, 16, 21};
       int sfb;
 #pragma unroll 1
@@ -1080,7 +1053,7 @@ __device__ __noinline__ void recalc_divide_sub_w(const Mp3Tables* T, GcWork* wk,
     if (a2 >= bigv) break;
     int bits = r01_bits[r2 - 2] + cod_info2->count1bits;
     if (gi->part2_3_length <= bits) break;
-    const int r2t = region_table_w(wk->ixb, a2, bigv, &bits);
+    const int r2t = region_table_w(wk->ixw, a2, bigv, &bits);
     if (gi->part2_3_length <= bits) continue;
     __syncwarp();
     if (cod_info2 != gi) copy_gi_w(gi, cod_info2);
@@ -1100,9 +1073,10 @@ __device__ __noinline__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* w
   const int lane = LANE;
   GranuleInfoDev* gi = &wk->b;
   GranuleInfoDev* c2 = &wk->w;
-  const short* ix = wk->ixb;
-  int* r01_bits = wk->nstart;          /* 23 entries each; reuse per-band scratch */
-  int* r01_div = wk->nlen;
+  const short* ix = wk->ixw;
+  /* 23 entries each; the noise cache and the distortion array are dead after outer_loop */
+  int* r01_bits = reinterpret_cast<int*>(wk->pn_noise_log);
+  int* r01_div = reinterpret_cast<int*>(wk->distort);
   int* r0_tbl = wk->pn_step;
   int* r1_tbl = reinterpret_cast<int*>(wk->pn_noise);
   copy_gi_w(c2, gi);
@@ -1310,21 +1284,22 @@ __device__ __noinline__ void pack_sideinfo(const Mp3Tables* T, FrameShared* fs, 
   for (int ch = 0; ch < nch; ch++) for (int b = 0; b < 4; b++) WH(fs->scfsi[ch][b], 1);
 #pragma unroll 1
   for (int gr = 0; gr < 2; gr++) for (int ch = 0; ch < nch; ch++) {
-    GranuleInfoDev* gi = &fs->fin[gr][ch].gi;
+    const GranuleInfoDev* gi = &fs->fin[gr * nch + ch];
     WH(gi->part2_3_length + gi->part2_length, 12);
     WH(gi->big_values / 2, 9);
     WH(gi->global_gain, 8);
     WH(gi->scalefac_compress, 4);
-    if (gi->table_select[0] == 14) gi->table_select[0] = 16;
-    if (gi->table_select[1] == 14) gi->table_select[1] = 16;
+    int ts0 = gi->table_select[0], ts1 = gi->table_select[1], ts2 = gi->table_select[2];
+    if (ts0 == 14) ts0 = 16;
+    if (ts1 == 14) ts1 = 16;
     if (gi->block_type != BT_NORM) {
       WH(1, 1); WH(gi->block_type, 2); WH(0, 1);
-      WH(gi->table_select[0], 5); WH(gi->table_select[1], 5);
+      WH(ts0, 5); WH(ts1, 5);
       WH(gi->subblock_gain[0], 3); WH(gi->subblock_gain[1], 3); WH(gi->subblock_gain[2], 3);
     } else {
       WH(0, 1);
-      if (gi->table_select[2] == 14) gi->table_select[2] = 16;
-      WH(gi->table_select[0], 5); WH(gi->table_select[1], 5); WH(gi->table_select[2], 5);
+      if (ts2 == 14) ts2 = 16;
+      WH(ts0, 5); WH(ts1, 5); WH(ts2, 5);
       WH(gi->region0_count, 4); WH(gi->region1_count, 3);
     }
     WH(gi->preflag, 1); WH(gi->scalefac_scale, 1); WH(gi->count1table_select, 1);
@@ -1355,11 +1330,12 @@ __device__ __noinline__ void granule_budget(FrameShared* fs, int nch, int mean_b
 
 /* ---- the frame kernel ------------------------------------------------------------------------------------ */
 /* grid-stride over a work list of frame rows.  block = 32 * nch threads. */
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, 14)
 k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, const float* __restrict__ xr,
                 const PsyRatioDev* __restrict__ ratio, const signed char* __restrict__ bt_final,
                 const double* __restrict__ ath_q, QuantFrameState* __restrict__ qs, GranuleInfoDev* __restrict__ ginfo_out,
-                short* __restrict__ l3enc_out, const int* __restrict__ list, const int* __restrict__ count_ptr, int count_direct,
+                short* __restrict__ l3enc_out, unsigned int* __restrict__ framebits, int keep_l3enc,
+                const int* __restrict__ list, const int* __restrict__ count_ptr, int count_direct,
                 int revalidate, uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FrameShared* fs = reinterpret_cast<FrameShared*>(smem_raw);
@@ -1378,8 +1354,10 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
     const double ath_adjust = ath_q[frow];
     __syncthreads();
     /* prologue: frame buffer, analog-silence thresholds, in-state */
+    unsigned int* const fbits = framebits + (size_t)frow * 368;
 #pragma unroll 1
-    for (int i = threadIdx.x; i < 368; i += blockDim.x) fs->bits[i] = 0;
+    for (int i = threadIdx.x; i < 368; i += blockDim.x) fbits[i] = 0;
+    if (threadIdx.x == 0) { fs->bits = fbits; fs->fin = ginfo_out + ((size_t)sd.unit_base + 2 * f) * nch; }
     if (threadIdx.x < 12) {
       const int g = threadIdx.x % 6;
       if (threadIdx.x < 6) fs->ath21[g] = ath_adjust_dev(ath_adjust, (double)T->ath_psfb21[g], T->ath_floor);
@@ -1445,6 +1423,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       const int bt = bt_final[urow * 2 + ch];
       /* masking of psy unit (2f+gr-1): halo-shifted row = unit_base + z + (2f+gr-1) + 1 */
       const PsyRatioDev* rt = ratio + ((size_t)sd.unit_base + z + 2 * f + gr) * nch + ch;
+      if (lane == 0) wk->ixg = l3enc_out + (urow * nch + ch) * 576;
       const bool have = gc_prepare_w(T, wk, fs, xr + (urow * nch + ch) * 576, bt, rt, ath_adjust);
       unsigned long long bsh = 0;
       if (have) outer_loop_w(T, wk, fs->targ_bits[ch], &old_value, &current_step, &bsh);
@@ -1454,20 +1433,21 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       /* iteration_finish_one (Quantize.js:1059-1078) */
       best_scalefac_store_w(wk, fs, gr, ch);
       best_huffman_divide_w(T, wk);
-      /* side info persists; the main data of this granule is packed straight from the working set */
-      GcFinal* fin = &fs->fin[gr][ch];
-      copy_gi_w(&fin->gi, &wk->b);
-      if (lane == 0) { fs->used_bits[ch] = wk->b.part2_3_length + wk->b.part2_length; if (gr == 0) q->used0[ch] = fs->used_bits[ch]; }
-      if (ginfo_out) copy_gi_w(&ginfo_out[urow * nch + ch], &wk->b);
-      if (l3enc_out) copy_ix_w(l3enc_out + (urow * nch + ch) * 576, wk->ixb);
+      /* the side info persists in HBM; the main data of this granule is packed straight from the working set */
+      copy_gi_w(&ginfo_out[urow * nch + ch], &wk->b);
+      if (lane == 0) {
+        fs->used_bits[ch] = fs->gc_bits[gr][ch] = wk->b.part2_3_length + wk->b.part2_length;
+        if (gr == 0) q->used0[ch] = fs->used_bits[ch];
+      }
+      if (keep_l3enc) copy_ix_w(wk->ixg, wk->ixw);
       __syncthreads();
       {
         /* bit position of this gc: side info, then gr0ch0, gr0ch1, gr1ch0, gr1ch1 back to back */
         int pos = 8 * T->sideinfo_len;
         for (int g2 = 0; g2 < gr; g2++)
-          for (int c = 0; c < nch; c++) pos += fs->fin[g2][c].gi.part2_3_length + fs->fin[g2][c].gi.part2_length;
-        for (int c = 0; c < ch; c++) pos += fs->fin[gr][c].gi.part2_3_length + fs->fin[gr][c].gi.part2_length;
-        pack_gc_w(T, fs, &wk->b, wk->ixb, wk->xr, pos);
+          for (int c = 0; c < nch; c++) pos += fs->gc_bits[g2][c];
+        for (int c = 0; c < ch; c++) pos += fs->gc_bits[gr][c];
+        pack_gc_w(T, fs, &wk->b, wk->ixw, wk->xr, pos);
       }
       __syncthreads();
     }
@@ -1477,14 +1457,14 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
     __syncthreads();
     {
       int pos = 8 * T->sideinfo_len;
-      for (int gr = 0; gr < 2; gr++) for (int c = 0; c < nch; c++) pos += fs->fin[gr][c].gi.part2_3_length + fs->fin[gr][c].gi.part2_length;
+      for (int gr = 0; gr < 2; gr++) for (int c = 0; c < nch; c++) pos += fs->gc_bits[gr][c];
       /* drain_into_ancillary (BitStream.js:175-213): "LAME" + the version string pushed through `>>` as numbers */
       if (threadIdx.x == 0) {
         int remaining = frame_bits - pos;
         const unsigned char tag[10] = {0x4c, 0x41, 0x4d, 0x45, 3, 0, 9, 8, 0, 4};
         int k = 0;
-        for (; k < 4 && remaining >= 8; k++) { put_bits(fs->bits, pos, tag[k], 8); pos += 8; remaining -= 8; }
-        if (remaining >= 32) for (; k < 10 && remaining >= 8; k++) { put_bits(fs->bits, pos, tag[k], 8); pos += 8; remaining -= 8; }
+        for (; k < 4 && remaining >= 8; k++) { put_bits(fbits, pos, tag[k], 8); pos += 8; remaining -= 8; }
+        if (remaining >= 32) for (; k < 10 && remaining >= 8; k++) { put_bits(fbits, pos, tag[k], 8); pos += 8; remaining -= 8; }
       }
     }
     __syncthreads();
@@ -1494,7 +1474,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
                             (pad_count(kabs - 1, T->frac_SpF, T->samplerate) - pad_count((long long)sd.frame0 - 1, T->frac_SpF, T->samplerate));
       uint8_t* dst = out + off;
 #pragma unroll 1
-      for (int i = threadIdx.x; i < frame_bytes; i += blockDim.x) dst[i] = (uint8_t)(fs->bits[i >> 2] >> (24 - 8 * (i & 3)));
+      for (int i = threadIdx.x; i < frame_bytes; i += blockDim.x) dst[i] = (uint8_t)(__ldcg(&fbits[i >> 2]) >> (24 - 8 * (i & 3)));
     }
     if (threadIdx.x == 0) q->valid = 1;
   }
@@ -1548,7 +1528,8 @@ __global__ void k_qstate_commit(StreamDesc* __restrict__ streams, int nstreams, 
 
 static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_streams, int S, int max_frames, long long F,
                      const float* d_xr, const PsyRatioDev* d_ratio, const signed char* d_bt, const double* d_ath_q,
-                     QuantFrameState* d_qs, GranuleInfoDev* d_ginfo, short* d_l3enc, int* d_list, int* d_counter, uint8_t* d_out,
+                     QuantFrameState* d_qs, GranuleInfoDev* d_ginfo, short* d_l3enc, unsigned int* d_framebits, int keep_l3enc,
+                     int* d_list, int* d_counter, uint8_t* d_out,
                      cudaStream_t st, cudaEvent_t ev_pass1, int* passes_out, long long* launches) {
   static bool attr_set = false;
   const size_t smem = sizeof(FrameShared);
@@ -1565,10 +1546,11 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     k_qstate_init<<<g, 128, 0, st>>>(d_streams, S, d_qs);
     (*launches)++;
   }
-  long long nblk = F < (long long)sms * 16 ? F : (long long)sms * 16;
+  /* one block per frame: the hardware block scheduler balances the uneven per-frame loop counts */
+  long long nblk = F < (1ll << 30) ? F : (1ll << 30);
   if (nblk < 1) nblk = 1;
-  k_quantize_pack<<<(int)nblk, threads, smem, st>>>(dT, d_streams, d_xr, d_ratio, d_bt, d_ath_q, d_qs, d_ginfo, d_l3enc, nullptr, nullptr,
-                                                    (int)F, 0, d_out);
+  k_quantize_pack<<<(int)nblk, threads, smem, st>>>(dT, d_streams, d_xr, d_ratio, d_bt, d_ath_q, d_qs, d_ginfo, d_l3enc, d_framebits, keep_l3enc,
+                                                    nullptr, nullptr, (int)F, 0, d_out);
   (*launches)++;
   if (cudaEventRecord(ev_pass1, st) != cudaSuccess) return -100;
   int passes = 1;
@@ -1580,9 +1562,9 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     if (cudaMemcpyAsync(&h_count, d_counter, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -100;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -100;
     if (h_count == 0) break;
-    long long nb = h_count < sms * 16 ? h_count : sms * 16;
-    k_quantize_pack<<<(int)nb, threads, smem, st>>>(dT, d_streams, d_xr, d_ratio, d_bt, d_ath_q, d_qs, d_ginfo, d_l3enc, d_list, nullptr,
-                                                    h_count, 1, d_out);
+    long long nb = h_count;
+    k_quantize_pack<<<(int)nb, threads, smem, st>>>(dT, d_streams, d_xr, d_ratio, d_bt, d_ath_q, d_qs, d_ginfo, d_l3enc, d_framebits, keep_l3enc,
+                                                    d_list, nullptr, h_count, 1, d_out);
     (*launches)++;
     passes++;
     if (passes > max_frames + 2) return -100;   /* cannot happen: each pass fixes at least the first dirty frame */

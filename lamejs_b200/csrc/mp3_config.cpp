@@ -257,6 +257,34 @@ int mp3_build_tables(int channels, int samplerate, int kbps, Mp3Tables* t) {
   }
   t->psfb21[6] = 576;
   t->psfb12[6] = 192;
+  {
+    Mp3Geo& L = t->geo[0];
+    Mp3Geo& S = t->geo[1];
+    memset(&L, 0, sizeof L); memset(&S, 0, sizeof S);
+    for (int sfb = 0; sfb < MP3_SFBMAX; sfb++) {
+      L.width[sfb] = (unsigned char)(sfb < 22 ? t->sfb_l[sfb + 1] - t->sfb_l[sfb] : 0);
+      L.window[sfb] = 3;
+      S.width[sfb] = (unsigned char)(t->sfb_s[sfb / 3 + 1] - t->sfb_s[sfb / 3]);
+      S.window[sfb] = (unsigned char)(sfb % 3);
+    }
+    for (int g = 0; g < 2; g++) {
+      int j = 0;
+      for (int sfb = 0; sfb <= MP3_SFBMAX; sfb++) { t->geo[g].start[sfb] = (short)j; if (sfb < MP3_SFBMAX) j += t->geo[g].width[sfb]; }
+    }
+    for (int i = 0; i < 576; i++) {
+      int s = 0;
+      while (t->sfb_l[s + 1] <= i) s++;
+      L.sfb_of_line[i] = (unsigned char)s;
+      L.reorder[i] = (short)i;
+      const int l = i / 3, w = i - 3 * l;
+      int sb = 0;
+      while (t->sfb_s[sb + 1] <= l) sb++;
+      const int st = t->sfb_s[sb], wd = t->sfb_s[sb + 1] - st;
+      const int dst = 3 * st + w * wd + (l - st);
+      S.reorder[i] = (short)dst;
+      S.sfb_of_line[dst] = (unsigned char)(3 * sb + w);
+    }
+  }
 
   /* ---- quantizer tables (QuantizePVT.js:344-356) ---- */
   t->pow43[0] = 0.0f;

@@ -19,6 +19,15 @@
 #define MP3_QMAX 257
 #define MP3_QMAX2 116
 
+/* Band geometry of one granule-channel as the quantizer walks it: [0] long / start / stop blocks (22 bands of the long
+ * partition, window 3), [1] short blocks (13 bands x 3 windows, lines reordered band-major, Quantize.js:262-278). */
+struct Mp3Geo {
+  unsigned char width[MP3_SFBMAX + 1], window[MP3_SFBMAX + 1];
+  short start[MP3_SFBMAX + 1];
+  unsigned char sfb_of_line[576];
+  short reorder[576];             /* position of MDCT line i in the quantizer's line order */
+};
+
 struct Mp3Tables {
   /* ---- scalars ---- */
   int nch, samplerate, kbps, mono;
@@ -40,6 +49,7 @@ struct Mp3Tables {
   /* ---- scalefactor bands ---- */
   int sfb_l[MP3_SBMAX_L + 1], sfb_s[MP3_SBMAX_S + 1], psfb21[7], psfb12[7];
   int bv_scf[576];
+  Mp3Geo geo[2];
   /* ---- psycho-acoustic partitions ---- */
   int numlines_l[MP3_CBANDS], numlines_s[MP3_CBANDS];
   int line0_l[MP3_CBANDS + 1], line0_s[MP3_CBANDS + 1];   /* prefix sums of numlines (ours) */

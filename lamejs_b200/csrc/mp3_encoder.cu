@@ -103,7 +103,9 @@ struct Workspace {
   double* d_ath_q = nullptr;              /* [frames] ATH.adjust after adjust_ATH (quantizer) */
   QuantFrameState* d_qstate = nullptr;    /* [frames] speculation bookkeeping */
   GranuleInfoDev* d_ginfo = nullptr;      /* [units][nch] side info of the final quantization */
-  short* d_l3enc = nullptr;               /* [units][nch][576] (debug tap) */
+  short* d_l3enc = nullptr;               /* [units][nch][576] parked best quantization of a gc; final lines when kept (debug tap) */
+  unsigned int* d_framebits = nullptr;    /* [frames][368] frame bit buffers */
+  bool keep_l3enc = false;
   int* d_dirty = nullptr;                 /* [frames] work list for re-quantization passes */
   int* d_counter = nullptr;               /* [4] */
   ScanChunk* d_scan = nullptr;            /* [frames / SCAN_FRAMES + nstreams] */
@@ -111,7 +113,7 @@ struct Workspace {
   void release() {
     cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_psy);
     cudaFree(d_ratio); cudaFree(d_ath_psy); cudaFree(d_ath_q); cudaFree(d_qstate); cudaFree(d_ginfo);
-    cudaFree(d_l3enc); cudaFree(d_dirty); cudaFree(d_counter); cudaFree(d_scan); d_scan = nullptr;
+    cudaFree(d_l3enc); cudaFree(d_framebits); d_framebits = nullptr; cudaFree(d_dirty); cudaFree(d_counter); cudaFree(d_scan); d_scan = nullptr;
     d_streams = nullptr; d_bt_final = d_bt_prev = nullptr; d_xr = nullptr; d_psy = nullptr; d_ratio = nullptr;
     d_ath_psy = d_ath_q = nullptr; d_qstate = nullptr; d_ginfo = nullptr; d_l3enc = nullptr; d_dirty = nullptr; d_counter = nullptr;
   }
@@ -128,7 +130,9 @@ struct Workspace {
     CK(cudaMalloc(&d_ath_q, sizeof(double) * (size_t)(F + 1)));
     CK(cudaMalloc(&d_qstate, sizeof(QuantFrameState) * (size_t)(F + 1)));
     CK(cudaMalloc(&d_ginfo, sizeof(GranuleInfoDev) * (size_t)U * nch));
-    if (want_l3enc) CK(cudaMalloc(&d_l3enc, sizeof(short) * (size_t)U * nch * 576));
+    keep_l3enc = want_l3enc;
+    CK(cudaMalloc(&d_l3enc, sizeof(short) * (size_t)U * nch * 576));
+    CK(cudaMalloc(&d_framebits, sizeof(unsigned int) * 368 * (size_t)(F + 1)));
     CK(cudaMalloc(&d_dirty, sizeof(int) * (size_t)(F + 1)));
     CK(cudaMalloc(&d_counter, sizeof(int) * 4));
     CK(cudaMalloc(&d_scan, sizeof(ScanChunk) * (size_t)(F / SCAN_FRAMES + S + 1)));
@@ -216,7 +220,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   int passes = 0;
   if (!stop_after_mdct) {
     int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, max_frames, total_frames, ws.d_xr, ws.d_ratio, ws.d_bt_final, ws.d_ath_q,
-                       ws.d_qstate, ws.d_ginfo, ws.d_l3enc, ws.d_dirty, ws.d_counter, d_out, st, ev[5], &passes, &g_launches);
+                       ws.d_qstate, ws.d_ginfo, ws.d_l3enc, ws.d_framebits, ws.keep_l3enc ? 1 : 0, ws.d_dirty, ws.d_counter, d_out, st, ev[5], &passes, &g_launches);
     if (rc) { g_err = "quantizer stage failed: " + std::string(cudaGetErrorString(cudaGetLastError())); return rc; }
   } else {
     CK(cudaEventRecord(ev[5], st));
