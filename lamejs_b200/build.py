@@ -24,13 +24,15 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: tuning builds (libmp3b200_<variant>.so with -D flags), selected at run time by MP3B200_LIB."""
+    out = LIB if variant is None else os.path.join(HERE, "libmp3b200_%s.so" % variant)
+    if variant is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -63,6 +63,9 @@ __device__ int g_t32l[16];
 __device__ int g_t33l[16];
 __constant__ int c_slen1_n[16];
 __constant__ int c_slen2_n[16];
+__device__ int g_slen_n[2][16];                  /* slen1_n / slen2_n, read with one index per lane */
+__device__ int g_scale_tab[2][16];               /* scale_long / scale_short */
+__device__ unsigned int g_table3[3][256];        /* lengths of tables (7,8,9) / (10,11,12) / (13,14,15) packed 11:11:10 */
 __constant__ int c_slen1_tab[16];
 __constant__ int c_slen2_tab[16];
 __constant__ int c_scale_short[16];
@@ -86,6 +89,22 @@ static int quant_upload_constants() {
   UP(g_table23, MP3_HUFF_TABLE23); UP(g_table56, MP3_HUFF_TABLE56);
   UP(c_pretab, pretab); UP(g_t32l, t32l); UP(g_t33l, t33l); UP(c_slen1_n, s1n); UP(c_slen2_n, s2n);
   UP(c_slen1_tab, s1t); UP(c_slen2_tab, s2t); UP(c_scale_short, ss); UP(c_scale_long, sl); UP(c_huf_noesc, hn);
+  {
+    static int sn[2][16], st[2][16];
+    static unsigned int t3[3][256];
+    for (int k = 0; k < 16; k++) { sn[0][k] = s1n[k]; sn[1][k] = s2n[k]; st[0][k] = sl[k]; st[1][k] = ss[k]; }
+    for (int c = 0; c < 3; c++) {
+      const int t1 = 7 + 3 * c, xl = MP3_HUFF_XLEN[t1];
+      for (int q = 0; q < 256; q++) {
+        unsigned int v = 0;
+        if (q < xl * xl)
+          v = (unsigned)MP3_HUFF_LEN[MP3_HUFF_OFF[t1] + q] | ((unsigned)MP3_HUFF_LEN[MP3_HUFF_OFF[t1 + 1] + q] << 11) |
+              ((unsigned)MP3_HUFF_LEN[MP3_HUFF_OFF[t1 + 2] + q] << 22);
+        t3[c][q] = v;
+      }
+    }
+    UP(g_slen_n, sn); UP(g_scale_tab, st); UP(g_table3, t3);
+  }
 #undef UP
   return 0;
 }
@@ -121,6 +140,18 @@ struct FrameShared {
 };
 
 #define LANE (threadIdx.x & 31)
+/* tuning knobs (tools/build_variants.py) */
+#define Q_PRAGMA(x) _Pragma(#x)
+#define Q_UNROLL(n) Q_PRAGMA(unroll n)
+#ifndef Q_RT_UNROLL
+#define Q_RT_UNROLL 1
+#endif
+#ifndef Q_CB_UNROLL
+#define Q_CB_UNROLL 1
+#endif
+#ifndef Q_MIN_BLOCKS
+#define Q_MIN_BLOCKS 14
+#endif
 /* one copy of the fdlibm routines per kernel instead of one per call site (instruction-cache footprint) */
 __device__ __noinline__ double q_log10(double x) { return m3_log10(x); }
 __device__ __noinline__ double q_pow(double x, double y) { return m3_pow(x, y); }
@@ -136,13 +167,13 @@ __device__ __noinline__ int region_table_w(const short* ix, int begin, int end, 
   const unsigned* w32 = reinterpret_cast<const unsigned*>(ix);
   const int p0 = (begin >> 1) + lane, p1 = end >> 1;
   unsigned m = 0;
-#pragma unroll 3
-  for (int p = p0; p < p1; p += 32) { const unsigned w = w32[p]; m = max(m, max(w & 0xffffu, w >> 16)); }
-  const int mx = (int)__reduce_max_sync(Q_FULL, m);
+Q_UNROLL(Q_RT_UNROLL)
+  for (int p = p0; p < p1; p += 32) m = __vmaxu2(m, w32[p]);        /* both 16-bit halves at once */
+  const int mx = (int)__reduce_max_sync(Q_FULL, max(m & 0xffffu, m >> 16));
   if (mx == 0) return 0;
   if (mx == 1) {
     int s = 0;
-#pragma unroll 3
+Q_UNROLL(Q_RT_UNROLL)
     for (int p = p0; p < p1; p += 32) { const unsigned w = w32[p]; s += hlen(1, (int)((w & 0xffffu) * 2 + (w >> 16))); }
     *bits += wsum(s);
     return 1;
@@ -152,7 +183,7 @@ __device__ __noinline__ int region_table_w(const short* ix, int begin, int end, 
     const unsigned xlen = (unsigned)c_huff_xlen[t1];
     const unsigned* tab = (t1 == 2) ? g_table23 : g_table56;
     unsigned s = 0;
-#pragma unroll 3
+Q_UNROLL(Q_RT_UNROLL)
     for (int p = p0; p < p1; p += 32) { const unsigned w = w32[p]; s += __ldg(&tab[(w & 0xffffu) * xlen + (w >> 16)]); }
     s = wsumu(s);
     int sum2 = (int)(s & 0xffff), sum = (int)(s >> 16);
@@ -163,17 +194,14 @@ __device__ __noinline__ int region_table_w(const short* ix, int begin, int end, 
   if (mx <= 15) {
     const int t1 = c_huf_noesc[mx - 1];
     const unsigned xlen = (unsigned)c_huff_xlen[t1];
-    const unsigned char* h1 = g_huff_len + c_huff_off[t1];
-    const unsigned char* h2 = g_huff_len + c_huff_off[t1 + 1];
-    const unsigned char* h3 = g_huff_len + c_huff_off[t1 + 2];
-    unsigned s = 0;                                   /* three sums of < 2^10 each packed 10:11:11 -- no carries */
-#pragma unroll 3
+    const unsigned int* h = g_table3[(t1 - 7) / 3];
+    unsigned s = 0;                                   /* three sums packed 11:11:10: a lane adds <= 9 pairs x <= 19 bits */
+Q_UNROLL(Q_RT_UNROLL)
     for (int p = p0; p < p1; p += 32) {
       const unsigned w = w32[p];
-      const unsigned q = (w & 0xffffu) * xlen + (w >> 16);
-      s += (unsigned)__ldg(&h1[q]) | ((unsigned)__ldg(&h2[q]) << 11) | ((unsigned)__ldg(&h3[q]) << 22);
+      s += __ldg(&h[(w & 0xffffu) * xlen + (w >> 16)]);
     }
-    /* per-lane partial: <= 9 pairs x 19 bits = 171 < 2^11; warp total <= 288 x 19 = 5472 needs 13 bits -> reduce fields separately */
+    /* the warp total (<= 288 x 19 = 5472) needs 13 bits: reduce the fields separately */
     int s1 = wsum((int)(s & 0x7ff)), s2 = wsum((int)((s >> 11) & 0x7ff)), s3 = wsum((int)(s >> 22));
     int t = t1;
     if (s1 > s2) { s1 = s2; t++; }
@@ -182,14 +210,14 @@ __device__ __noinline__ int region_table_w(const short* ix, int begin, int end, 
     return t;
   }
   if (mx > Q_IXMAX) { *bits = Q_LARGE_BITS; return -1; }
-  int choice2, choice;
-#pragma unroll 1
-  for (choice2 = 24; choice2 < 32; choice2++) if (c_huff_linmax[choice2] >= mx - 15) break;
-#pragma unroll 1
-  for (choice = choice2 - 8; choice < 24; choice++) if (c_huff_linmax[choice] >= mx - 15) break;
+  /* first table of 24..31, then first of (choice2 - 8)..23, whose linmax covers mx - 15: linmax is
+   * {1,3,7,15,63,255,1023,8191} for 16..23 and {15,31,63,127,255,511,2047,8191} for 24..31 (Tables.js ht[]) */
+  const int v = mx - 15;
+  const int choice2 = 24 + (v > 15) + (v > 31) + (v > 63) + (v > 127) + (v > 255) + (v > 511) + (v > 2047);
+  const int choice = max(choice2 - 8, 16 + (v > 1) + (v > 3) + (v > 7) + (v > 15) + (v > 63) + (v > 255) + (v > 1023));
   const unsigned linbits = (unsigned)c_huff_xlen[choice] * 65536u + (unsigned)c_huff_xlen[choice2];
   unsigned s = 0;
-#pragma unroll 3
+Q_UNROLL(Q_RT_UNROLL)
   for (int p = p0; p < p1; p += 32) {
     const unsigned w = w32[p];
     unsigned x = w & 0xffffu, y = w >> 16;
@@ -213,7 +241,7 @@ __device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short
   if (i0 > 576) i0 = 576;
   /* count1 = end of the last non-zero pair below i0 */
   int top = 0;
-#pragma unroll 3
+Q_UNROLL(Q_RT_UNROLL)
   for (int p = lane; p < (i0 >> 1); p += 32) if (w32[p] != 0) top = 2 * p + 2;
   const int count1 = wmax(top);
   /* quadruples of |x| <= 1 counted down from count1 (values are >= 0: "<= 1" == no bit above bit 0 in either half) */
@@ -277,8 +305,11 @@ __device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short
     gi->region0_count = r0; gi->region1_count = r1;
     gi->table_select[0] = ts0; gi->table_select[1] = ts1; gi->table_select[2] = ts2;
     if (use_prev) {
-      int sc = 0;
-      if (bigv != 0 && gi->block_type == BT_NORM) { while (T->sfb_l[sc] < bigv) sc++; }
+      int sc = 0;                                  /* first band edge at or above big_values */
+      if (bigv != 0 && gi->block_type == BT_NORM) {
+        if (bigv >= 576) sc = 22;
+        else { sc = T->geo[0].sfb_of_line[bigv]; if (T->sfb_l[sc] != bigv) sc++; }
+      }
       wk->pn_sfb_count1 = sc;
     }
   }
@@ -286,9 +317,12 @@ __device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short
   return bits;
 }
 
+/* pretab[sfb] (0 beyond band 20) from a packed literal: each lane asks for a different band */
+__device__ __forceinline__ int pretab_of(int sfb) { return sfb < 22 ? (int)((0x2fe95400000ull >> (2 * sfb)) & 3ull) : 0; }
+
 /* step of scalefactor band sfb (Takehiro.js:205-209 / QuantizePVT.js:744-747) */
 __device__ __forceinline__ int sfb_step(const GranuleInfoDev* gi, const GcWork* wk, int sfb) {
-  return gi->global_gain - ((gi->scalefac[sfb] + (gi->preflag != 0 ? c_pretab[sfb < 22 ? sfb : 21] : 0)) << (gi->scalefac_scale + 1)) -
+  return gi->global_gain - ((gi->scalefac[sfb] + (gi->preflag != 0 ? pretab_of(sfb) : 0)) << (gi->scalefac_scale + 1)) -
          gi->subblock_gain[wk->geo->window[sfb]] * 8;
 }
 
@@ -304,7 +338,7 @@ __device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, Granule
      * walk of quantize_xrpow reduces to: full quantizer below the truncation point, zeros from max_nonzero_coeff on.
      * Band starts are even, hence the quantised range ends at (mnz + 1) & ~1 (an odd tail length drops its last line). */
     const int qend = (mnz + 1) & ~1;
-#pragma unroll 3
+Q_UNROLL(Q_CB_UNROLL)
     for (int i = lane; i < 576; i += 32) {
       short v = 0;
       if (i < qend) {
@@ -352,7 +386,7 @@ __device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, Granule
   }
   __syncwarp();
   const double compare01 = (1.0 - 0.4054) / istep;
-#pragma unroll 3
+Q_UNROLL(Q_CB_UNROLL)
   for (int i = lane; i < 576; i += 32) {
     if (i >= zero_from) { ix[i] = 0; continue; }
     const int md = wk->mode[wk->geo->sfb_of_line[i]];
@@ -375,19 +409,33 @@ struct NoiseRes { int over_count; double over_SSD, max_noise; int bits; };
 __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const GranuleInfoDev* gi, const short* ix, NoiseRes* res) {
   const int lane = LANE;
   const int psymax = gi->psymax, mnz = gi->max_nonzero_coeff;
-  /* line cursor j is sequential (bands after the truncation point start where the previous one stopped) */
-  if (lane == 0) {
-    int j = 0;
+  /* Line cursor: a band starts where the previous one stopped.  Cached bands and bands that end at or below
+   * max_nonzero_coeff advance by their full (even) width, so up to the first non-cached band that crosses the truncation
+   * point every band starts at its nominal offset; from there on the walk is sequential (lane 0, usually 1-2 bands). */
+  int first_trunc = psymax;
 #pragma unroll 1
-    for (int sfb = 0; sfb < psymax; sfb++) {
-      const int s = sfb_step(gi, wk, sfb);
-      if (wk->pn_step[sfb] == s) { wk->nlen[sfb] = -1; j += wk->geo->width[sfb]; }
-      else {
-        int l = wk->geo->width[sfb] >> 1;
-        if ((j + wk->geo->width[sfb]) > mnz) { const int us = mnz - j + 1; l = us > 0 ? us >> 1 : 0; }
-        wk->nstart[sfb] = j; wk->nlen[sfb] = l;
-        j += 2 * l;
-      }
+  for (int s0 = 0; s0 < psymax; s0 += 32) {
+    const int sfb = s0 + lane;
+    int crosses = 0;
+    if (sfb < psymax) {
+      const int j = wk->geo->start[sfb], w = wk->geo->width[sfb];
+      if (wk->pn_step[sfb] == sfb_step(gi, wk, sfb)) wk->nlen[sfb] = -1;
+      else { wk->nstart[sfb] = (short)j; wk->nlen[sfb] = (short)(w >> 1); crosses = (j + w) > mnz; }
+    }
+    const unsigned m = __ballot_sync(Q_FULL, crosses);
+    if (m && first_trunc == psymax) first_trunc = s0 + __ffs(m) - 1;
+  }
+  __syncwarp();
+  if (lane == 0 && first_trunc < psymax) {
+    int j = wk->geo->start[first_trunc];
+#pragma unroll 1
+    for (int sfb = first_trunc; sfb < psymax; sfb++) {
+      const int w = wk->geo->width[sfb];
+      if (wk->nlen[sfb] < 0) { j += w; continue; }
+      int l = w >> 1;
+      if ((j + w) > mnz) { const int us = mnz - j + 1; l = us > 0 ? us >> 1 : 0; }
+      wk->nstart[sfb] = (short)j; wk->nlen[sfb] = (short)l;
+      j += 2 * l;
     }
   }
   __syncwarp();
@@ -441,44 +489,47 @@ __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const 
   res->over_count = over; res->over_SSD = ssd; res->max_noise = mxn;
 }
 
-/* scale_bitcount (Takehiro.js:980-1030), lane 0 only; returns true when no legal scalefac_compress exists */
-__device__ __noinline__ bool scale_bitcount_l0(GranuleInfoDev* gi) {
-  int k, sfb, max_slen1 = 0, max_slen2 = 0;
-  const int* tab;
+/* scale_bitcount (Takehiro.js:980-1030), MPEG-1, all lanes; returns true when no legal scalefac_compress exists */
+__device__ __noinline__ bool scale_bitcount_w(GranuleInfoDev* gi) {
+  const int lane = LANE;
   int* scalefac = gi->scalefac;
-  if (gi->block_type == BT_SHORT) tab = c_scale_short;
-  else {
-    tab = c_scale_long;
-    if (0 == gi->preflag) {
-#pragma unroll 1
-      for (sfb = 11; sfb < 21; sfb++) if (scalefac[sfb] < c_pretab[sfb]) break;
-      if (sfb == 21) {
-        gi->preflag = 1;
-#pragma unroll 1
-        for (sfb = 11; sfb < 21; sfb++) scalefac[sfb] -= c_pretab[sfb];
-      }
+  const bool is_short = gi->block_type == BT_SHORT;
+  const int sfbmax = gi->sfbmax, sfbdivide = gi->sfbdivide;
+  __syncwarp();
+  if (!is_short && 0 == gi->preflag) {
+    const bool in = lane >= 11 && lane < 21;
+    const int pt = pretab_of(lane);
+    const bool ok = !in || scalefac[lane] >= pt;
+    if (__all_sync(Q_FULL, ok)) {
+      if (in) scalefac[lane] -= pt;
+      if (lane == 0) gi->preflag = 1;
+      __syncwarp();
     }
   }
+  int m1 = 0, m2 = 0;
 #pragma unroll 1
-  for (sfb = 0; sfb < gi->sfbdivide; sfb++) if (max_slen1 < scalefac[sfb]) max_slen1 = scalefac[sfb];
-#pragma unroll 1
-  for (; sfb < gi->sfbmax; sfb++) if (max_slen2 < scalefac[sfb]) max_slen2 = scalefac[sfb];
-  gi->part2_length = Q_LARGE_BITS;
-#pragma unroll 1
-  for (k = 0; k < 16; k++) {
-    if (max_slen1 < c_slen1_n[k] && max_slen2 < c_slen2_n[k] && gi->part2_length > tab[k]) {
-      gi->part2_length = tab[k];
-      gi->scalefac_compress = k;
-    }
+  for (int sfb = lane; sfb < sfbmax; sfb += 32) {
+    const int v = scalefac[sfb];
+    if (sfb < sfbdivide) m1 = max(m1, v); else m2 = max(m2, v);
   }
-  return gi->part2_length == Q_LARGE_BITS;
+  m1 = wmax(m1); m2 = wmax(m2);
+  /* first k with the smallest table value among the legal ones: min over (value, k) */
+  int key = Q_LARGE_BITS * 16 + 15;
+  if (lane < 16 && m1 < __ldg(&g_slen_n[0][lane]) && m2 < __ldg(&g_slen_n[1][lane])) key = __ldg(&g_scale_tab[is_short ? 1 : 0][lane]) * 16 + lane;
+  key = __reduce_min_sync(Q_FULL, key);
+  const int p2 = key >> 4;
+  if (lane == 0) { gi->part2_length = p2; if (p2 != Q_LARGE_BITS) gi->scalefac_compress = key & 15; }
+  __syncwarp();
+  return p2 == Q_LARGE_BITS;
 }
 
-__device__ __noinline__ bool loop_break_l0(const GranuleInfoDev* gi, const GcWork* wk) {
+/* loop_break (Quantize.js:584-594): true when every band is amplified */
+__device__ __forceinline__ bool loop_break_w(const GranuleInfoDev* gi, const GcWork* wk) {
+  bool nz = true;
 #pragma unroll 1
-  for (int sfb = 0; sfb < gi->sfbmax; sfb++)
-    if (gi->scalefac[sfb] + gi->subblock_gain[wk->geo->window[sfb]] == 0) return false;
-  return true;
+  for (int sfb = LANE; sfb < gi->sfbmax; sfb += 32)
+    if (gi->scalefac[sfb] + gi->subblock_gain[wk->geo->window[sfb]] == 0) nz = false;
+  return __all_sync(Q_FULL, nz);
 }
 
 /* multiply xrpow of the bands flagged in wk->mode[] by `factor[band]` (amp_scalefac_bands / inc_scalefac_scale
@@ -507,14 +558,16 @@ __device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
   GranuleInfoDev* gi = &wk->w;
   /* ---- amp_scalefac_bands, noise_shaping_amp == 1 (Quantize.js:597-660) ---- */
   const double ifq = gi->scalefac_scale == 0 ? 1.29683955465100964055 : 1.68179283050742922612;
-  if (lane == 0) {
+  {
+    const int sfbmax = gi->sfbmax;
     double trigger = 0;
 #pragma unroll 1
-    for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (trigger < (double)wk->distort[sfb]) trigger = (double)wk->distort[sfb];
+    for (int sfb = lane; sfb < sfbmax; sfb += 32) if (trigger < (double)wk->distort[sfb]) trigger = (double)wk->distort[sfb];
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(Q_FULL, trigger, o); if (trigger < t) trigger = t; }
     if (trigger > 1.0) trigger = sqrt(trigger);     /* Math.pow(trigger, .5): fdlibm returns sqrt(x) for y == 0.5 */
     else trigger *= .95;
 #pragma unroll 1
-    for (int sfb = 0; sfb < gi->sfbmax; sfb++) {
+    for (int sfb = lane; sfb < sfbmax; sfb += 32) {
       const int amp = !((double)wk->distort[sfb] < trigger);
       wk->mode[sfb] = (unsigned char)amp;
       if (amp) gi->scalefac[sfb]++;
@@ -524,20 +577,9 @@ __device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
   scale_xrpow_w(wk, gi, ifq);
   /* ---- rest of balance_noise ---- */
   int* flag = &wk->scratch[0];
-  if (lane == 0) {
-    int ret;
-    bool status = loop_break_l0(gi, wk);
-    if (status) ret = 0;                         /* all bands amplified */
-    else {
-      status = scale_bitcount_l0(gi);
-      if (!status) ret = 1;
-      else ret = 2;                              /* scalefactors too large: try scalefac_scale / subblock_gain */
-    }
-    *flag = ret;
-  }
-  __syncwarp();
-  int r = *flag;
-  __syncwarp();
+  int r;
+  if (loop_break_w(gi, wk)) r = 0;                 /* all bands amplified */
+  else r = scale_bitcount_w(gi) ? 2 : 1;           /* 2: scalefactors too large, try scalefac_scale / subblock_gain */
   if (r == 0) return false;
   if (r == 1) return true;
   bool status = true;
@@ -546,18 +588,19 @@ __device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
   if (T->noise_shaping > 1) {
     if (0 == scale_now) {
       /* inc_scalefac_scale (Quantize.js:676-699) */
-      if (lane == 0) {
+      {
+        const int sfbmax = gi->sfbmax, pre = gi->preflag;
 #pragma unroll 1
-        for (int sfb = 0; sfb < gi->sfbmax; sfb++) {
+        for (int sfb = lane; sfb < sfbmax; sfb += 32) {
           int s = gi->scalefac[sfb];
-          if (gi->preflag != 0) s += c_pretab[sfb < 22 ? sfb : 21];
+          if (pre != 0) s += pretab_of(sfb);
           const int odd = (s & 1) != 0;
           if (odd) s++;
           wk->mode[sfb] = (unsigned char)odd;
           gi->scalefac[sfb] = s >> 1;
         }
-        gi->preflag = 0;
-        gi->scalefac_scale = 1;
+        __syncwarp();
+        if (lane == 0) { gi->preflag = 0; gi->scalefac_scale = 1; }
       }
       __syncwarp();
       scale_xrpow_w(wk, gi, 1.29683955465100964055);
@@ -610,18 +653,14 @@ __device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
         if (lane == 0 && (double)mx > gi->xrpow_max) gi->xrpow_max = (double)mx;
         __syncwarp();
       }
-      if (lane == 0) *flag = (*flag || loop_break_l0(gi, wk)) ? 1 : 0;
-      __syncwarp();
-      status = *flag != 0;
-      __syncwarp();
+      {
+        const int bailed = *flag;
+        __syncwarp();
+        status = bailed != 0 || loop_break_w(gi, wk);
+      }
     }
   }
-  if (!status) {
-    if (lane == 0) *flag = scale_bitcount_l0(gi) ? 1 : 0;
-    __syncwarp();
-    status = *flag != 0;
-    __syncwarp();
-  }
+  if (!status) status = scale_bitcount_w(gi);
   return !status;
 }
 
@@ -795,7 +834,7 @@ __device__ __noinline__ double ath_adjust_dev(double a, double x, double athFloo
 /* init_outer_loop + psfb21_analogsilence + init_xrpow + calc_xmin for one gc (Quantize.js:204-306,147-202,105-138;
  * QuantizePVT.js:569-719).  Returns false when the granule is digital silence (all l3_enc = 0). */
 __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameShared* fs, const float* __restrict__ xr_g, int block_type,
-                             const PsyRatioDev* __restrict__ ratio, double ath_adjust) {
+                             const PsyRatioDev* __restrict__ ratio, double ath_adjust, bool need_xmin) {
   const int lane = LANE;
   GranuleInfoDev* gi = &wk->b;
   const bool is_short = block_type == BT_SHORT;
@@ -892,7 +931,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
   /* ---- calc_xmin ---- */
   const double masking_lower = is_short ? T->masking_lower_short : T->masking_lower_long;
   if (!is_short) {
-    if (lane < 21) {
+    if (need_xmin && lane < 21) {
       const int gsfb = lane;
       int j = T->sfb_l[gsfb];
       const int width = wk->geo->width[gsfb];
@@ -921,7 +960,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
     if (lane == 0) gi->max_nonzero_coeff = mnz;
   } else {
 #pragma unroll 1
-    for (int t = lane; t < 36; t += 32) {
+    for (int t = lane; need_xmin && t < 36; t += 32) {
       const int sfb = t / 3, b = t - 3 * sfb;
       const int width = wk->geo->width[t];
       int j = 3 * T->sfb_s[sfb] + b * width;
@@ -942,7 +981,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
       wk->xmin[t] = o.v;
     }
     __syncwarp();
-    if (lane < 12) {   /* temporal smoothing across the three windows (useTemporal, QuantizePVT.js:707-714) */
+    if (need_xmin && lane < 12) {   /* temporal smoothing across the three windows (useTemporal, QuantizePVT.js:707-714) */
       f32s* p = reinterpret_cast<f32s*>(&wk->xmin[3 * lane]);
       if ((double)p[0] > (double)p[1]) p[1] += ((double)p[0] - (double)p[1]) * T->decay;
       if ((double)p[1] > (double)p[2]) p[2] += ((double)p[1] - (double)p[2]) * T->decay;
@@ -1037,9 +1076,12 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
     }
 #pragma unroll 1
     for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] == -2) gi->scalefac[sfb] = 0;
-    if (recalc != 0) scale_bitcount_l0(gi);
+    wk->scratch[0] = recalc;
   }
   __syncwarp();
+  const int recalc = wk->scratch[0];
+  __syncwarp();
+  if (recalc != 0) scale_bitcount_w(gi);
 }
 
 /* best_huffman_divide (Takehiro.js:727-800) on cod_info (wk->b / ixb); wk->w is free to use as cod_info2 */
@@ -1330,7 +1372,7 @@ __device__ __noinline__ void granule_budget(FrameShared* fs, int nch, int mean_b
 
 /* ---- the frame kernel ------------------------------------------------------------------------------------ */
 /* grid-stride over a work list of frame rows.  block = 32 * nch threads. */
-__global__ void __launch_bounds__(64, 14)
+__global__ void __launch_bounds__(64, Q_MIN_BLOCKS)
 k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, const float* __restrict__ xr,
                 const PsyRatioDev* __restrict__ ratio, const signed char* __restrict__ bt_final,
                 const double* __restrict__ ath_q, QuantFrameState* __restrict__ qs, GranuleInfoDev* __restrict__ ginfo_out,
@@ -1384,7 +1426,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       const size_t urow0 = (size_t)sd.unit_base + 2 * f;
       int ov = old_value, cs = current_step;
       const bool have0 = gc_prepare_w(T, wk, fs, xr + (urow0 * nch + ch) * 576, bt_final[urow0 * 2 + ch],
-                                      ratio + ((size_t)sd.unit_base + z + 2 * f) * nch + ch, ath_adjust);
+                                      ratio + ((size_t)sd.unit_base + z + 2 * f) * nch + ch, ath_adjust, false);
       unsigned long long h0 = 0;
       if (have0) { bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs); h0 = gi_hash(&wk->b); }
       if (lane == 0) {
@@ -1398,7 +1440,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
         if (threadIdx.x == 0) { fs->flag = 0; granule_budget(fs, nch, mean_bits, 1, q->used0[0], q->used0[1]); }
         __syncthreads();
         const bool have1 = gc_prepare_w(T, wk, fs, xr + ((urow0 + 1) * nch + ch) * 576, bt_final[(urow0 + 1) * 2 + ch],
-                                        ratio + ((size_t)sd.unit_base + z + 2 * f + 1) * nch + ch, ath_adjust);
+                                        ratio + ((size_t)sd.unit_base + z + 2 * f + 1) * nch + ch, ath_adjust, false);
         const int step0 = cs;
         if (have1) {
           bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs);
@@ -1424,7 +1466,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       /* masking of psy unit (2f+gr-1): halo-shifted row = unit_base + z + (2f+gr-1) + 1 */
       const PsyRatioDev* rt = ratio + ((size_t)sd.unit_base + z + 2 * f + gr) * nch + ch;
       if (lane == 0) wk->ixg = l3enc_out + (urow * nch + ch) * 576;
-      const bool have = gc_prepare_w(T, wk, fs, xr + (urow * nch + ch) * 576, bt, rt, ath_adjust);
+      const bool have = gc_prepare_w(T, wk, fs, xr + (urow * nch + ch) * 576, bt, rt, ath_adjust, true);
       unsigned long long bsh = 0;
       if (have) outer_loop_w(T, wk, fs->targ_bits[ch], &old_value, &current_step, &bsh);
       if (lane == 0) q->bs_hash[gr][ch] = bsh;

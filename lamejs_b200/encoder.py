@@ -18,9 +18,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path):
-        _build.build()
+    path = os.environ.get("MP3B200_LIB")          # tuning experiments: a variant built by tools/build_variants.py
+    if not path:
+        path = _build.LIB
+        if not os.path.exists(path):
+            _build.build()
     L = ctypes.CDLL(path)
     c_int, c_i64, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
     L.mp3b200_last_error.restype = ctypes.c_char_p
