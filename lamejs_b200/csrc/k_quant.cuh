@@ -65,7 +65,13 @@ __constant__ int c_slen1_n[16];
 __constant__ int c_slen2_n[16];
 __device__ int g_slen_n[2][16];                  /* slen1_n / slen2_n, read with one index per lane */
 __device__ int g_scale_tab[2][16];               /* scale_long / scale_short */
-__device__ unsigned int g_table3[3][256];        /* lengths of tables (7,8,9) / (10,11,12) / (13,14,15) packed 11:11:10 */
+/* Code lengths of a pair (x, y), both clamped to 15, at index x * 16 + y, for the table family of each "largest
+ * value" class -- three candidate tables packed 11:11:10 (a | b << 11 | c << 22; families with fewer tables repeat
+ * the last one, which never wins a strict comparison):
+ *   0: max 1 -> table 1          1: max 2 -> 2, 3        2: max 3 -> 5, 6       3: max 4-5 -> 7, 8, 9
+ *   4: max 6-7 -> 10, 11, 12     5: max 8-15 -> 13, 14, 15                      6: escape tables 16.. / 24.. (largetbl)
+ *   7: all zero (region without non-zero lines) */
+__device__ unsigned int g_cat_tab[8][256];
 __constant__ int c_slen1_tab[16];
 __constant__ int c_slen2_tab[16];
 __constant__ int c_scale_short[16];
@@ -91,19 +97,27 @@ static int quant_upload_constants() {
   UP(c_slen1_tab, s1t); UP(c_slen2_tab, s2t); UP(c_scale_short, ss); UP(c_scale_long, sl); UP(c_huf_noesc, hn);
   {
     static int sn[2][16], st[2][16];
-    static unsigned int t3[3][256];
+    static unsigned int ct[8][256];
     for (int k = 0; k < 16; k++) { sn[0][k] = s1n[k]; sn[1][k] = s2n[k]; st[0][k] = sl[k]; st[1][k] = ss[k]; }
-    for (int c = 0; c < 3; c++) {
-      const int t1 = 7 + 3 * c, xl = MP3_HUFF_XLEN[t1];
-      for (int q = 0; q < 256; q++) {
-        unsigned int v = 0;
-        if (q < xl * xl)
-          v = (unsigned)MP3_HUFF_LEN[MP3_HUFF_OFF[t1] + q] | ((unsigned)MP3_HUFF_LEN[MP3_HUFF_OFF[t1 + 1] + q] << 11) |
-              ((unsigned)MP3_HUFF_LEN[MP3_HUFF_OFF[t1 + 2] + q] << 22);
-        t3[c][q] = v;
+    static const int fam[6] = {1, 2, 5, 7, 10, 13};
+    for (int x = 0; x < 16; x++) for (int y = 0; y < 16; y++) {
+      const int q = x * 16 + y;
+      for (int c = 0; c < 6; c++) {
+        const int t1 = fam[c], xl = MP3_HUFF_XLEN[t1];
+        unsigned a = 0, b = 0, d = 0;
+        if (x < xl && y < xl) {
+          const int i = x * xl + y;
+          if (c == 0) a = b = d = MP3_HUFF_LEN[MP3_HUFF_OFF[1] + i];
+          else if (c == 1) { a = MP3_HUFF_TABLE23[i] >> 16; b = d = MP3_HUFF_TABLE23[i] & 0xffff; }       /* count_bit_noESC_from2 */
+          else if (c == 2) { a = MP3_HUFF_TABLE56[i] >> 16; b = d = MP3_HUFF_TABLE56[i] & 0xffff; }
+          else { a = MP3_HUFF_LEN[MP3_HUFF_OFF[t1] + i]; b = MP3_HUFF_LEN[MP3_HUFF_OFF[t1 + 1] + i]; d = MP3_HUFF_LEN[MP3_HUFF_OFF[t1 + 2] + i]; }
+        }
+        ct[c][q] = a | (b << 11) | (d << 22);
       }
+      { const unsigned a = MP3_HUFF_LARGETBL[q] >> 16, b = MP3_HUFF_LARGETBL[q] & 0xffff; ct[6][q] = a | (b << 11) | (b << 22); }
+      ct[7][q] = 0;
     }
-    UP(g_slen_n, sn); UP(g_scale_tab, st); UP(g_table3, t3);
+    UP(g_slen_n, sn); UP(g_scale_tab, st); UP(g_cat_tab, ct);
   }
 #undef UP
   return 0;
@@ -149,6 +163,9 @@ struct FrameShared {
 #ifndef Q_CB_UNROLL
 #define Q_CB_UNROLL 1
 #endif
+#ifndef Q_HELPER
+#define Q_HELPER __forceinline__
+#endif
 #ifndef Q_MIN_BLOCKS
 #define Q_MIN_BLOCKS 14
 #endif
@@ -160,8 +177,50 @@ __device__ __forceinline__ int wsum(int v) { return __reduce_add_sync(Q_FULL, v)
 __device__ __forceinline__ unsigned wsumu(unsigned v) { return __reduce_add_sync(Q_FULL, v); }
 __device__ __forceinline__ int hlen(int t, int i) { return __ldg(&g_huff_len[c_huff_off[t] + i]); }
 
-/* Huffman bits of the pairs [begin, end) (even bounds) -- choose_table (Takehiro.js:465-516) with its count_bit_*
- * callees, as one max pass and one sum pass; a pair is one 32-bit shared-memory word (x | y << 16). */
+/* ---- choose_table (Takehiro.js:465-516) with its count_bit_* callees, table-driven ------------------------------
+ * A region is classified by its largest value (RegionClass); one pass then adds, for every pair, the packed code
+ * lengths of the class's candidate tables (g_cat_tab) -- the same loop for every class, so a warp can sum several
+ * regions of different classes in one sweep.  A pair is one 32-bit shared-memory word (x | y << 16). */
+struct RegionClass { int cat; unsigned lin; int t1, t2; };   /* lin: linbits of (t1, t2, t2) packed like the table */
+__device__ Q_HELPER RegionClass region_class(int mx) {
+  RegionClass rc;
+  rc.lin = 0; rc.t2 = 0;
+  if (mx == 0) { rc.cat = 7; rc.t1 = 0; }
+  else if (mx <= 15) {
+    rc.t1 = c_huf_noesc[mx - 1];
+    rc.cat = mx <= 3 ? mx - 1 : (mx <= 5 ? 3 : (mx <= 7 ? 4 : 5));
+  } else {
+    /* first table of 24..31, then first of (t2 - 8)..23, whose linmax covers mx - 15: linmax is
+     * {1,3,7,15,63,255,1023,8191} for 16..23 and {15,31,63,127,255,511,2047,8191} for 24..31 (Tables.js ht[]) */
+    const int v = mx - 15;
+    rc.t2 = 24 + (v > 15) + (v > 31) + (v > 63) + (v > 127) + (v > 255) + (v > 511) + (v > 2047);
+    rc.t1 = max(rc.t2 - 8, 16 + (v > 1) + (v > 3) + (v > 7) + (v > 15) + (v > 63) + (v > 255) + (v > 1023));
+    const unsigned la = (unsigned)c_huff_xlen[rc.t1], lb = (unsigned)c_huff_xlen[rc.t2];
+    rc.lin = la | (lb << 11) | (lb << 22);
+    rc.cat = 6;
+  }
+  return rc;
+}
+/* packed lengths of one pair under class (cat, lin) */
+__device__ __forceinline__ unsigned pair_bits(unsigned w, int cat, unsigned lin) {
+  const unsigned x = w & 0xffffu, y = w >> 16;
+  const unsigned xe = min(x, 15u), ye = min(y, 15u);
+  return __ldg(&g_cat_tab[cat][xe * 16 + ye]) + ((x > 14u) + (y > 14u)) * lin;
+}
+/* table and bits of a region from the warp totals (a, b, c) of its three packed sums */
+__device__ Q_HELPER int region_pick(int mx, const RegionClass& rc, int a, int b, int c, int* bits) {
+  if (mx > Q_IXMAX) { *bits = Q_LARGE_BITS; return -1; }
+  if (mx == 0) return 0;
+  int t = rc.t1;
+  if (mx <= 15) {
+    if (a > b) { a = b; t++; }
+    if (a > c) { a = c; t = rc.t1 + 2; }
+  } else if (a > b) { a = b; t = rc.t2; }
+  *bits += a;
+  return t;
+}
+
+/* Huffman table and bits of the pairs [begin, end) (even bounds) */
 __device__ __noinline__ int region_table_w(const short* ix, int begin, int end, int* bits) {
   const int lane = LANE;
   const unsigned* w32 = reinterpret_cast<const unsigned*>(ix);
@@ -171,66 +230,14 @@ Q_UNROLL(Q_RT_UNROLL)
   for (int p = p0; p < p1; p += 32) m = __vmaxu2(m, w32[p]);        /* both 16-bit halves at once */
   const int mx = (int)__reduce_max_sync(Q_FULL, max(m & 0xffffu, m >> 16));
   if (mx == 0) return 0;
-  if (mx == 1) {
-    int s = 0;
+  const RegionClass rc = region_class(mx);
+  unsigned s = 0;                                  /* a lane adds <= 9 pairs x <= 45 bits per field */
 Q_UNROLL(Q_RT_UNROLL)
-    for (int p = p0; p < p1; p += 32) { const unsigned w = w32[p]; s += hlen(1, (int)((w & 0xffffu) * 2 + (w >> 16))); }
-    *bits += wsum(s);
-    return 1;
-  }
-  if (mx <= 3) {
-    int t1 = c_huf_noesc[mx - 1];
-    const unsigned xlen = (unsigned)c_huff_xlen[t1];
-    const unsigned* tab = (t1 == 2) ? g_table23 : g_table56;
-    unsigned s = 0;
-Q_UNROLL(Q_RT_UNROLL)
-    for (int p = p0; p < p1; p += 32) { const unsigned w = w32[p]; s += __ldg(&tab[(w & 0xffffu) * xlen + (w >> 16)]); }
-    s = wsumu(s);
-    int sum2 = (int)(s & 0xffff), sum = (int)(s >> 16);
-    if (sum > sum2) { sum = sum2; t1++; }
-    *bits += sum;
-    return t1;
-  }
-  if (mx <= 15) {
-    const int t1 = c_huf_noesc[mx - 1];
-    const unsigned xlen = (unsigned)c_huff_xlen[t1];
-    const unsigned int* h = g_table3[(t1 - 7) / 3];
-    unsigned s = 0;                                   /* three sums packed 11:11:10: a lane adds <= 9 pairs x <= 19 bits */
-Q_UNROLL(Q_RT_UNROLL)
-    for (int p = p0; p < p1; p += 32) {
-      const unsigned w = w32[p];
-      s += __ldg(&h[(w & 0xffffu) * xlen + (w >> 16)]);
-    }
-    /* the warp total (<= 288 x 19 = 5472) needs 13 bits: reduce the fields separately */
-    int s1 = wsum((int)(s & 0x7ff)), s2 = wsum((int)((s >> 11) & 0x7ff)), s3 = wsum((int)(s >> 22));
-    int t = t1;
-    if (s1 > s2) { s1 = s2; t++; }
-    if (s1 > s3) { s1 = s3; t = t1 + 2; }
-    *bits += s1;
-    return t;
-  }
-  if (mx > Q_IXMAX) { *bits = Q_LARGE_BITS; return -1; }
-  /* first table of 24..31, then first of (choice2 - 8)..23, whose linmax covers mx - 15: linmax is
-   * {1,3,7,15,63,255,1023,8191} for 16..23 and {15,31,63,127,255,511,2047,8191} for 24..31 (Tables.js ht[]) */
-  const int v = mx - 15;
-  const int choice2 = 24 + (v > 15) + (v > 31) + (v > 63) + (v > 127) + (v > 255) + (v > 511) + (v > 2047);
-  const int choice = max(choice2 - 8, 16 + (v > 1) + (v > 3) + (v > 7) + (v > 15) + (v > 63) + (v > 255) + (v > 1023));
-  const unsigned linbits = (unsigned)c_huff_xlen[choice] * 65536u + (unsigned)c_huff_xlen[choice2];
-  unsigned s = 0;
-Q_UNROLL(Q_RT_UNROLL)
-  for (int p = p0; p < p1; p += 32) {
-    const unsigned w = w32[p];
-    unsigned x = w & 0xffffu, y = w >> 16;
-    if (x > 14) { x = 15; s += linbits; }
-    if (y > 14) { y = 15; s += linbits; }
-    s += __ldg(&g_largetbl[x * 16 + y]);
-  }
-  s = wsumu(s);
-  int sum2 = (int)(s & 0xffff), sum = (int)(s >> 16);
-  int t1 = choice;
-  if (sum > sum2) { sum = sum2; t1 = choice2; }
-  *bits += sum;
-  return t1;
+  for (int p = p0; p < p1; p += 32) s += pair_bits(w32[p], rc.cat, rc.lin);
+  /* warp totals need up to 14 bits: reduce (a, b) as two 16-bit fields, c alone */
+  const unsigned ab = wsumu((s & 0x7ffu) | (((s >> 11) & 0x7ffu) << 16));
+  const int c = wsum((int)(s >> 22));
+  return region_pick(mx, rc, (int)(ab & 0xffffu), (int)(ab >> 16), c, bits);
 }
 
 /* noquant_count_bits (Takehiro.js:521-628).  gi scalars are updated by lane 0. */
@@ -280,22 +287,22 @@ Q_UNROLL(Q_RT_UNROLL)
     const int bt = gi->block_type;
     if (bt == BT_SHORT) {
       b1 = 3 * T->sfb_s[3];
-      if (b1 > bigv) b1 = bigv;
       b2 = bigv;
     } else if (bt == BT_NORM) {
       b1 = r0 = T->bv_scf[bigv - 2];
       b2 = r1 = T->bv_scf[bigv - 1];
       b2 = T->sfb_l[b1 + b2 + 2];
       b1 = T->sfb_l[b1 + 1];
-      if (b2 < bigv) ts2 = region_table_w(ix, b2, bigv, &bits);
     } else {
       r0 = 7; r1 = 22 - 1 - 7 - 1;
       b1 = T->sfb_l[7 + 1];
       b2 = bigv;
-      if (b1 > b2) b1 = b2;
     }
     b1 = min(b1, bigv);
     b2 = min(b2, bigv);
+    /* same order as the reference: region 2 (long blocks only), then 0, then 1; empty regions keep their table.
+     * One small routine called three times: the kernel is instruction-fetch bound, code reuse beats a fused sweep. */
+    if (bt == BT_NORM && b2 < bigv) ts2 = region_table_w(ix, b2, bigv, &bits);
     if (0 < b1) ts0 = region_table_w(ix, 0, b1, &bits);
     if (b1 < b2) ts1 = region_table_w(ix, b1, b2, &bits);
   }
@@ -330,7 +337,7 @@ __device__ __forceinline__ int sfb_step(const GranuleInfoDev* gi, const GcWork* 
 __device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, GranuleInfoDev* gi, short* ix, bool use_prev) {
   const int lane = LANE;
   const double istep = (double)T->ipow20[gi->global_gain];
-  if (gi->xrpow_max > (double)Q_IXMAX / istep) return Q_LARGE_BITS;
+  if (gi->xrpow_max > T->ixmax_over_istep[gi->global_gain]) return Q_LARGE_BITS;
   const int sfbmax = gi->block_type == BT_SHORT ? 38 : 21;
   const int mnz = gi->max_nonzero_coeff;
   if (!use_prev) {
@@ -385,7 +392,7 @@ Q_UNROLL(Q_CB_UNROLL)
     if (lane == 0) wk->mode[term] = 1;
   }
   __syncwarp();
-  const double compare01 = (1.0 - 0.4054) / istep;
+  const double compare01 = T->cmp01_over_istep[gi->global_gain];
 Q_UNROLL(Q_CB_UNROLL)
   for (int i = lane; i < 576; i += 32) {
     if (i >= zero_from) { ix[i] = 0; continue; }
@@ -439,23 +446,20 @@ __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const 
     }
   }
   __syncwarp();
-  int over = 0; double ssd = 0, mxn = -20.0;
+  int over = 0, ssd = 0; double mxn = -20.0;
 #pragma unroll 1
   for (int s0 = 0; s0 < psymax; s0 += 32) {
     const int sfb = s0 + lane;
     if (sfb < psymax) {
       const int s = sfb_step(gi, wk, sfb);
+      const bool cached = wk->nlen[sfb] < 0;
       double noise;
-      if (wk->nlen[sfb] < 0) {
-        noise = (double)wk->pn_noise[sfb];
-        f32s d; d = noise / (double)wk->xmin[sfb];
-        wk->distort[sfb] = d.v;
-        noise = (double)wk->pn_noise_log[sfb];
-      } else {
+      if (cached) noise = (double)wk->pn_noise[sfb];
+      else {
         const double step = (double)T->pow20[s + MP3_QMAX2];
         int j = wk->nstart[sfb];
         noise = 0;
-#pragma unroll 2
+#pragma unroll 1
         for (int l = wk->nlen[sfb]; l > 0; l--) {
           double temp;
           temp = fabs((double)wk->xr[j]) - (double)__ldg(&T->pow43[ix[j]]) * step; j++; noise += temp * temp;
@@ -463,30 +467,33 @@ __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const 
         }
         wk->pn_step[sfb] = s;
         { f32s t; t = noise; wk->pn_noise[sfb] = t.v; }
-        noise = noise / (double)wk->xmin[sfb];
-        { f32s t; t = noise; wk->distort[sfb] = t.v; }
+      }
+      noise = noise / (double)wk->xmin[sfb];       /* distort = noise / xmin from the cached or the fresh noise */
+      { f32s t; t = noise; wk->distort[sfb] = t.v; }
+      if (cached) noise = (double)wk->pn_noise_log[sfb];
+      else {
         noise = q_log10(js_dmax(noise, 1E-20));
         { f32s t; t = noise; wk->pn_noise_log[sfb] = t.v; }
       }
       if (noise > 0.0) {
         int tmp = js_trunc(noise * 10 + .5);
         if (tmp < 1) tmp = 1;
-        ssd += (double)tmp * (double)tmp;
+        ssd += tmp * tmp;
         over++;
       }
       mxn = js_dmax(mxn, noise);
     }
   }
-  /* integer-valued sums: order-free */
+  /* over_SSD is a sum of small squared integers (exact in a double in any order): integer warp sum */
+#pragma unroll 1
   for (int o = 16; o > 0; o >>= 1) {
-    ssd += __shfl_xor_sync(Q_FULL, ssd, o);
     const double other = __shfl_xor_sync(Q_FULL, mxn, o);
     mxn = js_dmax(mxn, other);
   }
   over = wsum(over);
   if (lane == 0) wk->pn_global_gain = gi->global_gain;
   __syncwarp();
-  res->over_count = over; res->over_SSD = ssd; res->max_noise = mxn;
+  res->over_count = over; res->over_SSD = (double)wsum(ssd); res->max_noise = mxn;
 }
 
 /* scale_bitcount (Takehiro.js:980-1030), MPEG-1, all lanes; returns true when no legal scalefac_compress exists */
@@ -552,36 +559,12 @@ __device__ __noinline__ void scale_xrpow_w(GcWork* wk, GranuleInfoDev* gi, doubl
   __syncwarp();
 }
 
-/* balance_noise (Quantize.js:783-846) on cod_info_w.  Returns true when a new scalefactor combination exists. */
-__device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
+/* second half of balance_noise: the scalefactors no longer fit -- switch to scalefac_scale 1 or raise a
+ * subblock_gain (rare; kept out of the hot function's instruction footprint) */
+__device__ __noinline__ bool balance_escalate_w(const Mp3Tables* T, GcWork* wk) {
   const int lane = LANE;
   GranuleInfoDev* gi = &wk->w;
-  /* ---- amp_scalefac_bands, noise_shaping_amp == 1 (Quantize.js:597-660) ---- */
-  const double ifq = gi->scalefac_scale == 0 ? 1.29683955465100964055 : 1.68179283050742922612;
-  {
-    const int sfbmax = gi->sfbmax;
-    double trigger = 0;
-#pragma unroll 1
-    for (int sfb = lane; sfb < sfbmax; sfb += 32) if (trigger < (double)wk->distort[sfb]) trigger = (double)wk->distort[sfb];
-    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(Q_FULL, trigger, o); if (trigger < t) trigger = t; }
-    if (trigger > 1.0) trigger = sqrt(trigger);     /* Math.pow(trigger, .5): fdlibm returns sqrt(x) for y == 0.5 */
-    else trigger *= .95;
-#pragma unroll 1
-    for (int sfb = lane; sfb < sfbmax; sfb += 32) {
-      const int amp = !((double)wk->distort[sfb] < trigger);
-      wk->mode[sfb] = (unsigned char)amp;
-      if (amp) gi->scalefac[sfb]++;
-    }
-  }
-  __syncwarp();
-  scale_xrpow_w(wk, gi, ifq);
-  /* ---- rest of balance_noise ---- */
   int* flag = &wk->scratch[0];
-  int r;
-  if (loop_break_w(gi, wk)) r = 0;                 /* all bands amplified */
-  else r = scale_bitcount_w(gi) ? 2 : 1;           /* 2: scalefactors too large, try scalefac_scale / subblock_gain */
-  if (r == 0) return false;
-  if (r == 1) return true;
   bool status = true;
   const int scale_now = gi->scalefac_scale, is_short_blk = gi->block_type == BT_SHORT;
   __syncwarp();                                    /* all lanes hold the decision inputs before lane 0 edits gi */
@@ -664,7 +647,40 @@ __device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
   return !status;
 }
 
-__device__ __forceinline__ void copy_gi_w(GranuleInfoDev* dst, const GranuleInfoDev* src) {
+
+/* balance_noise (Quantize.js:783-846) on cod_info_w.  Returns true when a new scalefactor combination exists. */
+__device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
+  const int lane = LANE;
+  GranuleInfoDev* gi = &wk->w;
+  /* ---- amp_scalefac_bands, noise_shaping_amp == 1 (Quantize.js:597-660) ---- */
+  const double ifq = gi->scalefac_scale == 0 ? 1.29683955465100964055 : 1.68179283050742922612;
+  {
+    const int sfbmax = gi->sfbmax;
+    double trigger = 0;
+#pragma unroll 1
+    for (int sfb = lane; sfb < sfbmax; sfb += 32) if (trigger < (double)wk->distort[sfb]) trigger = (double)wk->distort[sfb];
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(Q_FULL, trigger, o); if (trigger < t) trigger = t; }
+    if (trigger > 1.0) trigger = sqrt(trigger);     /* Math.pow(trigger, .5): fdlibm returns sqrt(x) for y == 0.5 */
+    else trigger *= .95;
+#pragma unroll 1
+    for (int sfb = lane; sfb < sfbmax; sfb += 32) {
+      const int amp = !((double)wk->distort[sfb] < trigger);
+      wk->mode[sfb] = (unsigned char)amp;
+      if (amp) gi->scalefac[sfb]++;
+    }
+  }
+  __syncwarp();
+  scale_xrpow_w(wk, gi, ifq);
+  /* ---- rest of balance_noise ---- */
+  int r;
+  if (loop_break_w(gi, wk)) r = 0;                 /* all bands amplified */
+  else r = scale_bitcount_w(gi) ? 2 : 1;           /* 2: scalefactors too large, try scalefac_scale / subblock_gain */
+  if (r == 0) return false;
+  if (r == 1) return true;
+  return balance_escalate_w(T, wk);
+}
+
+__device__ __noinline__ void copy_gi_w(GranuleInfoDev* dst, const GranuleInfoDev* src) {
   const int n = sizeof(GranuleInfoDev) / 4;
   const int* s = reinterpret_cast<const int*>(src);
   int* d = reinterpret_cast<int*>(dst);
@@ -673,7 +689,7 @@ __device__ __forceinline__ void copy_gi_w(GranuleInfoDev* dst, const GranuleInfo
   for (int i = LANE; i < n; i += 32) d[i] = s[i];
   __syncwarp();
 }
-__device__ __forceinline__ void copy_ix_w(short* dst, const short* src) {
+__device__ __noinline__ void copy_ix_w(short* dst, const short* src) {
   const int* s = reinterpret_cast<const int*>(src);
   int* d = reinterpret_cast<int*>(dst);
   __syncwarp();
@@ -1195,7 +1211,7 @@ __device__ __noinline__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* w
 }
 
 /* ---- bit packing (BitStream.js:110-138,428-689) --------------------------------------------------------- */
-__device__ __forceinline__ void put_bits(unsigned int* buf, int pos, unsigned int val, int n) {
+__device__ Q_HELPER void put_bits(unsigned int* buf, int pos, unsigned int val, int n) {
   if (n <= 0) return;
   val &= (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
   const int w = pos >> 5, off = pos & 31;

@@ -293,6 +293,11 @@ int mp3_build_tables(int channels, int samplerate, int kbps, Mp3Tables* t) {
     t->adj43[i] = (float)((i + 1) - m3_pow(0.5 * ((double)t->pow43[i] + (double)t->pow43[i + 1]), 0.75));
   t->adj43[MP3_PRECALC - 1] = 0.5f;
   for (int i = 0; i < MP3_QMAX; i++) t->ipow20[i] = (float)m3_pow(2.0, (i - 210) * -0.1875);
+  for (int i = 0; i < MP3_QMAX; i++) {
+    const double istep = (double)t->ipow20[i];
+    t->ixmax_over_istep[i] = 8206.0 / istep;
+    t->cmp01_over_istep[i] = (1.0 - 0.4054) / istep;
+  }
   for (int i = 0; i <= MP3_QMAX + MP3_QMAX2; i++) t->pow20[i] = (float)m3_pow(2.0, (i - 210 - MP3_QMAX2) * 0.25);
   for (int i = 0; i < MP3_SBMAX_L; i++) t->longfact[i] = (float)m3_pow(10, 0 / 4.0 / 10.0);   /* nspsytune bits 2.. are 0 */
   for (int i = 0; i < MP3_SBMAX_S; i++) t->shortfact[i] = (float)m3_pow(10, 0 / 4.0 / 10.0);

@@ -73,6 +73,9 @@ struct Mp3Tables {
   double tw[4 * 176];
   /* ---- quantizer ---- */
   float pow20[MP3_QMAX + MP3_QMAX2 + 1], ipow20[MP3_QMAX], pow43[MP3_PRECALC], adj43[MP3_PRECALC];
+  /* per global_gain: IXMAX_VAL / ipow20 (count_bits range check) and (1 - 0.4054) / ipow20 (0/1 quantizer threshold),
+   * the same IEEE double divisions the encoder would do per call (Takehiro.js:178,633) */
+  double ixmax_over_istep[MP3_QMAX], cmp01_over_istep[MP3_QMAX];
 };
 
 /* returns 0, or -1 when lamejs itself would fail / needs the resampler or the MPEG-2 path

@@ -21,8 +21,9 @@ struct f32s {
 };
 
 /* JS `0 | x` for finite |x| < 2^31 (all call sites on the hot path are range-checked by the reference:
- * count_bits rejects xrpow_max*istep > IXMAX_VAL before quantizing). NaN -> 0 like ToInt32. */
-__device__ __forceinline__ int js_trunc(double d) { return (d == d) ? (int)d : 0; }
+ * count_bits rejects xrpow_max*istep > IXMAX_VAL before quantizing). NaN -> 0 like ToInt32: that is what the
+ * hardware conversion (cvt.rzi.s32.f64) returns for NaN. */
+__device__ __forceinline__ int js_trunc(double d) { return __double2int_rz(d); }
 __device__ __forceinline__ double js_dmax(double a, double b) {   /* Math.max, no NaN/-0 inputs on our paths */
   return a > b ? a : b;
 }
