@@ -140,8 +140,12 @@ __device__ __forceinline__ int fht_tasks(int n, int stage) {
 __device__ __forceinline__ size_t psy_row(const StreamDesc& sd, int z, int u) { return (size_t)sd.unit_base + z + u + 1; }
 
 /* grid (max_units + 1, nch, nstreams) */
-__global__ void __launch_bounds__(PSY_THREADS)
-k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ out) {
+#ifndef PSY_MIN_BLOCKS
+#define PSY_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(PSY_THREADS, PSY_MIN_BLOCKS)
+k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ out,
+               float* __restrict__ fe_out) {
   const int z = blockIdx.z;
   const StreamDesc sd = streams[z];
   const int u = (int)blockIdx.x - 1;                 /* relative unit, -1 = halo */
@@ -169,6 +173,8 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   __shared__ f32s fes[3][129];
   __shared__ f32s s_max[MP3_CBANDS], s_avg[MP3_CBANDS];
   __shared__ f32s s_ebs[3][MP3_CBANDS];
+  __shared__ int s_peak[9];
+  if (tid < 9) s_peak[tid] = __float_as_int(1.0f);
 
   const int scale_applied = T->scale_applied;
   const double scale = T->scale;
@@ -230,13 +236,9 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   }
   __syncthreads();
 
-  /* 9 sub-block peaks of the high-passed signal (PsyModel.js:1125-1132) */
-  if (tid >= 224 && tid < 233) {
-    const int sbk = tid - 224;
-    double p = 1.;
-    for (int j = 0; j < 64; j++) { const double v = fabs((double)hp[sbk * 64 + j]); if (p < v) p = v; }
-    o->peaks[sbk] = (float)p;
-  }
+  /* 9 sub-block peaks of the high-passed signal (PsyModel.js:1125-1132): max(1, |hp|) over 64 samples each; the
+   * values are non-negative float32, whose order is the order of their bit patterns */
+  for (int i = tid; i < 576; i += PSY_THREADS) atomicMax(&s_peak[i >> 6], __float_as_int(fabsf(hp[i].v)));
   /* FHT stages: long transform (4 stages) and the three short ones (3 stages) share the loop */
   for (int stage = 0; stage < 4; stage++) {
     const int tl = fht_tasks(1024, stage);
@@ -280,12 +282,13 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
       o->eb_s[sb][b] = (float)ebb;
     }
   }
-  if (tid == PSY_THREADS - 1) {                      /* psycho_loudness_approx (PsyModel.js:241-249): ordered sum */
-    double lp = 0.0;
-    for (int i = 0; i < 512; ++i) lp += (double)fe[i] * (double)T->eql_w[i];
-    lp *= (1. / (14752. * 14752.) / 512);
-    o->loudness = (float)lp;
+  /* psycho_loudness_approx is one ordered 512-term sum: k_psy_loudness does it with a thread per unit instead of
+   * stalling this block on a single lane; hand it the line energies */
+  {
+    float* fg = fe_out + ((size_t)psy_row(sd, z, u) * nch + ch) * 512;
+    for (int j = tid; j < 512; j += PSY_THREADS) fg[j] = fe[j].v;
   }
+  if (tid < 9) o->peaks[tid] = __int_as_float(s_peak[tid]);
   __syncthreads();
 
   if (tid < npl) {                                   /* calc_mask_index_l (PsyModel.js:930-992) */
@@ -316,6 +319,26 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
       o->ecb_s[sb][b] = ecb;
     }
   }
+}
+
+/* psycho_loudness_approx (PsyModel.js:241-249): loudness = sum_i energy[i] * eql_w[i] (ordered, in double) scaled by
+ * 1 / (14752^2 * 512).  grid (ceil((max_units+1)/128), nch, nstreams), one thread per (unit, channel). */
+__global__ void __launch_bounds__(128)
+k_psy_loudness(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, const float* __restrict__ fe_in,
+               PsyUnit* __restrict__ out) {
+  const int z = blockIdx.z;
+  const StreamDesc& sd = streams[z];
+  const int u = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;
+  if (u >= 2 * sd.nframes) return;
+  if (2LL * sd.frame0 + u < 0) return;               /* psymodel_init row: loudness stays 0 */
+  const int ch = blockIdx.y, nch = T->nch;
+  const size_t row = psy_row(sd, z, u) * nch + ch;
+  const float* fe = fe_in + row * 512;
+  double lp = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < 512; ++i) lp += (double)fe[i] * (double)T->eql_w[i];
+  lp *= (1. / (14752. * 14752.) / 512);
+  out[row].loudness = (float)lp;
 }
 
 /* ---- attack candidates: needs peaks of unit u and u-1 (PsyModel.js:1105-1181) -------------------------- */

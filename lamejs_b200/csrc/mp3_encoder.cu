@@ -98,6 +98,7 @@ struct Workspace {
   signed char* d_bt_prev = nullptr;       /* [units][2] blocktype_old seen by the masking of this granule */
   float* d_xr = nullptr;                  /* [units][nch][576] */
   PsyUnit* d_psy = nullptr;               /* [units + nstreams][nch]  (one halo unit per stream in front) */
+  float* d_fe = nullptr;                  /* [units + nstreams][nch][512] long-FFT line energies (loudness input) */
   PsyRatioDev* d_ratio = nullptr;         /* [units + nstreams][nch]  masking of unit c (used by granule c+1) */
   double* d_ath_psy = nullptr;            /* [frames] ATH.adjust seen by the psy calls of the frame */
   double* d_ath_q = nullptr;              /* [frames] ATH.adjust after adjust_ATH (quantizer) */
@@ -111,7 +112,7 @@ struct Workspace {
   ScanChunk* d_scan = nullptr;            /* [frames / SCAN_FRAMES + nstreams] */
   ~Workspace() { release(); }
   void release() {
-    cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_psy);
+    cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_psy); cudaFree(d_fe); d_fe = nullptr;
     cudaFree(d_ratio); cudaFree(d_ath_psy); cudaFree(d_ath_q); cudaFree(d_qstate); cudaFree(d_ginfo);
     cudaFree(d_l3enc); cudaFree(d_framebits); d_framebits = nullptr; cudaFree(d_dirty); cudaFree(d_counter); cudaFree(d_scan); d_scan = nullptr;
     d_streams = nullptr; d_bt_final = d_bt_prev = nullptr; d_xr = nullptr; d_psy = nullptr; d_ratio = nullptr;
@@ -125,6 +126,7 @@ struct Workspace {
     CK(cudaMalloc(&d_bt_prev, (size_t)U * 2 + 16));
     CK(cudaMalloc(&d_xr, sizeof(float) * (size_t)U * nch * 576));
     CK(cudaMalloc(&d_psy, sizeof(PsyUnit) * (size_t)(U + S) * nch));
+    CK(cudaMalloc(&d_fe, sizeof(float) * 512 * (size_t)(U + S) * nch));
     CK(cudaMalloc(&d_ratio, sizeof(PsyRatioDev) * (size_t)(U + S) * nch));
     CK(cudaMalloc(&d_ath_psy, sizeof(double) * (size_t)(F + 1)));
     CK(cudaMalloc(&d_ath_q, sizeof(double) * (size_t)(F + 1)));
@@ -176,9 +178,13 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   /* K2: psy analysis, one block per (granule incl. 1 halo, channel, stream) */
   {
     dim3 grid(2 * max_frames + 1, nch, S);
-    k_psy_analysis<<<grid, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy);
+    k_psy_analysis<<<grid, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_fe);
     g_launches++;
     DBG("k_psy_analysis");
+    dim3 grid2((2 * max_frames + 1 + 127) / 128, nch, S);
+    k_psy_loudness<<<grid2, 128, 0, st>>>(cfg->dev, ws.d_streams, ws.d_fe, ws.d_psy);
+    g_launches++;
+    DBG("k_psy_loudness");
   }
   CK(cudaEventRecord(ev[1], st));
   /* K3a: attack pre-pass (parallel) + sequential per-stream scans */
