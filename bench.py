@@ -64,6 +64,33 @@ def cpu_reference_run(threads, streams_per_thread=1, frames=FRAMES):
     return audio_s / dt, dt
 
 
+def host_cores():
+    """Host threads this process can really use: the CPU affinity mask, capped by the cgroup CPU quota if there is one."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = max(1, min(n, int(quota / period + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
+def kernel_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_kernel_traffic.json)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))
+        return d["kernels"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.proc = index, [], set(), None
@@ -101,7 +128,7 @@ class ClockSampler:
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     frames = 2000   # bounded sample: cores x 2000 frames of the C2 sweep per step (~0.6 s of CPU work per core)
     for _ in range(args.warmup):
         cpu_reference_run(cores, 1, 500)
@@ -244,7 +271,8 @@ def main():
             k["gbps"] = units * k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else None
             k["frac"] = k["gbps"] / peak if k["gbps"] else None
         dom = max(kern, key=lambda k: kern[k]["ms"])
-        cpu_v, cpu_dt = cpu_reference_run(os.cpu_count() or 1, 1, 2000)
+        ncores = host_cores()
+        cpu_v, cpu_dt = cpu_reference_run(ncores, 1, 2000)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -256,10 +284,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": kern[dom]["frac"], "traffic": None,
+                         "frac": kern[dom]["frac"], "traffic": kernel_traffic(dom),
                          "note": "algorithmic bytes/launch = %d B x %d frame-channels; exact-double arithmetic keeps every kernel FP64/latency bound (DESIGN.md)" % (kern[dom]["bytes"], units)},
             "kernels": kern,
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": ncores, "kind": "port",
                              "sample": "one 2000-frame prefix of the C2 sweep per host thread, %.1f s wall; lamejs restatement (C++ -O2), lamejs itself needs a JS engine" % cpu_dt},
         }
         print(json.dumps(line))

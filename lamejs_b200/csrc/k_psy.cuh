@@ -342,7 +342,11 @@ k_psy_loudness(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
 }
 
 /* ---- attack candidates: needs peaks of unit u and u-1 (PsyModel.js:1105-1181) -------------------------- */
-__global__ void k_attack_prepass(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ psy) {
+/* what the sequential scans read per (unit, channel), packed densely: a PsyUnit is 2.6 KB, the scans need 8 bytes of it */
+struct ScanIn { unsigned attack4; float loudness; };
+
+__global__ void k_attack_prepass(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ psy,
+                                 ScanIn* __restrict__ sin) {
   const int z = blockIdx.z;
   const StreamDesc sd = streams[z];
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,6 +382,11 @@ __global__ void k_attack_prepass(const Mp3Tables* __restrict__ T, const StreamDe
       if (ratio < 1.7) { a[i] = 0; if (i == 1) a[0] = 0; }
     }
     for (int i = 0; i < 4; i++) cur->attack[i] = (unsigned char)a[i];
+    ScanIn si;
+    si.attack4 = (unsigned)a[0] | ((unsigned)a[1] << 8) | ((unsigned)a[2] << 16) | ((unsigned)a[3] << 24);
+    si.loudness = cur->loudness;
+    sin[psy_row(sd, z, u) * nch + ch] = si;
+    if (u == 0) { si.attack4 = 0; si.loudness = prev->loudness; sin[psy_row(sd, z, -1) * nch + ch] = si; }
   }
 }
 
@@ -385,16 +394,16 @@ __global__ void k_attack_prepass(const Mp3Tables* __restrict__ T, const StreamDe
  * Two recurrences run through a stream: the attack / block-type FSM (PsyModel.js:1183-1204, 784-826; state =
  * lastAttacks and blocktype_old of both channels) and the ATH auto-adjust IIR (Encoder.js:166-243; state = adjust,
  * adjustLimit).  Both forget their past quickly (two attack-free granules reset the FSM to (0, NORM); two loud frames
- * reset the ATH state to (1, 1)), so each 32-frame chunk is run from a guessed in-state by its own thread, the
+ * reset the ATH state to (1, 1)), so each 16-frame chunk is run from a guessed in-state by its own thread, the
  * guesses are checked against the predecessor's out-state, and only wrong chunks are redone until nothing changes.
  * The result equals the sequential scan exactly; the worst case degenerates to it.  One block per stream. */
-#define SCAN_FRAMES 32
-#define SCAN_THREADS 256
+#define SCAN_FRAMES 16
+#define SCAN_THREADS 1024
 struct ScanChunk { int fsm_in, fsm_out, dirty_fsm, dirty_ath; double ath_in[2], ath_out[2]; };
 
 __device__ __forceinline__ int fsm_pack(int la0, int la1, int o0, int o1) { return la0 | (la1 << 2) | (o0 << 4) | (o1 << 6); }
 
-__device__ void scan_fsm_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, const PsyUnit* psy, signed char* bt_final,
+__device__ void scan_fsm_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, const ScanIn* sin, signed char* bt_final,
                                signed char* bt_prev, int f0, int f1, ScanChunk* ck) {
   const int nch = T->nch, coupled = T->coupled_short_blocks;
   int la[2] = {ck->fsm_in & 3, (ck->fsm_in >> 2) & 3};
@@ -402,8 +411,7 @@ __device__ void scan_fsm_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, 
   for (int u = 2 * f0; u < 2 * f1; u++) {
     int uselong[2] = {1, 1};
     for (int ch = 0; ch < nch; ch++) {
-      const PsyUnit* p = psy + psy_row(sd, z, u) * nch + ch;
-      const unsigned av = *reinterpret_cast<const unsigned*>(p->attack);
+      const unsigned av = sin[psy_row(sd, z, u) * nch + ch].attack4;
       int a0 = av & 0xff, a1 = (av >> 8) & 0xff, a2 = (av >> 16) & 0xff, a3 = (av >> 24) & 0xff;
       if (a0 != 0 && la[ch] != 0) a0 = 0;
       if (la[ch] == 3 || (a0 + a1 + a2 + a3) != 0) {
@@ -433,7 +441,7 @@ __device__ void scan_fsm_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, 
   ck->fsm_out = fsm_pack(la[0], la[1], old[0], old[1]);
 }
 
-__device__ void scan_ath_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, const PsyUnit* psy, double* ath_psy,
+__device__ void scan_ath_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, const ScanIn* sin, double* ath_psy,
                                double* ath_q, int f0, int f1, ScanChunk* ck) {
   const int nch = T->nch;
   double adjust = ck->ath_in[0], limit = ck->ath_in[1];
@@ -441,8 +449,8 @@ __device__ void scan_ath_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, 
   for (int f = f0; f < f1; f++) {
     ath_psy[sd.frame_base + f] = adjust;
     /* loudness_sq[gr][ch] is the loudness of the unit BEFORE call 2f+gr (one-call delay, PsyModel.js:321-322) */
-    const PsyUnit* r0 = psy + psy_row(sd, z, 2 * f - 1) * nch;
-    const PsyUnit* r1 = psy + psy_row(sd, z, 2 * f) * nch;
+    const ScanIn* r0 = sin + psy_row(sd, z, 2 * f - 1) * nch;
+    const ScanIn* r1 = sin + psy_row(sd, z, 2 * f) * nch;
     double max_pow = (double)r0[0].loudness, gr2_max = (double)r1[0].loudness;
     if (nch == 2) { max_pow += (double)r0[1].loudness; gr2_max += (double)r1[1].loudness; }
     else { max_pow += max_pow; gr2_max += gr2_max; }
@@ -472,7 +480,7 @@ __device__ void scan_ath_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, 
 /* grid: nstreams blocks x SCAN_THREADS.  chunks: scratch rows [sd.scan_base, sd.scan_base + nchunks) */
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_stream_scan(const Mp3Tables* __restrict__ T, StreamDesc* __restrict__ streams, int nstreams,
-              const PsyUnit* __restrict__ psy, signed char* __restrict__ bt_final,
+              const ScanIn* __restrict__ sin, signed char* __restrict__ bt_final,
               signed char* __restrict__ bt_prev, double* __restrict__ ath_psy, double* __restrict__ ath_q,
               ScanChunk* __restrict__ scratch) {
   const int z = blockIdx.x;
@@ -491,8 +499,8 @@ k_stream_scan(const Mp3Tables* __restrict__ T, StreamDesc* __restrict__ streams,
   for (;;) {
     for (int c = tid; c < nchunks; c += SCAN_THREADS) {
       const int f0 = c * SCAN_FRAMES, f1 = min(sd.nframes, f0 + SCAN_FRAMES);
-      if (ck[c].dirty_fsm) scan_fsm_chunk(T, sd, z, psy, bt_final, bt_prev, f0, f1, &ck[c]);
-      if (ck[c].dirty_ath) scan_ath_chunk(T, sd, z, psy, ath_psy, ath_q, f0, f1, &ck[c]);
+      if (ck[c].dirty_fsm) scan_fsm_chunk(T, sd, z, sin, bt_final, bt_prev, f0, f1, &ck[c]);
+      if (ck[c].dirty_ath) scan_ath_chunk(T, sd, z, sin, ath_psy, ath_q, f0, f1, &ck[c]);
     }
     __syncthreads();
     int any = 0;
@@ -605,55 +613,61 @@ k_psy_masking(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ st
   }
   __syncthreads();
 
-  /* partition -> scalefactor band (convert_partition2scalefac_l/_s): ordered accumulation, one thread each */
-  if (ch < nch && b == 0) {
+  /* partition -> scalefactor band (convert_partition2scalefac_l/_s): every band is its own ordered accumulation over the
+   * slice of partitions the reference's cursor walk gives it (Mp3Conv), one thread per band (and sub-block) */
+  if (ch < nch && b < 22) {
+    const int sbi = b;
     f32s* en = reinterpret_cast<f32s*>(s_out[ch].en_l);
     f32s* thm = reinterpret_cast<f32s*>(s_out[ch].thm_l);
-    int sbi, p;
-    double enn = 0.0, thmm = 0.0;
-    for (sbi = p = 0; sbi < 22; ++p, ++sbi) {
-      const int bo = T->bo_l[sbi];
-      const int b_lim = bo < npl ? bo : npl;
-      while (p < b_lim) { enn += (double)s_eb[ch][p]; thmm += (double)s_thr[ch][p]; p++; }
+    const int init = T->conv_l.init[sbi];
+    if (init == -2) { en[sbi] = 0.0; thm[sbi] = 0.0; }
+    else {
+      double enn = 0.0, thmm = 0.0;
+      if (init >= 0) {
+        const double w_next = 1.0 - (double)T->bo_l_weight[sbi - 1];
+        enn = w_next * (double)s_eb[ch][init];
+        thmm = w_next * (double)s_thr[ch][init];
+      }
+      const int p1 = T->conv_l.end[sbi];
+      for (int p = T->conv_l.start[sbi]; p < p1; p++) { enn += (double)s_eb[ch][p]; thmm += (double)s_thr[ch][p]; }
       en[sbi] = enn; thm[sbi] = thmm;
-      if (p >= npl) { ++sbi; break; }
-      const double w_curr = (double)T->bo_l_weight[sbi], w_next = 1.0 - w_curr;
-      enn = w_curr * (double)s_eb[ch][p];
-      thmm = w_curr * (double)s_thr[ch][p];
-      en[sbi] += enn; thm[sbi] += thmm;
-      enn = w_next * (double)s_eb[ch][p];
-      thmm = w_next * (double)s_thr[ch][p];
+      const int bd = T->conv_l.bound[sbi];
+      if (bd >= 0) {
+        const double w_curr = (double)T->bo_l_weight[sbi];
+        en[sbi] += w_curr * (double)s_eb[ch][bd];
+        thm[sbi] += w_curr * (double)s_thr[ch][bd];
+      }
     }
-    for (; sbi < 22; ++sbi) { en[sbi] = 0.0; thm[sbi] = 0.0; }
-  } else if (ch < nch && b >= 1 && b <= 3) {
-    const int sblock = b - 1;
-    int sbi, p;
-    double enn = 0.0, thmm = 0.0;
+  } else if (ch < nch && b >= 22 && b < 22 + 39) {
+    const int q = b - 22, sbi = q / 3, sblock = q - 3 * sbi;
     f32s(*en)[3] = reinterpret_cast<f32s(*)[3]>(s_out[ch].en_s);
     f32s(*thm)[3] = reinterpret_cast<f32s(*)[3]>(s_out[ch].thm_s);
-    for (sbi = p = 0; sbi < 13; ++p, ++sbi) {
-      const int bo = T->bo_s[sbi];
-      const int b_lim = bo < nps ? bo : nps;
-      while (p < b_lim) { enn += (double)pu->eb_s[sblock][p]; thmm += (double)s_thr_s[ch][sblock][p]; p++; }
+    const int init = T->conv_s.init[sbi];
+    if (init == -2) { en[sbi][sblock] = 0.0; thm[sbi][sblock] = 0.0; }
+    else {
+      double enn = 0.0, thmm = 0.0;
+      if (init >= 0) {
+        const double w_next = 1.0 - (double)T->bo_s_weight[sbi - 1];
+        enn = w_next * (double)pu->eb_s[sblock][init];
+        thmm = w_next * (double)s_thr_s[ch][sblock][init];
+      }
+      const int p1 = T->conv_s.end[sbi];
+      for (int p = T->conv_s.start[sbi]; p < p1; p++) { enn += (double)pu->eb_s[sblock][p]; thmm += (double)s_thr_s[ch][sblock][p]; }
       en[sbi][sblock] = enn; thm[sbi][sblock] = thmm;
-      if (p >= nps) { ++sbi; break; }
-      const double w_curr = (double)T->bo_s_weight[sbi], w_next = 1.0 - w_curr;
-      enn = w_curr * (double)pu->eb_s[sblock][p];
-      thmm = w_curr * (double)s_thr_s[ch][sblock][p];
-      en[sbi][sblock] += enn; thm[sbi][sblock] += thmm;
-      enn = w_next * (double)pu->eb_s[sblock][p];
-      thmm = w_next * (double)s_thr_s[ch][sblock][p];
+      const int bd = T->conv_s.bound[sbi];
+      if (bd >= 0) {
+        const double w_curr = (double)T->bo_s_weight[sbi];
+        en[sbi][sblock] += w_curr * (double)pu->eb_s[sblock][bd];
+        thm[sbi][sblock] += w_curr * (double)s_thr_s[ch][sblock][bd];
+      }
     }
-    for (; sbi < 13; ++sbi) { en[sbi][sblock] = 0.0; thm[sbi][sblock] = 0.0; }
     /* pre-echo factor and pulse detection (PsyModel.js:1231-1266; NS_INTERP(.,thmm,0) == thmm) */
     const double e3 = (double)pu->peaks[sblock * 3 + 0], e4 = (double)pu->peaks[sblock * 3 + 1], e5 = (double)pu->peaks[sblock * 3 + 2];
-    for (int s = 0; s < 13; s++) {
-      double t = (double)thm[s][sblock];
-      t *= 0.8;
-      const double enn2 = e3 + e4 + e5;
-      if (e5 * 6 < enn2) { t *= 0.5; if (e4 * 6 < enn2) t *= 0.5; }
-      thm[s][sblock] = t;
-    }
+    double t = (double)thm[sbi][sblock];
+    t *= 0.8;
+    const double enn2 = e3 + e4 + e5;
+    if (e5 * 6 < enn2) { t *= 0.5; if (e4 * 6 < enn2) t *= 0.5; }
+    thm[sbi][sblock] = t;
   }
   __syncthreads();
   /* inter-channel masking (PsyModel.js:525-543), stereo with interChRatio > 0 */

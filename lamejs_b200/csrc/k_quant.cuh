@@ -192,9 +192,10 @@ __device__ Q_HELPER RegionClass region_class(int mx) {
   } else {
     /* first table of 24..31, then first of (t2 - 8)..23, whose linmax covers mx - 15: linmax is
      * {1,3,7,15,63,255,1023,8191} for 16..23 and {15,31,63,127,255,511,2047,8191} for 24..31 (Tables.js ht[]) */
-    const int v = mx - 15;
-    rc.t2 = 24 + (v > 15) + (v > 31) + (v > 63) + (v > 127) + (v > 255) + (v > 511) + (v > 2047);
-    rc.t1 = max(rc.t2 - 8, 16 + (v > 1) + (v > 3) + (v > 7) + (v > 15) + (v > 63) + (v > 255) + (v > 1023));
+    /* both counts depend only on the bit length n of v = mx - 15 (all thresholds are 2^k - 1): nibble n of the literals */
+    const int n = 32 - __clz(mx - 15);
+    rc.t2 = 24 + (int)((0x7777665432100000ull >> (4 * n)) & 15ull);
+    rc.t1 = max(rc.t2 - 8, 16 + (int)((0x7777766554432100ull >> (4 * n)) & 15ull));
     const unsigned la = (unsigned)c_huff_xlen[rc.t1], lb = (unsigned)c_huff_xlen[rc.t2];
     rc.lin = la | (lb << 11) | (lb << 22);
     rc.cat = 6;
@@ -743,13 +744,20 @@ __device__ __noinline__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int des
   return nBits;
 }
 
-/* fingerprint of a GranuleInfoDev (all lanes compute the same value) */
+/* fingerprint of a GranuleInfoDev (every lane returns the same value): each lane mixes its words with their position,
+ * the warp combines them with a sum and an xor (order-free, so no serial chain) */
 __device__ __noinline__ unsigned long long gi_hash(const GranuleInfoDev* gi) {
   const unsigned* w = reinterpret_cast<const unsigned*>(gi);
-  unsigned long long h = 1469598103934665603ull;
+  unsigned sum = 0, x = 0;
 #pragma unroll 1
-  for (int i = 0; i < (int)(sizeof(GranuleInfoDev) / 4); i++) { h ^= w[i]; h *= 1099511628211ull; }
-  return h;
+  for (int i = LANE; i < (int)(sizeof(GranuleInfoDev) / 4); i += 32) {
+    unsigned v = (w[i] ^ ((unsigned)i * 0x9E3779B9u)) * 0x85EBCA6Bu;
+    v ^= v >> 13; v *= 0xC2B2AE35u; v ^= v >> 16;
+    sum += v; x ^= __funnelshift_l(v, v, i & 31);
+  }
+  sum = __reduce_add_sync(Q_FULL, sum);
+  x = __reduce_xor_sync(Q_FULL, x);
+  return ((unsigned long long)sum << 32) | x;
 }
 
 /* outer_loop (Quantize.js:871-1052) for noise_shaping_amp 1, full_outer_loop 0, substep_shaping 0 */
@@ -879,36 +887,38 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
     for (int i = lane; i < 576; i += 32) wk->xr[__ldg(&geo->reorder[i])] = xr_g[i];
   }
   __syncwarp();
-  /* analog silence in the pseudo bands above sfb21 / sfb12 (sequential from the top; lane 0) */
-  if (lane == 0) {
-    if (!is_short) {
+  /* analog silence in the pseudo bands above sfb21 / sfb12 (Quantize.js:147-202): walking down from the top line, lines
+   * below the band's ATH are zeroed until the first one that is not.  Long blocks: the stop line is the highest line at or
+   * above its threshold (a max over lanes); everything above it is cleared in parallel.  Short blocks: lane 0, as written. */
+  if (!is_short) {
+    const int lo = T->psfb21[0];
+    const double lf = (double)T->longfact[21];
+    int keep = lo - 1;
+#pragma unroll 1
+    for (int j = lo + lane; j < 576; j += 32) {
+      int g = 0;
+      while (g < 5 && j >= T->psfb21[g + 1]) g++;
+      double ath21 = fs->ath21[g];
+      if (lf > 1e-12) ath21 *= lf;
+      if (!(fabs((double)wk->xr[j]) < ath21)) keep = j;
+    }
+    keep = wmax(keep);
+#pragma unroll 1
+    for (int j = keep + 1 + lane; j < 576; j += 32) wk->xr[j] = 0.0f;
+  } else if (lane == 0) {
+#pragma unroll 1
+    for (int block = 0; block < 3; block++) {
       bool stop = false;
 #pragma unroll 1
       for (int g = 5; g >= 0 && !stop; g--) {
-        const int start = T->psfb21[g], end = T->psfb21[g + 1];
-        double ath21 = fs->ath21[g];
-        if ((double)T->longfact[21] > 1e-12) ath21 *= (double)T->longfact[21];
+        const int start = T->sfb_s[12] * 3 + (T->sfb_s[13] - T->sfb_s[12]) * block + (T->psfb12[g] - T->psfb12[0]);
+        const int end = start + (T->psfb12[g + 1] - T->psfb12[g]);
+        double ath12 = fs->ath12[g];
+        if ((double)T->shortfact[12] > 1e-12) ath12 *= (double)T->shortfact[12];
 #pragma unroll 1
         for (int j = end - 1; j >= start; j--) {
-          if (fabs((double)wk->xr[j]) < ath21) wk->xr[j] = 0.0f;
+          if (fabs((double)wk->xr[j]) < ath12) wk->xr[j] = 0.0f;
           else { stop = true; break; }
-        }
-      }
-    } else {
-#pragma unroll 1
-      for (int block = 0; block < 3; block++) {
-        bool stop = false;
-#pragma unroll 1
-        for (int g = 5; g >= 0 && !stop; g--) {
-          const int start = T->sfb_s[12] * 3 + (T->sfb_s[13] - T->sfb_s[12]) * block + (T->psfb12[g] - T->psfb12[0]);
-          const int end = start + (T->psfb12[g + 1] - T->psfb12[g]);
-          double ath12 = fs->ath12[g];
-          if ((double)T->shortfact[12] > 1e-12) ath12 *= (double)T->shortfact[12];
-#pragma unroll 1
-          for (int j = end - 1; j >= start; j--) {
-            if (fabs((double)wk->xr[j]) < ath12) wk->xr[j] = 0.0f;
-            else { stop = true; break; }
-          }
         }
       }
     }

@@ -384,6 +384,22 @@ int mp3_build_tables(int channels, int samplerate, int kbps, Mp3Tables* t) {
     t->line0_s[t->npart_s] = line;
     if (build_spreading(lay, norm, t->s3lo_s, t->s3hi_s, t->s3off_s, t->s3_ss) < 0) return -1;
   }
+  /* band slices of convert_partition2scalefac_l/_s: replay the cursor walk on the tables alone */
+  for (int pass = 0; pass < 2; pass++) {
+    Mp3Conv& cv = pass == 0 ? t->conv_l : t->conv_s;
+    const int nb = pass == 0 ? MP3_SBMAX_L : MP3_SBMAX_S, np = pass == 0 ? t->npart_l : t->npart_s;
+    const int* bo = pass == 0 ? t->bo_l : t->bo_s;
+    int sbi, p, init = -1;
+    for (sbi = p = 0; sbi < nb; ++p, ++sbi) {
+      const int b_lim = bo[sbi] < np ? bo[sbi] : np;
+      cv.init[sbi] = (short)init; cv.start[sbi] = (short)p;
+      while (p < b_lim) p++;
+      cv.end[sbi] = (short)p;
+      if (p >= np) { cv.bound[sbi] = -1; ++sbi; break; }
+      cv.bound[sbi] = (short)p; init = p;
+    }
+    for (; sbi < nb; ++sbi) { cv.init[sbi] = -2; cv.start[sbi] = cv.end[sbi] = 0; cv.bound[sbi] = -1; }
+  }
   t->ma_max_i1 = m3_pow(10, (8 + 1) / 16.0);
   t->ma_max_i2 = m3_pow(10, (23 + 1) / 16.0);
   t->ma_max_m = m3_pow(10, 15 / 10.0);

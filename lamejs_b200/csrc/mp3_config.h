@@ -28,6 +28,11 @@ struct Mp3Geo {
   short reorder[576];             /* position of MDCT line i in the quantizer's line order */
 };
 
+/* convert_partition2scalefac (PsyModel.js:1206-1266) walks partitions and bands with one cursor; its control flow depends
+ * only on the tables, so each band's slice is worked out once: band sbi starts from (1 - weight[sbi-1]) * x[init] (init >= 0),
+ * adds x[start..end) in order, is stored, then gains weight[sbi] * x[bound] (bound >= 0).  init == -2: band stays 0. */
+struct Mp3Conv { short init[MP3_SBMAX_L], start[MP3_SBMAX_L], end[MP3_SBMAX_L], bound[MP3_SBMAX_L]; };
+
 struct Mp3Tables {
   /* ---- scalars ---- */
   int nch, samplerate, kbps, mono;
@@ -59,6 +64,7 @@ struct Mp3Tables {
   float s3_ll[MP3_S3_MAX], s3_ss[MP3_S3_MAX];
   int bo_l[MP3_SBMAX_L], bo_s[MP3_SBMAX_S];
   float bo_l_weight[MP3_SBMAX_L], bo_s_weight[MP3_SBMAX_S];
+  Mp3Conv conv_l, conv_s;
   float ath_cb_l[MP3_CBANDS], ath_cb_s[MP3_CBANDS];
   float eql_w[512];
   /* ---- ATH per scalefactor band ---- */

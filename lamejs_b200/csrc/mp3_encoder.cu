@@ -98,6 +98,7 @@ struct Workspace {
   signed char* d_bt_prev = nullptr;       /* [units][2] blocktype_old seen by the masking of this granule */
   float* d_xr = nullptr;                  /* [units][nch][576] */
   PsyUnit* d_psy = nullptr;               /* [units + nstreams][nch]  (one halo unit per stream in front) */
+  ScanIn* d_scan_in = nullptr;            /* [units + nstreams][nch] attack candidates + loudness for the scans */
   float* d_fe = nullptr;                  /* [units + nstreams][nch][512] long-FFT line energies (loudness input) */
   PsyRatioDev* d_ratio = nullptr;         /* [units + nstreams][nch]  masking of unit c (used by granule c+1) */
   double* d_ath_psy = nullptr;            /* [frames] ATH.adjust seen by the psy calls of the frame */
@@ -112,7 +113,7 @@ struct Workspace {
   ScanChunk* d_scan = nullptr;            /* [frames / SCAN_FRAMES + nstreams] */
   ~Workspace() { release(); }
   void release() {
-    cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_psy); cudaFree(d_fe); d_fe = nullptr;
+    cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_psy); cudaFree(d_fe); d_fe = nullptr; cudaFree(d_scan_in); d_scan_in = nullptr;
     cudaFree(d_ratio); cudaFree(d_ath_psy); cudaFree(d_ath_q); cudaFree(d_qstate); cudaFree(d_ginfo);
     cudaFree(d_l3enc); cudaFree(d_framebits); d_framebits = nullptr; cudaFree(d_dirty); cudaFree(d_counter); cudaFree(d_scan); d_scan = nullptr;
     d_streams = nullptr; d_bt_final = d_bt_prev = nullptr; d_xr = nullptr; d_psy = nullptr; d_ratio = nullptr;
@@ -127,6 +128,7 @@ struct Workspace {
     CK(cudaMalloc(&d_xr, sizeof(float) * (size_t)U * nch * 576));
     CK(cudaMalloc(&d_psy, sizeof(PsyUnit) * (size_t)(U + S) * nch));
     CK(cudaMalloc(&d_fe, sizeof(float) * 512 * (size_t)(U + S) * nch));
+    CK(cudaMalloc(&d_scan_in, sizeof(ScanIn) * (size_t)(U + S) * nch));
     CK(cudaMalloc(&d_ratio, sizeof(PsyRatioDev) * (size_t)(U + S) * nch));
     CK(cudaMalloc(&d_ath_psy, sizeof(double) * (size_t)(F + 1)));
     CK(cudaMalloc(&d_ath_q, sizeof(double) * (size_t)(F + 1)));
@@ -190,9 +192,9 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   /* K3a: attack pre-pass (parallel) + sequential per-stream scans */
   {
     dim3 grid((2 * max_frames + 127) / 128, 1, S);
-    k_attack_prepass<<<grid, 128, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy);
+    k_attack_prepass<<<grid, 128, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_scan_in);
     DBG("k_attack_prepass");
-    k_stream_scan<<<S, SCAN_THREADS, 0, st>>>(cfg->dev, ws.d_streams, S, ws.d_psy, ws.d_bt_final, ws.d_bt_prev, ws.d_ath_psy, ws.d_ath_q, ws.d_scan);
+    k_stream_scan<<<S, SCAN_THREADS, 0, st>>>(cfg->dev, ws.d_streams, S, ws.d_scan_in, ws.d_bt_final, ws.d_bt_prev, ws.d_ath_psy, ws.d_ath_q, ws.d_scan);
     g_launches += 2;
     DBG("k_stream_scan");
   }
