@@ -242,15 +242,12 @@ Q_UNROLL(Q_RT_UNROLL)
 }
 
 /* noquant_count_bits (Takehiro.js:521-628).  gi scalars are updated by lane 0. */
-__device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short* ix, GranuleInfoDev* gi, GcWork* wk, bool use_prev) {
+/* `top`: per lane, end (2p + 2) of its last non-zero pair below i0 = min(576, (max_nonzero_coeff + 2) & ~1), found by
+ * the quantising loop of the caller while it had the pair in a register */
+__device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short* ix, GranuleInfoDev* gi, GcWork* wk, bool use_prev, int top) {
   const int lane = LANE;
   const unsigned* w32 = reinterpret_cast<const unsigned*>(ix);
-  int i0 = ((gi->max_nonzero_coeff + 2) >> 1) << 1;
-  if (i0 > 576) i0 = 576;
   /* count1 = end of the last non-zero pair below i0 */
-  int top = 0;
-Q_UNROLL(Q_RT_UNROLL)
-  for (int p = lane; p < (i0 >> 1); p += 32) if (w32[p] != 0) top = 2 * p + 2;
   const int count1 = wmax(top);
   /* quadruples of |x| <= 1 counted down from count1 (values are >= 0: "<= 1" == no bit above bit 0 in either half) */
   int a1 = 0, a2 = 0, nq = 0;
@@ -341,24 +338,29 @@ __device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, Granule
   if (gi->xrpow_max > T->ixmax_over_istep[gi->global_gain]) return Q_LARGE_BITS;
   const int sfbmax = gi->block_type == BT_SHORT ? 38 : 21;
   const int mnz = gi->max_nonzero_coeff;
+  unsigned* iw32 = reinterpret_cast<unsigned*>(ix);
+  const int i0h = min(576, ((mnz + 2) >> 1) << 1) >> 1;    /* noquant_count_bits looks for count1 below this pair index */
   if (!use_prev) {
     /* bin_search_StepSize path (prevNoise == null): no band is cached and none uses the 0/1 quantizer, so the band
      * walk of quantize_xrpow reduces to: full quantizer below the truncation point, zeros from max_nonzero_coeff on.
      * Band starts are even, hence the quantised range ends at (mnz + 1) & ~1 (an odd tail length drops its last line). */
     const int qend = (mnz + 1) & ~1;
+    int top = 0;
 Q_UNROLL(Q_CB_UNROLL)
-    for (int i = lane; i < 576; i += 32) {
-      short v = 0;
-      if (i < qend) {
-        double x = (double)wk->xrpow[i] * istep;
-        const int rx = js_trunc(x);
-        x += (double)__ldg(&T->adj43[rx]);
-        v = (short)js_trunc(x);
+    for (int p = lane; p < 288; p += 32) {            /* two lines per step: one 64-bit load, one 32-bit store */
+      unsigned v = 0;
+      if (2 * p < qend) {
+        const float2 xp = *reinterpret_cast<const float2*>(&wk->xrpow[2 * p]);
+        double x0 = (double)xp.x * istep, x1 = (double)xp.y * istep;
+        x0 += (double)__ldg(&T->adj43[js_trunc(x0)]);
+        x1 += (double)__ldg(&T->adj43[js_trunc(x1)]);
+        v = (unsigned)js_trunc(x0) | ((unsigned)js_trunc(x1) << 16);
+        if (v != 0 && p < i0h) top = 2 * p + 2;
       }
-      ix[i] = v;
+      iw32[p] = v;
     }
     __syncwarp();
-    return noquant_count_bits_w(T, ix, gi, wk, false);
+    return noquant_count_bits_w(T, ix, gi, wk, false, top);
   }
   const bool prev_data_use = use_prev && (gi->global_gain == wk->pn_global_gain);
   const bool calc_step = prev_data_use || gi->block_type == BT_NORM;
@@ -394,22 +396,37 @@ Q_UNROLL(Q_CB_UNROLL)
   }
   __syncwarp();
   const double compare01 = T->cmp01_over_istep[gi->global_gain];
+  int top = 0;
 Q_UNROLL(Q_CB_UNROLL)
-  for (int i = lane; i < 576; i += 32) {
-    if (i >= zero_from) { ix[i] = 0; continue; }
-    const int md = wk->mode[wk->geo->sfb_of_line[i]];
-    if (md == 0) continue;
-    const double xp = (double)wk->xrpow[i];
-    if (md == 2) ix[i] = (compare01 > xp) ? 0 : 1;
+  for (int p = lane; p < 288; p += 32) {              /* pairs never straddle a band: band starts and widths are even */
+    const int i = 2 * p;
+    unsigned v;
+    if (i >= zero_from) { v = 0; iw32[p] = 0; }
     else {
-      double x = xp * istep;
-      const int rx = js_trunc(x);
-      x += (double)__ldg(&T->adj43[rx]);
-      ix[i] = (short)js_trunc(x);
+      const int md = wk->mode[wk->geo->sfb_of_line[i]];
+      const bool z1 = (i + 1) >= zero_from;           /* zero_from may be odd: only the pair's second line is cleared */
+      if (md == 0) {
+        v = iw32[p];
+        if (z1) { v &= 0xffffu; iw32[p] = v; }
+      } else {
+        const float2 xp = *reinterpret_cast<const float2*>(&wk->xrpow[i]);
+        unsigned v0, v1;
+        if (md == 2) { v0 = (compare01 > (double)xp.x) ? 0u : 1u; v1 = (compare01 > (double)xp.y) ? 0u : 1u; }
+        else {
+          double x0 = (double)xp.x * istep, x1 = (double)xp.y * istep;
+          x0 += (double)__ldg(&T->adj43[js_trunc(x0)]);
+          x1 += (double)__ldg(&T->adj43[js_trunc(x1)]);
+          v0 = (unsigned)js_trunc(x0); v1 = (unsigned)js_trunc(x1);
+        }
+        if (z1) v1 = 0;
+        v = v0 | (v1 << 16);
+        iw32[p] = v;
+      }
     }
+    if (v != 0 && p < i0h) top = 2 * p + 2;
   }
   __syncwarp();
-  return noquant_count_bits_w(T, ix, gi, wk, use_prev);
+  return noquant_count_bits_w(T, ix, gi, wk, use_prev, top);
 }
 
 /* calc_noise (QuantizePVT.js:725-878) for quant_comp 9: over_count, over_SSD, max_noise (+ distort[]) */
@@ -544,17 +561,22 @@ __device__ __forceinline__ bool loop_break_w(const GranuleInfoDev* gi, const GcW
  * line loops, Quantize.js:650-655,690-695) and fold the new values into xrpow_max */
 __device__ __noinline__ void scale_xrpow_w(GcWork* wk, GranuleInfoDev* gi, double f34) {
   const int lane = LANE;
+  const int sfbmax = gi->sfbmax;
   float mx = 0.0f;
 #pragma unroll 1
-  for (int i = lane; i < 576; i += 32) {
-    const int sfb = wk->geo->sfb_of_line[i];
-    if (sfb < gi->sfbmax && wk->mode[sfb]) {
-      f32s v; v.v = wk->xrpow[i];
-      v *= f34;
-      wk->xrpow[i] = v.v;
-      mx = fmaxf(mx, v.v);
+  for (int p = lane; p < 288; p += 32) {              /* a pair of lines lies in one band */
+    const int sfb = wk->geo->sfb_of_line[2 * p];
+    if (sfb < sfbmax && wk->mode[sfb]) {
+      float2* xp = reinterpret_cast<float2*>(&wk->xrpow[2 * p]);
+      float2 x = *xp;
+      f32s v0, v1; v0.v = x.x; v1.v = x.y;
+      v0 *= f34; v1 *= f34;
+      x.x = v0.v; x.y = v1.v;
+      *xp = x;
+      mx = fmaxf(mx, fmaxf(v0.v, v1.v));
     }
   }
+#pragma unroll 1
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(Q_FULL, mx, o));
   if (lane == 0 && (double)mx > gi->xrpow_max) gi->xrpow_max = (double)mx;
   __syncwarp();
