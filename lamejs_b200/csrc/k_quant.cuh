@@ -124,7 +124,7 @@ static int quant_upload_constants() {
 }
 
 /* ---- per-warp working set (shared memory) ---------------------------------------------------------------- */
-struct GcWork {
+struct __align__(16) GcWork {
   float xr[576];                 /* gi.xr after short-block reorder and analog-silence zeroing */
   float xrpow[576];
   short ixw[576];                /* the one quantised-line buffer: cod_info_w.l3_enc; cod_info.l3_enc (best so far) is
@@ -233,8 +233,14 @@ Q_UNROLL(Q_RT_UNROLL)
   if (mx == 0) return 0;
   const RegionClass rc = region_class(mx);
   unsigned s = 0;                                  /* a lane adds <= 9 pairs x <= 45 bits per field */
+  if (rc.cat == 6) {
 Q_UNROLL(Q_RT_UNROLL)
-  for (int p = p0; p < p1; p += 32) s += pair_bits(w32[p], rc.cat, rc.lin);
+    for (int p = p0; p < p1; p += 32) s += pair_bits(w32[p], 6, rc.lin);
+  } else {                                         /* no value above 15: the pair is its own table index */
+    const unsigned int* tab = g_cat_tab[rc.cat];
+Q_UNROLL(Q_RT_UNROLL)
+    for (int p = p0; p < p1; p += 32) { const unsigned w = w32[p]; s += __ldg(&tab[((w & 0xfu) << 4) | (w >> 16)]); }
+  }
   /* warp totals need up to 14 bits: reduce (a, b) as two 16-bit fields, c alone */
   const unsigned ab = wsumu((s & 0x7ffu) | (((s >> 11) & 0x7ffu) << 16));
   const int c = wsum((int)(s >> 22));
@@ -478,10 +484,12 @@ __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const 
         int j = wk->nstart[sfb];
         noise = 0;
 #pragma unroll 1
-        for (int l = wk->nlen[sfb]; l > 0; l--) {
+        for (int l = wk->nlen[sfb]; l > 0; l--, j += 2) {          /* j is even: one 64-bit and one 32-bit load per pair */
+          const float2 x = *reinterpret_cast<const float2*>(&wk->xr[j]);
+          const unsigned q = *reinterpret_cast<const unsigned*>(&ix[j]);
           double temp;
-          temp = fabs((double)wk->xr[j]) - (double)__ldg(&T->pow43[ix[j]]) * step; j++; noise += temp * temp;
-          temp = fabs((double)wk->xr[j]) - (double)__ldg(&T->pow43[ix[j]]) * step; j++; noise += temp * temp;
+          temp = fabs((double)x.x) - (double)__ldg(&T->pow43[q & 0xffffu]) * step; noise += temp * temp;
+          temp = fabs((double)x.y) - (double)__ldg(&T->pow43[q >> 16]) * step; noise += temp * temp;
         }
         wk->pn_step[sfb] = s;
         { f32s t; t = noise; wk->pn_noise[sfb] = t.v; }
@@ -902,8 +910,9 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
   const Mp3Geo* geo = &T->geo[is_short ? 1 : 0];
   if (lane == 0) wk->geo = geo;
   if (!is_short) {
-#pragma unroll 3
-    for (int i = lane; i < 576; i += 32) wk->xr[i] = xr_g[i];
+#pragma unroll 1
+    for (int q = lane; q < 144; q += 32)             /* rows are 2304 B apart: 16-byte vectors */
+      reinterpret_cast<float4*>(wk->xr)[q] = __ldg(reinterpret_cast<const float4*>(xr_g) + q);
   } else {
 #pragma unroll 3
     for (int i = lane; i < 576; i += 32) wk->xr[__ldg(&geo->reorder[i])] = xr_g[i];
@@ -950,13 +959,16 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
   {
     float mx = 0.0f, amax = 0.0f;
 #pragma unroll 1
-    for (int i = lane; i < 576; i += 32) {
-      const double tmp = fabs((double)wk->xr[i]);
-      f32s p; p = sqrt(tmp * sqrt(tmp));
-      wk->xrpow[i] = p.v;
-      mx = fmaxf(mx, p.v);
-      amax = fmaxf(amax, (float)tmp);
+    for (int p = lane; p < 288; p += 32) {
+      const float2 x = *reinterpret_cast<const float2*>(&wk->xr[2 * p]);
+      const double t0 = fabs((double)x.x), t1 = fabs((double)x.y);
+      f32s p0, p1; p0 = sqrt(t0 * sqrt(t0)); p1 = sqrt(t1 * sqrt(t1));
+      float2 o; o.x = p0.v; o.y = p1.v;
+      *reinterpret_cast<float2*>(&wk->xrpow[2 * p]) = o;
+      mx = fmaxf(mx, fmaxf(p0.v, p1.v));
+      amax = fmaxf(amax, fmaxf((float)t0, (float)t1));
     }
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(Q_FULL, mx, o)); amax = fmaxf(amax, __shfl_xor_sync(Q_FULL, amax, o)); }
     /* sum > 1e-20 ? (Quantize.js:129): a running sum of non-negative terms is >= its largest term */
     bool energy;
@@ -1052,7 +1064,7 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
       const int j = wk->geo->start[sfb];
       bool any = false;
 #pragma unroll 1
-      for (int l = 0; l < wk->geo->width[sfb]; l++) if (wk->ixw[j + l] != 0) { any = true; break; }
+      for (int l = 0; l < wk->geo->width[sfb]; l += 2) if (*reinterpret_cast<const unsigned*>(&wk->ixw[j + l]) != 0) { any = true; break; }
       wk->mode[sfb] = any ? 1 : 0;
     }
   }
