@@ -32,6 +32,7 @@ struct PsyUnit {
   float loudness;                   /* psycho_loudness_approx */
   unsigned char mask_idx[MP3_CBANDS];
   unsigned char attack[4];          /* pre-FSM ns_attacks[0..3] */
+  unsigned char fe_valid;           /* this launch wrote the row's line energies: k_psy_loudness owns `loudness` */
 };
 struct PsyRatioDev { float en_l[22], thm_l[22], en_s[13][3], thm_s[13][3]; };
 
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(PSY_THREADS, PSY_MIN_BLOCKS)
 k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ out,
                float* __restrict__ fe_out) {
   const int z = blockIdx.z;
-  const StreamDesc sd = streams[z];
+  const StreamDesc& sd = streams[z];
   const int u = (int)blockIdx.x - 1;                 /* relative unit, -1 = halo */
   if (u >= 2 * sd.nframes) return;
   const int ch = blockIdx.y;
@@ -160,7 +161,7 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     for (int i = tid; i < 3 * MP3_CBANDS; i += PSY_THREADS) { (&o->ecb_s[0][0])[i] = 1.0; (&o->eb_s[0][0])[i] = 0.0f; }
     if (tid < MP3_CBANDS) { o->eb_l[tid] = 0.0f; o->mask_idx[tid] = 0; }
     if (tid < 9) o->peaks[tid] = 10.0f;
-    if (tid == 0) o->loudness = 0.0f;
+    if (tid == 0) { o->loudness = 0.0f; o->fe_valid = 0; }
     if (tid < 4) o->attack[tid] = 0;
     return;
   }
@@ -289,6 +290,7 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     for (int j = tid; j < 512; j += PSY_THREADS) fg[j] = fe[j].v;
   }
   if (tid < 9) o->peaks[tid] = __int_as_float(s_peak[tid]);
+  if (tid == 9) o->fe_valid = 1;
   __syncthreads();
 
   if (tid < npl) {                                   /* calc_mask_index_l (PsyModel.js:930-992) */
@@ -322,23 +324,33 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
 }
 
 /* psycho_loudness_approx (PsyModel.js:241-249): loudness = sum_i energy[i] * eql_w[i] (ordered, in double) scaled by
- * 1 / (14752^2 * 512).  grid (ceil((max_units+1)/128), nch, nstreams), one thread per (unit, channel). */
-__global__ void __launch_bounds__(128)
-k_psy_loudness(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, const float* __restrict__ fe_in,
-               PsyUnit* __restrict__ out) {
-  const int z = blockIdx.z;
-  const StreamDesc& sd = streams[z];
-  const int u = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;
-  if (u >= 2 * sd.nframes) return;
-  if (2LL * sd.frame0 + u < 0) return;               /* psymodel_init row: loudness stays 0 */
-  const int ch = blockIdx.y, nch = T->nch;
-  const size_t row = psy_row(sd, z, u) * nch + ch;
-  const float* fe = fe_in + row * 512;
+ * 1 / (14752^2 * 512).  One thread per (unit, channel) row owns the ordered sum; the 128 rows of a block are streamed
+ * through shared memory in 32-column tiles so that the HBM reads are whole 128-byte lines.
+ * grid (ceil(rows / 128)), rows = all (unit+halo, channel) rows of the batch; `valid` marks rows K2 filled. */
+#define LOUD_ROWS 128
+__global__ void __launch_bounds__(LOUD_ROWS)
+k_psy_loudness(const Mp3Tables* __restrict__ T, const float* __restrict__ fe_in, PsyUnit* __restrict__ out, long long nrows) {
+  __shared__ float tile[LOUD_ROWS][33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long row0 = (long long)blockIdx.x * LOUD_ROWS;
   double lp = 0.0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 512; c0 += 32) {
 #pragma unroll 4
-  for (int i = 0; i < 512; ++i) lp += (double)fe[i] * (double)T->eql_w[i];
-  lp *= (1. / (14752. * 14752.) / 512);
-  out[row].loudness = (float)lp;
+    for (int r = warp; r < LOUD_ROWS; r += LOUD_ROWS / 32) {
+      const long long row = row0 + r;
+      tile[r][lane] = row < nrows ? fe_in[row * 512 + c0 + lane] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) lp += (double)tile[tid][i] * (double)T->eql_w[c0 + i];
+    __syncthreads();
+  }
+  const long long row = row0 + tid;
+  if (row < nrows && out[row].fe_valid) {
+    lp *= (1. / (14752. * 14752.) / 512);
+    out[row].loudness = (float)lp;
+  }
 }
 
 /* ---- attack candidates: needs peaks of unit u and u-1 (PsyModel.js:1105-1181) -------------------------- */
@@ -348,7 +360,7 @@ struct ScanIn { unsigned attack4; float loudness; };
 __global__ void k_attack_prepass(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ psy,
                                  ScanIn* __restrict__ sin) {
   const int z = blockIdx.z;
-  const StreamDesc sd = streams[z];
+  const StreamDesc& sd = streams[z];
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= 2 * sd.nframes) return;
   const int nch = T->nch;
@@ -485,7 +497,7 @@ k_stream_scan(const Mp3Tables* __restrict__ T, StreamDesc* __restrict__ streams,
               ScanChunk* __restrict__ scratch) {
   const int z = blockIdx.x;
   if (z >= nstreams) return;
-  const StreamDesc sd = streams[z];
+  const StreamDesc& sd = streams[z];
   const int nchunks = (sd.nframes + SCAN_FRAMES - 1) / SCAN_FRAMES;
   ScanChunk* ck = scratch + sd.scan_base;
   const int tid = threadIdx.x;
@@ -560,7 +572,7 @@ __global__ void __launch_bounds__(MASK_THREADS)
 k_psy_masking(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, const PsyUnit* __restrict__ psy,
               const signed char* __restrict__ bt_prev, const double* __restrict__ ath_psy, PsyRatioDev* __restrict__ ratio) {
   const int z = blockIdx.z;
-  const StreamDesc sd = streams[z];
+  const StreamDesc& sd = streams[z];
   const int u = (int)blockIdx.x - 1;
   if (u >= 2 * sd.nframes) return;
   const int nch = T->nch;

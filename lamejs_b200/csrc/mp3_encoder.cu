@@ -183,8 +183,8 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     k_psy_analysis<<<grid, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_fe);
     g_launches++;
     DBG("k_psy_analysis");
-    dim3 grid2((2 * max_frames + 1 + 127) / 128, nch, S);
-    k_psy_loudness<<<grid2, 128, 0, st>>>(cfg->dev, ws.d_streams, ws.d_fe, ws.d_psy);
+    const long long psy_rows = (2 * total_frames + S) * nch;   /* rows unit_base + z + u + 1 of every stream */
+    k_psy_loudness<<<(unsigned)((psy_rows + LOUD_ROWS - 1) / LOUD_ROWS), LOUD_ROWS, 0, st>>>(cfg->dev, ws.d_fe, ws.d_psy, psy_rows);
     g_launches++;
     DBG("k_psy_loudness");
   }
