@@ -45,6 +45,16 @@ int mp3b200_flush(mp3b200_encoder* h, uint8_t* out, int cap);
 /* Replaces garbage collection of the Mp3Encoder object. */
 void mp3b200_destroy(mp3b200_encoder* h);
 
+/* Batched encodeBuffer / flush over N live encoders of one configuration (SURVEY.md 8(b) "Batch"): equivalent to
+ * calling mp3b200_encode / mp3b200_flush on every handle in turn, but the frames all handles complete in this call
+ * are encoded by ONE pipeline launch (handle i = stream i).  left[i]/right[i]: nsamples[i] Int16 (right or right[i]
+ * NULL: mono / duplicate left); out[i] receives out_bytes[i] bytes (cap[i] >= trunc(1.25 * nsamples[i] + 7200) like
+ * lamejs, 0 = unchecked); out_bytes[i] < 0 reports a per-handle error (NULL handle -3, buffer too small -1).
+ * A JS caller loops over its encoders instead (worker-example/worker.js, worker-realtime.js:46). */
+int mp3b200_encode_batch(mp3b200_encoder* const* handles, const int16_t* const* left, const int16_t* const* right,
+                         const int* nsamples, uint8_t* const* out, const int* cap, int nstreams, int* out_bytes);
+int mp3b200_flush_batch(mp3b200_encoder* const* handles, uint8_t* const* out, const int* cap, int nstreams, int* out_bytes);
+
 /* ---- batch extension (same semantics, many independent streams per launch sequence) -------------------
  * Equivalent to, for each stream s: e = new Mp3Encoder(ch, sr, kbps); bytes = e.encodeBuffer(L_s, R_s) ++
  * e.flush().  This is the throughput path (a JS caller would loop over encoders, worker-example/worker.js). */

@@ -32,6 +32,8 @@ def lib():
     L.mp3b200_encode.argtypes = [vp, vp, vp, c_int, vp, c_int]
     L.mp3b200_flush.argtypes = [vp, vp, c_int]
     L.mp3b200_destroy.argtypes = [vp]
+    L.mp3b200_encode_batch.argtypes = [vp, vp, vp, vp, vp, vp, c_int, vp]
+    L.mp3b200_flush_batch.argtypes = [vp, vp, vp, c_int, vp]
     L.mp3b200_destroy.restype = None
     L.mp3b200_stream_bytes.restype = c_i64
     L.mp3b200_stream_bytes.argtypes = [c_int, c_int, c_int, c_i64]
@@ -100,6 +102,43 @@ class Mp3Encoder:
             pass
 
 
+def encode_batch(encoders, lefts, rights=None):
+    """encodeBuffer on many live Mp3Encoder objects of one configuration in ONE pipeline launch (SURVEY 8(b) batch row):
+    returns [enc.encodeBuffer(l, r) for ...] byte strings."""
+    L = lib()
+    S = len(encoders)
+    lefts = [np.ascontiguousarray(x, dtype=np.int16) for x in lefts]
+    rights = lefts if rights is None else [np.ascontiguousarray(x if x is not None else l, dtype=np.int16) for x, l in zip(rights, lefts)]
+    ns = np.array([len(x) for x in lefts], dtype=np.int32)
+    caps = np.array([int(1.25 * n + 7200) for n in ns], dtype=np.int32)
+    outs = [np.empty(int(c), dtype=np.uint8) for c in caps]
+    hp = (ctypes.c_void_p * S)(*[e._h for e in encoders])
+    lp = (ctypes.c_void_p * S)(*[x.ctypes.data for x in lefts])
+    rp = (ctypes.c_void_p * S)(*[x.ctypes.data for x in rights])
+    op = (ctypes.c_void_p * S)(*[x.ctypes.data for x in outs])
+    got = np.zeros(S, dtype=np.int32)
+    _check(L.mp3b200_encode_batch(hp, lp, rp, ns.ctypes.data, op, caps.ctypes.data, S, got.ctypes.data))
+    for g in got:
+        _check(int(g))
+    return [o[: int(g)].tobytes() for o, g in zip(outs, got)]
+
+
+def flush_batch(encoders):
+    """flush() on many live Mp3Encoder objects in one pipeline launch."""
+    L = lib()
+    S = len(encoders)
+    cap = 7200 + 8 * 1441
+    outs = [np.empty(cap, dtype=np.uint8) for _ in range(S)]
+    hp = (ctypes.c_void_p * S)(*[e._h for e in encoders])
+    op = (ctypes.c_void_p * S)(*[x.ctypes.data for x in outs])
+    caps = np.full(S, cap, dtype=np.int32)
+    got = np.zeros(S, dtype=np.int32)
+    _check(L.mp3b200_flush_batch(hp, op, caps.ctypes.data, S, got.ctypes.data))
+    for g in got:
+        _check(int(g))
+    return [o[: int(g)].tobytes() for o, g in zip(outs, got)]
+
+
 def encode_streams(channels, samplerate, kbps, lefts, rights=None):
     """Batch extension: encodeBuffer(whole stream) + flush() for many independent streams in one launch sequence.
     Host buffers in, list of bytes out."""
@@ -109,6 +148,8 @@ def encode_streams(channels, samplerate, kbps, lefts, rights=None):
     rights = lefts if (rights is None or channels == 1) else [np.ascontiguousarray(x, dtype=np.int16) for x in rights]
     ns = np.array([len(x) for x in lefts], dtype=np.int64)
     nb = [stream_bytes(channels, samplerate, kbps, int(n)) for n in ns]
+    if any(b < 0 for b in nb):
+        raise Mp3B200Error("unsupported configuration: channels=%d samplerate=%d kbps=%d (lame_init_params would resample)" % (channels, samplerate, kbps))
     outs = [np.empty(b, dtype=np.uint8) for b in nb]
     lp = (ctypes.c_void_p * S)(*[x.ctypes.data for x in lefts])
     rp = (ctypes.c_void_p * S)(*[x.ctypes.data for x in rights])

@@ -64,3 +64,18 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inc")):
                 s = open(os.path.join(d, f)).read()
                 assert "oracle_lib" not in s and "liblamejs_oracle" not in s and "oracle/" not in s.replace("the oracle/", ""), f
+
+
+def test_config_matrix_acceptance_and_sizes_match_oracle(M, oracle):
+    """Host logic only: for every MPEG-1 bitrate x mono/stereo x native rate the library accepts exactly the
+    configurations the oracle (lame_init_params restatement) accepts, and predicts the oracle's byte count."""
+    from synth import make_signal
+    for sr in (32000, 44100, 48000):
+        l, r = make_signal("noise", 2000, sr, 1)
+        for kbps in (32, 40, 48, 56, 64, 80, 96, 112, 123, 128, 160, 192, 224, 256, 320):
+            for ch in (1, 2):
+                try:
+                    want = len(oracle.encode_stream(ch, sr, kbps, l, r if ch == 2 else None)[0])
+                except Exception:
+                    want = -1
+                assert M.stream_bytes(ch, sr, kbps, len(l)) == want, (ch, sr, kbps)

@@ -140,3 +140,51 @@ def test_c4_mono_octave_streams_and_c5_bursts(M, oracle):
     ref, _, tr = oracle.encode_stream(2, 44100, 128, lb, rb, trace_frames=700)
     assert out == ref
     assert set(np.unique(tr["blocktype"])) == {0, 1, 2, 3}      # START/SHORT/STOP all exercised
+
+
+def test_batched_live_encoders_one_launch_per_call(M, oracle):
+    """SURVEY 8(b) batch row: N live Mp3Encoder objects fed different chunk sizes through mp3b200_encode_batch /
+    mp3b200_flush_batch -- every per-call byte string equals what lamejs' encodeBuffer / flush returns for that
+    stream (oracle), including calls that complete no frame and encoders that receive nothing in a call."""
+    sigs = [make_signal(k, n, 44100, 40 + i) for i, (k, n) in enumerate([("noise", 9000), ("burst", 14000), ("sweep", 5000), ("white", 1)])]
+    encs = [M.Mp3Encoder(2, 44100, 128) for _ in sigs]
+    refs = [oracle.OracleEncoder(2, 44100, 128) for _ in sigs]
+    pos = [0] * len(sigs)
+    chunks = [700, 2500, 1152, 1]
+    for rnd in range(8):
+        ls, rs = [], []
+        for i, (l, r) in enumerate(sigs):
+            n = 0 if (rnd + i) % 5 == 4 else chunks[i]
+            ls.append(l[pos[i]:pos[i] + n]); rs.append(r[pos[i]:pos[i] + n]); pos[i] += len(ls[-1])
+        got = M.encode_batch(encs, ls, rs)
+        for i in range(len(sigs)):
+            want = refs[i].encode_buffer(ls[i], rs[i]) if len(ls[i]) else b""
+            assert got[i] == want, (rnd, i)
+    got = M.flush_batch(encs)
+    for i in range(len(sigs)):
+        assert got[i] == refs[i].flush(), i
+    assert M.flush_batch(encs) == [b""] * len(sigs)
+    for e, r in zip(encs, refs):
+        e.close(); r.close()
+
+
+@pytest.mark.parametrize("sr", [32000, 44100, 48000])
+def test_config_matrix(M, oracle, sr):
+    """Every MPEG-1 bitrate (and an off-ladder one that lamejs snaps, worker-realtime.js passes 123) x mono/stereo at
+    each native sample rate: short noisy + transient streams, byte-exact against the oracle.  Configurations that
+    lamejs would resample (the C ABI returns -1) are skipped, but the oracle must agree that they are unsupported."""
+    l, r = make_signal("burst", 9 * 1152 + 100, sr, 77)
+    l2, r2 = make_signal("noise", 7 * 1152, sr, 78)
+    tried = 0
+    for kbps in (32, 40, 48, 56, 64, 80, 96, 112, 123, 128, 160, 192, 224, 256, 320):
+        for ch in (1, 2):
+            try:
+                outs = M.encode_streams(ch, sr, kbps, [l, l2], [r, r2] if ch == 2 else None)
+            except M.Mp3B200Error:
+                with pytest.raises(Exception):
+                    oracle.encode_stream(ch, sr, kbps, l, r if ch == 2 else None)
+                continue
+            tried += 1
+            assert outs[0] == oracle.encode_stream(ch, sr, kbps, l, r if ch == 2 else None)[0], (ch, sr, kbps)
+            assert outs[1] == oracle.encode_stream(ch, sr, kbps, l2, r2 if ch == 2 else None)[0], (ch, sr, kbps)
+    assert tried >= 8
