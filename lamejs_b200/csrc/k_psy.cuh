@@ -146,7 +146,7 @@ __device__ __forceinline__ size_t psy_row(const StreamDesc& sd, int z, int u) { 
 #endif
 __global__ void __launch_bounds__(PSY_THREADS, PSY_MIN_BLOCKS)
 k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ out,
-               float* __restrict__ fe_out) {
+               float* __restrict__ fe_out, int chunk, int nchunks) {
   const int z = blockIdx.z;
   const StreamDesc& sd = streams[z];
   const int u = (int)blockIdx.x - 1;                 /* relative unit, -1 = halo */
@@ -154,6 +154,16 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   const int ch = blockIdx.y;
   const int nch = T->nch;
   const long long c = 2LL * sd.frame0 + u;           /* absolute psy call index */
+  if (nchunks > 1) {
+    /* the host uploads every stream's PCM in `nchunks` time slices and launches this kernel once per slice as it
+     * lands: a unit belongs to the slice that holds the last sample of its 1024-sample window */
+    const long long n = sd.pcm_end - sd.pcm_base;
+    long long last = 576 * c - 224 + 1023 - sd.pcm_base;
+    if (last > n - 1) last = n - 1;
+    int mine = 0;
+    while (mine < nchunks - 1 && last >= n * (mine + 1) / nchunks) mine++;
+    if (mine != chunk) return;
+  }
   PsyUnit* o = out + psy_row(sd, z, u) * nch + ch;
   const int tid = threadIdx.x;
 

@@ -159,8 +159,13 @@ struct Timings { float psy = 0, scan = 0, mask = 0, fb = 0, q1 = 0, qn = 0, tota
 
 /* Runs the whole pipeline for the streams described in `h_streams` (device pointers already set).
  * d_out: device output buffer.  force_bt: optional host array [units][nch] of block types (debug). */
+/* pcm_chunks > 1: the caller uploads each stream's PCM in that many time slices on another stream and records
+ * pcm_ready[j] after slice j; the psy analysis of slice j starts as soon as it has landed. */
+struct PcmArrival { int chunks = 1; cudaEvent_t* ready = nullptr; };
+
 int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams, uint8_t* d_out, const int32_t* force_bt,
-                 bool stop_after_mdct, Timings* tm, cudaStream_t st) {
+                 bool stop_after_mdct, Timings* tm, cudaStream_t st, const PcmArrival* arrival = nullptr) {
+
   const int S = (int)h_streams.size();
   const int nch = cfg->host.nch;
   int max_frames = 0;
@@ -180,9 +185,13 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   /* K2: psy analysis, one block per (granule incl. 1 halo, channel, stream) */
   {
     dim3 grid(2 * max_frames + 1, nch, S);
-    k_psy_analysis<<<grid, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_fe);
-    g_launches++;
-    DBG("k_psy_analysis");
+    const int nchunks = arrival ? arrival->chunks : 1;
+    for (int j = 0; j < nchunks; j++) {
+      if (arrival) CK(cudaStreamWaitEvent(st, arrival->ready[j], 0));
+      k_psy_analysis<<<grid, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_fe, j, nchunks);
+      g_launches++;
+      DBG("k_psy_analysis");
+    }
     const long long psy_rows = (2 * total_frames + S) * nch;   /* rows unit_base + z + u + 1 of every stream */
     k_psy_loudness<<<(unsigned)((psy_rows + LOUD_ROWS - 1) / LOUD_ROWS), LOUD_ROWS, 0, st>>>(cfg->dev, ws.d_fe, ws.d_psy, psy_rows);
     g_launches++;
@@ -199,6 +208,13 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     DBG("k_stream_scan");
   }
   CK(cudaEventRecord(ev[2], st));
+  if (force_bt) {   /* debug: override block decision for the filterbank */
+    std::vector<signed char> bt((size_t)ws.units * 2, 0);
+    for (long long u = 0; u < ws.units; u++)
+      for (int c = 0; c < nch; c++) bt[u * 2 + c] = (signed char)force_bt[u * nch + c];
+    CK(cudaMemcpyAsync(ws.d_bt_final, bt.data(), bt.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
   /* K3b: masking thresholds */
   {
     dim3 grid(2 * max_frames + 1, 1, S);
@@ -207,14 +223,8 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     DBG("k_psy_masking");
   }
   CK(cudaEventRecord(ev[3], st));
-  if (force_bt) {   /* debug: override block decision for the filterbank */
-    std::vector<signed char> bt((size_t)ws.units * 2, 0);
-    for (long long u = 0; u < ws.units; u++)
-      for (int c = 0; c < nch; c++) bt[u * 2 + c] = (signed char)force_bt[u * nch + c];
-    CK(cudaMemcpyAsync(ws.d_bt_final, bt.data(), bt.size(), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-  }
-  /* K1: filterbank + MDCT */
+  /* K1: filterbank + MDCT.  (Running it on a second stream beside K3b was measured: the two kernels slow each other
+   * down by exactly what the overlap would save, 0.61 ms either way.) */
   {
     dim3 grid((2 * max_frames + FB_G - 1) / FB_G, nch, S);
     const size_t smem = sizeof(double) * FB_PCM_WORDS + sizeof(float) * ((FB_G + 1) * 18 * FB_SLAB_STRIDE);
@@ -287,12 +297,13 @@ int64_t mp3b200_stream_bytes(int channels, int samplerate, int kbps, int64_t nsa
   return r;
 }
 
-int mp3b200_encode_streams_device(int channels, int samplerate, int kbps, int nstreams, const int16_t* d_pcm,
-                                  const int64_t* pcm_off, const int64_t* nsamples, uint8_t* d_out,
-                                  const int64_t* out_off, float* timings_ms) {
-  Config* cfg;
-  int rc = get_config(channels, samplerate, kbps, &cfg);
-  if (rc) return rc;
+}  // extern "C"
+
+namespace {
+int encode_streams_device_impl(Config* cfg, int channels, int nstreams, const int16_t* d_pcm, const int64_t* pcm_off,
+                               const int64_t* nsamples, uint8_t* d_out, const int64_t* out_off, float* timings_ms,
+                               const PcmArrival* arrival) {
+  int rc = 0;
   std::vector<StreamDesc> sds(nstreams);
   long long U = 0, F = 0;
   for (int s = 0; s < nstreams; s++) {
@@ -313,13 +324,37 @@ int mp3b200_encode_streams_device(int channels, int samplerate, int kbps, int ns
     if (rc) return rc;
   }
   Timings tm;
-  rc = run_pipeline(cfg, ws, sds, d_out, nullptr, false, &tm, 0);
+  rc = run_pipeline(cfg, ws, sds, d_out, nullptr, false, &tm, 0, arrival);
   if (rc) return rc;
   if (timings_ms) {
     timings_ms[0] = tm.psy; timings_ms[1] = tm.scan; timings_ms[2] = tm.mask; timings_ms[3] = tm.fb;
     timings_ms[4] = tm.q1; timings_ms[5] = tm.qn; timings_ms[6] = tm.total; timings_ms[7] = (float)tm.passes;
   }
   return 0;
+}
+
+/* upload stream + arrival events of the host-buffer batch call */
+struct Uploader {
+  enum { MAX_CHUNKS = 4 };
+  cudaStream_t st = nullptr; cudaEvent_t ready[MAX_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
+  int init() {
+    if (st) return 0;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : ready) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int mp3b200_encode_streams_device(int channels, int samplerate, int kbps, int nstreams, const int16_t* d_pcm,
+                                  const int64_t* pcm_off, const int64_t* nsamples, uint8_t* d_out,
+                                  const int64_t* out_off, float* timings_ms) {
+  Config* cfg;
+  int rc = get_config(channels, samplerate, kbps, &cfg);
+  if (rc) return rc;
+  return encode_streams_device_impl(cfg, channels, nstreams, d_pcm, pcm_off, nsamples, d_out, out_off, timings_ms, nullptr);
 }
 
 int mp3b200_encode_streams(int channels, int samplerate, int kbps, int nstreams, const int16_t* const* left,
@@ -352,11 +387,25 @@ int mp3b200_encode_streams(int channels, int samplerate, int kbps, int nstreams,
     CK(cudaMalloc(&d_out, (size_t)tot_bytes + 8));
     out_cap = (size_t)tot_bytes + 8;
   }
-  for (int s = 0; s < nstreams; s++) {
-    CK(cudaMemcpyAsync(d_pcm + pcm_off[s], left[s], sizeof(int16_t) * nsamples[s], cudaMemcpyHostToDevice, 0));
-    if (channels == 2) CK(cudaMemcpyAsync(d_pcm + pcm_off[s] + nsamples[s], right[s], sizeof(int16_t) * nsamples[s], cudaMemcpyHostToDevice, 0));
+  /* Upload in time slices on a copy stream; the psy analysis of a slice starts when it has landed, so only the first
+   * slice's transfer is exposed.  Many small streams are uploaded whole (one slice): per-copy overhead would win. */
+  static thread_local Uploader up;
+  rc = up.init();
+  if (rc) return rc;
+  PcmArrival arr;
+  arr.chunks = (nstreams <= 8 && tot_samples >= (1 << 20)) ? Uploader::MAX_CHUNKS : 1;
+  arr.ready = up.ready;
+  for (int j = 0; j < arr.chunks; j++) {
+    for (int s = 0; s < nstreams; s++) {
+      const int64_t lo = nsamples[s] * j / arr.chunks, hi = nsamples[s] * (j + 1) / arr.chunks;
+      if (hi <= lo) continue;
+      CK(cudaMemcpyAsync(d_pcm + pcm_off[s] + lo, left[s] + lo, sizeof(int16_t) * (hi - lo), cudaMemcpyHostToDevice, up.st));
+      if (channels == 2)
+        CK(cudaMemcpyAsync(d_pcm + pcm_off[s] + nsamples[s] + lo, right[s] + lo, sizeof(int16_t) * (hi - lo), cudaMemcpyHostToDevice, up.st));
+    }
+    CK(cudaEventRecord(up.ready[j], up.st));
   }
-  rc = mp3b200_encode_streams_device(channels, samplerate, kbps, nstreams, d_pcm, pcm_off.data(), nsamples, d_out, out_off.data(), nullptr);
+  rc = encode_streams_device_impl(cfg, channels, nstreams, d_pcm, pcm_off.data(), nsamples, d_out, out_off.data(), nullptr, &arr);
   if (rc == 0) {
     for (int s = 0; s < nstreams; s++)
       if (cudaMemcpyAsync(out[s], d_out + out_off[s], (size_t)out_bytes[s], cudaMemcpyDeviceToHost, 0) != cudaSuccess) rc = MP3B200_ERR_CUDA;
