@@ -154,6 +154,13 @@ struct FrameShared {
 };
 
 #define LANE (threadIdx.x & 31)
+/* -DQ_STATS: call counters for tuning (tools/profile_run.py prints them); absent from the product build */
+#ifdef Q_STATS
+__device__ unsigned long long g_qstats[16];
+#define QSTAT(i) do { if (LANE == 0) atomicAdd(&g_qstats[i], 1ull); } while (0)
+#else
+#define QSTAT(i) do { } while (0)
+#endif
 /* tuning knobs (tools/build_variants.py) */
 #define Q_PRAGMA(x) _Pragma(#x)
 #define Q_UNROLL(n) Q_PRAGMA(unroll n)
@@ -165,6 +172,9 @@ struct FrameShared {
 #endif
 #ifndef Q_HELPER
 #define Q_HELPER __forceinline__
+#endif
+#ifndef Q_SPEC_STEP
+#define Q_SPEC_STEP 32
 #endif
 #ifndef Q_MIN_BLOCKS
 #define Q_MIN_BLOCKS 14
@@ -730,7 +740,7 @@ __device__ __noinline__ void copy_ix_w(short* dst, const short* src) {
 }
 
 /* bin_search_StepSize (Quantize.js:322-381) on cod_info (wk->b / ixb) */
-__device__ __noinline__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int desired_rate, int* old_value, int* current_step) {
+__device__ __noinline__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int desired_rate, int* old_value, int* current_step, int stat_base = 0) {
   GranuleInfoDev* gi = &wk->b;
   int nBits;
   int CurrentStep = *current_step;
@@ -744,6 +754,7 @@ __device__ __noinline__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int des
     int step;
     if (LANE == 0) gi->global_gain = gain;
     __syncwarp();
+    QSTAT(stat_base);
     nBits = count_bits_w(T, wk, gi, wk->ixw, false);
     if (CurrentStep == 1 || nBits == desired_rate) break;
     if (nBits > desired_rate) {
@@ -765,6 +776,7 @@ __device__ __noinline__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int des
     gain++;
     if (LANE == 0) gi->global_gain = gain;
     __syncwarp();
+    QSTAT(stat_base + 1);
     nBits = count_bits_w(T, wk, gi, wk->ixw, false);
   }
   *current_step = (start - gain >= 4) ? 4 : 2;
@@ -821,6 +833,7 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
     int p23, gg;
     if (best_here) { copy_ix_w(wk->ixg, wk->ixw); best_here = false; }   /* park the best lines before re-quantising */
     for (;;) {                                     /* while (count_bits > huff_bits && global_gain <= maxggain) global_gain++ */
+      QSTAT(8);
       p23 = count_bits_w(T, wk, w, wk->ixw, true);
       gg = w->global_gain;
       __syncwarp();                                /* every lane has read the gain before lane 0 bumps it */
@@ -833,6 +846,7 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
     if (gg > maxggain) break;
     if (best.over_count == 0) {
       for (;;) {
+        QSTAT(9);
         p23 = count_bits_w(T, wk, w, wk->ixw, true);
         gg = w->global_gain;
         __syncwarp();
@@ -844,6 +858,7 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
       __syncwarp();
       if (gg > maxggain) break;
     }
+    QSTAT(10);
     calc_noise_w(T, wk, w, wk->ixw, &cur);
     cur.bits = w->part2_3_length;
     /* quant_compare, case 9 (Quantize.js:493-505,560-567) */
@@ -1474,6 +1489,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
     const int frame_bits = 8 * frame_bytes;
     const int mean_bits = (frame_bits - T->sideinfo_len * 8) / 2;      /* Reservoir.js:83 (exact: multiple of 4) */
     int old_value = fs->old_value[ch], current_step = fs->current_step[ch];
+    const bool speculative = !revalidate && f != 0;    /* in-state guessed by k_qstate_init */
 
     if (revalidate) {
       /* Re-validation of an already encoded frame under a corrected in-state.  The in-state enters only through the
@@ -1488,7 +1504,8 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       const bool have0 = gc_prepare_w(T, wk, fs, xr + (urow0 * nch + ch) * 576, bt_final[urow0 * 2 + ch],
                                       ratio + ((size_t)sd.unit_base + z + 2 * f) * nch + ch, ath_adjust, false);
       unsigned long long h0 = 0;
-      if (have0) { bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs); h0 = gi_hash(&wk->b); }
+      QSTAT(12);
+      if (have0) { bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs, 2); h0 = gi_hash(&wk->b); }
       if (lane == 0) {
         if (ov != q->bs_gain0[ch] || h0 != q->bs_hash[0][ch]) atomicOr(&fs->flag, 1);
         else if (cs != q->bs_step0[ch]) atomicOr(&fs->flag, 2);
@@ -1503,7 +1520,8 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
                                         ratio + ((size_t)sd.unit_base + z + 2 * f + 1) * nch + ch, ath_adjust, false);
         const int step0 = cs;
         if (have1) {
-          bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs);
+          QSTAT(13);
+          bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs, 4);
           const unsigned long long h1 = gi_hash(&wk->b);
           if (lane == 0 && (ov != q->out_old[ch] || h1 != q->bs_hash[1][ch])) atomicOr(&fs->flag, 1);
         }
@@ -1513,6 +1531,7 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
         if (!(verdict & 1) && lane == 0) { q->bs_step0[ch] = step0; q->out_old[ch] = ov; q->out_step[ch] = cs; }
       }
       if (!(verdict & 1)) continue;
+      QSTAT(14);
       if (threadIdx.x == 0) fs->flag = 0;
       __syncthreads();
     }
@@ -1528,7 +1547,12 @@ k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ 
       if (lane == 0) wk->ixg = l3enc_out + (urow * nch + ch) * 576;
       const bool have = gc_prepare_w(T, wk, fs, xr + (urow * nch + ch) * 576, bt, rt, ath_adjust, true);
       unsigned long long bsh = 0;
+      QSTAT(11);
       if (have) outer_loop_w(T, wk, fs->targ_bits[ch], &old_value, &current_step, &bsh);
+      /* a frame encoded from a guessed in-state also guesses the step gr1's search starts with: 2, what a stationary
+       * signal produces (the formula would give 4 whenever the guessed start lies 4 above the landing gain); the value
+       * used is recorded, and re-validation re-runs gr1's search only when the true step differs from it */
+      if (gr == 0 && speculative) current_step = 2;
       if (lane == 0) q->bs_hash[gr][ch] = bsh;
       /* state right after gr0's bin search (pass-through when the granule is silent): re-validation key */
       if (gr == 0 && lane == 0) { q->bs_gain0[ch] = old_value; q->bs_step0[ch] = current_step; }
@@ -1592,9 +1616,11 @@ __global__ void k_qstate_init(const StreamDesc* __restrict__ streams, int nstrea
   q->stream = z; q->rel_frame = f; q->valid = 0;
 #pragma unroll 1
   for (int c = 0; c < 2; c++) {
-    /* first frame: the stream's true state; others: speculation (re-validated afterwards) */
+    /* first frame: the stream's true state; others: speculation (re-validated afterwards).  The speculative search
+     * starts with a step of Q_SPEC_STEP -- a real state only ever holds 2 or 4 -- so that it brackets the target in a
+     * few big strides and then halves down to 1, landing where the search from the true state lands. */
     q->in_old[c] = f == 0 ? sd.old_value[c] : 180;
-    q->in_step[c] = f == 0 ? sd.current_step[c] : 2;
+    q->in_step[c] = f == 0 ? sd.current_step[c] : Q_SPEC_STEP;
     q->out_old[c] = q->out_step[c] = 0;
   }
 }

@@ -277,6 +277,13 @@ long long bytes_for(const Mp3Tables& t, long long frames) {
 extern "C" {
 
 const char* mp3b200_last_error(void) { return g_err.c_str(); }
+#ifdef Q_STATS
+int mp3b200_debug_qstats(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, g_qstats, sizeof(unsigned long long) * 16) != cudaSuccess) return MP3B200_ERR_CUDA;
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_qstats, z, sizeof z); }
+  return 0;
+}
+#endif
 int64_t mp3b200_launch_count(void) { return g_launches; }
 
 int mp3b200_set_device(int device) {

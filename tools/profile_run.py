@@ -27,3 +27,14 @@ print("timings ms [psy, scan, mask, fb, q1, qn, total, passes]:", [round(float(x
 import hashlib
 print("sha256:", hashlib.sha256(out[:nb].cpu().numpy().tobytes()).hexdigest()[:16], "lib:", os.environ.get("MP3B200_LIB", "default"))
 print("x realtime:", (M.stream_frames(n) * 1152 / 44100) / (tm[6] / 1000))
+
+if hasattr(M.lib(), "mp3b200_debug_qstats"):
+    import ctypes
+    st = (ctypes.c_ulonglong * 16)()
+    M.lib().mp3b200_debug_qstats(st, 1)
+    names = ["bs1 search", "bs1 tail", "reval-gr0 search", "reval-gr0 tail", "reval-gr1 search", "reval-gr1 tail", "-", "-", "outer huff loop",
+             "outer best loop", "calc_noise(outer)", "gc encoded", "reval gr0", "reval gr1", "reval failed -> re-encode", "-"]
+    gcs = max(1, st[11])
+    print("call counters over %d encodes (per encoded gc in brackets):" % reps)
+    for n_, v in zip(names, st):
+        if n_ != "-": print("  %-28s %10d  [%.2f]" % (n_, v, v / gcs))
