@@ -832,7 +832,9 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
     if (huff_bits <= 0) break;
     int p23, gg;
     if (best_here) { copy_ix_w(wk->ixg, wk->ixw); best_here = false; }   /* park the best lines before re-quantising */
+    int sc_in;                                     /* prev_noise.sfb_count1 as the last count_bits call of this loop saw it */
     for (;;) {                                     /* while (count_bits > huff_bits && global_gain <= maxggain) global_gain++ */
+      sc_in = wk->pn_sfb_count1;
       QSTAT(8);
       p23 = count_bits_w(T, wk, w, wk->ixw, true);
       gg = w->global_gain;
@@ -845,9 +847,14 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
     __syncwarp();
     if (gg > maxggain) break;
     if (best.over_count == 0) {
+      /* The reference calls count_bits again at the very gain the loop above stopped at.  Its only input that the
+       * previous call can have changed is prev_noise.sfb_count1 (everything else -- gain, scalefactors, xrpow, the cached
+       * lines and tables of cod_info_w -- is what that call left behind); if that value did not change the repeat would
+       * recompute the identical state and bit count, so it is skipped. */
+      bool repeat = wk->pn_sfb_count1 == sc_in;
       for (;;) {
-        QSTAT(9);
-        p23 = count_bits_w(T, wk, w, wk->ixw, true);
+        if (!repeat) { QSTAT(9); p23 = count_bits_w(T, wk, w, wk->ixw, true); }
+        repeat = false;
         gg = w->global_gain;
         __syncwarp();
         if (!(p23 > best_part2_3_length && gg <= maxggain)) break;
