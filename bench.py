@@ -272,7 +272,7 @@ def main():
             k["frac"] = k["gbps"] / peak if k["gbps"] else None
         dom = max(kern, key=lambda k: kern[k]["ms"])
         ncores = host_cores()
-        cpu_v, cpu_dt = cpu_reference_run(ncores, 1, 2000)
+        cpu_v, cpu_dt = cpu_reference_run(ncores, 1, 5000)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -288,7 +288,7 @@ def main():
                          "note": "algorithmic bytes/launch = %d B x %d frame-channels; exact-double arithmetic keeps every kernel FP64/latency bound (DESIGN.md)" % (kern[dom]["bytes"], units)},
             "kernels": kern,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": ncores, "kind": "port",
-                             "sample": "one 2000-frame prefix of the C2 sweep per host thread, %.1f s wall; lamejs restatement (C++ -O2), lamejs itself needs a JS engine" % cpu_dt},
+                             "sample": "one 5000-frame prefix of the C2 sweep per host thread, %.1f s wall; lamejs restatement (C++ -O2), lamejs itself needs a JS engine" % cpu_dt},
         }
         print(json.dumps(line))
     if world > 1:
