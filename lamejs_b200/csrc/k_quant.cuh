@@ -316,9 +316,9 @@ __device__ __noinline__ int noquant_count_bits_w(const Mp3Tables* T, const short
     b2 = min(b2, bigv);
     /* same order as the reference: region 2 (long blocks only), then 0, then 1; empty regions keep their table.
      * One small routine called three times: the kernel is instruction-fetch bound, code reuse beats a fused sweep. */
-    if (bt == BT_NORM && b2 < bigv) ts2 = region_table_w(ix, b2, bigv, &bits);
-    if (0 < b1) ts0 = region_table_w(ix, 0, b1, &bits);
-    if (b1 < b2) ts1 = region_table_w(ix, b1, b2, &bits);
+    if (bt == BT_NORM && b2 < bigv) { QSTAT(15); ts2 = region_table_w(ix, b2, bigv, &bits); }
+    if (0 < b1) { QSTAT(15); ts0 = region_table_w(ix, 0, b1, &bits); }
+    if (b1 < b2) { QSTAT(15); ts1 = region_table_w(ix, b1, b2, &bits); }
   }
   __syncwarp();
   if (lane == 0) {
@@ -1166,28 +1166,149 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
   if (recalc != 0) scale_bitcount_w(gi);
 }
 
-/* best_huffman_divide (Takehiro.js:727-800) on cod_info (wk->b / ixb); wk->w is free to use as cod_info2 */
-__device__ __noinline__ void recalc_divide_sub_w(const Mp3Tables* T, GcWork* wk, const GranuleInfoDev* cod_info2, const int* r01_bits,
-                                    const int* r01_div, const int* r0_tbl, const int* r1_tbl) {
+/* ---- best_huffman_divide (Takehiro.js:666-800) on cod_info (wk->b); wk->w is free to use as cod_info2 -----------------
+ * recalc_divide_init tries every region0/region1 split (up to 16 x 8 choose_table calls) and recalc_divide_sub every
+ * region2 start.  All those regions are unions of whole scalefactor bands (plus the partial band below big_values), so the
+ * work is done once per band: largest value, number of escape values, and the packed code-length sums under every table
+ * class the band can appear in (a band's class can only be raised by its neighbours).  A region is then a max and a few
+ * adds over its bands.  The scratch overlays xrpow, which is dead once outer_loop has returned. */
+struct DivScratch {
+  unsigned ab[23][7];               /* band b, class c: field a | field b << 16 (valid for c >= the band's own class) */
+  unsigned short cc[23][7];         /* field c */
+  unsigned short bmax[23], nesc[23];
+  int r0bits[16]; unsigned char r0t[16];
+  int cbits[128]; unsigned char ct1[128];   /* (r0, r1) combinations; reused per region2 start by recalc_divide_sub */
+};
+static_assert(sizeof(DivScratch) <= 576 * sizeof(float), "DivScratch must fit into the xrpow array");
+
+/* per-band statistics of the pairs below big_values; returns the number of bands (a partial last band counts) */
+__device__ __noinline__ int band_stats_w(const Mp3Tables* T, const short* ix, int bigv, DivScratch* ds) {
+  const int lane = LANE;
+  const unsigned* w32 = reinterpret_cast<const unsigned*>(ix);
+  int B = 0;
+  while (B < 22 && T->sfb_l[B + 1] <= bigv) B++;                 /* bands 0..B-1 lie entirely below big_values */
+  const int nb = (B < 22 && T->sfb_l[B] < bigv) ? B + 1 : B;      /* band B = [sfb_l[B], big_values) if not empty */
+  __syncwarp();
+#pragma unroll 1
+  for (int b = lane; b < nb; b += 32) {
+    const int lo = T->sfb_l[b] >> 1, hi = (b < B ? T->sfb_l[b + 1] : bigv) >> 1;
+    unsigned m = 0, ne = 0;
+#pragma unroll 1
+    for (int p = lo; p < hi; p++) { const unsigned w = w32[p]; m = __vmaxu2(m, w); ne += ((w & 0xffffu) > 14u) + ((w >> 16) > 14u); }
+    ds->bmax[b] = (unsigned short)max(m & 0xffffu, m >> 16);
+    ds->nesc[b] = (unsigned short)ne;
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int t = lane; t < nb * 7; t += 32) {                       /* one (band, class) task per lane and round */
+    const int b = t / 7, c = t - 7 * b;
+    const int mx = ds->bmax[b];
+    const int lowc = mx <= 1 ? 0 : (mx <= 3 ? mx - 1 : (mx <= 5 ? 3 : (mx <= 7 ? 4 : (mx <= 15 ? 5 : 6))));
+    if (c < lowc) continue;
+    const unsigned int* tab = g_cat_tab[c];
+    const int lo = T->sfb_l[b] >> 1, hi = (b < B ? T->sfb_l[b + 1] : bigv) >> 1;
+    unsigned sa = 0, sb = 0, sc = 0;
+#pragma unroll 1
+    for (int p = lo; p < hi; p++) {
+      const unsigned w = w32[p];
+      const unsigned v = __ldg(&tab[min(w & 0xffffu, 15u) * 16 + min(w >> 16, 15u)]);
+      sa += v & 0x7ffu; sb += (v >> 11) & 0x7ffu; sc += v >> 22;
+    }
+    ds->ab[b][c] = sa | (sb << 16);
+    ds->cc[b][c] = (unsigned short)sc;
+  }
+  __syncwarp();
+  return nb;
+}
+
+/* choose_table over the bands b0..b1 from the statistics: table, and its bits added to *bits */
+__device__ __forceinline__ int region_from_bands(const DivScratch* ds, int b0, int b1, int* bits) {
+  int mx = 0;
+#pragma unroll 1
+  for (int b = b0; b <= b1; b++) mx = max(mx, (int)ds->bmax[b]);
+  if (mx == 0) return 0;
+  const RegionClass rc = region_class(mx);
+  int sa = 0, sb = 0, sc = 0, ne = 0;
+#pragma unroll 1
+  for (int b = b0; b <= b1; b++) {
+    const unsigned u = ds->ab[b][rc.cat];
+    sa += (int)(u & 0xffffu); sb += (int)(u >> 16); sc += ds->cc[b][rc.cat]; ne += ds->nesc[b];
+  }
+  if (rc.cat == 6) { sa += ne * (int)(rc.lin & 0x7ffu); sb += ne * (int)((rc.lin >> 11) & 0x7ffu); sc = sb; }
+  return region_pick(mx, rc, sa, sb, sc, bits);
+}
+
+/* recalc_divide_init (Takehiro.js:666-700): best (region0, region1) split for every region1 end */
+__device__ __noinline__ void divide_init_w(const Mp3Tables* T, DivScratch* ds, int bigv, int* r01_bits, int* r01_div, int* r0_tbl, int* r1_tbl) {
+  const int lane = LANE;
+  if (lane < 16) {
+    int bits0 = -1, t0 = 0;
+    if (T->sfb_l[lane + 1] < bigv) { bits0 = 0; t0 = region_from_bands(ds, 0, lane, &bits0); }
+    ds->r0bits[lane] = bits0; ds->r0t[lane] = (unsigned char)t0;
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int k = lane; k < 128; k += 32) {
+    const int r0 = k >> 3, r1 = k & 7;
+    int bits = -1, t1 = 0;
+    if (ds->r0bits[r0] >= 0 && r0 + r1 + 2 <= 22 && T->sfb_l[r0 + r1 + 2] < bigv) {
+      bits = ds->r0bits[r0];
+      t1 = region_from_bands(ds, r0 + 1, r0 + r1 + 1, &bits);
+    }
+    ds->cbits[k] = bits; ds->ct1[k] = (unsigned char)t1;
+  }
+  __syncwarp();
+  if (lane < 23) {                                   /* the reference visits r0 ascending and keeps the first minimum */
+    const int sidx = lane;
+    int best = Q_LARGE_BITS;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 16; r0++) {
+      const int r1 = sidx - r0;
+      if (r1 < 0 || r1 > 7) continue;
+      const int bits = ds->cbits[r0 * 8 + r1];
+      if (bits < 0) continue;
+      if (best > bits) { best = bits; r01_div[sidx] = r0; r0_tbl[sidx] = ds->r0t[r0]; r1_tbl[sidx] = ds->ct1[r0 * 8 + r1]; }
+    }
+    r01_bits[sidx] = best;
+  }
+  __syncwarp();
+}
+
+/* recalc_divide_sub (Takehiro.js:702-725); `ds` holds the statistics for cod_info2->big_values */
+__device__ __noinline__ void recalc_divide_sub_w(const Mp3Tables* T, GcWork* wk, DivScratch* ds, int nb, const GranuleInfoDev* cod_info2,
+                                                 const int* r01_bits, const int* r01_div, const int* r0_tbl, const int* r1_tbl) {
+  const int lane = LANE;
   GranuleInfoDev* gi = &wk->b;
   const int bigv = cod_info2->big_values;
+  /* region2 = bands r2 .. nb-1 for every candidate start */
+  if (lane + 2 <= 22) {
+    const int r2 = lane + 2;
+    int bits2 = 0, t2 = 0;
+    if (T->sfb_l[r2] < bigv) t2 = region_from_bands(ds, r2, nb - 1, &bits2);
+    ds->cbits[r2] = bits2; ds->ct1[r2] = (unsigned char)t2;
+  }
+  __syncwarp();
+  int cur = gi->part2_3_length, best_r2 = -1;
+  const int c1bits = cod_info2->count1bits;
 #pragma unroll 1
-  for (int r2 = 2; r2 < 22 + 1; r2++) {
-    const int a2 = T->sfb_l[r2];
-    if (a2 >= bigv) break;
-    int bits = r01_bits[r2 - 2] + cod_info2->count1bits;
-    if (gi->part2_3_length <= bits) break;
-    const int r2t = region_table_w(wk->ixw, a2, bigv, &bits);
-    if (gi->part2_3_length <= bits) continue;
-    __syncwarp();
+  for (int r2 = 2; r2 < 22 + 1; r2++) {               /* the sequential acceptance rule, on precomputed numbers */
+    if (T->sfb_l[r2] >= bigv) break;
+    int bits = r01_bits[r2 - 2] + c1bits;
+    if (cur <= bits) break;
+    bits += ds->cbits[r2];
+    if (cur <= bits) continue;
+    cur = bits; best_r2 = r2;
+  }
+  __syncwarp();
+  if (best_r2 >= 0) {
     if (cod_info2 != gi) copy_gi_w(gi, cod_info2);
-    if (LANE == 0) {
-      gi->part2_3_length = bits;
-      gi->region0_count = r01_div[r2 - 2];
-      gi->region1_count = r2 - 2 - r01_div[r2 - 2];
-      gi->table_select[0] = r0_tbl[r2 - 2];
-      gi->table_select[1] = r1_tbl[r2 - 2];
-      gi->table_select[2] = r2t;
+    if (lane == 0) {
+      gi->part2_3_length = cur;
+      gi->region0_count = r01_div[best_r2 - 2];
+      gi->region1_count = best_r2 - 2 - r01_div[best_r2 - 2];
+      gi->table_select[0] = r0_tbl[best_r2 - 2];
+      gi->table_select[1] = r1_tbl[best_r2 - 2];
+      gi->table_select[2] = ds->ct1[best_r2];
     }
     __syncwarp();
   }
@@ -1203,33 +1324,13 @@ __device__ __noinline__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* w
   int* r01_div = reinterpret_cast<int*>(wk->distort);
   int* r0_tbl = wk->pn_step;
   int* r1_tbl = reinterpret_cast<int*>(wk->pn_noise);
+  DivScratch* ds = reinterpret_cast<DivScratch*>(wk->xrpow);
   copy_gi_w(c2, gi);
   if (gi->block_type == BT_NORM) {
-    /* recalc_divide_init (Takehiro.js:666-700) */
     const int bigv = gi->big_values;
-#pragma unroll 1
-    for (int i = lane; i < 23; i += 32) r01_bits[i] = Q_LARGE_BITS;
-    __syncwarp();
-#pragma unroll 1
-    for (int r0 = 0; r0 < 16; r0++) {
-      const int a1 = T->sfb_l[r0 + 1];
-      if (a1 >= bigv) break;
-      int r0bits = 0;
-      const int r0t = region_table_w(ix, 0, a1, &r0bits);
-#pragma unroll 1
-      for (int r1 = 0; r1 < 8; r1++) {
-        const int a2 = T->sfb_l[r0 + r1 + 2];
-        if (a2 >= bigv) break;
-        int bits = r0bits;
-        const int r1t = region_table_w(ix, a1, a2, &bits);
-        if (r01_bits[r0 + r1] > bits) {
-          __syncwarp();
-          if (lane == 0) { r01_bits[r0 + r1] = bits; r01_div[r0 + r1] = r0; r0_tbl[r0 + r1] = r0t; r1_tbl[r0 + r1] = r1t; }
-          __syncwarp();
-        }
-      }
-    }
-    recalc_divide_sub_w(T, wk, c2, r01_bits, r01_div, r0_tbl, r1_tbl);
+    const int nb = band_stats_w(T, ix, bigv, ds);
+    divide_init_w(T, ds, bigv, r01_bits, r01_div, r0_tbl, r1_tbl);
+    recalc_divide_sub_w(T, wk, ds, nb, c2, r01_bits, r01_div, r0_tbl, r1_tbl);
   }
   int i = c2->big_values;
   if (i == 0 || (ix[i - 2] | ix[i - 1]) > 1) return;
@@ -1261,8 +1362,10 @@ __device__ __noinline__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* w
   }
   __syncwarp();
   if (a1 > a2) a1 = a2;
-  if (c2->block_type == BT_NORM) recalc_divide_sub_w(T, wk, c2, r01_bits, r01_div, r0_tbl, r1_tbl);
-  else {
+  if (c2->block_type == BT_NORM) {
+    const int nb2 = band_stats_w(T, ix, i, ds);        /* big_values moved down: the partial last band changed */
+    recalc_divide_sub_w(T, wk, ds, nb2, c2, r01_bits, r01_div, r0_tbl, r1_tbl);
+  } else {
     int p23 = a1;
     int b1 = T->sfb_l[7 + 1];
     if (b1 > i) b1 = i;
