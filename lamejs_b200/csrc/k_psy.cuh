@@ -346,10 +346,15 @@ k_psy_loudness(const Mp3Tables* __restrict__ T, const float* __restrict__ fe_in,
   double lp = 0.0;
 #pragma unroll 1
   for (int c0 = 0; c0 < 512; c0 += 32) {
-#pragma unroll 4
-    for (int r = warp; r < LOUD_ROWS; r += LOUD_ROWS / 32) {
-      const long long row = row0 + r;
-      tile[r][lane] = row < nrows ? fe_in[row * 512 + c0 + lane] : 0.0f;
+    {
+      float v[32];                                   /* all 32 row segments of this warp in flight before any is used */
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
+        const long long row = row0 + warp + k * (LOUD_ROWS / 32);
+        v[k] = row < nrows ? __ldcs(&fe_in[row * 512 + c0 + lane]) : 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < 32; k++) tile[warp + k * (LOUD_ROWS / 32)][lane] = v[k];
     }
     __syncthreads();
 #pragma unroll 4

@@ -173,6 +173,9 @@ __device__ unsigned long long g_qstats[16];
 #ifndef Q_HELPER
 #define Q_HELPER __forceinline__
 #endif
+#ifndef Q_SPEC_START
+#define Q_SPEC_START 180
+#endif
 #ifndef Q_SPEC_STEP
 #define Q_SPEC_STEP 32
 #endif
@@ -1729,7 +1732,7 @@ __global__ void k_qstate_init(const StreamDesc* __restrict__ streams, int nstrea
     /* first frame: the stream's true state; others: speculation (re-validated afterwards).  The speculative search
      * starts with a step of Q_SPEC_STEP -- a real state only ever holds 2 or 4 -- so that it brackets the target in a
      * few big strides and then halves down to 1, landing where the search from the true state lands. */
-    q->in_old[c] = f == 0 ? sd.old_value[c] : 180;
+    q->in_old[c] = f == 0 ? sd.old_value[c] : Q_SPEC_START;
     q->in_step[c] = f == 0 ? sd.current_step[c] : Q_SPEC_STEP;
     q->out_old[c] = q->out_step[c] = 0;
   }

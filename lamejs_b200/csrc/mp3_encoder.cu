@@ -178,8 +178,8 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     scan_rows += (s.nframes + SCAN_FRAMES - 1) / SCAN_FRAMES;
   }
   CK(cudaMemcpyAsync(ws.d_streams, h_streams.data(), sizeof(StreamDesc) * S, cudaMemcpyHostToDevice, st));
-  cudaEvent_t ev[8];
-  for (auto& e : ev) CK(cudaEventCreate(&e));
+  static thread_local cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (!ev[0]) for (auto& e : ev) CK(cudaEventCreate(&e));   /* created once per host thread */
   CK(cudaEventRecord(ev[0], st));
 
   /* K2: psy analysis, one block per (granule incl. 1 halo, channel, stream) */
@@ -256,7 +256,6 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     cudaEventElapsedTime(&tm->total, ev[0], ev[6]);
     tm->passes = passes;
   }
-  for (auto& e : ev) cudaEventDestroy(e);
   return 0;
 }
 
