@@ -294,7 +294,10 @@ __device__ __forceinline__ void mdct_short_dev(f32s* io) {
 
 /* grid: (ceil(max_granules / FB_G), nch, nstreams); block: FB_THREADS.
  * blocktype: int8 [granule row][2]; xr_out: float [granule row][nch][576]. */
-__global__ void __launch_bounds__(FB_THREADS, 2)
+#ifndef FB_MIN_BLOCKS
+#define FB_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(FB_THREADS, FB_MIN_BLOCKS)
 k_filterbank_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams,
                   const signed char* __restrict__ blocktype, float* __restrict__ xr_out) {
   const StreamDesc sd = streams[blockIdx.z];
