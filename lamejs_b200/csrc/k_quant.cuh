@@ -1094,30 +1094,43 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
     }
   }
   __syncwarp();
+  const int sfbmax = gi->sfbmax;
+  int recalc_w = 0;                                  /* warp-uniform copy of `recalc` up to the scfsi step */
+  {
+    bool z = false;
+#pragma unroll 1
+    for (int sfb = lane; sfb < sfbmax; sfb += 32) if (!wk->mode[sfb]) { gi->scalefac[sfb] = -2; z = true; }
+    if (__any_sync(Q_FULL, z)) recalc_w = -2;
+  }
+  __syncwarp();
+  if (0 == gi->scalefac_scale && 0 == gi->preflag) {
+    int sor = 0;
+#pragma unroll 1
+    for (int sfb = lane; sfb < sfbmax; sfb += 32) { const int v = gi->scalefac[sfb]; if (v > 0) sor |= v; }
+    sor = (int)__reduce_or_sync(Q_FULL, (unsigned)sor);
+    if (0 == (sor & 1) && sor != 0) {
+#pragma unroll 1
+      for (int sfb = lane; sfb < sfbmax; sfb += 32) { const int v = gi->scalefac[sfb]; if (v > 0) gi->scalefac[sfb] = v >> 1; }
+      __syncwarp();
+      if (lane == 0) gi->scalefac_scale = 1;
+      recalc_w = 1;
+    }
+  }
+  __syncwarp();
+  if (0 == gi->preflag && gi->block_type != BT_SHORT) {
+    const bool in = lane >= 11 && lane < 21;
+    const int v = in ? gi->scalefac[lane] : 0, pt = pretab_of(lane);
+    const bool ok = !in || !(v < pt && v != -2);
+    if (__all_sync(Q_FULL, ok)) {
+      if (in && v > 0) gi->scalefac[lane] = v - pt;
+      __syncwarp();
+      if (lane == 0) gi->preflag = 1;
+      recalc_w = 1;
+    }
+  }
+  __syncwarp();
   if (lane == 0) {
-    int recalc = 0;
-#pragma unroll 1
-    for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (!wk->mode[sfb]) gi->scalefac[sfb] = recalc = -2;
-    if (0 == gi->scalefac_scale && 0 == gi->preflag) {
-      int s = 0;
-#pragma unroll 1
-      for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] > 0) s |= gi->scalefac[sfb];
-      if (0 == (s & 1) && s != 0) {
-#pragma unroll 1
-        for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] > 0) gi->scalefac[sfb] >>= 1;
-        gi->scalefac_scale = recalc = 1;
-      }
-    }
-    if (0 == gi->preflag && gi->block_type != BT_SHORT) {
-      int sfb;
-#pragma unroll 1
-      for (sfb = 11; sfb < 21; sfb++) if (gi->scalefac[sfb] < c_pretab[sfb] && gi->scalefac[sfb] != -2) break;
-      if (sfb == 21) {
-#pragma unroll 1
-        for (sfb = 11; sfb < 21; sfb++) if (gi->scalefac[sfb] > 0) gi->scalefac[sfb] -= c_pretab[sfb];
-        gi->preflag = recalc = 1;
-      }
-    }
+    int recalc = recalc_w;
 #pragma unroll 1
     for (int i = 0; i < 4; i++) fs->scfsi[ch][i] = 0;
     if (gr == 1 && fs->fin[ch].block_type != BT_SHORT && gi->block_type != BT_SHORT) {
@@ -1159,10 +1172,11 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
       }
       recalc = 0;
     }
-#pragma unroll 1
-    for (int sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] == -2) gi->scalefac[sfb] = 0;
     wk->scratch[0] = recalc;
   }
+  __syncwarp();
+#pragma unroll 1
+  for (int sfb = lane; sfb < sfbmax; sfb += 32) if (gi->scalefac[sfb] == -2) gi->scalefac[sfb] = 0;
   __syncwarp();
   const int recalc = wk->scratch[0];
   __syncwarp();
