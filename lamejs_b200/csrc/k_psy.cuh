@@ -146,10 +146,10 @@ __device__ __forceinline__ size_t psy_row(const StreamDesc& sd, int z, int u) { 
 #endif
 __global__ void __launch_bounds__(PSY_THREADS, PSY_MIN_BLOCKS)
 k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ out,
-               float* __restrict__ fe_out, int chunk, int nchunks) {
+               float* __restrict__ fe_out, int chunk, int nchunks, int u_base) {
   const int z = blockIdx.z;
   const StreamDesc& sd = streams[z];
-  const int u = (int)blockIdx.x - 1;                 /* relative unit, -1 = halo */
+  const int u = (int)blockIdx.x + u_base;             /* relative unit, -1 = halo */
   if (u >= 2 * sd.nframes) return;
   const int ch = blockIdx.y;
   const int nch = T->nch;

@@ -162,6 +162,7 @@ struct Timings { float psy = 0, scan = 0, mask = 0, fb = 0, q1 = 0, qn = 0, tota
 /* pcm_chunks > 1: the caller uploads each stream's PCM in that many time slices on another stream and records
  * pcm_ready[j] after slice j; the psy analysis of slice j starts as soon as it has landed. */
 struct PcmArrival { int chunks = 1; cudaEvent_t* ready = nullptr; };
+enum { MP3_MAX_PCM_CHUNKS = 8 };
 
 int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams, uint8_t* d_out, const int32_t* force_bt,
                  bool stop_after_mdct, Timings* tm, cudaStream_t st, const PcmArrival* arrival = nullptr) {
@@ -184,11 +185,29 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
 
   /* K2: psy analysis, one block per (granule incl. 1 halo, channel, stream) */
   {
-    dim3 grid(2 * max_frames + 1, nch, S);
     const int nchunks = arrival ? arrival->chunks : 1;
+    /* units (relative index, -1 = halo) each upload slice completes, over all streams: the kernel's own rule
+     * (k_psy_analysis) evaluated on the host, so that a slice's launch covers only its range of units */
+    int u_lo[MP3_MAX_PCM_CHUNKS], u_hi[MP3_MAX_PCM_CHUNKS];
+    for (int j = 0; j < nchunks; j++) { u_lo[j] = 2 * max_frames; u_hi[j] = -1; }
+    if (nchunks > 1) {
+      for (const auto& sd : h_streams) {
+        const long long n = sd.pcm_end - sd.pcm_base;
+        for (int u = -1; u < 2 * sd.nframes; u++) {
+          long long last = 576 * (2LL * sd.frame0 + u) - 224 + 1023 - sd.pcm_base;
+          if (last > n - 1) last = n - 1;
+          int mine = 0;
+          while (mine < nchunks - 1 && last >= n * (mine + 1) / nchunks) mine++;
+          if (u < u_lo[mine]) u_lo[mine] = u;
+          if (u + 1 > u_hi[mine]) u_hi[mine] = u + 1;
+        }
+      }
+    } else { u_lo[0] = -1; u_hi[0] = 2 * max_frames; }
     for (int j = 0; j < nchunks; j++) {
       if (arrival) CK(cudaStreamWaitEvent(st, arrival->ready[j], 0));
-      k_psy_analysis<<<grid, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_fe, j, nchunks);
+      if (u_hi[j] <= u_lo[j]) continue;
+      dim3 gridj(u_hi[j] - u_lo[j], nch, S);
+      k_psy_analysis<<<gridj, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_fe, j, nchunks, u_lo[j]);
       g_launches++;
       DBG("k_psy_analysis");
     }
@@ -341,8 +360,8 @@ int encode_streams_device_impl(Config* cfg, int channels, int nstreams, const in
 
 /* upload stream + arrival events of the host-buffer batch call */
 struct Uploader {
-  enum { MAX_CHUNKS = 4 };
-  cudaStream_t st = nullptr; cudaEvent_t ready[MAX_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
+  enum { MAX_CHUNKS = MP3_MAX_PCM_CHUNKS };
+  cudaStream_t st = nullptr; cudaEvent_t ready[MAX_CHUNKS] = {};
   int init() {
     if (st) return 0;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
