@@ -1,4 +1,4 @@
-/* k_psy.cuh -- K2 / K3a / K3b: psycho-acoustic model (lamejs L3psycho_anal_ns) as four kernels.
+/* k_psy.cuh -- K2 / K2b / K3pre / K3a / K3b: psycho-acoustic model (lamejs L3psycho_anal_ns) as five kernels.
  *
  * Reference: src/js/PsyModel.js L3psycho_anal_ns :1000-1383 with compute_ffts :251-324, mask_add :403-473,
  * calc_interchannel_masking :525-543, convert_partition2scalefac_s/_l :644-734, compute_masking_s :736-782,
@@ -8,7 +8,8 @@
  * lamejs runs one psy call per granule ("unit" c, analysing stream samples [576c-224, 576c+800)) and carries
  * state from call to call.  Here the work is split by what it depends on:
  *   k_psy_analysis   pure function of PCM: fs/4 HPF + 9 sub-block peaks, 1024-pt and 3x256-pt FHT, line
- *                    energies, partition energies / tonality index, short-block spreading sums, loudness
+ *                    energies, partition energies / tonality index, short-block spreading sums
+ *   k_psy_loudness   the 512-term ordered loudness sum of every unit, one thread each (psycho_loudness_approx)
  *   k_attack_prepass pure function of two consecutive units: attack candidates (before the lastAttacks FSM)
  *   k_stream_scan    the only sequential part: per stream, the attack / block-type FSM and the ATH-adjust IIR
  *   k_psy_masking    long-block spreading with mask_add (needs ATH.adjust), short thresholds (need the previous

@@ -54,11 +54,6 @@ __device__ unsigned short g_huff_code[1666];
 __device__ unsigned char g_huff_len[1666];
 __constant__ int c_huff_off[34];
 __constant__ int c_huff_xlen[34];
-__constant__ int c_huff_linmax[34];
-__device__ unsigned int g_largetbl[256];
-__device__ unsigned int g_table23[9];
-__device__ unsigned int g_table56[16];
-__constant__ int c_pretab[22];
 __device__ int g_t32l[16];
 __device__ int g_t33l[16];
 __constant__ int c_slen1_n[16];
@@ -74,12 +69,9 @@ __device__ int g_scale_tab[2][16];               /* scale_long / scale_short */
 __device__ unsigned int g_cat_tab[8][256];
 __constant__ int c_slen1_tab[16];
 __constant__ int c_slen2_tab[16];
-__constant__ int c_scale_short[16];
-__constant__ int c_scale_long[16];
 __constant__ int c_huf_noesc[15];
 
 static int quant_upload_constants() {
-  static const int pretab[22] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2, 0};
   static const int t32l[16] = {1, 5, 5, 7, 5, 8, 7, 9, 5, 7, 7, 9, 7, 9, 9, 10};
   static const int t33l[16] = {4, 5, 5, 6, 5, 6, 6, 7, 5, 6, 6, 7, 6, 7, 7, 8};
   static const int s1n[16] = {1, 1, 1, 1, 8, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 16};
@@ -91,10 +83,9 @@ static int quant_upload_constants() {
   static const int hn[15] = {1, 2, 5, 7, 7, 10, 10, 13, 13, 13, 13, 13, 13, 13, 13};
 #define UP(sym, src) if (cudaMemcpyToSymbol(sym, src, sizeof(src)) != cudaSuccess) return -100
   UP(g_huff_code, MP3_HUFF_CODE); UP(g_huff_len, MP3_HUFF_LEN); UP(c_huff_off, MP3_HUFF_OFF);
-  UP(c_huff_xlen, MP3_HUFF_XLEN); UP(c_huff_linmax, MP3_HUFF_LINMAX); UP(g_largetbl, MP3_HUFF_LARGETBL);
-  UP(g_table23, MP3_HUFF_TABLE23); UP(g_table56, MP3_HUFF_TABLE56);
-  UP(c_pretab, pretab); UP(g_t32l, t32l); UP(g_t33l, t33l); UP(c_slen1_n, s1n); UP(c_slen2_n, s2n);
-  UP(c_slen1_tab, s1t); UP(c_slen2_tab, s2t); UP(c_scale_short, ss); UP(c_scale_long, sl); UP(c_huf_noesc, hn);
+  UP(c_huff_xlen, MP3_HUFF_XLEN);
+  UP(g_t32l, t32l); UP(g_t33l, t33l); UP(c_slen1_n, s1n); UP(c_slen2_n, s2n);
+  UP(c_slen1_tab, s1t); UP(c_slen2_tab, s2t); UP(c_huf_noesc, hn);
   {
     static int sn[2][16], st[2][16];
     static unsigned int ct[8][256];
@@ -188,7 +179,6 @@ __device__ __noinline__ double q_pow(double x, double y) { return m3_pow(x, y); 
 __device__ __forceinline__ int wmax(int v) { return __reduce_max_sync(Q_FULL, v); }
 __device__ __forceinline__ int wsum(int v) { return __reduce_add_sync(Q_FULL, v); }
 __device__ __forceinline__ unsigned wsumu(unsigned v) { return __reduce_add_sync(Q_FULL, v); }
-__device__ __forceinline__ int hlen(int t, int i) { return __ldg(&g_huff_len[c_huff_off[t] + i]); }
 
 /* ---- choose_table (Takehiro.js:465-516) with its count_bit_* callees, table-driven ------------------------------
  * A region is classified by its largest value (RegionClass); one pass then adds, for every pair, the packed code
