@@ -1776,11 +1776,14 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
                      QuantFrameState* d_qs, GranuleInfoDev* d_ginfo, short* d_l3enc, unsigned int* d_framebits, int keep_l3enc,
                      int* d_list, int* d_counter, uint8_t* d_out,
                      cudaStream_t st, cudaEvent_t ev_pass1, int* passes_out, long long* launches) {
-  static bool attr_set = false;
+  static int attr_dev = -1;               /* the attribute is per device: re-apply after mp3b200_set_device */
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  const bool attr_set = attr_dev == cur_dev;
   const size_t smem = sizeof(FrameShared);
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_quantize_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
-    attr_set = true;
+    attr_dev = cur_dev;
   }
   const int threads = 32 * hT.nch;
   int dev = 0, sms = 148;

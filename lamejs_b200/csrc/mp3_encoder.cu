@@ -247,8 +247,10 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   {
     dim3 grid((2 * max_frames + FB_G - 1) / FB_G, nch, S);
     const size_t smem = sizeof(double) * FB_PCM_WORDS + sizeof(float) * ((FB_G + 1) * 18 * FB_SLAB_STRIDE);
-    static bool fb_attr = false;
-    if (!fb_attr) { CK(cudaFuncSetAttribute(k_filterbank_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); fb_attr = true; }
+    static int fb_attr_dev = -1;          /* per device: re-apply after mp3b200_set_device */
+    int cur_dev = 0;
+    CK(cudaGetDevice(&cur_dev));
+    if (fb_attr_dev != cur_dev) { CK(cudaFuncSetAttribute(k_filterbank_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); fb_attr_dev = cur_dev; }
     k_filterbank_mdct<<<grid, FB_THREADS, smem, st>>>(cfg->dev, ws.d_streams, ws.d_bt_final, ws.d_xr);
     g_launches++;
     DBG("k_filterbank_mdct");
