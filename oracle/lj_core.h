@@ -9,7 +9,8 @@
  * PARITY UNPINNED: the reference holds no golden vectors (src/js/Tests.js
  * compares nothing) and no JS engine exists in the build image, so this
  * restatement could not be checked against lamejs output.  It is pinned only
- * by derivable known answers (tests/test_oracle_kat.py).
+ * by derivable known answers (tests/test_oracle_kat.py) and by decoding its output
+ * with an independent ISO 11172-3 decoder (tests/test_oracle_decode.py).
  *
  * Arithmetic model: every JS local is an IEEE double; a
  * store into a Float32Array rounds to float32 (RNE), a store into an
