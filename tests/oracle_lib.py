@@ -52,7 +52,10 @@ _lib = None
 
 
 def build():
-    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+    import fcntl
+    with open(os.path.join(ORACLE_DIR, ".build.lock"), "w") as lk:   # pytest-xdist workers build once, in turn
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
 
 
 def lib():

@@ -1,0 +1,125 @@
+"""The pin against the reference itself.  tests/golden/lamejs_golden.json holds SHA-256 / length / per-call sizes
+of the bytes REAL lamejs produced (unmodified /root/reference executed by Qt's QJSEngine, see tools/jsrun/ and
+tests/golden/make_lamejs_golden.py).  The oracle must reproduce every fixture it supports on CPU; the CUDA path must
+reproduce them through the C-ABI on the B200; and when the engine + /root/reference are present (this container, not
+the GPU box) a few randomly drawn inputs are pushed through lamejs live."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from synth import make_signal
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+FIX = json.load(open(os.path.join(HERE, "golden", "lamejs_golden.json")))["cases"]
+
+
+def _supported(oracle, c):
+    try:
+        e = oracle.OracleEncoder(c["channels"], c["samplerate"], c["kbps"])
+    except ValueError:
+        return False
+    e.close()
+    return True
+
+
+def _check(c, data, sizes):
+    assert len(data) == c["bytes"]
+    assert data[:48].hex() == c["head"]
+    assert hashlib.sha256(data).hexdigest() == c["sha256"]
+    if sizes is not None:
+        assert len(sizes) == c["calls"]
+        assert hashlib.sha256(json.dumps([int(s) for s in sizes]).encode()).hexdigest() == c["sizes_sha256"]
+
+
+NAMES = sorted(k for k, v in FIX.items() if "error" not in v)
+
+
+def test_fixture_inventory():
+    assert len(NAMES) >= 250 and not [k for k, v in FIX.items() if "error" in v]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_matches_lamejs(oracle, name):
+    c = FIX[name]
+    if not _supported(oracle, c):
+        pytest.skip("configuration needs the resampler / MPEG-2 row")
+    l, r = make_signal(c["kind"], c["samples"], c["samplerate"], c["seed"])
+    data, sizes, _ = oracle.encode_stream(c["channels"], c["samplerate"], c["kbps"], l, r if c["channels"] == 2 else None,
+                                          chunk=c["chunk"] or None)
+    _check(c, data, sizes)
+
+
+def test_oracle_supports_every_native_rate_fixture(oracle):
+    """No silent skips: every MPEG-1 configuration without resampling must be checked above."""
+    n = sum(1 for k in NAMES if _supported(oracle, FIX[k]))
+    assert n >= 70, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_matches_lamejs(name):
+    import lamejs_b200 as M
+
+    c = FIX[name]
+    try:
+        enc = M.Mp3Encoder(c["channels"], c["samplerate"], c["kbps"])
+    except M.Mp3B200Error:
+        pytest.skip("configuration needs the resampler / MPEG-2 row")
+    l, r = make_signal(c["kind"], c["samples"], c["samplerate"], c["seed"])
+    n = len(l)
+    step = c["chunk"] or max(n, 1)
+    out, sizes = bytearray(), []
+    for i in range(0, n, step):
+        b = enc.encode_buffer(l[i:i + step], r[i:i + step] if c["channels"] == 2 else None)
+        sizes.append(len(b))
+        out += b
+    b = enc.flush()
+    sizes.append(len(b))
+    out += b
+    enc.close()
+    _check(c, bytes(out), sizes)
+
+
+def _engine():
+    sys.path.insert(0, os.path.join(ROOT, "tools", "jsrun"))
+    import ref_lamejs
+    return ref_lamejs if ref_lamejs.available() else None
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_matches_live_lamejs_on_random_inputs(oracle, seed):
+    """Fresh inputs nobody has seen: random configuration, random signal kind, random chunking."""
+    R = _engine()
+    if R is None:
+        pytest.skip("no JS engine / reference here (GPU box)")
+    rng = np.random.default_rng(0xA11CE + seed)
+    ch = int(rng.integers(1, 3))
+    sr = int(rng.choice([32000, 44100, 48000]))
+    kbps = int(rng.choice([128, 160, 192, 224, 256, 320]))
+    kind = str(rng.choice(["noise", "white", "octave", "burst"]))
+    n = int(rng.integers(5, 40)) * 1152 + int(rng.integers(0, 1152))
+    chunk = [None, 1152, int(rng.integers(1, 4000))][int(rng.integers(0, 3))]
+    l, r = make_signal(kind, n, sr, 1000 + seed)
+    ref, ref_sizes, _ = R.encode(ch, sr, kbps, l, r, chunk=chunk)
+    got, sizes, _ = oracle.encode_stream(ch, sr, kbps, l, r if ch == 2 else None, chunk=chunk)
+    assert sizes == ref_sizes
+    assert got == ref
+
+
+def test_loader_and_libm_independence():
+    """lame.all.js and the src/js modules give the same bytes; so does swapping the engine's libm for fdlibm."""
+    R = _engine()
+    if R is None:
+        pytest.skip("no JS engine / reference here (GPU box)")
+    l, r = make_signal("burst", 30 * 1152, 44100, 77)
+    a, _, _ = R.encode(2, 44100, 128, l, r)
+    b, _, _ = R.encode(2, 44100, 128, l, r, loader="modules")
+    assert a == b
+    if os.path.exists(os.path.join(ROOT, "tools", "jsrun", "fdlibm.js")):
+        c, _, _ = R.encode(2, 44100, 128, l, r, fdlibm=True)
+        assert a == c
