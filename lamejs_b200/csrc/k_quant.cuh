@@ -45,8 +45,18 @@ struct QuantFrameState {
   int used0[2];                     /* bits gr0 spent per channel (part2_3_length + part2_length) */
   unsigned long long bs_hash[2][2]; /* [gr][ch] fingerprint of cod_info right after the bin search: stale fields such as
                                        table_select[] of an empty region depend on the gains the search visited */
+  int scfsi[2][4];                  /* [ch][band group], decided while gr1 is finished */
+  int redo;                         /* re-validation pass: Q_R0(ch) gr0 rate loop must be redone, Q_R1S(ch) gr1 search must be
+                                       re-run (start step changed), Q_R1(ch) gr1 rate loop must be redone */
   int valid;
 };
+#define Q_R0(ch) (1 << (ch))
+#define Q_R1S(ch) (4 << (ch))
+#define Q_R1(ch) (16 << (ch))
+#define Q_R0_ANY 3
+#define Q_R1_ANY 48
+/* what the prepare kernel hands to the search / rate-loop kernels besides the xr and xrpow rows */
+struct GcPrep { float xmin[MP3_SFBMAX]; int have, mnz, block_type; double xrpow_max; };
 
 /* tables indexed by data (different index per lane) live in global memory and are read through the read-only
  * cache (__ldg): divergent __constant__ reads would serialise 32-fold */
@@ -131,17 +141,11 @@ struct __align__(16) GcWork {
   int scratch[8];
   double dscratch[4];
 };
-struct FrameShared {
-  GcWork wk[2];
-  const GranuleInfoDev* fin;      /* finished side info of this frame in HBM: fin[gr * nch + ch] */
-  unsigned int* bits;             /* frame bit buffer in HBM (368 words, <= 1441 bytes), filled with atomic ORs */
-  int gc_bits[2][2];              /* part2_3_length + part2_length of the finished gcs [gr][ch] */
-  int targ_bits[2];
-  int used_bits[2];               /* part2_3_length + part2_length of gr0, per channel */
-  int scfsi[2][4];
-  int old_value[2], current_step[2];
-  double ath21[6], ath12[6];
-  int flag;
+/* everything one warp (= one granule-channel task) keeps in shared memory */
+struct __align__(16) WarpShared {
+  GcWork wk;
+  double ath[6];                  /* analog-silence thresholds of the pseudo bands (psfb21 or psfb12) of this gc */
+  int scfsi[4];
 };
 
 #define LANE (threadIdx.x & 31)
@@ -341,7 +345,8 @@ __device__ __forceinline__ int sfb_step(const GranuleInfoDev* gi, const GcWork* 
 }
 
 /* count_bits (Takehiro.js:630-660) = range check + quantize_xrpow (:171-314) + noquant_count_bits */
-__device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, GranuleInfoDev* gi, short* ix, bool use_prev) {
+template <bool use_prev>
+__device__ __noinline__ int count_bits_w(const Mp3Tables* T, GcWork* wk, GranuleInfoDev* gi, short* ix) {
   const int lane = LANE;
   const double istep = (double)T->ipow20[gi->global_gain];
   if (gi->xrpow_max > T->ixmax_over_istep[gi->global_gain]) return Q_LARGE_BITS;
@@ -748,7 +753,7 @@ __device__ __noinline__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int des
     if (LANE == 0) gi->global_gain = gain;
     __syncwarp();
     QSTAT(stat_base);
-    nBits = count_bits_w(T, wk, gi, wk->ixw, false);
+    nBits = count_bits_w<false>(T, wk, gi, wk->ixw);
     if (CurrentStep == 1 || nBits == desired_rate) break;
     if (nBits > desired_rate) {
       if (Direction == 2) flagGoneOver = true;
@@ -770,7 +775,7 @@ __device__ __noinline__ int bin_search_w(const Mp3Tables* T, GcWork* wk, int des
     if (LANE == 0) gi->global_gain = gain;
     __syncwarp();
     QSTAT(stat_base + 1);
-    nBits = count_bits_w(T, wk, gi, wk->ixw, false);
+    nBits = count_bits_w<false>(T, wk, gi, wk->ixw);
   }
   *current_step = (start - gain >= 4) ? 4 : 2;
   *old_value = gain;
@@ -796,9 +801,9 @@ __device__ __noinline__ unsigned long long gi_hash(const GranuleInfoDev* gi) {
 }
 
 /* outer_loop (Quantize.js:871-1052) for noise_shaping_amp 1, full_outer_loop 0, substep_shaping 0 */
-__device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int targ_bits, int* old_value, int* current_step,
-                                          unsigned long long* bs_hash) {
-  /* note: *old_value / *current_step are final right after bin_search_w below (outer_loop never touches them again) */
+/* The bin search that opens outer_loop (Quantize.js:884) runs in its own kernel (k_q_search); this is everything after it.
+ * gfc.OldValue / CurrentStep are final right after the search (outer_loop never touches them again). */
+__device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int targ_bits) {
   const int lane = LANE;
   NoiseRes best, cur;
   int best_part2_3_length = 9999999;
@@ -806,8 +811,6 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
   for (int i = lane; i < MP3_SFBMAX; i += 32) { wk->pn_step[i] = 0; wk->pn_noise[i] = 0.0f; wk->pn_noise_log[i] = 0.0f; }
   if (lane == 0) { wk->pn_global_gain = 0; wk->pn_sfb_count1 = 0; }
   __syncwarp();
-  bin_search_w(T, wk, targ_bits, old_value, current_step);
-  *bs_hash = gi_hash(&wk->b);
   calc_noise_w(T, wk, &wk->b, wk->ixw, &best);
   best.bits = wk->b.part2_3_length;
   copy_gi_w(&wk->w, &wk->b);
@@ -829,7 +832,7 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
     for (;;) {                                     /* while (count_bits > huff_bits && global_gain <= maxggain) global_gain++ */
       sc_in = wk->pn_sfb_count1;
       QSTAT(8);
-      p23 = count_bits_w(T, wk, w, wk->ixw, true);
+      p23 = count_bits_w<true>(T, wk, w, wk->ixw);
       gg = w->global_gain;
       __syncwarp();                                /* every lane has read the gain before lane 0 bumps it */
       if (!(p23 > huff_bits && gg <= maxggain)) break;
@@ -846,7 +849,7 @@ __device__ __noinline__ void outer_loop_w(const Mp3Tables* T, GcWork* wk, int ta
        * recompute the identical state and bit count, so it is skipped. */
       bool repeat = wk->pn_sfb_count1 == sc_in;
       for (;;) {
-        if (!repeat) { QSTAT(9); p23 = count_bits_w(T, wk, w, wk->ixw, true); }
+        if (!repeat) { QSTAT(9); p23 = count_bits_w<true>(T, wk, w, wk->ixw); }
         repeat = false;
         gg = w->global_gain;
         __syncwarp();
@@ -902,8 +905,9 @@ __device__ __noinline__ double ath_adjust_dev(double a, double x, double athFloo
 
 /* init_outer_loop + psfb21_analogsilence + init_xrpow + calc_xmin for one gc (Quantize.js:204-306,147-202,105-138;
  * QuantizePVT.js:569-719).  Returns false when the granule is digital silence (all l3_enc = 0). */
-__device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameShared* fs, const float* __restrict__ xr_g, int block_type,
-                             const PsyRatioDev* __restrict__ ratio, double ath_adjust, bool need_xmin) {
+__device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, const double* ath_ps, const float* __restrict__ xr_g, int block_type,
+                             const PsyRatioDev* __restrict__ ratio, double ath_adjust) {
+  const bool need_xmin = true;
   const int lane = LANE;
   GranuleInfoDev* gi = &wk->b;
   const bool is_short = block_type == BT_SHORT;
@@ -944,7 +948,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
     for (int j = lo + lane; j < 576; j += 32) {
       int g = 0;
       while (g < 5 && j >= T->psfb21[g + 1]) g++;
-      double ath21 = fs->ath21[g];
+      double ath21 = ath_ps[g];
       if (lf > 1e-12) ath21 *= lf;
       if (!(fabs((double)wk->xr[j]) < ath21)) keep = j;
     }
@@ -959,7 +963,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
       for (int g = 5; g >= 0 && !stop; g--) {
         const int start = T->sfb_s[12] * 3 + (T->sfb_s[13] - T->sfb_s[12]) * block + (T->psfb12[g] - T->psfb12[0]);
         const int end = start + (T->psfb12[g + 1] - T->psfb12[g]);
-        double ath12 = fs->ath12[g];
+        double ath12 = ath_ps[g];
         if ((double)T->shortfact[12] > 1e-12) ath12 *= (double)T->shortfact[12];
 #pragma unroll 1
         for (int j = end - 1; j >= start; j--) {
@@ -1068,7 +1072,8 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, FrameS
 }
 
 /* best_scalefac_store without the scfsi part (Takehiro.js:809-875), then scfsi_calc for gr1 (lane 0 logic) */
-__device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, int gr, int ch) {
+/* g0: final side info of gr0 of the same channel (HBM), read only when gr == 1; scfsi[4]: this channel's flags */
+__device__ __noinline__ void best_scalefac_store_w(GcWork* wk, int* scfsi, const GranuleInfoDev* __restrict__ g0, int gr) {
   const int lane = LANE;
   GranuleInfoDev* gi = &wk->b;
   /* bands whose quantised lines are all zero */
@@ -1122,10 +1127,10 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
   if (lane == 0) {
     int recalc = recalc_w;
 #pragma unroll 1
-    for (int i = 0; i < 4; i++) fs->scfsi[ch][i] = 0;
-    if (gr == 1 && fs->fin[ch].block_type != BT_SHORT && gi->block_type != BT_SHORT) {
+    for (int i = 0; i < 4; i++) scfsi[i] = 0;
+    if (gr == 1 && g0->block_type != BT_SHORT && gi->block_type != BT_SHORT) {
       /* scfsi_calc (Takehiro.js:877-943) */
-      const int* g0sf = fs->fin[ch].scalefac;
+      const int* g0sf = g0->scalefac;
       const int band[5] = {0, 6, 11, 16, 21};
       int sfb;
 #pragma unroll 1
@@ -1136,7 +1141,7 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, FrameShared* fs, 
         if (sfb == band[i + 1]) {
 #pragma unroll 1
           for (sfb = band[i]; sfb < band[i + 1]; sfb++) gi->scalefac[sfb] = -1;
-          fs->scfsi[ch][i] = 1;
+          scfsi[i] = 1;
         }
       }
       int s1 = 0, c1 = 0;
@@ -1400,10 +1405,9 @@ __device__ Q_HELPER void put_bits(unsigned int* buf, int pos, unsigned int val, 
 }
 
 /* main data of one gc, starting at bit `pos` of the frame buffer; returns nothing (lengths are already known) */
-__device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, const GranuleInfoDev* gi, const short* ixq,
+__device__ __noinline__ void pack_gc_w(const Mp3Tables* T, unsigned int* buf, const GranuleInfoDev* gi, const short* ixq,
                                        const float* xrq, int pos) {
   const int lane = LANE;
-  unsigned int* buf = fs->bits;
   /* scalefactors (writeMainData, BitStream.js:609-625): serial, <= 36 values */
   if (lane == 0) {
     const int slen1 = c_slen1_tab[gi->scalefac_compress], slen2 = c_slen2_tab[gi->scalefac_compress];
@@ -1504,8 +1508,9 @@ __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, FrameShared* fs, cons
 }
 
 /* header + side info (encodeSideInfo2, BitStream.js:259-426, MPEG-1) by one thread */
-__device__ __noinline__ void pack_sideinfo(const Mp3Tables* T, FrameShared* fs, int padding) {
-  unsigned int* buf = fs->bits;
+/* fin: the frame's four (two) finished GranuleInfoDev in HBM, [gr * nch + ch]; scfsi: [ch][4] */
+__device__ __noinline__ void pack_sideinfo(const Mp3Tables* T, unsigned int* buf, const GranuleInfoDev* __restrict__ fin,
+                                           const int* scfsi, int padding) {
   int p = 0;
 #define WH(v, n) do { put_bits(buf, p, (unsigned)(v), (n)); p += (n); } while (0)
   const int nch = T->nch;
@@ -1515,10 +1520,10 @@ __device__ __noinline__ void pack_sideinfo(const Mp3Tables* T, FrameShared* fs, 
   WH(0, 9);
   WH(0, nch == 2 ? 3 : 5);
 #pragma unroll 1
-  for (int ch = 0; ch < nch; ch++) for (int b = 0; b < 4; b++) WH(fs->scfsi[ch][b], 1);
+  for (int ch = 0; ch < nch; ch++) for (int b = 0; b < 4; b++) WH(scfsi[ch * 4 + b], 1);
 #pragma unroll 1
   for (int gr = 0; gr < 2; gr++) for (int ch = 0; ch < nch; ch++) {
-    const GranuleInfoDev* gi = &fs->fin[gr * nch + ch];
+    const GranuleInfoDev* gi = &fin[gr * nch + ch];
     WH(gi->part2_3_length + gi->part2_length, 12);
     WH(gi->big_values / 2, 9);
     WH(gi->global_gain, 8);
@@ -1543,183 +1548,304 @@ __device__ __noinline__ void pack_sideinfo(const Mp3Tables* T, FrameShared* fs, 
 
 /* on_pe with the reservoir disabled (QuantizePVT.js:421-484 + Reservoir.js:190-229): gr0 gets mean_bits, gr1 additionally
  * what gr0 left over; per channel trunc(tbits / nch), capped at 4095, rescaled if the pair exceeds 7680; PE never matters
- * because extra_bits == 0 */
-__device__ __noinline__ void granule_budget(FrameShared* fs, int nch, int mean_bits, int gr, int used0, int used1) {
+ * because extra_bits == 0.  Returns targ_bits of channel `ch` (every lane computes the same value). */
+__device__ __forceinline__ int granule_budget(int nch, int mean_bits, int gr, int used0, int used1, int ch) {
   int tbits = mean_bits;
   if (gr == 1) {
     const int resv = -(used0 + (nch == 2 ? used1 : 0)) + mean_bits;   /* ResvSize + mean_bits */
     if (resv * 10 > 0) tbits += resv;
   }
-#pragma unroll 1
-  for (int c = 0; c < nch; c++) {
-    double t = (double)tbits / nch;
-    if (t > 4095) t = 4095;
-    fs->targ_bits[c] = (int)t;
-  }
-  int bits = 0;
-#pragma unroll 1
-  for (int c = 0; c < nch; c++) bits += fs->targ_bits[c];
-  if (bits > 7680) for (int c = 0; c < nch; c++) { fs->targ_bits[c] = fs->targ_bits[c] * 7680; fs->targ_bits[c] = (int)((double)fs->targ_bits[c] / bits); }
+  double t = (double)tbits / nch;
+  if (t > 4095) t = 4095;
+  int targ = (int)t;                      /* the same value for every channel */
+  const int bits = targ * nch;
+  if (bits > 7680) { targ = targ * 7680; targ = (int)((double)targ / bits); }
+  (void)ch;
+  return targ;
 }
 
-/* ---- the frame kernel ------------------------------------------------------------------------------------ */
-/* grid-stride over a work list of frame rows.  block = 32 * nch threads. */
-__global__ void __launch_bounds__(64, Q_MIN_BLOCKS)
-k_quantize_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, const float* __restrict__ xr,
-                const PsyRatioDev* __restrict__ ratio, const signed char* __restrict__ bt_final,
-                const double* __restrict__ ath_q, QuantFrameState* __restrict__ qs, GranuleInfoDev* __restrict__ ginfo_out,
-                short* __restrict__ l3enc_out, unsigned int* __restrict__ framebits, int keep_l3enc,
-                const int* __restrict__ list, const int* __restrict__ count_ptr, int count_direct,
-                int revalidate, uint8_t* __restrict__ out) {
+/* ---- the quantizer pipeline ---------------------------------------------------------------------------------------
+ * One frame's four granule-channels depend on each other only through a few scalars (gr1's bit budget needs the bits both
+ * channels spent in gr0; bin_search_StepSize starts at the gain the previous granule of the channel ended with), so the
+ * rate loop is cut into phases, each its own kernel over ALL frames of the batch:
+ *     k_q_prepare            init_outer_loop + analog silence + init_xrpow + calc_xmin       task = granule-channel
+ *     k_q_search  (gr0)      bin_search_StepSize                                             task = (frame, channel)
+ *     k_q_outer   (gr0)      noise-shaping loop + iteration_finish_one                       task = (frame, channel)
+ *     k_q_search  (gr1), k_q_outer (gr1)
+ *     k_q_pack               format_bitstream                                                task = frame
+ * A task is one warp; warps pull tasks from an atomic counter (persistent blocks), so uneven loop counts balance at warp
+ * granularity and no warp ever waits for another.  Every kernel's code fits the SM's 32 KB instruction cache level (the
+ * single fused kernel of round 1 had a 135 KB body and was instruction-fetch bound) and all resident warps run the same few
+ * loops.  The hand-over (prepared xr / xrpow rows, the quantised lines, side info) goes through HBM/L2: ~20 KB per
+ * granule-channel per pass against ~35 k warp instructions of work. */
+#ifndef Q_WARPS
+#define Q_WARPS 4
+#endif
+#ifndef Q_BLOCKS_PER_SM
+#define Q_BLOCKS_PER_SM 7
+#endif
+#define Q_THREADS (32 * Q_WARPS)
+
+__device__ __forceinline__ int next_task(int* counter) {
+  int t = 0;
+  if (LANE == 0) t = atomicAdd(counter, 1);
+  return __shfl_sync(Q_FULL, t, 0);
+}
+__device__ __forceinline__ WarpShared* warp_shared() {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FrameShared* fs = reinterpret_cast<FrameShared*>(smem_raw);
-  const int nch = T->nch;
-  const int ch = threadIdx.x >> 5, lane = LANE;
-  GcWork* wk = &fs->wk[ch];
-  const int nwork = count_ptr ? *count_ptr : count_direct;
+  return reinterpret_cast<WarpShared*>(smem_raw) + (threadIdx.x >> 5);
+}
+/* init_outer_loop's scalar part (Quantize.js:204-260) for the search / rate-loop kernels, from what k_q_prepare kept */
+__device__ __forceinline__ void gi_init_w(GranuleInfoDev* gi, const GcPrep* __restrict__ pr) {
+  __syncwarp();
+  int* w = reinterpret_cast<int*>(gi);
 #pragma unroll 1
-  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+  for (int i = LANE; i < (int)(sizeof(GranuleInfoDev) / 4); i += 32) w[i] = 0;
+  __syncwarp();
+  if (LANE == 0) {
+    const int bt = pr->block_type;
+    const bool is_short = bt == BT_SHORT;
+    gi->global_gain = 210; gi->block_type = bt;
+    gi->sfb_lmax = is_short ? 0 : 21; gi->sfb_smin = is_short ? 0 : 12; gi->psy_lmax = is_short ? 0 : 21;
+    gi->psymax = is_short ? 36 : 21; gi->sfbmax = is_short ? 36 : 21; gi->sfbdivide = is_short ? 18 : 11;
+    gi->max_nonzero_coeff = pr->mnz; gi->xrpow_max = pr->xrpow_max;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void copy_row16_w(void* dst, const void* src, int nbytes) {   /* 16-byte vectors, coalesced */
+  __syncwarp();
+  const int n = nbytes >> 4;
+#pragma unroll 1
+  for (int i = LANE; i < n; i += 32) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(src)[i];
+  __syncwarp();
+}
+struct FrameGeom { int z, f, padding, frame_bytes, mean_bits; long long kabs; };
+__device__ __forceinline__ FrameGeom frame_geom(const Mp3Tables* T, const StreamDesc* streams, const QuantFrameState* q) {
+  FrameGeom g;
+  g.z = q->stream; g.f = q->rel_frame;
+  g.kabs = (long long)streams[g.z].frame0 + g.f;
+  g.padding = (int)(pad_count(g.kabs, T->frac_SpF, T->samplerate) - pad_count(g.kabs - 1, T->frac_SpF, T->samplerate));
+  g.frame_bytes = T->frame_bytes_nopad + g.padding;
+  g.mean_bits = (8 * g.frame_bytes - T->sideinfo_len * 8) / 2;      /* Reservoir.js:83 (exact: multiple of 4) */
+  return g;
+}
+
+/* ---- phase 1: everything of a granule-channel that does not depend on the bit budget ---- */
+__global__ void __launch_bounds__(Q_THREADS, Q_BLOCKS_PER_SM)
+k_q_prepare(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, const float* __restrict__ xr,
+            const PsyRatioDev* __restrict__ ratio, const signed char* __restrict__ bt_final, const double* __restrict__ ath_q,
+            const QuantFrameState* __restrict__ qs, float* __restrict__ xrq, float* __restrict__ xrpow_g, GcPrep* __restrict__ prep,
+            int nframes, int* __restrict__ counter) {
+  WarpShared* ws = warp_shared();
+  GcWork* wk = &ws->wk;
+  const int lane = LANE, nch = T->nch;
+  const int ntasks = nframes * 2 * nch;
+#pragma unroll 1
+  for (int t = next_task(counter); t < ntasks; t = next_task(counter)) {
+    const int frow = t / (2 * nch), rem = t - frow * 2 * nch, gr = rem / nch, ch = rem - gr * nch;
+    const QuantFrameState* q = qs + frow;
+    const int z = q->stream, f = q->rel_frame;
+    const StreamDesc& sd = streams[z];
+    const double ath_adjust = ath_q[frow];
+    const size_t urow = (size_t)sd.unit_base + 2 * f + gr, gidx = urow * nch + ch;
+    const int bt = bt_final[urow * 2 + ch];
+    /* masking of psy unit (2f+gr-1): halo-shifted row = unit_base + z + (2f+gr-1) + 1 */
+    const PsyRatioDev* rt = ratio + ((size_t)sd.unit_base + z + 2 * f + gr) * nch + ch;
+    __syncwarp();
+    if (lane < 6) ws->ath[lane] = ath_adjust_dev(ath_adjust, (double)(bt == BT_SHORT ? T->ath_psfb12[lane] : T->ath_psfb21[lane]), T->ath_floor);
+    __syncwarp();
+    const bool have = gc_prepare_w(T, wk, ws->ath, xr + gidx * 576, bt, rt, ath_adjust);
+    copy_row16_w(xrq + gidx * 576, wk->xr, 2304);
+    copy_row16_w(xrpow_g + gidx * 576, wk->xrpow, 2304);
+    GcPrep* pr = prep + gidx;
+#pragma unroll 1
+    for (int i = lane; i < MP3_SFBMAX; i += 32) pr->xmin[i] = wk->xmin[i];
+    if (lane == 0) { pr->have = have ? 1 : 0; pr->mnz = wk->b.max_nonzero_coeff; pr->block_type = bt; pr->xrpow_max = wk->b.xrpow_max; }
+  }
+}
+
+/* ---- phase 2/4: bin_search_StepSize of granule `gr` for every (frame, channel) of the work list ----
+ * revalidate = 0: first pass over all frames (in-state of frames other than a stream's first is a guess).
+ * revalidate = 1: frames listed by k_qstate_verify, whose true in-state is now known.  The in-state enters a frame only
+ * through the two searches: gr0 starts at (OldValue, CurrentStep); gr1 starts at gr0's gain with the step derived from where
+ * gr0 started.  If gr0 lands on the recorded gain with the same cod_info fingerprint, its bytes and the bits it spent stand;
+ * gr1's search is then re-run only if its start step changed, and stands if it lands on the recorded gain too.  Whatever
+ * does not stand is flagged in q->redo for the rate-loop and pack kernels of this pass. */
+__global__ void __launch_bounds__(Q_THREADS, Q_BLOCKS_PER_SM)
+k_q_search(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs,
+           GranuleInfoDev* __restrict__ ginfo, short* __restrict__ l3enc, const float* __restrict__ xrpow_g,
+           const GcPrep* __restrict__ prep, int gr, const int* __restrict__ list, const int* __restrict__ count_ptr, int count_direct,
+           int revalidate, int* __restrict__ counter) {
+  WarpShared* ws = warp_shared();
+  GcWork* wk = &ws->wk;
+  const int lane = LANE, nch = T->nch;
+  const int ntasks = (count_ptr ? *count_ptr : count_direct) * nch;
+#pragma unroll 1
+  for (int t = next_task(counter); t < ntasks; t = next_task(counter)) {
+    const int wi = t / nch, ch = t - wi * nch;
     const int frow = list ? list[wi] : wi;
     QuantFrameState* q = qs + frow;
-    const int z = q->stream;
-    const StreamDesc& sd = streams[z];
-    const int f = q->rel_frame;
-    const long long kabs = (long long)sd.frame0 + f;
-    const double ath_adjust = ath_q[frow];
-    __syncthreads();
-    /* prologue: frame buffer, analog-silence thresholds, in-state */
-    unsigned int* const fbits = framebits + (size_t)frow * 368;
+    const int flags = revalidate ? q->redo : 0;
+    if (revalidate && gr == 1 && !(flags & (Q_R0_ANY | Q_R1S(ch)))) continue;
+    const FrameGeom fg = frame_geom(T, streams, q);
+    const StreamDesc& sd = streams[fg.z];
+    const size_t urow = (size_t)sd.unit_base + 2 * fg.f + gr, gidx = urow * nch + ch;
+    const int targ = granule_budget(nch, fg.mean_bits, gr, q->used0[0], q->used0[1], ch);
+    int ov = gr == 0 ? q->in_old[ch] : q->bs_gain0[ch];
+    int cs = gr == 0 ? q->in_step[ch] : q->bs_step0[ch];
+    const GcPrep* pr = prep + gidx;
+    const bool have = pr->have != 0;
+    gi_init_w(&wk->b, pr);
+    if (lane == 0) wk->geo = &T->geo[pr->block_type == BT_SHORT ? 1 : 0];
+    unsigned long long h = 0;
+    if (have) {
+      copy_row16_w(wk->xrpow, xrpow_g + gidx * 576, 2304);
+      QSTAT(revalidate ? 12 + gr : 11);
+      bin_search_w(T, wk, targ, &ov, &cs, revalidate ? 2 + 2 * gr : 0);
+      h = gi_hash(&wk->b);
+    } else {
+      __syncwarp();
 #pragma unroll 1
-    for (int i = threadIdx.x; i < 368; i += blockDim.x) fbits[i] = 0;
-    if (threadIdx.x == 0) { fs->bits = fbits; fs->fin = ginfo_out + ((size_t)sd.unit_base + 2 * f) * nch; }
-    if (threadIdx.x < 12) {
-      const int g = threadIdx.x % 6;
-      if (threadIdx.x < 6) fs->ath21[g] = ath_adjust_dev(ath_adjust, (double)T->ath_psfb21[g], T->ath_floor);
-      else fs->ath12[g] = ath_adjust_dev(ath_adjust, (double)T->ath_psfb12[g], T->ath_floor);
+      for (int i = lane; i < 288; i += 32) reinterpret_cast<unsigned*>(wk->ixw)[i] = 0;
+      __syncwarp();
     }
-    if (threadIdx.x < 2) { fs->old_value[threadIdx.x] = q->in_old[threadIdx.x]; fs->current_step[threadIdx.x] = q->in_step[threadIdx.x]; fs->used_bits[threadIdx.x] = 0; }
-    if (threadIdx.x == 0) fs->flag = 0;
-    __syncthreads();
-
-    const int padding = (int)(pad_count(kabs, T->frac_SpF, T->samplerate) - pad_count(kabs - 1, T->frac_SpF, T->samplerate));
-    const int frame_bytes = T->frame_bytes_nopad + padding;
-    const int frame_bits = 8 * frame_bytes;
-    const int mean_bits = (frame_bits - T->sideinfo_len * 8) / 2;      /* Reservoir.js:83 (exact: multiple of 4) */
-    int old_value = fs->old_value[ch], current_step = fs->current_step[ch];
-    const bool speculative = !revalidate && f != 0;    /* in-state guessed by k_qstate_init */
-
-    if (revalidate) {
-      /* Re-validation of an already encoded frame under a corrected in-state.  The in-state enters only through the
-       * bin searches: gr0 starts at (OldValue, CurrentStep); gr1 starts at gr0's gain with CurrentStep derived from
-       * where gr0 started.  If gr0 lands on the recorded gain, gr0's bytes and the bits it spent are unchanged; if then
-       * gr1's search (re-run only when its CurrentStep changed) lands on the recorded gain too, the whole frame and
-       * its out-state are unchanged.  Otherwise fall through to a full re-encode. */
-      if (threadIdx.x == 0) granule_budget(fs, nch, mean_bits, 0, 0, 0);
-      __syncthreads();
-      const size_t urow0 = (size_t)sd.unit_base + 2 * f;
-      int ov = old_value, cs = current_step;
-      const bool have0 = gc_prepare_w(T, wk, fs, xr + (urow0 * nch + ch) * 576, bt_final[urow0 * 2 + ch],
-                                      ratio + ((size_t)sd.unit_base + z + 2 * f) * nch + ch, ath_adjust, false);
-      unsigned long long h0 = 0;
-      QSTAT(12);
-      if (have0) { bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs, 2); h0 = gi_hash(&wk->b); }
-      if (lane == 0) {
-        if (ov != q->bs_gain0[ch] || h0 != q->bs_hash[0][ch]) atomicOr(&fs->flag, 1);
-        else if (cs != q->bs_step0[ch]) atomicOr(&fs->flag, 2);
-      }
-      __syncthreads();
-      int verdict = fs->flag;
-      __syncthreads();
-      if (!(verdict & 1) && (verdict & 2)) {
-        if (threadIdx.x == 0) { fs->flag = 0; granule_budget(fs, nch, mean_bits, 1, q->used0[0], q->used0[1]); }
-        __syncthreads();
-        const bool have1 = gc_prepare_w(T, wk, fs, xr + ((urow0 + 1) * nch + ch) * 576, bt_final[(urow0 + 1) * 2 + ch],
-                                        ratio + ((size_t)sd.unit_base + z + 2 * f + 1) * nch + ch, ath_adjust, false);
-        const int step0 = cs;
-        if (have1) {
-          QSTAT(13);
-          bin_search_w(T, wk, fs->targ_bits[ch], &ov, &cs, 4);
-          const unsigned long long h1 = gi_hash(&wk->b);
-          if (lane == 0 && (ov != q->out_old[ch] || h1 != q->bs_hash[1][ch])) atomicOr(&fs->flag, 1);
-        }
-        __syncthreads();
-        verdict = fs->flag;
-        __syncthreads();
-        if (!(verdict & 1) && lane == 0) { q->bs_step0[ch] = step0; q->out_old[ch] = ov; q->out_step[ch] = cs; }
-      }
-      if (!(verdict & 1)) continue;
-      QSTAT(14);
-      if (threadIdx.x == 0) fs->flag = 0;
-      __syncthreads();
-    }
-
-#pragma unroll 1
-    for (int gr = 0; gr < 2; gr++) {
-      if (threadIdx.x == 0) granule_budget(fs, nch, mean_bits, gr, fs->used_bits[0], fs->used_bits[1]);
-      __syncthreads();
-      const size_t urow = (size_t)sd.unit_base + 2 * f + gr;
-      const int bt = bt_final[urow * 2 + ch];
-      /* masking of psy unit (2f+gr-1): halo-shifted row = unit_base + z + (2f+gr-1) + 1 */
-      const PsyRatioDev* rt = ratio + ((size_t)sd.unit_base + z + 2 * f + gr) * nch + ch;
-      if (lane == 0) wk->ixg = l3enc_out + (urow * nch + ch) * 576;
-      const bool have = gc_prepare_w(T, wk, fs, xr + (urow * nch + ch) * 576, bt, rt, ath_adjust, true);
-      unsigned long long bsh = 0;
-      QSTAT(11);
-      if (have) outer_loop_w(T, wk, fs->targ_bits[ch], &old_value, &current_step, &bsh);
+    bool store;
+    if (!revalidate) {
+      store = true;
       /* a frame encoded from a guessed in-state also guesses the step gr1's search starts with: 2, what a stationary
        * signal produces (the formula would give 4 whenever the guessed start lies 4 above the landing gain); the value
        * used is recorded, and re-validation re-runs gr1's search only when the true step differs from it */
-      if (gr == 0 && speculative) current_step = 2;
-      if (lane == 0) q->bs_hash[gr][ch] = bsh;
-      /* state right after gr0's bin search (pass-through when the granule is silent): re-validation key */
-      if (gr == 0 && lane == 0) { q->bs_gain0[ch] = old_value; q->bs_step0[ch] = current_step; }
-      /* iteration_finish_one (Quantize.js:1059-1078) */
-      best_scalefac_store_w(wk, fs, gr, ch);
-      best_huffman_divide_w(T, wk);
-      /* the side info persists in HBM; the main data of this granule is packed straight from the working set */
-      copy_gi_w(&ginfo_out[urow * nch + ch], &wk->b);
+      if (gr == 0 && fg.f != 0) cs = 2;
       if (lane == 0) {
-        fs->used_bits[ch] = fs->gc_bits[gr][ch] = wk->b.part2_3_length + wk->b.part2_length;
-        if (gr == 0) q->used0[ch] = fs->used_bits[ch];
+        q->bs_hash[gr][ch] = h;
+        if (gr == 0) { q->bs_gain0[ch] = ov; q->bs_step0[ch] = cs; }
+        else { q->out_old[ch] = ov; q->out_step[ch] = cs; }
       }
-      if (keep_l3enc) copy_ix_w(wk->ixg, wk->ixw);
-      __syncthreads();
-      {
-        /* bit position of this gc: side info, then gr0ch0, gr0ch1, gr1ch0, gr1ch1 back to back */
-        int pos = 8 * T->sideinfo_len;
-        for (int g2 = 0; g2 < gr; g2++)
-          for (int c = 0; c < nch; c++) pos += fs->gc_bits[g2][c];
-        for (int c = 0; c < ch; c++) pos += fs->gc_bits[gr][c];
-        pack_gc_w(T, fs, &wk->b, wk->ixw, wk->xr, pos);
+    } else if (gr == 0) {
+      store = ov != q->bs_gain0[ch] || h != q->bs_hash[0][ch];
+      const bool step_changed = cs != q->bs_step0[ch];
+      __syncwarp();
+      if (lane == 0) {
+        if (store) { q->bs_gain0[ch] = ov; q->bs_step0[ch] = cs; q->bs_hash[0][ch] = h; atomicOr(&q->redo, Q_R0(ch)); }
+        else if (step_changed) { q->bs_step0[ch] = cs; atomicOr(&q->redo, Q_R1S(ch)); }
       }
-      __syncthreads();
-    }
-    if (lane == 0) { q->out_old[ch] = old_value; q->out_step[ch] = current_step; }
-    /* ---- format_bitstream: side info, main data, ancillary stuffing ---- */
-    if (threadIdx.x == 0) pack_sideinfo(T, fs, padding);
-    __syncthreads();
-    {
-      int pos = 8 * T->sideinfo_len;
-      for (int gr = 0; gr < 2; gr++) for (int c = 0; c < nch; c++) pos += fs->gc_bits[gr][c];
-      /* drain_into_ancillary (BitStream.js:175-213): "LAME" + the version string pushed through `>>` as numbers */
-      if (threadIdx.x == 0) {
-        int remaining = frame_bits - pos;
-        const unsigned char tag[10] = {0x4c, 0x41, 0x4d, 0x45, 3, 0, 9, 8, 0, 4};
-        int k = 0;
-        for (; k < 4 && remaining >= 8; k++) { put_bits(fbits, pos, tag[k], 8); pos += 8; remaining -= 8; }
-        if (remaining >= 32) for (; k < 10 && remaining >= 8; k++) { put_bits(fbits, pos, tag[k], 8); pos += 8; remaining -= 8; }
+    } else {
+      store = (flags & Q_R0_ANY) || ov != q->out_old[ch] || h != q->bs_hash[1][ch];
+      __syncwarp();
+      if (lane == 0) {
+        q->out_step[ch] = cs;
+        if (store) { q->out_old[ch] = ov; q->bs_hash[1][ch] = h; atomicOr(&q->redo, Q_R1(ch)); }
       }
     }
-    __syncthreads();
-    /* store the frame (big-endian bit order -> bytes) */
-    {
-      const long long off = sd.out_base + (long long)f * T->frame_bytes_nopad +
-                            (pad_count(kabs - 1, T->frac_SpF, T->samplerate) - pad_count((long long)sd.frame0 - 1, T->frac_SpF, T->samplerate));
-      uint8_t* dst = out + off;
+    if (store) {
+      copy_row16_w(l3enc + gidx * 576, wk->ixw, 1152);
+      copy_gi_w(&ginfo[gidx], &wk->b);
+    }
+  }
+}
+
+/* ---- phase 3/5: noise-shaping loop (outer_loop after its search) + iteration_finish_one of granule `gr` ---- */
+__global__ void __launch_bounds__(Q_THREADS, Q_BLOCKS_PER_SM)
+k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs,
+          GranuleInfoDev* __restrict__ ginfo, short* __restrict__ l3enc, const float* __restrict__ xrq,
+          const float* __restrict__ xrpow_g, const GcPrep* __restrict__ prep, int gr, const int* __restrict__ list,
+          const int* __restrict__ count_ptr, int count_direct, int revalidate, int* __restrict__ counter) {
+  WarpShared* ws = warp_shared();
+  GcWork* wk = &ws->wk;
+  const int lane = LANE, nch = T->nch;
+  const int ntasks = (count_ptr ? *count_ptr : count_direct) * nch;
 #pragma unroll 1
-      for (int i = threadIdx.x; i < frame_bytes; i += blockDim.x) dst[i] = (uint8_t)(__ldcg(&fbits[i >> 2]) >> (24 - 8 * (i & 3)));
+  for (int t = next_task(counter); t < ntasks; t = next_task(counter)) {
+    const int wi = t / nch, ch = t - wi * nch;
+    const int frow = list ? list[wi] : wi;
+    QuantFrameState* q = qs + frow;
+    if (revalidate && !(q->redo & (gr == 0 ? Q_R0(ch) : Q_R1(ch)))) continue;
+    const FrameGeom fg = frame_geom(T, streams, q);
+    const StreamDesc& sd = streams[fg.z];
+    const size_t urow = (size_t)sd.unit_base + 2 * fg.f + gr, gidx = urow * nch + ch;
+    const int targ = granule_budget(nch, fg.mean_bits, gr, q->used0[0], q->used0[1], ch);
+    const GcPrep* pr = prep + gidx;
+    const bool have = pr->have != 0;
+    short* const ixrow = l3enc + gidx * 576;
+    __syncwarp();
+    if (lane == 0) { wk->geo = &T->geo[pr->block_type == BT_SHORT ? 1 : 0]; wk->ixg = ixrow; }
+    copy_gi_w(&wk->b, &ginfo[gidx]);
+    copy_row16_w(wk->ixw, ixrow, 1152);
+    if (have) {
+      copy_row16_w(wk->xr, xrq + gidx * 576, 2304);
+      copy_row16_w(wk->xrpow, xrpow_g + gidx * 576, 2304);
+#pragma unroll 1
+      for (int i = lane; i < MP3_SFBMAX; i += 32) wk->xmin[i] = pr->xmin[i];
+      __syncwarp();
+      outer_loop_w(T, wk, targ);
     }
-    if (threadIdx.x == 0) q->valid = 1;
+    /* iteration_finish_one (Quantize.js:1059-1078) */
+    best_scalefac_store_w(wk, ws->scfsi, gr == 1 ? &ginfo[gidx - nch] : nullptr, gr);
+    best_huffman_divide_w(T, wk);
+    copy_gi_w(&ginfo[gidx], &wk->b);
+    copy_row16_w(ixrow, wk->ixw, 1152);
+    if (gr == 0) { if (lane == 0) q->used0[ch] = wk->b.part2_3_length + wk->b.part2_length; }
+    else if (lane < 4) q->scfsi[ch][lane] = ws->scfsi[lane];
+  }
+}
+
+/* ---- phase 6: format_bitstream (BitStream.js:836-901): side info, main data, ancillary stuffing, one warp per frame ---- */
+struct __align__(16) PackShared {
+  unsigned int bits[368];         /* frame bit buffer (<= 1441 bytes), filled with shared-memory atomic ORs */
+  short ix[576];
+  float xr[576];                  /* only the signs are read */
+  GranuleInfoDev gi;
+  int scfsi[8];
+};
+__global__ void __launch_bounds__(Q_THREADS)
+k_q_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs,
+         const GranuleInfoDev* __restrict__ ginfo, const short* __restrict__ l3enc, const float* __restrict__ xrq,
+         const int* __restrict__ list, const int* __restrict__ count_ptr, int count_direct, int revalidate,
+         int* __restrict__ counter, uint8_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PackShared* ps = reinterpret_cast<PackShared*>(smem_raw) + (threadIdx.x >> 5);
+  const int lane = LANE, nch = T->nch;
+  const int ntasks = count_ptr ? *count_ptr : count_direct;
+#pragma unroll 1
+  for (int t = next_task(counter); t < ntasks; t = next_task(counter)) {
+    const int frow = list ? list[t] : t;
+    QuantFrameState* q = qs + frow;
+    if (revalidate && !(q->redo & (Q_R0_ANY | Q_R1_ANY))) continue;
+    const FrameGeom fg = frame_geom(T, streams, q);
+    const StreamDesc& sd = streams[fg.z];
+    const size_t g0 = ((size_t)sd.unit_base + 2 * fg.f) * nch;       /* first of the frame's 2 * nch granule-channels */
+    __syncwarp();
+#pragma unroll 1
+    for (int i = lane; i < 368; i += 32) ps->bits[i] = 0;
+    if (lane < 8) ps->scfsi[lane] = q->scfsi[lane >> 2][lane & 3];
+    __syncwarp();
+    int pos = 8 * T->sideinfo_len;
+#pragma unroll 1
+    for (int k = 0; k < 2 * nch; k++) {                              /* gr0ch0, gr0ch1, gr1ch0, gr1ch1 back to back */
+      copy_gi_w(&ps->gi, &ginfo[g0 + k]);
+      copy_row16_w(ps->ix, l3enc + (g0 + k) * 576, 1152);
+      copy_row16_w(ps->xr, xrq + (g0 + k) * 576, 2304);
+      pack_gc_w(T, ps->bits, &ps->gi, ps->ix, ps->xr, pos);
+      pos += ps->gi.part2_3_length + ps->gi.part2_length;
+      __syncwarp();
+    }
+    if (lane == 0) {
+      pack_sideinfo(T, ps->bits, ginfo + g0, ps->scfsi, fg.padding);
+      /* drain_into_ancillary (BitStream.js:175-213): "LAME" + the version string pushed through `>>` as numbers */
+      int remaining = 8 * fg.frame_bytes - pos;
+      const unsigned char tag[10] = {0x4c, 0x41, 0x4d, 0x45, 3, 0, 9, 8, 0, 4};
+      int k = 0;
+      for (; k < 4 && remaining >= 8; k++) { put_bits(ps->bits, pos, tag[k], 8); pos += 8; remaining -= 8; }
+      if (remaining >= 32) for (; k < 10 && remaining >= 8; k++) { put_bits(ps->bits, pos, tag[k], 8); pos += 8; remaining -= 8; }
+    }
+    __syncwarp();
+    /* store the frame (big-endian bit order -> bytes) at its closed-form offset */
+    const long long off = sd.out_base + (long long)fg.f * T->frame_bytes_nopad +
+                          (pad_count(fg.kabs - 1, T->frac_SpF, T->samplerate) - pad_count((long long)sd.frame0 - 1, T->frac_SpF, T->samplerate));
+    uint8_t* dst = out + off;
+#pragma unroll 1
+    for (int i = lane; i < fg.frame_bytes; i += 32) dst[i] = (uint8_t)(ps->bits[i >> 2] >> (24 - 8 * (i & 3)));
+    if (lane == 0) q->valid = 1;
   }
 }
 
@@ -1730,7 +1856,7 @@ __global__ void k_qstate_init(const StreamDesc* __restrict__ streams, int nstrea
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= sd.nframes) return;
   QuantFrameState* q = qs + sd.frame_base + f;
-  q->stream = z; q->rel_frame = f; q->valid = 0;
+  q->stream = z; q->rel_frame = f; q->valid = 0; q->redo = 0;
 #pragma unroll 1
   for (int c = 0; c < 2; c++) {
     /* first frame: the stream's true state; others: speculation (re-validated afterwards).  The speculative search
@@ -1739,6 +1865,8 @@ __global__ void k_qstate_init(const StreamDesc* __restrict__ streams, int nstrea
     q->in_old[c] = f == 0 ? sd.old_value[c] : Q_SPEC_START;
     q->in_step[c] = f == 0 ? sd.current_step[c] : Q_SPEC_STEP;
     q->out_old[c] = q->out_step[c] = 0;
+    q->used0[c] = 0; q->bs_gain0[c] = q->bs_step0[c] = 0;
+    for (int b = 0; b < 4; b++) q->scfsi[c][b] = 0;
   }
 }
 
@@ -1756,6 +1884,7 @@ __global__ void k_qstate_verify(const StreamDesc* __restrict__ streams, QuantFra
   if (!same) {
 #pragma unroll 1
     for (int c = 0; c < 2; c++) { q->in_old[c] = p->out_old[c]; q->in_step[c] = p->out_step[c]; }
+    q->redo = 0;
     list[atomicAdd(counter, 1)] = (int)r;
   }
 }
@@ -1771,53 +1900,78 @@ __global__ void k_qstate_commit(StreamDesc* __restrict__ streams, int nstreams, 
   for (int c = 0; c < 2; c++) { sd.old_value[c] = q->out_old[c]; sd.current_step[c] = q->out_step[c]; }
 }
 
+/* device buffers of the quantizer stage (owned by the Workspace) */
+struct QuantBuffers {
+  const float* xr; const PsyRatioDev* ratio; const signed char* bt; const double* ath_q;
+  QuantFrameState* qs; GranuleInfoDev* ginfo; short* l3enc; float* xrq; float* xrpow; GcPrep* prep;
+  int* list; int* counter;        /* counter[0]: work-list length; counter[1..Q_NCOUNTERS): task counters, one per launch */
+};
+#define Q_NCOUNTERS 256
+
 static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_streams, int S, int max_frames, long long F,
-                     const float* d_xr, const PsyRatioDev* d_ratio, const signed char* d_bt, const double* d_ath_q,
-                     QuantFrameState* d_qs, GranuleInfoDev* d_ginfo, short* d_l3enc, unsigned int* d_framebits, int keep_l3enc,
-                     int* d_list, int* d_counter, uint8_t* d_out,
-                     cudaStream_t st, cudaEvent_t ev_pass1, int* passes_out, long long* launches) {
-  static int attr_dev = -1;               /* the attribute is per device: re-apply after mp3b200_set_device */
-  int cur_dev = 0;
-  cudaGetDevice(&cur_dev);
-  const bool attr_set = attr_dev == cur_dev;
-  const size_t smem = sizeof(FrameShared);
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_quantize_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
-    attr_dev = cur_dev;
-  }
-  const int threads = 32 * hT.nch;
+                     const QuantBuffers& B, uint8_t* d_out, cudaStream_t st, cudaEvent_t ev_pass1, int* passes_out,
+                     std::atomic<long long>* launches) {
+  static std::mutex attr_mu;
+  static bool attr_done[64] = {};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = sizeof(WarpShared) * Q_WARPS, smem_pack = sizeof(PackShared) * Q_WARPS;
+  {
+    std::lock_guard<std::mutex> lk(attr_mu);
+    if (dev < 64 && !attr_done[dev]) {            /* the attribute is per device */
+      if (cudaFuncSetAttribute(k_q_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
+      if (cudaFuncSetAttribute(k_q_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
+      if (cudaFuncSetAttribute(k_q_outer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
+      if (cudaFuncSetAttribute(k_q_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pack) != cudaSuccess) return -100;
+      attr_done[dev] = true;
+    }
+  }
+  if (F <= 0) { *passes_out = 0; return 0; }
+  const int nch = hT.nch;
+  int next_counter = Q_NCOUNTERS;                 /* forces the first memset */
+  auto fresh_counter = [&]() -> int* {            /* a zeroed task counter for the next launch */
+    if (next_counter >= Q_NCOUNTERS) { cudaMemsetAsync(B.counter + 1, 0, sizeof(int) * (Q_NCOUNTERS - 1), st); next_counter = 1; }
+    return B.counter + next_counter++;
+  };
+  auto grid_for = [&](long long tasks, int per_sm) -> int {   /* persistent blocks, never more than the tasks need */
+    long long g = (tasks + Q_WARPS - 1) / Q_WARPS, cap = (long long)sms * per_sm;
+    if (g > cap) g = cap;
+    return (int)(g < 1 ? 1 : g);
+  };
   {
     dim3 g((max_frames + 127) / 128, S);
-    k_qstate_init<<<g, 128, 0, st>>>(d_streams, S, d_qs);
+    k_qstate_init<<<g, 128, 0, st>>>(d_streams, S, B.qs);
     (*launches)++;
   }
-  /* one block per frame: the hardware block scheduler balances the uneven per-frame loop counts */
-  long long nblk = F < (1ll << 30) ? F : (1ll << 30);
-  if (nblk < 1) nblk = 1;
-  k_quantize_pack<<<(int)nblk, threads, smem, st>>>(dT, d_streams, d_xr, d_ratio, d_bt, d_ath_q, d_qs, d_ginfo, d_l3enc, d_framebits, keep_l3enc,
-                                                    nullptr, nullptr, (int)F, 0, d_out);
+  k_q_prepare<<<grid_for(F * 2 * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.xr, B.ratio, B.bt, B.ath_q, B.qs, B.xrq, B.xrpow,
+                                                                              B.prep, (int)F, fresh_counter());
   (*launches)++;
+  auto run_pass = [&](const int* list, const int* count_ptr, long long count, int reval) {
+    const int gq = grid_for(count * nch, Q_BLOCKS_PER_SM), gp = grid_for(count, 8);
+    for (int gr = 0; gr < 2; gr++) {
+      k_q_search<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, gr, list, count_ptr, (int)count, reval, fresh_counter());
+      k_q_outer<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, gr, list, count_ptr, (int)count, reval, fresh_counter());
+    }
+    k_q_pack<<<gp, Q_THREADS, smem_pack, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, list, count_ptr, (int)count, reval, fresh_counter(), d_out);
+    (*launches) += 5;
+  };
+  run_pass(nullptr, nullptr, F, 0);
   if (cudaEventRecord(ev_pass1, st) != cudaSuccess) return -100;
   int passes = 1;
   for (;;) {
-    if (cudaMemsetAsync(d_counter, 0, sizeof(int), st) != cudaSuccess) return -100;
-    k_qstate_verify<<<(int)((F + 255) / 256), 256, 0, st>>>(d_streams, d_qs, F, d_list, d_counter);
+    if (cudaMemsetAsync(B.counter, 0, sizeof(int), st) != cudaSuccess) return -100;
+    k_qstate_verify<<<(int)((F + 255) / 256), 256, 0, st>>>(d_streams, B.qs, F, B.list, B.counter);
     (*launches)++;
     int h_count = 0;
-    if (cudaMemcpyAsync(&h_count, d_counter, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -100;
+    if (cudaMemcpyAsync(&h_count, B.counter, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -100;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -100;
     if (h_count == 0) break;
-    long long nb = h_count;
-    k_quantize_pack<<<(int)nb, threads, smem, st>>>(dT, d_streams, d_xr, d_ratio, d_bt, d_ath_q, d_qs, d_ginfo, d_l3enc, d_framebits, keep_l3enc,
-                                                    d_list, nullptr, h_count, 1, d_out);
-    (*launches)++;
+    run_pass(B.list, nullptr, h_count, 1);
     passes++;
     if (passes > max_frames + 2) return -100;   /* cannot happen: each pass fixes at least the first dirty frame */
   }
-  k_qstate_commit<<<(S + 63) / 64, 64, 0, st>>>(d_streams, S, d_qs);
+  k_qstate_commit<<<(S + 63) / 64, 64, 0, st>>>(d_streams, S, B.qs);
   (*launches)++;
   *passes_out = passes;
   return 0;

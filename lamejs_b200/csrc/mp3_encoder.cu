@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -28,7 +29,7 @@ namespace {
 thread_local std::string g_err;
 std::mutex g_mu;
 int g_device = 0;
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 bool g_consts_ready = false;
 
 #define CK(call)                                                                                  \
@@ -105,9 +106,10 @@ struct Workspace {
   double* d_ath_q = nullptr;              /* [frames] ATH.adjust after adjust_ATH (quantizer) */
   QuantFrameState* d_qstate = nullptr;    /* [frames] speculation bookkeeping */
   GranuleInfoDev* d_ginfo = nullptr;      /* [units][nch] side info of the final quantization */
-  short* d_l3enc = nullptr;               /* [units][nch][576] parked best quantization of a gc; final lines when kept (debug tap) */
-  unsigned int* d_framebits = nullptr;    /* [frames][368] frame bit buffers */
-  bool keep_l3enc = false;
+  short* d_l3enc = nullptr;               /* [units][nch][576] quantised lines of a gc: after the search, parked best, final */
+  float* d_xrq = nullptr;                 /* [units][nch][576] xr as the quantizer sees it (reordered, analog silence zeroed) */
+  float* d_xrpow = nullptr;               /* [units][nch][576] |xr|^(3/4) */
+  GcPrep* d_prep = nullptr;               /* [units][nch] xmin + scalars of the prepared granule-channel */
   int* d_dirty = nullptr;                 /* [frames] work list for re-quantization passes */
   int* d_counter = nullptr;               /* [4] */
   ScanChunk* d_scan = nullptr;            /* [frames / SCAN_FRAMES + nstreams] */
@@ -115,7 +117,7 @@ struct Workspace {
   void release() {
     cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_psy); cudaFree(d_fe); d_fe = nullptr; cudaFree(d_scan_in); d_scan_in = nullptr;
     cudaFree(d_ratio); cudaFree(d_ath_psy); cudaFree(d_ath_q); cudaFree(d_qstate); cudaFree(d_ginfo);
-    cudaFree(d_l3enc); cudaFree(d_framebits); d_framebits = nullptr; cudaFree(d_dirty); cudaFree(d_counter); cudaFree(d_scan); d_scan = nullptr;
+    cudaFree(d_l3enc); cudaFree(d_xrq); d_xrq = nullptr; cudaFree(d_xrpow); d_xrpow = nullptr; cudaFree(d_prep); d_prep = nullptr; cudaFree(d_dirty); cudaFree(d_counter); cudaFree(d_scan); d_scan = nullptr;
     d_streams = nullptr; d_bt_final = d_bt_prev = nullptr; d_xr = nullptr; d_psy = nullptr; d_ratio = nullptr;
     d_ath_psy = d_ath_q = nullptr; d_qstate = nullptr; d_ginfo = nullptr; d_l3enc = nullptr; d_dirty = nullptr; d_counter = nullptr;
   }
@@ -134,11 +136,13 @@ struct Workspace {
     CK(cudaMalloc(&d_ath_q, sizeof(double) * (size_t)(F + 1)));
     CK(cudaMalloc(&d_qstate, sizeof(QuantFrameState) * (size_t)(F + 1)));
     CK(cudaMalloc(&d_ginfo, sizeof(GranuleInfoDev) * (size_t)U * nch));
-    keep_l3enc = want_l3enc;
+    (void)want_l3enc;
     CK(cudaMalloc(&d_l3enc, sizeof(short) * (size_t)U * nch * 576));
-    CK(cudaMalloc(&d_framebits, sizeof(unsigned int) * 368 * (size_t)(F + 1)));
+    CK(cudaMalloc(&d_xrq, sizeof(float) * (size_t)U * nch * 576));
+    CK(cudaMalloc(&d_xrpow, sizeof(float) * (size_t)U * nch * 576));
+    CK(cudaMalloc(&d_prep, sizeof(GcPrep) * (size_t)U * nch));
     CK(cudaMalloc(&d_dirty, sizeof(int) * (size_t)(F + 1)));
-    CK(cudaMalloc(&d_counter, sizeof(int) * 4));
+    CK(cudaMalloc(&d_counter, sizeof(int) * Q_NCOUNTERS));
     CK(cudaMalloc(&d_scan, sizeof(ScanChunk) * (size_t)(F / SCAN_FRAMES + S + 1)));
     return 0;
   }
@@ -258,8 +262,10 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   CK(cudaEventRecord(ev[4], st));
   int passes = 0;
   if (!stop_after_mdct) {
-    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, max_frames, total_frames, ws.d_xr, ws.d_ratio, ws.d_bt_final, ws.d_ath_q,
-                       ws.d_qstate, ws.d_ginfo, ws.d_l3enc, ws.d_framebits, ws.keep_l3enc ? 1 : 0, ws.d_dirty, ws.d_counter, d_out, st, ev[5], &passes, &g_launches);
+    QuantBuffers qb;
+    qb.xr = ws.d_xr; qb.ratio = ws.d_ratio; qb.bt = ws.d_bt_final; qb.ath_q = ws.d_ath_q; qb.qs = ws.d_qstate; qb.ginfo = ws.d_ginfo;
+    qb.l3enc = ws.d_l3enc; qb.xrq = ws.d_xrq; qb.xrpow = ws.d_xrpow; qb.prep = ws.d_prep; qb.list = ws.d_dirty; qb.counter = ws.d_counter;
+    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, max_frames, total_frames, qb, d_out, st, ev[5], &passes, &g_launches);
     if (rc) { g_err = "quantizer stage failed: " + std::string(cudaGetErrorString(cudaGetLastError())); return rc; }
   } else {
     CK(cudaEventRecord(ev[5], st));

@@ -75,7 +75,7 @@ def test_gpu_matches_lamejs(name):
     step = c["chunk"] or max(n, 1)
     out, sizes = bytearray(), []
     for i in range(0, n, step):
-        b = enc.encode_buffer(l[i:i + step], r[i:i + step] if c["channels"] == 2 else None)
+        b = enc.encodeBuffer(l[i:i + step], r[i:i + step] if c["channels"] == 2 else None)
         sizes.append(len(b))
         out += b
     b = enc.flush()
