@@ -600,7 +600,10 @@ k_psy_masking(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ st
       const float big = (float)1e20;
       for (int i = tid; i < nch * 122; i += MASK_THREADS) (&out[0].en_l[0])[i] = big;
     }
-    return;        /* c >= 0: the streaming handle pre-fills this row from its carried state */
+    else if (sd.halo_in) {   /* streaming handle: masking of the unit before frame0, carried on the device */
+      for (int i = tid; i < nch * 122; i += MASK_THREADS) (&out[0].en_l[0])[i] = sd.halo_in[i];
+    }
+    return;
   }
   __shared__ f32s s_thr[2][MP3_CBANDS + 2], s_eb[2][MP3_CBANDS + 2];
   __shared__ f32s s_thr_s[2][3][MP3_CBANDS + 2];
@@ -709,6 +712,8 @@ k_psy_masking(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ st
   }
   __syncthreads();
   for (int i = tid; i < nch * 122; i += MASK_THREADS) (&out[0].en_l[0])[i] = (&s_out[0].en_l[0])[i];
+  if (sd.halo_out && u == 2 * sd.nframes - 1)
+    for (int i = tid; i < nch * 122; i += MASK_THREADS) sd.halo_out[i] = (&s_out[0].en_l[0])[i];
 }
 
 #endif

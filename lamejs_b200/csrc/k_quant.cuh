@@ -1675,7 +1675,7 @@ __global__ void __launch_bounds__(Q_THREADS, Q_BLOCKS_PER_SM)
 k_q_search(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs,
            GranuleInfoDev* __restrict__ ginfo, short* __restrict__ l3enc, const float* __restrict__ xrpow_g,
            const GcPrep* __restrict__ prep, int gr, const int* __restrict__ list, const int* __restrict__ count_ptr, int count_direct,
-           int revalidate, int* __restrict__ counter) {
+           int revalidate, int* __restrict__ counter, int* __restrict__ list2, int* __restrict__ count2) {
   WarpShared* ws = warp_shared();
   GcWork* wk = &ws->wk;
   const int lane = LANE, nch = T->nch;
@@ -1726,8 +1726,11 @@ k_q_search(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ strea
       const bool step_changed = cs != q->bs_step0[ch];
       __syncwarp();
       if (lane == 0) {
-        if (store) { q->bs_gain0[ch] = ov; q->bs_step0[ch] = cs; q->bs_hash[0][ch] = h; atomicOr(&q->redo, Q_R0(ch)); }
-        else if (step_changed) { q->bs_step0[ch] = cs; atomicOr(&q->redo, Q_R1S(ch)); }
+        int old = -1;
+        if (store) { q->bs_gain0[ch] = ov; q->bs_step0[ch] = cs; q->bs_hash[0][ch] = h; old = atomicOr(&q->redo, Q_R0(ch)); }
+        else if (step_changed) { q->bs_step0[ch] = cs; old = atomicOr(&q->redo, Q_R1S(ch)); }
+        /* frames with anything left to do go on the short list the remaining kernels of this pass walk */
+        if (old == 0) list2[atomicAdd(count2, 1)] = frow;
       }
     } else {
       store = (flags & Q_R0_ANY) || ov != q->out_old[ch] || h != q->bs_hash[1][ch];
@@ -1760,6 +1763,7 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
     const int frow = list ? list[wi] : wi;
     QuantFrameState* q = qs + frow;
     if (revalidate && !(q->redo & (gr == 0 ? Q_R0(ch) : Q_R1(ch)))) continue;
+    if (revalidate) QSTAT(14);
     const FrameGeom fg = frame_geom(T, streams, q);
     const StreamDesc& sd = streams[fg.z];
     const size_t urow = (size_t)sd.unit_base + 2 * fg.f + gr, gidx = urow * nch + ch;
@@ -1779,11 +1783,38 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
       __syncwarp();
       outer_loop_w(T, wk, targ);
     }
-    /* iteration_finish_one (Quantize.js:1059-1078) */
+    copy_gi_w(&ginfo[gidx], &wk->b);
+    copy_row16_w(ixrow, wk->ixw, 1152);
+  }
+}
+
+/* ---- iteration_finish_one (Quantize.js:1059-1078) of granule `gr`: best_scalefac_store (+ scfsi in gr1) and
+ * best_huffman_divide.  Needs only the quantised lines and the side info; its 25 KB of code stay out of the rate loop's
+ * instruction-cache footprint. ---- */
+__global__ void __launch_bounds__(Q_THREADS, Q_BLOCKS_PER_SM)
+k_q_finish(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs,
+           GranuleInfoDev* __restrict__ ginfo, short* __restrict__ l3enc, int gr, const int* __restrict__ list,
+           const int* __restrict__ count_ptr, int count_direct, int revalidate, int* __restrict__ counter) {
+  WarpShared* ws = warp_shared();
+  GcWork* wk = &ws->wk;
+  const int lane = LANE, nch = T->nch;
+  const int ntasks = (count_ptr ? *count_ptr : count_direct) * nch;
+#pragma unroll 1
+  for (int t = next_task(counter); t < ntasks; t = next_task(counter)) {
+    const int wi = t / nch, ch = t - wi * nch;
+    const int frow = list ? list[wi] : wi;
+    QuantFrameState* q = qs + frow;
+    if (revalidate && !(q->redo & (gr == 0 ? Q_R0(ch) : Q_R1(ch)))) continue;
+    const StreamDesc& sd = streams[q->stream];
+    const size_t urow = (size_t)sd.unit_base + 2 * q->rel_frame + gr, gidx = urow * nch + ch;
+    short* const ixrow = l3enc + gidx * 576;
+    copy_gi_w(&wk->b, &ginfo[gidx]);
+    copy_row16_w(wk->ixw, ixrow, 1152);
+    if (lane == 0) wk->geo = &T->geo[wk->b.block_type == BT_SHORT ? 1 : 0];
+    __syncwarp();
     best_scalefac_store_w(wk, ws->scfsi, gr == 1 ? &ginfo[gidx - nch] : nullptr, gr);
     best_huffman_divide_w(T, wk);
     copy_gi_w(&ginfo[gidx], &wk->b);
-    copy_row16_w(ixrow, wk->ixw, 1152);
     if (gr == 0) { if (lane == 0) q->used0[ch] = wk->b.part2_3_length + wk->b.part2_length; }
     else if (lane < 4) q->scfsi[ch][lane] = ws->scfsi[lane];
   }
@@ -1811,6 +1842,7 @@ k_q_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams
     const int frow = list ? list[t] : t;
     QuantFrameState* q = qs + frow;
     if (revalidate && !(q->redo & (Q_R0_ANY | Q_R1_ANY))) continue;
+    if (revalidate) QSTAT(5);
     const FrameGeom fg = frame_geom(T, streams, q);
     const StreamDesc& sd = streams[fg.z];
     const size_t g0 = ((size_t)sd.unit_base + 2 * fg.f) * nch;       /* first of the frame's 2 * nch granule-channels */
@@ -1904,7 +1936,8 @@ __global__ void k_qstate_commit(StreamDesc* __restrict__ streams, int nstreams, 
 struct QuantBuffers {
   const float* xr; const PsyRatioDev* ratio; const signed char* bt; const double* ath_q;
   QuantFrameState* qs; GranuleInfoDev* ginfo; short* l3enc; float* xrq; float* xrpow; GcPrep* prep;
-  int* list; int* counter;        /* counter[0]: work-list length; counter[1..Q_NCOUNTERS): task counters, one per launch */
+  int* list; int* counter;        /* list: 2 x (frames + 1) entries (verify list, short list); counter[0..1]: their lengths;
+                                     counter[2..Q_NCOUNTERS): task counters, one per launch */
 };
 #define Q_NCOUNTERS 256
 
@@ -1923,6 +1956,7 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
       if (cudaFuncSetAttribute(k_q_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
       if (cudaFuncSetAttribute(k_q_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
       if (cudaFuncSetAttribute(k_q_outer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
+      if (cudaFuncSetAttribute(k_q_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
       if (cudaFuncSetAttribute(k_q_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pack) != cudaSuccess) return -100;
       attr_done[dev] = true;
     }
@@ -1931,7 +1965,7 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
   const int nch = hT.nch;
   int next_counter = Q_NCOUNTERS;                 /* forces the first memset */
   auto fresh_counter = [&]() -> int* {            /* a zeroed task counter for the next launch */
-    if (next_counter >= Q_NCOUNTERS) { cudaMemsetAsync(B.counter + 1, 0, sizeof(int) * (Q_NCOUNTERS - 1), st); next_counter = 1; }
+    if (next_counter >= Q_NCOUNTERS) { cudaMemsetAsync(B.counter + 2, 0, sizeof(int) * (Q_NCOUNTERS - 2), st); next_counter = 2; }
     return B.counter + next_counter++;
   };
   auto grid_for = [&](long long tasks, int per_sm) -> int {   /* persistent blocks, never more than the tasks need */
@@ -1947,27 +1981,35 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
   k_q_prepare<<<grid_for(F * 2 * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.xr, B.ratio, B.bt, B.ath_q, B.qs, B.xrq, B.xrpow,
                                                                               B.prep, (int)F, fresh_counter());
   (*launches)++;
-  auto run_pass = [&](const int* list, const int* count_ptr, long long count, int reval) {
+  /* counter[0]: length of the verify list; counter[1]: length of the short list (frames a re-validation pass must touch
+   * beyond gr0's search); the task counters start at 2 */
+  auto run_pass = [&](long long count, int reval) {
     const int gq = grid_for(count * nch, Q_BLOCKS_PER_SM), gp = grid_for(count, 8);
-    for (int gr = 0; gr < 2; gr++) {
-      k_q_search<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, gr, list, count_ptr, (int)count, reval, fresh_counter());
-      k_q_outer<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, gr, list, count_ptr, (int)count, reval, fresh_counter());
-    }
-    k_q_pack<<<gp, Q_THREADS, smem_pack, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, list, count_ptr, (int)count, reval, fresh_counter(), d_out);
-    (*launches) += 5;
+    const int* l1 = reval ? B.list : nullptr;                   /* all listed frames */
+    const int* l2 = reval ? B.list + (F + 1) : nullptr;          /* short list, length on the device */
+    const int* c2 = reval ? B.counter + 1 : nullptr;
+    k_q_search<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, 0, l1, nullptr, (int)count, reval, fresh_counter(),
+                                            B.list + (F + 1), B.counter + 1);
+    k_q_outer<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 0, l2, c2, (int)count, reval, fresh_counter());
+    k_q_finish<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 0, l2, c2, (int)count, reval, fresh_counter());
+    k_q_search<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, 1, l2, c2, (int)count, reval, fresh_counter(), nullptr, nullptr);
+    k_q_outer<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 1, l2, c2, (int)count, reval, fresh_counter());
+    k_q_finish<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 1, l2, c2, (int)count, reval, fresh_counter());
+    k_q_pack<<<gp, Q_THREADS, smem_pack, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, l2, c2, (int)count, reval, fresh_counter(), d_out);
+    (*launches) += 7;
   };
-  run_pass(nullptr, nullptr, F, 0);
+  run_pass(F, 0);
   if (cudaEventRecord(ev_pass1, st) != cudaSuccess) return -100;
   int passes = 1;
   for (;;) {
-    if (cudaMemsetAsync(B.counter, 0, sizeof(int), st) != cudaSuccess) return -100;
+    if (cudaMemsetAsync(B.counter, 0, 2 * sizeof(int), st) != cudaSuccess) return -100;
     k_qstate_verify<<<(int)((F + 255) / 256), 256, 0, st>>>(d_streams, B.qs, F, B.list, B.counter);
     (*launches)++;
     int h_count = 0;
     if (cudaMemcpyAsync(&h_count, B.counter, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -100;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -100;
     if (h_count == 0) break;
-    run_pass(B.list, nullptr, h_count, 1);
+    run_pass(h_count, 1);
     passes++;
     if (passes > max_frames + 2) return -100;   /* cannot happen: each pass fixes at least the first dirty frame */
   }

@@ -43,6 +43,10 @@ struct StreamDesc {
   long long out_base;      /* byte offset of frame0 in the output buffer */
   int scan_base;           /* first row of this stream in the scan-chunk scratch */
   int pad_;
+  /* streaming handles: masking (en/thm, nch x 122 floats) of the psy unit before frame0, carried on the device between
+   * calls; halo_out receives the masking of this launch's last unit.  Both null for whole-stream batches. */
+  const float* halo_in;
+  float* halo_out;
   /* sequential state at the start of frame0 (lamejs gfc.* carried across frames) */
   double ath_adjust, ath_adjust_limit;
   int blocktype_old[2], last_attacks[2];

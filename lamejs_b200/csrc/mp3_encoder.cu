@@ -27,10 +27,12 @@
 namespace {
 
 thread_local std::string g_err;
-std::mutex g_mu;
-int g_device = 0;
+std::mutex g_mu;                          /* guards g_device, g_configs, the per-device flags below */
+int g_device = 0;                         /* device of configurations / handles / batch calls created from now on */
 std::atomic<long long> g_launches{0};
-bool g_consts_ready = false;
+enum { MP3_MAX_DEVICES = 64 };
+bool g_consts_ready[MP3_MAX_DEVICES] = {};   /* __constant__ / __device__ tables are per device */
+bool g_fb_attr_done[MP3_MAX_DEVICES] = {};
 
 #define CK(call)                                                                                  \
   do {                                                                                            \
@@ -43,15 +45,18 @@ bool g_consts_ready = false;
     }                                                                                             \
   } while (0)
 
-struct Config { Mp3Tables host; Mp3Tables* dev; };
+struct Config { Mp3Tables host; Mp3Tables* dev; int device; };
 std::map<std::tuple<int, int, int, int>, Config*> g_configs;   /* (device, ch, sr, kbps) */
+std::map<std::tuple<int, int, int>, std::pair<int, int>> g_byte_geom;   /* (ch, sr, kbps) -> frame_bytes_nopad, frac_SpF */
 
-int ensure_device() {
+/* g_mu held.  Makes `dev` current for the calling thread and uploads the constant tables once per device. */
+int ensure_device(int dev) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n <= 0) { g_err = "no CUDA device available (libmp3b200 has no CPU fallback)"; return MP3B200_ERR_CUDA; }
-  CK(cudaSetDevice(g_device));
-  if (!g_consts_ready) {
+  if (dev < 0 || dev >= n || dev >= MP3_MAX_DEVICES) { g_err = "invalid CUDA device"; return MP3B200_ERR_CUDA; }
+  CK(cudaSetDevice(dev));
+  if (!g_consts_ready[dev]) {
     CK(cudaMemcpyToSymbol(c_enwindow, MP3_ENWINDOW, sizeof(double) * 285));
     CK(cudaMemcpyToSymbol(c_mdct_win, MP3_MDCT_WIN, sizeof(double) * 144));
     CK(cudaMemcpyToSymbol(c_sb_order, MP3_SB_ORDER, sizeof(int) * 32));
@@ -59,20 +64,22 @@ int ensure_device() {
     if (rc) return rc;
     rc = quant_upload_constants();
     if (rc) return rc;
-    g_consts_ready = true;
+    g_consts_ready[dev] = true;
   }
   return 0;
 }
 
 int get_config(int ch, int sr, int kbps, Config** out) {
   std::lock_guard<std::mutex> lk(g_mu);
-  int rc = ensure_device();
+  const int dev = g_device;
+  int rc = ensure_device(dev);
   if (rc) return rc;
-  auto key = std::make_tuple(g_device, ch, sr, kbps);
+  auto key = std::make_tuple(dev, ch, sr, kbps);
   auto it = g_configs.find(key);
   if (it != g_configs.end()) { *out = it->second; return 0; }
   Config* c = new Config();
   if (mp3_build_tables(ch, sr, kbps, &c->host) != 0) { delete c; g_err = "unsupported configuration"; return MP3B200_ERR_CONFIG; }
+  c->device = dev;
   CK(cudaMalloc(&c->dev, sizeof(Mp3Tables)));
   CK(cudaMemcpy(c->dev, &c->host, sizeof(Mp3Tables), cudaMemcpyHostToDevice));
   g_configs[key] = c;
@@ -141,12 +148,75 @@ struct Workspace {
     CK(cudaMalloc(&d_xrq, sizeof(float) * (size_t)U * nch * 576));
     CK(cudaMalloc(&d_xrpow, sizeof(float) * (size_t)U * nch * 576));
     CK(cudaMalloc(&d_prep, sizeof(GcPrep) * (size_t)U * nch));
-    CK(cudaMalloc(&d_dirty, sizeof(int) * (size_t)(F + 1)));
+    CK(cudaMalloc(&d_dirty, sizeof(int) * 2 * (size_t)(F + 1)));
     CK(cudaMalloc(&d_counter, sizeof(int) * Q_NCOUNTERS));
     CK(cudaMalloc(&d_scan, sizeof(ScanChunk) * (size_t)(F / SCAN_FRAMES + S + 1)));
     return 0;
   }
 };
+
+/* Everything a host thread needs to drive the GPU: its own non-blocking stream (threads encoding through distinct handles
+ * or batches never serialise on the legacy default stream), events, workspace and staging buffers.  Bound to one device;
+ * re-created when the thread is used with a configuration of another device. */
+enum { MP3_MAX_PCM_CHUNKS = 8 };
+struct ThreadCtx {
+  int device = -1;
+  cudaStream_t st = nullptr, up_st = nullptr;
+  cudaEvent_t ev[8] = {}, ev_in = nullptr, ready[MP3_MAX_PCM_CHUNKS] = {};
+  Workspace ws;
+  int16_t* d_pcm = nullptr; size_t d_pcm_cap = 0;
+  uint8_t* d_out = nullptr; size_t d_out_cap = 0;
+  uint8_t* h_pin = nullptr; size_t h_pin_cap = 0;       /* pinned host staging */
+  void release() {
+    if (device < 0) return;
+    cudaSetDevice(device);
+    ws.release(); ws.units = ws.frames = 0; ws.nstreams = 0;
+    cudaFree(d_pcm); d_pcm = nullptr; d_pcm_cap = 0;
+    cudaFree(d_out); d_out = nullptr; d_out_cap = 0;
+    cudaFreeHost(h_pin); h_pin = nullptr; h_pin_cap = 0;
+    for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : ready) if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (ev_in) { cudaEventDestroy(ev_in); ev_in = nullptr; }
+    if (st) { cudaStreamDestroy(st); st = nullptr; }
+    if (up_st) { cudaStreamDestroy(up_st); up_st = nullptr; }
+    device = -1;
+  }
+  ~ThreadCtx() { release(); }
+  int use(int dev) {
+    CK(cudaSetDevice(dev));
+    if (device == dev) return 0;
+    release();
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&up_st, cudaStreamNonBlocking));
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    for (auto& e : ready) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    device = dev;
+    return 0;
+  }
+  int need_pcm(size_t samples) {
+    if (d_pcm_cap >= samples) return 0;
+    cudaFree(d_pcm); d_pcm = nullptr; d_pcm_cap = 0;
+    CK(cudaMalloc(&d_pcm, sizeof(int16_t) * samples));
+    d_pcm_cap = samples;
+    return 0;
+  }
+  int need_out(size_t bytes) {
+    if (d_out_cap >= bytes) return 0;
+    cudaFree(d_out); d_out = nullptr; d_out_cap = 0;
+    CK(cudaMalloc(&d_out, bytes));
+    d_out_cap = bytes;
+    return 0;
+  }
+  int need_pin(size_t bytes) {
+    if (h_pin_cap >= bytes) return 0;
+    cudaFreeHost(h_pin); h_pin = nullptr; h_pin_cap = 0;
+    CK(cudaMallocHost(&h_pin, bytes));
+    h_pin_cap = bytes;
+    return 0;
+  }
+};
+thread_local ThreadCtx t_ctx;
 
 /* MP3B200_DEBUG_SYNC=1: synchronise after every launch and name the failing kernel */
 bool debug_sync() { static int v = -1; if (v < 0) { const char* e = getenv("MP3B200_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; } return v == 1; }
@@ -166,10 +236,14 @@ struct Timings { float psy = 0, scan = 0, mask = 0, fb = 0, q1 = 0, qn = 0, tota
 /* pcm_chunks > 1: the caller uploads each stream's PCM in that many time slices on another stream and records
  * pcm_ready[j] after slice j; the psy analysis of slice j starts as soon as it has landed. */
 struct PcmArrival { int chunks = 1; cudaEvent_t* ready = nullptr; };
-enum { MP3_MAX_PCM_CHUNKS = 8 };
 
+/* All launches go to the calling thread's stream (t_ctx.st), which first waits for whatever the caller queued on the
+ * legacy default stream (torch and plain CUDA callers produce their device buffers there); the call returns after the
+ * stream has drained, so the results are visible to any stream afterwards. */
 int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams, uint8_t* d_out, const int32_t* force_bt,
-                 bool stop_after_mdct, Timings* tm, cudaStream_t st, const PcmArrival* arrival = nullptr) {
+                 bool stop_after_mdct, Timings* tm, const PcmArrival* arrival = nullptr, bool sync = true) {
+  cudaStream_t st = t_ctx.st;
+  cudaEvent_t* ev = t_ctx.ev;
 
   const int S = (int)h_streams.size();
   const int nch = cfg->host.nch;
@@ -182,9 +256,10 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     s.scan_base = scan_rows;
     scan_rows += (s.nframes + SCAN_FRAMES - 1) / SCAN_FRAMES;
   }
+  if (S == 0 || total_frames == 0) { if (tm) *tm = Timings(); return 0; }   /* empty batch: nothing to launch */
+  CK(cudaEventRecord(t_ctx.ev_in, cudaStreamLegacy));
+  CK(cudaStreamWaitEvent(st, t_ctx.ev_in, 0));
   CK(cudaMemcpyAsync(ws.d_streams, h_streams.data(), sizeof(StreamDesc) * S, cudaMemcpyHostToDevice, st));
-  static thread_local cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  if (!ev[0]) for (auto& e : ev) CK(cudaEventCreate(&e));   /* created once per host thread */
   CK(cudaEventRecord(ev[0], st));
 
   /* K2: psy analysis, one block per (granule incl. 1 halo, channel, stream) */
@@ -251,10 +326,10 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   {
     dim3 grid((2 * max_frames + FB_G - 1) / FB_G, nch, S);
     const size_t smem = sizeof(double) * FB_PCM_WORDS + sizeof(float) * ((FB_G + 1) * 18 * FB_SLAB_STRIDE);
-    static int fb_attr_dev = -1;          /* per device: re-apply after mp3b200_set_device */
-    int cur_dev = 0;
-    CK(cudaGetDevice(&cur_dev));
-    if (fb_attr_dev != cur_dev) { CK(cudaFuncSetAttribute(k_filterbank_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); fb_attr_dev = cur_dev; }
+    {
+      std::lock_guard<std::mutex> lk(g_mu);   /* the attribute is per device */
+      if (!g_fb_attr_done[cfg->device]) { CK(cudaFuncSetAttribute(k_filterbank_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g_fb_attr_done[cfg->device] = true; }
+    }
     k_filterbank_mdct<<<grid, FB_THREADS, smem, st>>>(cfg->dev, ws.d_streams, ws.d_bt_final, ws.d_xr);
     g_launches++;
     DBG("k_filterbank_mdct");
@@ -271,6 +346,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     CK(cudaEventRecord(ev[5], st));
   }
   CK(cudaEventRecord(ev[6], st));
+  if (!sync) return 0;                     /* the caller queues its copies behind the kernels and synchronises once */
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   if (tm) {
@@ -314,20 +390,32 @@ int64_t mp3b200_launch_count(void) { return g_launches; }
 
 int mp3b200_set_device(int device) {
   int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { g_err = "invalid CUDA device"; return MP3B200_ERR_CUDA; }
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n || device >= MP3_MAX_DEVICES) { g_err = "invalid CUDA device"; return MP3B200_ERR_CUDA; }
   std::lock_guard<std::mutex> lk(g_mu);
-  if (device != g_device) { g_device = device; g_consts_ready = false; }
+  g_device = device;      /* existing handles keep the device they were created on */
   return 0;
 }
 
 int64_t mp3b200_stream_frames(int64_t nsamples) { return frames_for(nsamples); }
 
 int64_t mp3b200_stream_bytes(int channels, int samplerate, int kbps, int64_t nsamples) {
-  Mp3Tables* t = new Mp3Tables();
-  int64_t r = -1;
-  if (mp3_build_tables(channels, samplerate, kbps, t) == 0) r = bytes_for(*t, frames_for(nsamples));
-  delete t;
-  return r;
+  /* the byte geometry of a configuration is two integers; building the full tables costs ~1 ms, so it is done once */
+  std::pair<int, int> geom;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_tuple(channels, samplerate, kbps);
+    auto it = g_byte_geom.find(key);
+    if (it == g_byte_geom.end()) {
+      Mp3Tables* t = new Mp3Tables();
+      const int rc = mp3_build_tables(channels, samplerate, kbps, t);
+      geom = rc == 0 ? std::make_pair(t->frame_bytes_nopad, t->frac_SpF) : std::make_pair(-1, 0);
+      delete t;
+      g_byte_geom[key] = geom;
+    } else geom = it->second;
+  }
+  if (geom.first < 0 || nsamples < 0) return -1;
+  const long long frames = frames_for(nsamples);
+  return frames * geom.first + pad_count(frames - 1, geom.second, samplerate);
 }
 
 }  // extern "C"
@@ -351,13 +439,17 @@ int encode_streams_device_impl(Config* cfg, int channels, int nstreams, const in
     init_stream_state(sd);
     U += 2LL * sd.nframes; F += sd.nframes;
   }
-  static thread_local Workspace ws;
+  if (nstreams == 0 || F == 0) {            /* empty batch: success, nothing launched */
+    if (timings_ms) for (int i = 0; i < 8; i++) timings_ms[i] = 0.0f;
+    return MP3B200_OK;
+  }
+  Workspace& ws = t_ctx.ws;
   if (ws.units < U || ws.frames < F || ws.nstreams < nstreams || ws.nch != cfg->host.nch) {
     rc = ws.alloc(nstreams, cfg->host.nch, U, F, false);
     if (rc) return rc;
   }
   Timings tm;
-  rc = run_pipeline(cfg, ws, sds, d_out, nullptr, false, &tm, 0, arrival);
+  rc = run_pipeline(cfg, ws, sds, d_out, nullptr, false, &tm, arrival);
   if (rc) return rc;
   if (timings_ms) {
     timings_ms[0] = tm.psy; timings_ms[1] = tm.scan; timings_ms[2] = tm.mask; timings_ms[3] = tm.fb;
@@ -366,17 +458,6 @@ int encode_streams_device_impl(Config* cfg, int channels, int nstreams, const in
   return 0;
 }
 
-/* upload stream + arrival events of the host-buffer batch call */
-struct Uploader {
-  enum { MAX_CHUNKS = MP3_MAX_PCM_CHUNKS };
-  cudaStream_t st = nullptr; cudaEvent_t ready[MAX_CHUNKS] = {};
-  int init() {
-    if (st) return 0;
-    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (auto& e : ready) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    return 0;
-  }
-};
 }  // namespace
 
 extern "C" {
@@ -384,8 +465,11 @@ extern "C" {
 int mp3b200_encode_streams_device(int channels, int samplerate, int kbps, int nstreams, const int16_t* d_pcm,
                                   const int64_t* pcm_off, const int64_t* nsamples, uint8_t* d_out,
                                   const int64_t* out_off, float* timings_ms) {
+  if (nstreams < 0) { g_err = "negative stream count"; return MP3B200_ERR_HANDLE; }
   Config* cfg;
   int rc = get_config(channels, samplerate, kbps, &cfg);
+  if (rc) return rc;
+  rc = t_ctx.use(cfg->device);
   if (rc) return rc;
   return encode_streams_device_impl(cfg, channels, nstreams, d_pcm, pcm_off, nsamples, d_out, out_off, timings_ms, nullptr);
 }
@@ -393,6 +477,7 @@ int mp3b200_encode_streams_device(int channels, int samplerate, int kbps, int ns
 int mp3b200_encode_streams(int channels, int samplerate, int kbps, int nstreams, const int16_t* const* left,
                            const int16_t* const* right, const int64_t* nsamples, uint8_t* const* out,
                            const int64_t* cap, int64_t* out_bytes) {
+  if (nstreams < 0) { g_err = "negative stream count"; return MP3B200_ERR_HANDLE; }
   Config* cfg;
   int rc = get_config(channels, samplerate, kbps, &cfg);
   if (rc) return rc;
@@ -407,42 +492,36 @@ int mp3b200_encode_streams(int channels, int samplerate, int kbps, int nstreams,
     out_bytes[s] = b;
     tot_bytes += b;
   }
+  if (nstreams == 0) return MP3B200_OK;
+  rc = t_ctx.use(cfg->device);
+  if (rc) return rc;
   /* grow-only staging buffers: a steady stream of batches does not pay cudaMalloc/cudaFree per call */
-  static thread_local int16_t* d_pcm = nullptr; static thread_local size_t pcm_cap = 0;
-  static thread_local uint8_t* d_out = nullptr; static thread_local size_t out_cap = 0;
-  if (pcm_cap < (size_t)tot_samples + 8) {
-    cudaFree(d_pcm); d_pcm = nullptr; pcm_cap = 0;
-    CK(cudaMalloc(&d_pcm, sizeof(int16_t) * ((size_t)tot_samples + 8)));
-    pcm_cap = (size_t)tot_samples + 8;
-  }
-  if (out_cap < (size_t)tot_bytes + 8) {
-    cudaFree(d_out); d_out = nullptr; out_cap = 0;
-    CK(cudaMalloc(&d_out, (size_t)tot_bytes + 8));
-    out_cap = (size_t)tot_bytes + 8;
-  }
+  rc = t_ctx.need_pcm((size_t)tot_samples + 8);
+  if (rc) return rc;
+  rc = t_ctx.need_out((size_t)tot_bytes + 8);
+  if (rc) return rc;
+  int16_t* d_pcm = t_ctx.d_pcm;
+  uint8_t* d_out = t_ctx.d_out;
   /* Upload in time slices on a copy stream; the psy analysis of a slice starts when it has landed, so only the first
    * slice's transfer is exposed.  Many small streams are uploaded whole (one slice): per-copy overhead would win. */
-  static thread_local Uploader up;
-  rc = up.init();
-  if (rc) return rc;
   PcmArrival arr;
-  arr.chunks = (nstreams <= 8 && tot_samples >= (1 << 20)) ? Uploader::MAX_CHUNKS : 1;
-  arr.ready = up.ready;
+  arr.chunks = (nstreams <= 8 && tot_samples >= (1 << 20)) ? MP3_MAX_PCM_CHUNKS : 1;
+  arr.ready = t_ctx.ready;
   for (int j = 0; j < arr.chunks; j++) {
     for (int s = 0; s < nstreams; s++) {
       const int64_t lo = nsamples[s] * j / arr.chunks, hi = nsamples[s] * (j + 1) / arr.chunks;
       if (hi <= lo) continue;
-      CK(cudaMemcpyAsync(d_pcm + pcm_off[s] + lo, left[s] + lo, sizeof(int16_t) * (hi - lo), cudaMemcpyHostToDevice, up.st));
+      CK(cudaMemcpyAsync(d_pcm + pcm_off[s] + lo, left[s] + lo, sizeof(int16_t) * (hi - lo), cudaMemcpyHostToDevice, t_ctx.up_st));
       if (channels == 2)
-        CK(cudaMemcpyAsync(d_pcm + pcm_off[s] + nsamples[s] + lo, right[s] + lo, sizeof(int16_t) * (hi - lo), cudaMemcpyHostToDevice, up.st));
+        CK(cudaMemcpyAsync(d_pcm + pcm_off[s] + nsamples[s] + lo, right[s] + lo, sizeof(int16_t) * (hi - lo), cudaMemcpyHostToDevice, t_ctx.up_st));
     }
-    CK(cudaEventRecord(up.ready[j], up.st));
+    CK(cudaEventRecord(t_ctx.ready[j], t_ctx.up_st));
   }
   rc = encode_streams_device_impl(cfg, channels, nstreams, d_pcm, pcm_off.data(), nsamples, d_out, out_off.data(), nullptr, &arr);
   if (rc == 0) {
     for (int s = 0; s < nstreams; s++)
-      if (cudaMemcpyAsync(out[s], d_out + out_off[s], (size_t)out_bytes[s], cudaMemcpyDeviceToHost, 0) != cudaSuccess) rc = MP3B200_ERR_CUDA;
-    if (cudaStreamSynchronize(0) != cudaSuccess) rc = MP3B200_ERR_CUDA;
+      if (cudaMemcpyAsync(out[s], d_out + out_off[s], (size_t)out_bytes[s], cudaMemcpyDeviceToHost, t_ctx.st) != cudaSuccess) rc = MP3B200_ERR_CUDA;
+    if (cudaStreamSynchronize(t_ctx.st) != cudaSuccess) rc = MP3B200_ERR_CUDA;
   }
   return rc;
 }
@@ -453,6 +532,8 @@ int mp3b200_debug_stages(int channels, int samplerate, int kbps, const int16_t* 
                          int32_t* l3_enc, int32_t* ginfo, uint8_t* bytes_out, int64_t bytes_cap) {
   Config* cfg;
   int rc = get_config(channels, samplerate, kbps, &cfg);
+  if (rc) return rc;
+  rc = t_ctx.use(cfg->device);
   if (rc) return rc;
   const int nch = cfg->host.nch;
   const long long F = frames_for(nsamples), U = 2 * F;
@@ -473,7 +554,7 @@ int mp3b200_debug_stages(int channels, int samplerate, int kbps, const int16_t* 
   rc = ws.alloc(1, nch, U, F, true);
   if (rc) { cudaFree(d_pcm); cudaFree(d_out); return rc; }
   const bool only_mdct = (l3_enc == nullptr && ginfo == nullptr && bytes_out == nullptr);
-  rc = run_pipeline(cfg, ws, sds, d_out, force_blocktype, only_mdct, nullptr, 0);
+  rc = run_pipeline(cfg, ws, sds, d_out, force_blocktype, only_mdct, nullptr);
   if (rc == 0) {
     if (xr) CK(cudaMemcpy(xr, ws.d_xr, sizeof(float) * (size_t)U * nch * 576, cudaMemcpyDeviceToHost));
     if (blocktype) {

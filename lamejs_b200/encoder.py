@@ -144,6 +144,8 @@ def encode_streams(channels, samplerate, kbps, lefts, rights=None):
     Host buffers in, list of bytes out."""
     L = lib()
     S = len(lefts)
+    if S == 0:
+        return []
     lefts = [np.ascontiguousarray(x, dtype=np.int16) for x in lefts]
     rights = lefts if (rights is None or channels == 1) else [np.ascontiguousarray(x, dtype=np.int16) for x in rights]
     ns = np.array([len(x) for x in lefts], dtype=np.int64)
@@ -202,6 +204,8 @@ def debug_stages(channels, samplerate, kbps, left, right=None, force_blocktype=N
     p_l3 = alloc("l3_enc", (F, 2, nch, 576), np.int32)
     p_gi = alloc("ginfo", (F, 2, nch, 16), np.int32)
     nb = stream_bytes(channels, samplerate, kbps, n)
+    if nb < 0:
+        raise Mp3B200Error("unsupported configuration: channels=%d samplerate=%d kbps=%d" % (channels, samplerate, kbps))
     p_by = alloc("bytes", (nb,), np.uint8)
     _check(L.mp3b200_debug_stages(channels, samplerate, kbps, left.ctypes.data, right.ctypes.data, n,
                                   fb.ctypes.data if fb is not None else None, p_xr, p_bt, p_enl, p_thl, p_ens, p_ths, p_ath,

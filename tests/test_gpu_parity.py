@@ -188,3 +188,68 @@ def test_config_matrix(M, oracle, sr):
             assert outs[0] == oracle.encode_stream(ch, sr, kbps, l, r if ch == 2 else None)[0], (ch, sr, kbps)
             assert outs[1] == oracle.encode_stream(ch, sr, kbps, l2, r2 if ch == 2 else None)[0], (ch, sr, kbps)
     assert tried >= 8
+
+
+@pytest.mark.gpu
+def test_four_host_threads_with_own_handles(oracle):
+    """SURVEY 8(b) threading row: distinct handles are usable concurrently from distinct host threads (each thread drives
+    its own CUDA stream); every stream's bytes equal the oracle's."""
+    import threading
+
+    import lamejs_b200 as M
+
+    cfgs = [(2, 44100, 128, "burst"), (1, 44100, 128, "octave"), (2, 48000, 320, "white"), (2, 32000, 192, "noise")]
+    res, err = [None] * 4, []
+
+    def work(i):
+        try:
+            ch, sr, kbps, kind = cfgs[i]
+            l, r = make_signal(kind, 40 * 1152 + 37 * i, sr, 300 + i)
+            enc = M.Mp3Encoder(ch, sr, kbps)
+            out = bytearray()
+            for k in range(0, len(l), 1152):
+                out += enc.encodeBuffer(l[k:k + 1152], r[k:k + 1152] if ch == 2 else None)
+            out += enc.flush()
+            enc.close()
+            res[i] = bytes(out)
+        except Exception as e:   # noqa: BLE001
+            err.append((i, repr(e)))
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not err, err
+    for i, (ch, sr, kbps, kind) in enumerate(cfgs):
+        l, r = make_signal(kind, 40 * 1152 + 37 * i, sr, 300 + i)
+        ref, _, _ = oracle.encode_stream(ch, sr, kbps, l, r if ch == 2 else None, chunk=1152)
+        assert res[i] == ref, i
+
+
+@pytest.mark.gpu
+def test_empty_batch_and_error_paths_keep_the_stream_intact(oracle):
+    import ctypes
+
+    import lamejs_b200 as M
+
+    assert M.encode_streams(2, 44100, 128, [], []) == []
+    L = M.lib()
+    # a too-small output buffer fails the call but not the stream: the next call delivers the backlog
+    l, r = make_signal("noise", 6 * 1152, 44100, 41)
+    ref, _, _ = oracle.encode_stream(2, 44100, 128, l, r)
+    h = ctypes.c_void_p()
+    assert L.mp3b200_create(2, 44100, 128, ctypes.byref(h)) == 0
+    small = np.empty(100, dtype=np.uint8)
+    big = np.empty(20000, dtype=np.uint8)
+    rc = L.mp3b200_encode(h, l.ctypes.data, r.ctypes.data, len(l), small.ctypes.data, len(small))
+    assert rc < 0
+    got = bytearray()
+    rc = L.mp3b200_encode(h, l.ctypes.data, r.ctypes.data, 0, big.ctypes.data, len(big))
+    assert rc > 0
+    got += big[:rc].tobytes()
+    rc = L.mp3b200_flush(h, big.ctypes.data, len(big))
+    assert rc > 0
+    got += big[:rc].tobytes()
+    L.mp3b200_destroy(h)
+    assert bytes(got) == ref

@@ -32,8 +32,8 @@ if hasattr(M.lib(), "mp3b200_debug_qstats"):
     import ctypes
     st = (ctypes.c_ulonglong * 16)()
     M.lib().mp3b200_debug_qstats(st, 1)
-    names = ["bs1 search", "bs1 tail", "reval-gr0 search", "reval-gr0 tail", "reval-gr1 search", "divide_sub region calls", "divide_init r0 calls", "divide_init r1 calls", "outer huff loop",
-             "outer best loop", "calc_noise(outer)", "gc encoded", "reval gr0", "reval gr1", "reval failed -> re-encode", "noquant region calls"]
+    names = ["bs1 search", "bs1 tail", "reval-gr0 search", "reval-gr0 tail", "reval-gr1 search", "reval packs", "divide_init r0 calls", "divide_init r1 calls", "outer huff loop",
+             "outer best loop", "calc_noise(outer)", "gc encoded", "reval gr0", "reval gr1", "reval rate loops (gc)", "noquant region calls"]
     gcs = max(1, st[11])
     print("call counters over %d encodes (per encoded gc in brackets):" % reps)
     for n_, v in zip(names, st):
