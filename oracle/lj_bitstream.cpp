@@ -68,7 +68,7 @@ static void writeheader(LjEnc* e, int val, int j) {
 static void encodeSideInfo2(LjEnc* e) {
   e->hdr_ptr = 0;
   memset(e->hdr_buf, 0, e->sideinfo_len);
-  writeheader(e, 0xfff, 12);
+  writeheader(e, e->out_samplerate < 16000 ? 0xffe : 0xfff, 12);   /* MPEG-2.5 sync word */
   writeheader(e, e->version, 1);
   writeheader(e, 4 - 3, 2);
   writeheader(e, 1, 1);                        /* !error_protection */
@@ -81,6 +81,7 @@ static void encodeSideInfo2(LjEnc* e) {
   writeheader(e, 0, 1);                        /* copyright */
   writeheader(e, 1, 1);                        /* original */
   writeheader(e, 0, 2);                        /* emphasis */
+  if (e->version == 1) {
   writeheader(e, e->main_data_begin, 9);
   if (e->channels_out == 2) writeheader(e, 0, 3);
   else writeheader(e, 0, 5);
@@ -116,6 +117,42 @@ static void encodeSideInfo2(LjEnc* e) {
         writeheader(e, gi->region1_count, 3);
       }
       writeheader(e, gi->preflag, 1);
+      writeheader(e, gi->scalefac_scale, 1);
+      writeheader(e, gi->count1table_select, 1);
+    }
+  }
+  } else {
+    /* MPEG-2 / 2.5 (BitStream.js:352-404): one granule, 9-bit scalefac_compress, no preflag bit, no scfsi */
+    writeheader(e, e->main_data_begin, 8);
+    writeheader(e, 0, e->channels_out);          /* private_bits */
+    for (int ch = 0; ch < e->channels_out; ch++) {
+      GrInfo* gi = &e->tt[0][ch];
+      writeheader(e, gi->part2_3_length + gi->part2_length, 12);
+      writeheader(e, gi->big_values / 2, 9);
+      writeheader(e, gi->global_gain, 8);
+      writeheader(e, gi->scalefac_compress, 9);
+      if (gi->block_type != NORM_TYPE) {
+        writeheader(e, 1, 1);
+        writeheader(e, gi->block_type, 2);
+        writeheader(e, gi->mixed_block_flag, 1);
+        if (gi->table_select[0] == 14) gi->table_select[0] = 16;
+        writeheader(e, gi->table_select[0], 5);
+        if (gi->table_select[1] == 14) gi->table_select[1] = 16;
+        writeheader(e, gi->table_select[1], 5);
+        writeheader(e, gi->subblock_gain[0], 3);
+        writeheader(e, gi->subblock_gain[1], 3);
+        writeheader(e, gi->subblock_gain[2], 3);
+      } else {
+        writeheader(e, 0, 1);
+        if (gi->table_select[0] == 14) gi->table_select[0] = 16;
+        writeheader(e, gi->table_select[0], 5);
+        if (gi->table_select[1] == 14) gi->table_select[1] = 16;
+        writeheader(e, gi->table_select[1], 5);
+        if (gi->table_select[2] == 14) gi->table_select[2] = 16;
+        writeheader(e, gi->table_select[2], 5);
+        writeheader(e, gi->region0_count, 4);
+        writeheader(e, gi->region1_count, 3);
+      }
       writeheader(e, gi->scalefac_scale, 1);
       writeheader(e, gi->count1table_select, 1);
     }
@@ -202,6 +239,36 @@ static int LongHuffmancodebits(LjEnc* e, const GrInfo* gi) {
 
 static int writeMainData(LjEnc* e) {
   int tot_bits = 0;
+  if (e->version != 1) {   /* MPEG-2 / 2.5 (BitStream.js:641-687) */
+    for (int ch = 0; ch < e->channels_out; ch++) {
+      const GrInfo* gi = &e->tt[0][ch];
+      int data_bits = 0, scale_bits = 0, sfb = 0;
+      if (gi->block_type == SHORT_TYPE) {
+        for (int part = 0; part < 4; part++) {
+          const int sfbs = gi->sfb_partition_table[part] / 3, slen = gi->slen[part];
+          for (int i = 0; i < sfbs; i++, sfb++) {
+            putbits2(e, gi->scalefac[sfb * 3 + 0] > 0 ? gi->scalefac[sfb * 3 + 0] : 0, slen);
+            putbits2(e, gi->scalefac[sfb * 3 + 1] > 0 ? gi->scalefac[sfb * 3 + 1] : 0, slen);
+            putbits2(e, gi->scalefac[sfb * 3 + 2] > 0 ? gi->scalefac[sfb * 3 + 2] : 0, slen);
+            scale_bits += 3 * slen;
+          }
+        }
+        data_bits += ShortHuffmancodebits(e, gi);
+      } else {
+        for (int part = 0; part < 4; part++) {
+          const int sfbs = gi->sfb_partition_table[part], slen = gi->slen[part];
+          for (int i = 0; i < sfbs; i++, sfb++) {
+            putbits2(e, gi->scalefac[sfb] > 0 ? gi->scalefac[sfb] : 0, slen);
+            scale_bits += slen;
+          }
+        }
+        data_bits += LongHuffmancodebits(e, gi);
+      }
+      data_bits += huffman_coder_count1(e, gi);
+      tot_bits += scale_bits + data_bits;
+    }
+    return tot_bits;
+  }
   for (int gr = 0; gr < 2; gr++) {
     for (int ch = 0; ch < e->channels_out; ch++) {
       const GrInfo* gi = &e->tt[gr][ch];

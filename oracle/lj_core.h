@@ -84,6 +84,7 @@ struct GrInfo {
   int width[SFBMAX], window[SFBMAX];
   int count1bits;
   int slen[4];
+  const int* sfb_partition_table;   /* MPEG-2 LSF: row of nr_of_sfb_block (QuantizePVT.js:116-122) */
   int max_nonzero_coeff;
 };
 

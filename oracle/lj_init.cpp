@@ -14,6 +14,11 @@
 #include "lj_encoder.h"
 
 static const int bitrate_table_mpeg1[16] = {0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, -1};
+/* Tables.js:494-498: [0] MPEG-2, [1] MPEG-1, [2] MPEG-2.5 */
+static const int bitrate_table[3][16] = {
+  {0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160, -1},
+  {0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, -1},
+  {0, 8, 16, 24, 32, 40, 48, 56, 64, -1, -1, -1, -1, -1, -1, -1}};
 
 /* Lame.js:248-283 */
 static int nearestBitrateFullIndex(int bitrate) {
@@ -144,7 +149,7 @@ static void apply_abr_preset(LjEnc* e, int preset) {
 
 static int framebits(int version, int bitrate_index, int out_samplerate, int padding) {
   /* BitStream.js:83-98: bitrate_index != 0 always; `0 | a/b + padding` */
-  int bit_rate = bitrate_table_mpeg1[bitrate_index];
+  int bit_rate = bitrate_table[version][bitrate_index];
   int bytes = js_toint32((double)((version + 1) * 72000 * bit_rate) / out_samplerate + padding);
   return 8 * bytes;
 }
@@ -183,15 +188,21 @@ int lj_init_params(LjEnc* e, int channels, int samplerate, int kbps) {
   lowpassfreq = js_min(20500, lowpassfreq);
   lowpassfreq = js_min(e->out_samplerate / 2.0, lowpassfreq);
   if (e->out_samplerate != e->in_samplerate) return -1; /* resampler path: SURVEY 8(f1), not built */
-  switch (e->out_samplerate) {
+  switch (e->out_samplerate) {   /* SmpFrqIndex (Lame.js:369-402): version 1 = MPEG-1, 0 = MPEG-2 and MPEG-2.5 */
     case 44100: e->version = 1; e->samplerate_index = 0; break;
     case 48000: e->version = 1; e->samplerate_index = 1; break;
     case 32000: e->version = 1; e->samplerate_index = 2; break;
-    default: return -1; /* MPEG-2/2.5 LSF path not built */
+    case 22050: e->version = 0; e->samplerate_index = 0; break;
+    case 24000: e->version = 0; e->samplerate_index = 1; break;
+    case 16000: e->version = 0; e->samplerate_index = 2; break;
+    case 11025: e->version = 0; e->samplerate_index = 0; break;
+    case 12000: e->version = 0; e->samplerate_index = 1; break;
+    case 8000: e->version = 0; e->samplerate_index = 2; break;
+    default: return -1;
   }
   e->compression_ratio = e->out_samplerate * 16 * e->channels_out / (1.e3 * e->brate);
-  e->mode_gr = 2;
-  e->framesize = 1152;
+  e->mode_gr = e->out_samplerate <= 24000 ? 1 : 2;
+  e->framesize = 576 * e->mode_gr;
   e->highpass1 = e->highpass2 = 0;
   if (lowpassfreq > 0) {
     e->lowpass2 = 2. * lowpassfreq;
@@ -200,29 +211,43 @@ int lj_init_params(LjEnc* e, int channels, int samplerate, int kbps) {
     e->lowpass2 /= e->out_samplerate;
   } else { e->lowpass1 = e->lowpass2 = 0; }
   init_params_ppflt(e);
-  /* FindNearestBitrate / BitrateIndex (Lame.js:408-443) */
+  /* FindNearestBitrate / BitrateIndex (Lame.js:408-443): below 16 kHz the MPEG-2.5 row is searched */
   {
-    int bitrate = bitrate_table_mpeg1[1];
+    const int* bt = bitrate_table[e->out_samplerate < 16000 ? 2 : e->version];
+    int bitrate = bt[1];
     for (int i = 2; i <= 14; i++)
-      if (abs(bitrate_table_mpeg1[i] - e->brate) < abs(bitrate - e->brate)) bitrate = bitrate_table_mpeg1[i];
+      if (bt[i] > 0 && abs(bt[i] - e->brate) < abs(bitrate - e->brate)) bitrate = bt[i];
     e->brate = bitrate;
     e->bitrate_index = -1;
-    for (int i = 0; i <= 14; i++) if (bitrate_table_mpeg1[i] > 0 && bitrate_table_mpeg1[i] == e->brate) { e->bitrate_index = i; break; }
+    for (int i = 0; i <= 14; i++) if (bt[i] > 0 && bt[i] == e->brate) { e->bitrate_index = i; break; }
     if (e->bitrate_index <= 0) return -1;
   }
   /* bitstream init */
   e->bs_byteidx = -1; e->bs_bitidx = 0; e->bs_totbit = 0; e->hdr_pending = 0;
   /* sfb tables (Lame.js:1079-1101; QuantizePVT.js:137-204) */
   {
-    static const int sfl[3][23] = {
+    /* QuantizePVT.js:137-204 sfBandIndex: 22.05, 24, 16 kHz (MPEG-2); 44.1, 48, 32 kHz (MPEG-1); 11.025, 12, 8 kHz (MPEG-2.5) */
+    static const int sfl[9][23] = {
+      {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
+      {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 114, 136, 162, 194, 232, 278, 332, 394, 464, 540, 576},
+      {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
       {0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 52, 62, 74, 90, 110, 134, 162, 196, 238, 288, 342, 418, 576},
       {0, 4, 8, 12, 16, 20, 24, 30, 36, 42, 50, 60, 72, 88, 106, 128, 156, 190, 230, 276, 330, 384, 576},
-      {0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 54, 66, 82, 102, 126, 156, 194, 240, 296, 364, 448, 550, 576}};
-    static const int sfs[3][14] = {
+      {0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 54, 66, 82, 102, 126, 156, 194, 240, 296, 364, 448, 550, 576},
+      {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
+      {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
+      {0, 12, 24, 36, 48, 60, 72, 88, 108, 132, 160, 192, 232, 280, 336, 400, 476, 566, 568, 570, 572, 574, 576}};
+    static const int sfs[9][14] = {
+      {0, 4, 8, 12, 18, 24, 32, 42, 56, 74, 100, 132, 174, 192},
+      {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 136, 180, 192},
+      {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 134, 174, 192},
       {0, 4, 8, 12, 16, 22, 30, 40, 52, 66, 84, 106, 136, 192},
       {0, 4, 8, 12, 16, 22, 28, 38, 50, 64, 80, 100, 126, 192},
-      {0, 4, 8, 12, 16, 22, 30, 42, 58, 78, 104, 138, 180, 192}};
-    int j = e->samplerate_index;
+      {0, 4, 8, 12, 16, 22, 30, 42, 58, 78, 104, 138, 180, 192},
+      {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 134, 174, 192},
+      {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 134, 174, 192},
+      {0, 8, 16, 24, 36, 52, 72, 96, 124, 160, 162, 164, 166, 192}};
+    int j = e->samplerate_index + 3 * e->version + 6 * (e->out_samplerate < 16000 ? 1 : 0);
     for (int i = 0; i < SBMAX_l + 1; i++) e->sfb_l[i] = sfl[j][i];
     for (int i = 0; i < PSFB21 + 1; i++) {
       double size = (e->sfb_l[22] - e->sfb_l[21]) / (double)PSFB21;   /* JS float division */
@@ -238,7 +263,8 @@ int lj_init_params(LjEnc* e, int channels, int samplerate, int kbps) {
     }
     e->psfb12[PSFB12] = 192;
   }
-  e->sideinfo_len = (e->channels_out == 1) ? 4 + 17 : 4 + 32;
+  if (e->version == 1) e->sideinfo_len = (e->channels_out == 1) ? 4 + 17 : 4 + 32;
+  else e->sideinfo_len = (e->channels_out == 1) ? 4 + 9 : 4 + 17;
   for (int k = 0; k < 19; k++) e->pefirbuf[k] = 700 * e->mode_gr * e->channels_out;
   if (e->ATHtype == -1) e->ATHtype = 4;
   /* cbr: apply_preset(brate) */
@@ -410,7 +436,7 @@ static int encode_buffer_sample(LjEnc* e, F32* in0, F32* in1, int nsamples, uint
       if (e->channels_out == 2) in1[i] *= e->scale;
     }
   }
-  const int mf_needed = 1904; /* calcNeeded: max(1024+1152-272, 512+1152-32) */
+  const int mf_needed = e->framesize + 752; /* calcNeeded (Lame.js:1516-1525): max(1024 + framesize - 272, 512 + framesize - 32) */
   int pos = 0;
   while (nsamples > 0) {
     int n_out = e->framesize < nsamples ? e->framesize : nsamples;
@@ -470,7 +496,7 @@ int lj_flush(LjEnc* e, uint8_t* out, int cap) {
   static const int16_t zeros[1152] = {0};
   int imp3 = 0, mp3count = 0;
   int samples_to_encode = e->mf_samples_to_encode - POSTDELAY;
-  const int mf_needed = 1904;
+  const int mf_needed = e->framesize + 752;
   if (e->mf_samples_to_encode < 1) return 0;
   int end_padding = e->framesize - (samples_to_encode % e->framesize);
   if (end_padding < 576) end_padding += e->framesize;

@@ -3,6 +3,7 @@
  * mdct_long :981-1051, mdct_sub48 :1053-1161.  Same statement order; doubles with
  * Float32Array store points (sb_sample, xr, work are F32).
  */
+#include <string.h>
 #include "lj_encoder.h"
 #include "lj_tables.h"
 
@@ -360,5 +361,7 @@ void lj_mdct_sub48(LjEnc* e, const F32* w0, const F32* w1) {
     }
     wk = w1;
     wkPos = 286;
+    if (e->mode_gr == 1)   /* NewMDCT.js:1154-1159 */
+      for (int i = 0; i < 18; i++) memcpy(e->sb_sample[ch][0][i], e->sb_sample[ch][1][i], sizeof(F32) * 32);
   }
 }

@@ -727,6 +727,7 @@ static void best_huffman_divide(const LjEnc* e, GrInfo* gi) {
   int r01_bits[7 + 15 + 1], r01_div[7 + 15 + 1], r0_tbl[7 + 15 + 1], r1_tbl[7 + 15 + 1];
   memset(r01_div, 0, sizeof r01_div); memset(r0_tbl, 0, sizeof r0_tbl); memset(r1_tbl, 0, sizeof r1_tbl);
   const int* ix = gi->l3_enc;
+  if (gi->block_type == SHORT_TYPE && e->mode_gr == 1) return;   /* "SHORT BLOCK stuff fails for MPEG2" (Takehiro.js:735-737) */
   cod_info2 = *gi;
   if (gi->block_type == NORM_TYPE) {
     recalc_divide_init(e, gi, ix, r01_bits, r01_div, r0_tbl, r1_tbl);
@@ -832,6 +833,55 @@ static bool scale_bitcount(GrInfo* cod_info) {
   return cod_info->part2_length == LARGE_BITS;
 }
 
+/* QuantizePVT.js:116-122 */
+static const int nr_of_sfb_block[6][3][4] = {
+  {{6, 5, 5, 5}, {9, 9, 9, 9}, {6, 9, 9, 9}}, {{6, 5, 7, 3}, {9, 9, 12, 6}, {6, 9, 12, 6}}, {{11, 10, 0, 0}, {18, 18, 0, 0}, {15, 18, 0, 0}},
+  {{7, 7, 7, 0}, {12, 12, 12, 0}, {6, 15, 12, 0}}, {{6, 6, 6, 3}, {12, 9, 9, 6}, {6, 12, 9, 6}}, {{8, 8, 5, 0}, {15, 12, 9, 0}, {6, 18, 9, 0}}};
+
+/* scale_bitcount_lsf (Takehiro.js:1036-1132): MPEG-2 / 2.5 scalefactor coding */
+static bool scale_bitcount_lsf(GrInfo* cod_info) {
+  static const int max_range_sfac_tab[6][4] = {{15, 15, 7, 7}, {15, 15, 7, 0}, {7, 3, 0, 0}, {15, 31, 31, 0}, {7, 7, 7, 0}, {3, 3, 0, 0}};
+  static const int log2tab[16] = {0, 1, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4};
+  int table_number, row_in_table, partition, nr_sfb, window, i, sfb;
+  bool over;
+  int max_sfac[4] = {0, 0, 0, 0};
+  const int* scalefac = cod_info->scalefac;
+  table_number = cod_info->preflag != 0 ? 2 : 0;
+  if (cod_info->block_type == SHORT_TYPE) {
+    row_in_table = 1;
+    const int* partition_table = nr_of_sfb_block[table_number][row_in_table];
+    for (sfb = 0, partition = 0; partition < 4; partition++) {
+      nr_sfb = partition_table[partition] / 3;
+      for (i = 0; i < nr_sfb; i++, sfb++)
+        for (window = 0; window < 3; window++)
+          if (scalefac[sfb * 3 + window] > max_sfac[partition]) max_sfac[partition] = scalefac[sfb * 3 + window];
+    }
+  } else {
+    row_in_table = 0;
+    const int* partition_table = nr_of_sfb_block[table_number][row_in_table];
+    for (sfb = 0, partition = 0; partition < 4; partition++) {
+      nr_sfb = partition_table[partition];
+      for (i = 0; i < nr_sfb; i++, sfb++)
+        if (scalefac[sfb] > max_sfac[partition]) max_sfac[partition] = scalefac[sfb];
+    }
+  }
+  for (over = false, partition = 0; partition < 4; partition++)
+    if (max_sfac[partition] > max_range_sfac_tab[table_number][partition]) over = true;
+  if (!over) {
+    cod_info->sfb_partition_table = nr_of_sfb_block[table_number][row_in_table];
+    for (partition = 0; partition < 4; partition++) cod_info->slen[partition] = log2tab[max_sfac[partition]];
+    const int slen1 = cod_info->slen[0], slen2 = cod_info->slen[1], slen3 = cod_info->slen[2], slen4 = cod_info->slen[3];
+    switch (table_number) {
+      case 0: cod_info->scalefac_compress = (((slen1 * 5) + slen2) << 4) + (slen3 << 2) + slen4; break;
+      case 1: cod_info->scalefac_compress = 400 + (((slen1 * 5) + slen2) << 2) + slen3; break;
+      case 2: cod_info->scalefac_compress = 500 + (slen1 * 3) + slen2; break;
+    }
+    cod_info->part2_length = 0;
+    for (partition = 0; partition < 4; partition++) cod_info->part2_length += cod_info->slen[partition] * cod_info->sfb_partition_table[partition];
+  }
+  return over;
+}
+
 static void best_scalefac_store(LjEnc* e, int gr, int ch) {
   GrInfo* gi = &e->tt[gr][ch];
   int sfb, i, j, l;
@@ -864,7 +914,7 @@ static void best_scalefac_store(LjEnc* e, int gr, int ch) {
     recalc = 0;
   }
   for (sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] == -2) gi->scalefac[sfb] = 0;
-  if (recalc != 0) scale_bitcount(gi);
+  if (recalc != 0) { if (e->mode_gr == 2) scale_bitcount(gi); else scale_bitcount_lsf(gi); }
 }
 
 /* ---------------------------------------------------------------- Quantize.js */
@@ -975,6 +1025,7 @@ static void init_outer_loop(LjEnc* e, GrInfo* cod_info) {
     }
   }
   cod_info->count1bits = 0;
+  cod_info->sfb_partition_table = nr_of_sfb_block[0][0];
   cod_info->slen[0] = cod_info->slen[1] = cod_info->slen[2] = cod_info->slen[3] = 0;
   cod_info->max_nonzero_coeff = 575;
   for (int i = 0; i < SFBMAX; i++) cod_info->scalefac[i] = 0;
@@ -1153,7 +1204,7 @@ static bool balance_noise(LjEnc* e, GrInfo* cod_info, const F32* distort, F32* x
   amp_scalefac_bands(e, cod_info, distort, xrpow, bRefine);
   bool status = loop_break(cod_info);
   if (status) return false;
-  status = scale_bitcount(cod_info);
+  status = e->mode_gr == 2 ? scale_bitcount(cod_info) : scale_bitcount_lsf(cod_info);
   if (!status) return true;
   if (e->noise_shaping > 1) {
     for (int i = 0; i < SFBMAX; i++) e->pseudohalf[i] = 0;
@@ -1165,7 +1216,7 @@ static bool balance_noise(LjEnc* e, GrInfo* cod_info, const F32* distort, F32* x
         status = (inc_subblock_gain(e, cod_info, xrpow) || loop_break(cod_info));
     }
   }
-  if (!status) status = scale_bitcount(cod_info);
+  if (!status) status = e->mode_gr == 2 ? scale_bitcount(cod_info) : scale_bitcount_lsf(cod_info);
   return !status;
 }
 
