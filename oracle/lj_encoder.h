@@ -73,6 +73,15 @@ struct LjEnc {
   GrInfo tt[2][2];
   int main_data_begin, resvDrain_pre, resvDrain_post;
   int scfsi[2][4];
+  /* resampler (Lame.js:1691-1843): per-call state exactly as lamejs keeps it */
+  double resample_ratio;
+  int resample_init;
+  int rs_bpc, rs_filter_l;
+  F32 inbuf_old[2][33];
+  F32 (*blackfilt)[33];          /* [2 * bpc + 1][BLACKSIZE] */
+  double itime[2];
+  /* gfc.in_buffer_0/1 (Lame.js:1373-1379): grow-only Float32Arrays; a fractional length truncates, stale contents stay */
+  F32* inb[2]; int inb_len; double inb_nsamples;
   /* stream driver */
   F32 mfbuf[2][MFSIZE];
   int mf_size, mf_samples_to_encode;

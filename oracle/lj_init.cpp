@@ -11,6 +11,7 @@
  */
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 #include "lj_encoder.h"
 
 static const int bitrate_table_mpeg1[16] = {0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, -1};
@@ -187,7 +188,6 @@ int lj_init_params(LjEnc* e, int channels, int samplerate, int kbps) {
   e->out_samplerate = optimum_samplefreq(js_toint32(lowpassfreq), e->in_samplerate);
   lowpassfreq = js_min(20500, lowpassfreq);
   lowpassfreq = js_min(e->out_samplerate / 2.0, lowpassfreq);
-  if (e->out_samplerate != e->in_samplerate) return -1; /* resampler path: SURVEY 8(f1), not built */
   switch (e->out_samplerate) {   /* SmpFrqIndex (Lame.js:369-402): version 1 = MPEG-1, 0 = MPEG-2 and MPEG-2.5 */
     case 44100: e->version = 1; e->samplerate_index = 0; break;
     case 48000: e->version = 1; e->samplerate_index = 1; break;
@@ -203,6 +203,7 @@ int lj_init_params(LjEnc* e, int channels, int samplerate, int kbps) {
   e->compression_ratio = e->out_samplerate * 16 * e->channels_out / (1.e3 * e->brate);
   e->mode_gr = e->out_samplerate <= 24000 ? 1 : 2;
   e->framesize = 576 * e->mode_gr;
+  e->resample_ratio = (double)e->in_samplerate / e->out_samplerate;
   e->highpass1 = e->highpass2 = 0;
   if (lowpassfreq > 0) {
     e->lowpass2 = 2. * lowpassfreq;
@@ -423,28 +424,121 @@ static int encode_mp3_frame(LjEnc* e, uint8_t* mp3buf, int mp3buf_size) {
   return mp3count;
 }
 
-/* Lame.js:1527-1667 (no resampling: fill_buffer copies min(framesize, nsamples)) */
-static int encode_buffer_sample(LjEnc* e, F32* in0, F32* in1, int nsamples, uint8_t* mp3buf, int mp3buf_size) {
+/* ---- resampler: fill_buffer_resample (Lame.js:1719-1843), blackman (:1691-1714), gcd (:1684) ---- */
+static int rs_gcd(int i, int j) { return j != 0 ? rs_gcd(j, i % j) : i; }
+static double rs_blackman(double x, double fcn, int l) {
+  const double PI = 3.141592653589793;
+  double wcn = (PI * fcn);
+  x /= l;
+  if (x < 0) x = 0;
+  if (x > 1) x = 1;
+  double x2 = x - .5;
+  double bkwn = 0.42 - 0.5 * cos(2 * x * PI) + 0.08 * cos(4 * x * PI);
+  if (fabs(x2) < 1e-9) return (wcn / PI);
+  return (bkwn * sin(l * wcn * x2) / (PI * l * x2));
+}
+/* a read `arr[idx]` of a Float32Array of length n with a JS number index: undefined (-> NaN in arithmetic) unless idx is an
+ * integer inside the array */
+static inline double f32arr_get(const F32* arr, int n, double idx) {
+  if (!(idx >= 0) || idx != floor(idx) || idx >= n) return NAN;
+  return (double)arr[(int)idx];
+}
+static int fill_buffer_resample(LjEnc* e, F32* outbuf, int outbufPos, int desired_len, const F32* inbuf, int inbuf_n,
+                                double in_bufferPos, double len, double* num_used, int ch) {
+  int i, j = 0, k;
+  int bpc = e->out_samplerate / rs_gcd(e->out_samplerate, e->in_samplerate);
+  if (bpc > 320) bpc = 320;
+  const int intratio = (fabs(e->resample_ratio - floor(.5 + e->resample_ratio)) < .0001) ? 1 : 0;
+  double fcn = 1.00 / e->resample_ratio;
+  if (fcn > 1.00) fcn = 1.00;
+  int filter_l = 31;
+  filter_l += intratio;
+  const int BLACKSIZE = filter_l + 1;
+  const double half = filter_l / 2.0;          /* `filter_l / 2` is a float division in JS: 15.5 or 16 */
+  if (e->resample_init == 0) {
+    memset(e->inbuf_old, 0, sizeof e->inbuf_old);
+    e->blackfilt = (F32(*)[33])calloc(2 * bpc + 1, sizeof(F32[33]));
+    e->itime[0] = e->itime[1] = 0;
+    for (j = 0; j <= 2 * bpc; j++) {
+      double sum = 0.;
+      double offset = (j - bpc) / (2. * bpc);
+      for (i = 0; i <= filter_l; i++) {
+        const double v = rs_blackman(i - offset, fcn, filter_l);
+        e->blackfilt[j][i] = v;                 /* `sum += a[i] = v` adds the unrounded double */
+        sum += v;
+      }
+      for (i = 0; i <= filter_l; i++) e->blackfilt[j][i] /= sum;
+    }
+    e->resample_init = 1;
+    j = 0;
+  }
+  e->rs_bpc = bpc; e->rs_filter_l = filter_l;
+  F32* inbuf_old = e->inbuf_old[ch];
+  for (k = 0; k < desired_len; k++) {
+    double time0 = k * e->resample_ratio;
+    j = js_toint32(floor(time0 - e->itime[ch]));
+    if ((filter_l + j - half) >= len) break;
+    double offset = (time0 - e->itime[ch] - (j + .5 * (filter_l % 2)));
+    int joff = js_toint32(floor((offset * 2 * bpc) + bpc + .5));
+    double xvalue = 0.;
+    for (i = 0; i <= filter_l; ++i) {
+      int j2 = js_toint32(i + j - half);       /* 0 | x truncates toward zero */
+      double y = (j2 < 0) ? f32arr_get(inbuf_old, BLACKSIZE, BLACKSIZE + j2) : f32arr_get(inbuf, inbuf_n, in_bufferPos + j2);
+      xvalue += y * (double)e->blackfilt[joff][i];
+    }
+    outbuf[outbufPos + k] = xvalue;
+  }
+  double nu = filter_l + j - half;
+  if (len < nu) nu = len;                       /* Math.min(len, ...) (no NaN operands here) */
+  *num_used = nu;
+  e->itime[ch] += nu - k * e->resample_ratio;
+  if (nu >= BLACKSIZE) {
+    for (i = 0; i < BLACKSIZE; i++) inbuf_old[i] = f32arr_get(inbuf, inbuf_n, in_bufferPos + nu + i - BLACKSIZE);
+  } else {
+    double n_shift = BLACKSIZE - nu;
+    F32 tmp[33];
+    memcpy(tmp, inbuf_old, sizeof tmp);        /* the JS loop reads ahead of what it writes (i + num_used >= i): in place is safe */
+    for (i = 0; i < n_shift; ++i) inbuf_old[i] = f32arr_get(inbuf_old, BLACKSIZE, i + nu);
+    for (j = 0; i < BLACKSIZE; ++i, ++j) inbuf_old[i] = f32arr_get(inbuf, inbuf_n, in_bufferPos + j);
+    (void)tmp;
+  }
+  return k;
+}
+
+/* Lame.js:1527-1667.  nsamples is a JS number: lame_encode_flush passes a fractional count when it resamples. */
+static int encode_buffer_sample(LjEnc* e, F32* in0, F32* in1, int in_n, double nsamples, uint8_t* mp3buf, int mp3buf_size) {
   int mp3size = 0;
   if (nsamples == 0) return 0;
   int mp3out = lj_copy_buffer(e, mp3buf, mp3buf_size);
   if (mp3out < 0) return mp3out;
   mp3buf += mp3out; mp3size += mp3out;
   if (bs_NEQ(e->scale, 0) && bs_NEQ(e->scale, 1.0)) {
-    for (int i = 0; i < nsamples; ++i) {
+    for (int i = 0; i < nsamples && i < in_n; ++i) {
       in0[i] *= e->scale;
       if (e->channels_out == 2) in1[i] *= e->scale;
     }
   }
   const int mf_needed = e->framesize + 752; /* calcNeeded (Lame.js:1516-1525): max(1024 + framesize - 272, 512 + framesize - 32) */
-  int pos = 0;
+  const bool resample = (e->resample_ratio < .9999) || (e->resample_ratio > 1.0001);
+  double pos = 0;
   while (nsamples > 0) {
-    int n_out = e->framesize < nsamples ? e->framesize : nsamples;
-    for (int i = 0; i < n_out; ++i) {
-      e->mfbuf[0][e->mf_size + i] = in0[pos + i];
-      if (e->channels_out == 2) e->mfbuf[1][e->mf_size + i] = in1[pos + i];
+    int n_out; double n_in;
+    if (resample) {
+      n_out = 0; n_in = 0;
+      for (int ch = 0; ch < e->channels_out; ch++) {
+        double used;
+        n_out = fill_buffer_resample(e, e->mfbuf[ch], e->mf_size, e->framesize, ch == 0 ? in0 : in1, in_n, pos, nsamples, &used, ch);
+        n_in = used;
+      }
+    } else {
+      n_out = e->framesize < nsamples ? e->framesize : (int)nsamples;
+      n_in = n_out;
+      for (int i = 0; i < n_out; ++i) {
+        e->mfbuf[0][e->mf_size + i] = in0[(int)pos + i];
+        if (e->channels_out == 2) e->mfbuf[1][e->mf_size + i] = in1[(int)pos + i];
+      }
     }
-    nsamples -= n_out; pos += n_out;
+    nsamples -= n_in; pos += n_in;
     e->mf_size += n_out;
     if (e->mf_samples_to_encode < 1) e->mf_samples_to_encode = ENCDELAY + POSTDELAY;
     e->mf_samples_to_encode += n_out;
@@ -464,6 +558,24 @@ static int encode_buffer_sample(LjEnc* e, F32* in0, F32* in1, int nsamples, uint
   return mp3size;
 }
 
+/* lame_encode_buffer (Lame.js:1490-1514) incl. update_inbuffer_size (:1373-1379) */
+static int encode_buffer(LjEnc* e, const int16_t* left, const int16_t* right, int src_n, double nsamples, uint8_t* out, int cap) {
+  if (nsamples == 0) return 0;
+  if (e->inb[0] == NULL || e->inb_nsamples < nsamples) {
+    const int n = (int)nsamples;               /* new Float32Array(x): ToIndex truncates */
+    free(e->inb[0]); free(e->inb[1]);
+    e->inb[0] = (F32*)calloc(n > 0 ? n : 1, sizeof(F32));
+    e->inb[1] = (F32*)calloc(n > 0 ? n : 1, sizeof(F32));
+    e->inb_len = n; e->inb_nsamples = nsamples;
+  }
+  for (int i = 0; i < nsamples; i++) {
+    if (i >= e->inb_len) break;                /* writes past the typed array are dropped */
+    e->inb[0][i] = i < src_n ? left[i] : 0;
+    if (e->num_channels > 1) e->inb[1][i] = i < src_n ? right[i] : 0;
+  }
+  return encode_buffer_sample(e, e->inb[0], e->inb[1], e->inb_len, nsamples, out, cap);
+}
+
 extern "C" {
 
 LjEnc* lj_create(int channels, int samplerate, int kbps) {
@@ -472,43 +584,47 @@ LjEnc* lj_create(int channels, int samplerate, int kbps) {
   if (lj_init_params(e, channels, samplerate, kbps) != 0) { free(e->s3_ll); free(e->s3_ss); free(e); return NULL; }
   return e;
 }
-void lj_destroy(LjEnc* e) { if (e) { free(e->s3_ll); free(e->s3_ss); free(e); } }
+/* output sample rate lame_init_params chooses (0 if the configuration is rejected before that point) */
+int lj_query_out_samplerate(int channels, int samplerate, int kbps) {
+  LjEnc* e = (LjEnc*)calloc(1, sizeof(LjEnc));
+  if (!e) return 0;
+  lj_init_params(e, channels, samplerate, kbps);
+  const int r = e->out_samplerate;
+  free(e->s3_ll); free(e->s3_ss); free(e);
+  return r;
+}
+void lj_destroy(LjEnc* e) { if (e) { free(e->s3_ll); free(e->s3_ss); free(e->blackfilt); free(e->inb[0]); free(e->inb[1]); free(e); } }
 
 /* index.js:117-130 + Lame.js:1490-1514.  Returns bytes written or a negative lame error. */
 int lj_encode(LjEnc* e, const int16_t* left, const int16_t* right, int n, uint8_t* out, int cap) {
   if (!e) return -3;
   if (n == 0) return 0;
   if (e->channels_out == 1 || e->num_channels == 1) right = left;
-  F32* in0 = (F32*)malloc(sizeof(F32) * n);
-  F32* in1 = (F32*)malloc(sizeof(F32) * n);
-  for (int i = 0; i < n; i++) {
-    in0[i] = left[i];
-    if (e->num_channels > 1) in1[i] = right[i];
-  }
-  int r = encode_buffer_sample(e, in0, in1, n, out, cap);
-  free(in0); free(in1);
-  return r;
+  return encode_buffer(e, left, right, n, (double)n, out, cap);
 }
 
-/* index.js:132-135 + Lame.js:1381-1488 */
+/* index.js:132-135 + Lame.js:1381-1488; sample counts are JS numbers (fractional when resampling) */
 int lj_flush(LjEnc* e, uint8_t* out, int cap) {
   if (!e) return -3;
   static const int16_t zeros[1152] = {0};
   int imp3 = 0, mp3count = 0;
-  int samples_to_encode = e->mf_samples_to_encode - POSTDELAY;
+  double samples_to_encode = e->mf_samples_to_encode - POSTDELAY;
   const int mf_needed = e->framesize + 752;
   if (e->mf_samples_to_encode < 1) return 0;
-  int end_padding = e->framesize - (samples_to_encode % e->framesize);
+  if (e->in_samplerate != e->out_samplerate) samples_to_encode += 16. * e->out_samplerate / e->in_samplerate;
+  double end_padding = e->framesize - fmod(samples_to_encode, (double)e->framesize);
   if (end_padding < 576) end_padding += e->framesize;
-  int frames_left = (samples_to_encode + end_padding) / e->framesize;
+  double frames_left = (samples_to_encode + end_padding) / e->framesize;
   while (frames_left > 0 && imp3 >= 0) {
-    int bunch = mf_needed - e->mf_size;
+    double bunch = mf_needed - e->mf_size;
     int frame_num = e->frameNum;
+    bunch *= e->in_samplerate;
+    bunch /= e->out_samplerate;
     if (bunch > 1152) bunch = 1152;
     if (bunch < 1) bunch = 1;
     int remaining = cap - mp3count;
     if (cap == 0) remaining = 0;
-    imp3 = lj_encode(e, zeros, zeros, bunch, out, remaining);
+    imp3 = encode_buffer(e, zeros, zeros, 1152, bunch, out, remaining);
     if (imp3 > 0) { out += imp3; mp3count += imp3; }
     frames_left -= (frame_num != e->frameNum) ? 1 : 0;
   }

@@ -71,9 +71,15 @@ def lib():
         L.lj_destroy.argtypes = [ctypes.c_void_p]
         L.lj_set_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.lj_trace_count.argtypes = [ctypes.c_void_p]
+        L.lj_query_out_samplerate.argtypes = [ctypes.c_int] * 3
         assert L.lj_trace_size() == TRACE_DTYPE.itemsize, (L.lj_trace_size(), TRACE_DTYPE.itemsize)
         _lib = L
     return _lib
+
+
+def out_samplerate(channels, samplerate, kbps):
+    """Output sample rate lame_init_params picks (Lame.js:285-364): != samplerate means lamejs resamples."""
+    return lib().lj_query_out_samplerate(channels, samplerate, kbps)
 
 
 class OracleEncoder:

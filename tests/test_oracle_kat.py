@@ -56,10 +56,24 @@ def test_header_bytes_and_frame_sizes(oracle, ch, sr, kbps, b2, b3, flen):
     assert off == len(data)
 
 
-def test_unsupported_configs(oracle):
-    for ch, sr, kbps in [(2, 44100, 64), (2, 22050, 64), (1, 8000, 32)]:   # resampler / MPEG-2 paths: not built
-        with pytest.raises(ValueError):
-            oracle.OracleEncoder(ch, sr, kbps)
+@pytest.mark.parametrize("ch,sr,kbps,out_sr,b1,b2,flen", [
+    (2, 22050, 64, 22050, 0xF3, 0x80, 208),     # MPEG-2: version bit 0, bitrate index 8 (64k), rate index 0; 72000*64/22050 = 208.98
+    (1, 16000, 32, 16000, 0xF3, 0x48, 144),     # MPEG-2 16 kHz, bitrate index 4 (32k), rate index 2
+    (1, 8000, 32, 8000, 0xE3, 0x48, 288),       # MPEG-2.5: sync 0xFFE, 72000*32/8000 = 288
+    (2, 44100, 64, 24000, 0xF3, 0x84, 192),     # lamejs resamples 44.1k -> 24k at this bitrate (optimum_samplefreq)
+])
+def test_lsf_header_bytes_and_frame_sizes(oracle, ch, sr, kbps, out_sr, b1, b2, flen):
+    """MPEG-2 / 2.5 KATs derived from the bitstream syntax (BitStream.js:259-282, :83-98): sync + version + layer +
+    no-CRC byte, bitrate/samplerate index byte (padding bit masked), frame length floor(72000 * kbps / out_sr) (+1)."""
+    assert oracle.out_samplerate(ch, sr, kbps) == out_sr
+    l, r = make_signal("noise", 8 * 1152, sr, 5)
+    data, _, _ = oracle.encode_stream(ch, sr, kbps, l, r if ch == 2 else None, chunk=1152)
+    off, k = 0, 0
+    while off < len(data):
+        assert data[off] == 0xFF and data[off + 1] == b1 and (data[off + 2] & 0xFD) == b2, (k, data[off:off + 4].hex())
+        off += flen + ((data[off + 2] >> 1) & 1)
+        k += 1
+    assert off == len(data) and k >= 8
 
 
 @pytest.mark.parametrize("kind,ch,sr,kbps", [("noise", 2, 44100, 128), ("burst", 2, 44100, 128), ("white", 2, 48000, 320),
