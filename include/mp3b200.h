@@ -28,9 +28,14 @@ typedef struct mp3b200_encoder mp3b200_encoder;
 int mp3b200_set_device(int device);
 
 /* Replaces `new lamejs.Mp3Encoder(channels, samplerate, kbps)` (src/js/index.js:66-115).
- * channels 1|2; samplerate 32000|44100|48000 (MPEG-1, no resampling); kbps snapped to the nearest legal
- * MPEG-1 rate like FindNearestBitrate (src/js/Lame.js:408-423).  Configurations for which lamejs would
- * resample (out_samplerate != in_samplerate) return MP3B200_ERR_CONFIG. */
+ * channels 1|2; samplerate 8000|11025|12000|16000|22050|24000 (MPEG-2 / 2.5 LSF: one granule, 576-sample frames) or
+ * 32000|44100|48000 (MPEG-1); kbps snapped to the nearest legal rate of that MPEG version like FindNearestBitrate
+ * (src/js/Lame.js:408-423).  Configurations for which lamejs would RESAMPLE (lame_init_params picks out_samplerate !=
+ * in_samplerate from the bitrate's low-pass, Lame.js:285-364 -- e.g. 44.1 kHz stereo below 112 kbps) return
+ * MP3B200_ERR_CONFIG: the CPU oracle models lamejs's resampler byte for byte (all 306 reference fixtures), but lamejs
+ * reads its input with fractional / out-of-range typed-array indices there (whole-buffer calls and every flush of a
+ * non-integer rate ratio put NaN samples into the stream, oracle/lj_init.cpp fill_buffer_resample), so that row is not
+ * offered as a drop-in. */
 int mp3b200_create(int channels, int samplerate, int kbps, mp3b200_encoder** out);
 
 /* Replaces `encodeBuffer(left, right)` (src/js/index.js:117-130 -> Lame.js:1490-1667).  `right` may be NULL
@@ -61,7 +66,11 @@ int mp3b200_flush_batch(mp3b200_encoder* const* handles, uint8_t* const* out, co
 
 /* Number of bytes / frames that stream of `nsamples` per channel produces (closed form: CBR, no reservoir). */
 int64_t mp3b200_stream_bytes(int channels, int samplerate, int kbps, int64_t nsamples);
-int64_t mp3b200_stream_frames(int64_t nsamples);
+int64_t mp3b200_stream_frames(int64_t nsamples);                 /* MPEG-1 configurations (1152-sample frames) */
+/* any accepted configuration (MPEG-2 / 2.5 frames carry 576 samples); -1 if the configuration is rejected */
+int64_t mp3b200_stream_frames_cfg(int channels, int samplerate, int kbps, int64_t nsamples);
+/* granules per frame: 2 (MPEG-1: 32 / 44.1 / 48 kHz) or 1 (MPEG-2 / 2.5: 8 .. 24 kHz); -1 if rejected */
+int mp3b200_granules_per_frame(int channels, int samplerate, int kbps);
 
 /* Host buffers.  left[s]/right[s]: nsamples[s] Int16 each (right NULL or ignored for mono).  out[s] receives
  * out_bytes[s] = mp3b200_stream_bytes(...) bytes (cap[s] must be >= that).  Returns 0 or a negative error. */
@@ -72,8 +81,12 @@ int mp3b200_encode_streams(int channels, int samplerate, int kbps, int nstreams,
 /* Device-resident variant for benchmarking kernel throughput: d_pcm is ONE device allocation holding, per
  * stream s, nsamples[s] Int16 of the left channel at sample offset pcm_off[s] and (stereo) the right channel at
  * pcm_off[s] + nsamples[s].  d_out is a device buffer; stream s is written at out_off[s].  `timings_ms`
- * (optional, 8 floats) receives per-kernel CUDA-event times: [0] psy analysis, [1] scan, [2] masking,
- * [3] filterbank+MDCT, [4] quantize+pack pass 1, [5] later passes, [6] total, [7] number of quantizer passes. */
+ * (optional, 16 floats) receives per-kernel CUDA-event times in ms: [0] psy analysis, [1] scan, [2] masking,
+ * [3] filterbank+MDCT, [4] quantizer first pass (all of its kernels), [5] re-validation passes, [6] total, [7] number of
+ * quantizer passes; first pass by kernel: [8] k_q_prepare, [9] k_q_search (gr0 + gr1), [10] k_q_outer (gr0 + gr1),
+ * [11] k_q_finish (gr0 + gr1), [12] k_q_pack; [13..15] reserved (0).
+ * The call runs on a stream of its own that first waits for work already queued on the legacy default stream (where torch /
+ * plain CUDA callers produced d_pcm) and returns after that stream has drained. */
 int mp3b200_encode_streams_device(int channels, int samplerate, int kbps, int nstreams, const int16_t* d_pcm,
                                   const int64_t* pcm_off, const int64_t* nsamples, uint8_t* d_out,
                                   const int64_t* out_off, float* timings_ms);

@@ -302,11 +302,11 @@ k_filterbank_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict_
                   const signed char* __restrict__ blocktype, float* __restrict__ xr_out) {
   const StreamDesc sd = streams[blockIdx.z];
   const int ch = blockIdx.y;
-  const int ngr = sd.nframes * 2;
+  const int ngr = sd.nframes * T->mode_gr;
   const int g0 = blockIdx.x * FB_G;                 /* first granule (relative to frame0) of this block */
   if (g0 >= ngr) return;
   const int gcount = min(FB_G, ngr - g0);
-  const long long c0 = 2LL * sd.frame0 + g0;        /* absolute granule index */
+  const long long c0 = (long long)T->mode_gr * sd.frame0 + g0;   /* absolute granule index */
   const int nch = T->nch;
 
   extern __shared__ double smem_d[];

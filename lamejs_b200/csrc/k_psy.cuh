@@ -151,10 +151,10 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   const int z = blockIdx.z;
   const StreamDesc& sd = streams[z];
   const int u = (int)blockIdx.x + u_base;             /* relative unit, -1 = halo */
-  if (u >= 2 * sd.nframes) return;
+  if (u >= T->mode_gr * sd.nframes) return;
   const int ch = blockIdx.y;
   const int nch = T->nch;
-  const long long c = 2LL * sd.frame0 + u;           /* absolute psy call index */
+  const long long c = (long long)T->mode_gr * sd.frame0 + u;   /* absolute psy call index (one call per granule) */
   if (nchunks > 1) {
     /* the host uploads every stream's PCM in `nchunks` time slices and launches this kernel once per slice as it
      * lands: a unit belongs to the slice that holds the last sample of its 1024-sample window */
@@ -378,7 +378,7 @@ __global__ void k_attack_prepass(const Mp3Tables* __restrict__ T, const StreamDe
   const int z = blockIdx.z;
   const StreamDesc& sd = streams[z];
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= 2 * sd.nframes) return;
+  if (u >= T->mode_gr * sd.nframes) return;
   const int nch = T->nch;
   const double thr = T->attack_threshold;
   for (int ch = 0; ch < nch; ch++) {
@@ -436,7 +436,8 @@ __device__ void scan_fsm_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, 
   const int nch = T->nch, coupled = T->coupled_short_blocks;
   int la[2] = {ck->fsm_in & 3, (ck->fsm_in >> 2) & 3};
   int old[2] = {(ck->fsm_in >> 4) & 3, (ck->fsm_in >> 6) & 3};
-  for (int u = 2 * f0; u < 2 * f1; u++) {
+  const int G = T->mode_gr;
+  for (int u = G * f0; u < G * f1; u++) {
     int uselong[2] = {1, 1};
     for (int ch = 0; ch < nch; ch++) {
       const unsigned av = sin[psy_row(sd, z, u) * nch + ch].attack4;
@@ -477,12 +478,18 @@ __device__ void scan_ath_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, 
   for (int f = f0; f < f1; f++) {
     ath_psy[sd.frame_base + f] = adjust;
     /* loudness_sq[gr][ch] is the loudness of the unit BEFORE call 2f+gr (one-call delay, PsyModel.js:321-322) */
-    const ScanIn* r0 = sin + psy_row(sd, z, 2 * f - 1) * nch;
-    const ScanIn* r1 = sin + psy_row(sd, z, 2 * f) * nch;
-    double max_pow = (double)r0[0].loudness, gr2_max = (double)r1[0].loudness;
-    if (nch == 2) { max_pow += (double)r0[1].loudness; gr2_max += (double)r1[1].loudness; }
-    else { max_pow += max_pow; gr2_max += gr2_max; }
-    max_pow = js_dmax(max_pow, gr2_max);
+    const int G = T->mode_gr;
+    const ScanIn* r0 = sin + psy_row(sd, z, G * f - 1) * nch;
+    double max_pow = (double)r0[0].loudness;
+    if (nch == 2) max_pow += (double)r0[1].loudness;
+    else max_pow += max_pow;
+    if (G == 2) {                                     /* Encoder.js:187: the second granule only exists in MPEG-1 */
+      const ScanIn* r1 = sin + psy_row(sd, z, G * f) * nch;
+      double gr2_max = (double)r1[0].loudness;
+      if (nch == 2) gr2_max += (double)r1[1].loudness;
+      else gr2_max += gr2_max;
+      max_pow = js_dmax(max_pow, gr2_max);
+    }
     max_pow *= 0.5;
     max_pow *= sens;
     if (max_pow > 0.03125) {
@@ -590,9 +597,9 @@ k_psy_masking(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ st
   const int z = blockIdx.z;
   const StreamDesc& sd = streams[z];
   const int u = (int)blockIdx.x - 1;
-  if (u >= 2 * sd.nframes) return;
+  if (u >= T->mode_gr * sd.nframes) return;
   const int nch = T->nch;
-  const long long c = 2LL * sd.frame0 + u;
+  const long long c = (long long)T->mode_gr * sd.frame0 + u;
   const int tid = threadIdx.x, ch = tid >> 6, b = tid & 63;
   PsyRatioDev* out = ratio + psy_row(sd, z, u) * nch;
   if (u < 0) {
@@ -611,7 +618,7 @@ k_psy_masking(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ st
   const int npl = T->npart_l, nps = T->npart_s;
   const PsyUnit* pu = (ch < nch) ? psy + psy_row(sd, z, u) * nch + ch : nullptr;
   const PsyUnit* pp = (ch < nch) ? psy + psy_row(sd, z, u - 1) * nch + ch : nullptr;
-  const double ath_adjust = ath_psy[sd.frame_base + (u >> 1)];
+  const double ath_adjust = ath_psy[sd.frame_base + u / T->mode_gr];
 
   if (ch < nch) {
     /* long-block spreading + mask_add (PsyModel.js:1274-1324); thr[b] = ecb because pcfact == 0 */
@@ -712,7 +719,7 @@ k_psy_masking(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ st
   }
   __syncthreads();
   for (int i = tid; i < nch * 122; i += MASK_THREADS) (&out[0].en_l[0])[i] = (&s_out[0].en_l[0])[i];
-  if (sd.halo_out && u == 2 * sd.nframes - 1)
+  if (sd.halo_out && u == T->mode_gr * sd.nframes - 1)
     for (int i = tid; i < nch * 122; i += MASK_THREADS) sd.halo_out[i] = (&s_out[0].en_l[0])[i];
 }
 

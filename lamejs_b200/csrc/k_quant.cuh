@@ -35,6 +35,9 @@ struct GranuleInfoDev {
   int subblock_gain[4];
   int count1bits, sfbmax, sfbdivide, sfb_lmax, psymax, psy_lmax, sfb_smin, max_nonzero_coeff;
   int scalefac[MP3_SFBMAX];
+  int slen[4];                      /* MPEG-2 / 2.5 (LSF): scalefactor bit widths of the four partitions (scale_bitcount_lsf) */
+  int part_row;                     /* LSF: row of nr_of_sfb_block[0]: 0 long {6,5,5,5}, 1 short {9,9,9,9} */
+  int pad_;
   double xrpow_max;
 };
 struct QuantFrameState {
@@ -564,6 +567,41 @@ __device__ __noinline__ bool scale_bitcount_w(GranuleInfoDev* gi) {
   return p2 == Q_LARGE_BITS;
 }
 
+/* scale_bitcount_lsf (Takehiro.js:1036-1132), MPEG-2 / 2.5, all lanes; returns true when a partition's largest scalefactor
+ * exceeds its range (the side info fields are then left as they were, like the reference).  preflag is never set on the LSF
+ * path (scale_bitcount and the pre-emphasis step of best_scalefac_store are MPEG-1 only; inc_scalefac_scale clears it), so
+ * only partition table 0 occurs: long {6,5,5,5}, short {9,9,9,9} bands, ranges {15,15,7,7}. */
+__device__ __noinline__ bool scale_bitcount_lsf_w(GranuleInfoDev* gi) {
+  const int lane = LANE;
+  const bool is_short = gi->block_type == BT_SHORT;
+  __syncwarp();
+  /* partition of scalefactor index i: long bands 0-5 | 6-10 | 11-15 | 16-20; short: 9 consecutive (band, window) entries each */
+  int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  const int n = is_short ? 36 : 21;
+#pragma unroll 1
+  for (int i = lane; i < n; i += 32) {
+    const int v = gi->scalefac[i];
+    const int p = is_short ? i / 9 : (i < 6 ? 0 : (i - 6) / 5 + 1);
+    if (p == 0) m0 = max(m0, v); else if (p == 1) m1 = max(m1, v); else if (p == 2) m2 = max(m2, v); else m3 = max(m3, v);
+  }
+  m0 = wmax(m0); m1 = wmax(m1); m2 = wmax(m2); m3 = wmax(m3);
+  const bool over = m0 > 15 || m1 > 15 || m2 > 7 || m3 > 7;
+  if (!over && lane == 0) {
+    /* log2tab (Takehiro.js:1138): bits needed for 0..15 */
+    const int s1 = m0 ? 32 - __clz(m0) : 0, s2 = m1 ? 32 - __clz(m1) : 0, s3 = m2 ? 32 - __clz(m2) : 0, s4 = m3 ? 32 - __clz(m3) : 0;
+    gi->slen[0] = s1; gi->slen[1] = s2; gi->slen[2] = s3; gi->slen[3] = s4;
+    gi->part_row = is_short ? 1 : 0;
+    gi->scalefac_compress = (((s1 * 5) + s2) << 4) + (s3 << 2) + s4;
+    gi->part2_length = is_short ? 9 * (s1 + s2 + s3 + s4) : 6 * s1 + 5 * (s2 + s3 + s4);
+  }
+  __syncwarp();
+  return over;
+}
+/* scale_bitcount of the stream's MPEG version (Quantize.js:814-817,840-843; Takehiro.js:937-941) */
+__device__ __forceinline__ bool scale_bitcount_any_w(GranuleInfoDev* gi, int mode_gr) {
+  return mode_gr == 2 ? scale_bitcount_w(gi) : scale_bitcount_lsf_w(gi);
+}
+
 /* loop_break (Quantize.js:584-594): true when every band is amplified */
 __device__ __forceinline__ bool loop_break_w(const GranuleInfoDev* gi, const GcWork* wk) {
   bool nz = true;
@@ -682,7 +720,7 @@ __device__ __noinline__ bool balance_escalate_w(const Mp3Tables* T, GcWork* wk) 
       }
     }
   }
-  if (!status) status = scale_bitcount_w(gi);
+  if (!status) status = scale_bitcount_any_w(gi, T->mode_gr);
   return !status;
 }
 
@@ -713,7 +751,7 @@ __device__ __noinline__ bool balance_noise_w(const Mp3Tables* T, GcWork* wk) {
   /* ---- rest of balance_noise ---- */
   int r;
   if (loop_break_w(gi, wk)) r = 0;                 /* all bands amplified */
-  else r = scale_bitcount_w(gi) ? 2 : 1;           /* 2: scalefactors too large, try scalefac_scale / subblock_gain */
+  else r = scale_bitcount_any_w(gi, T->mode_gr) ? 2 : 1;   /* 2: scalefactors too large, try scalefac_scale / subblock_gain */
   if (r == 0) return false;
   if (r == 1) return true;
   return balance_escalate_w(T, wk);
@@ -1073,7 +1111,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, const 
 
 /* best_scalefac_store without the scfsi part (Takehiro.js:809-875), then scfsi_calc for gr1 (lane 0 logic) */
 /* g0: final side info of gr0 of the same channel (HBM), read only when gr == 1; scfsi[4]: this channel's flags */
-__device__ __noinline__ void best_scalefac_store_w(GcWork* wk, int* scfsi, const GranuleInfoDev* __restrict__ g0, int gr) {
+__device__ __noinline__ void best_scalefac_store_w(GcWork* wk, int* scfsi, const GranuleInfoDev* __restrict__ g0, int gr, int mode_gr) {
   const int lane = LANE;
   GranuleInfoDev* gi = &wk->b;
   /* bands whose quantised lines are all zero */
@@ -1112,7 +1150,7 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, int* scfsi, const
     }
   }
   __syncwarp();
-  if (0 == gi->preflag && gi->block_type != BT_SHORT) {
+  if (0 == gi->preflag && gi->block_type != BT_SHORT && mode_gr == 2) {
     const bool in = lane >= 11 && lane < 21;
     const int v = in ? gi->scalefac[lane] : 0, pt = pretab_of(lane);
     const bool ok = !in || !(v < pt && v != -2);
@@ -1175,7 +1213,7 @@ __device__ __noinline__ void best_scalefac_store_w(GcWork* wk, int* scfsi, const
   __syncwarp();
   const int recalc = wk->scratch[0];
   __syncwarp();
-  if (recalc != 0) scale_bitcount_w(gi);
+  if (recalc != 0) scale_bitcount_any_w(gi, mode_gr);
 }
 
 /* ---- best_huffman_divide (Takehiro.js:666-800) on cod_info (wk->b); wk->w is free to use as cod_info2 -----------------
@@ -1337,6 +1375,7 @@ __device__ __noinline__ void best_huffman_divide_w(const Mp3Tables* T, GcWork* w
   int* r0_tbl = wk->pn_step;
   int* r1_tbl = reinterpret_cast<int*>(wk->pn_noise);
   DivScratch* ds = reinterpret_cast<DivScratch*>(wk->xrpow);
+  if (gi->block_type == BT_SHORT && T->mode_gr == 1) return;   /* "SHORT BLOCK stuff fails for MPEG2" (Takehiro.js:735-737) */
   copy_gi_w(c2, gi);
   if (gi->block_type == BT_NORM) {
     const int bigv = gi->big_values;
@@ -1409,7 +1448,16 @@ __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, unsigned int* buf, co
                                        const float* xrq, int pos) {
   const int lane = LANE;
   /* scalefactors (writeMainData, BitStream.js:609-625): serial, <= 36 values */
-  if (lane == 0) {
+  if (lane == 0 && T->mode_gr == 1) {
+    /* MPEG-2 / 2.5 (BitStream.js:641-687): four partitions, slen bits each, negative (unused) scalefactors sent as 0 */
+    int p = pos, i = 0;
+#pragma unroll 1
+    for (int part = 0; part < 4; part++) {
+      const int cnt = gi->part_row == 1 ? 9 : (part == 0 ? 6 : 5), sl = gi->slen[part];
+#pragma unroll 1
+      for (int k = 0; k < cnt; k++, i++) { put_bits(buf, p, (unsigned)max(gi->scalefac[i], 0), sl); p += sl; }
+    }
+  } else if (lane == 0) {
     const int slen1 = c_slen1_tab[gi->scalefac_compress], slen2 = c_slen2_tab[gi->scalefac_compress];
     int p = pos;
 #pragma unroll 1
@@ -1514,20 +1562,25 @@ __device__ __noinline__ void pack_sideinfo(const Mp3Tables* T, unsigned int* buf
   int p = 0;
 #define WH(v, n) do { put_bits(buf, p, (unsigned)(v), (n)); p += (n); } while (0)
   const int nch = T->nch;
-  WH(0xfff, 12); WH(1, 1); WH(4 - 3, 2); WH(1, 1);
+  WH(T->mpeg25 ? 0xffe : 0xfff, 12); WH(T->version, 1); WH(4 - 3, 2); WH(1, 1);
   WH(T->bitrate_index, 4); WH(T->samplerate_index, 2); WH(padding, 1); WH(0, 1);
   WH(T->mono ? 3 : 0, 2); WH(0, 2); WH(0, 1); WH(1, 1); WH(0, 2);
-  WH(0, 9);
-  WH(0, nch == 2 ? 3 : 5);
+  if (T->version == 1) {
+    WH(0, 9);
+    WH(0, nch == 2 ? 3 : 5);
 #pragma unroll 1
-  for (int ch = 0; ch < nch; ch++) for (int b = 0; b < 4; b++) WH(scfsi[ch * 4 + b], 1);
+    for (int ch = 0; ch < nch; ch++) for (int b = 0; b < 4; b++) WH(scfsi[ch * 4 + b], 1);
+  } else {
+    WH(0, 8);                       /* main_data_begin */
+    WH(0, nch);                     /* private bits */
+  }
 #pragma unroll 1
-  for (int gr = 0; gr < 2; gr++) for (int ch = 0; ch < nch; ch++) {
+  for (int gr = 0; gr < T->mode_gr; gr++) for (int ch = 0; ch < nch; ch++) {
     const GranuleInfoDev* gi = &fin[gr * nch + ch];
     WH(gi->part2_3_length + gi->part2_length, 12);
     WH(gi->big_values / 2, 9);
     WH(gi->global_gain, 8);
-    WH(gi->scalefac_compress, 4);
+    WH(gi->scalefac_compress, T->version == 1 ? 4 : 9);
     int ts0 = gi->table_select[0], ts1 = gi->table_select[1], ts2 = gi->table_select[2];
     if (ts0 == 14) ts0 = 16;
     if (ts1 == 14) ts1 = 16;
@@ -1541,7 +1594,8 @@ __device__ __noinline__ void pack_sideinfo(const Mp3Tables* T, unsigned int* buf
       WH(ts0, 5); WH(ts1, 5); WH(ts2, 5);
       WH(gi->region0_count, 4); WH(gi->region1_count, 3);
     }
-    WH(gi->preflag, 1); WH(gi->scalefac_scale, 1); WH(gi->count1table_select, 1);
+    if (T->version == 1) WH(gi->preflag, 1);
+    WH(gi->scalefac_scale, 1); WH(gi->count1table_select, 1);
   }
 #undef WH
 }
@@ -1626,7 +1680,7 @@ __device__ __forceinline__ FrameGeom frame_geom(const Mp3Tables* T, const Stream
   g.kabs = (long long)streams[g.z].frame0 + g.f;
   g.padding = (int)(pad_count(g.kabs, T->frac_SpF, T->samplerate) - pad_count(g.kabs - 1, T->frac_SpF, T->samplerate));
   g.frame_bytes = T->frame_bytes_nopad + g.padding;
-  g.mean_bits = (8 * g.frame_bytes - T->sideinfo_len * 8) / 2;      /* Reservoir.js:83 (exact: multiple of 4) */
+  g.mean_bits = (8 * g.frame_bytes - T->sideinfo_len * 8) / T->mode_gr;   /* Reservoir.js:83 (exact: a multiple of 4 / of 8) */
   return g;
 }
 
@@ -1639,18 +1693,19 @@ k_q_prepare(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stre
   WarpShared* ws = warp_shared();
   GcWork* wk = &ws->wk;
   const int lane = LANE, nch = T->nch;
-  const int ntasks = nframes * 2 * nch;
+  const int G = T->mode_gr;
+  const int ntasks = nframes * G * nch;
 #pragma unroll 1
   for (int t = next_task(counter); t < ntasks; t = next_task(counter)) {
-    const int frow = t / (2 * nch), rem = t - frow * 2 * nch, gr = rem / nch, ch = rem - gr * nch;
+    const int frow = t / (G * nch), rem = t - frow * G * nch, gr = rem / nch, ch = rem - gr * nch;
     const QuantFrameState* q = qs + frow;
     const int z = q->stream, f = q->rel_frame;
     const StreamDesc& sd = streams[z];
     const double ath_adjust = ath_q[frow];
-    const size_t urow = (size_t)sd.unit_base + 2 * f + gr, gidx = urow * nch + ch;
+    const size_t urow = (size_t)sd.unit_base + G * f + gr, gidx = urow * nch + ch;
     const int bt = bt_final[urow * 2 + ch];
-    /* masking of psy unit (2f+gr-1): halo-shifted row = unit_base + z + (2f+gr-1) + 1 */
-    const PsyRatioDev* rt = ratio + ((size_t)sd.unit_base + z + 2 * f + gr) * nch + ch;
+    /* masking of psy unit (G f + gr - 1): halo-shifted row = unit_base + z + (G f + gr - 1) + 1 */
+    const PsyRatioDev* rt = ratio + ((size_t)sd.unit_base + z + G * f + gr) * nch + ch;
     __syncwarp();
     if (lane < 6) ws->ath[lane] = ath_adjust_dev(ath_adjust, (double)(bt == BT_SHORT ? T->ath_psfb12[lane] : T->ath_psfb21[lane]), T->ath_floor);
     __syncwarp();
@@ -1689,7 +1744,7 @@ k_q_search(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ strea
     if (revalidate && gr == 1 && !(flags & (Q_R0_ANY | Q_R1S(ch)))) continue;
     const FrameGeom fg = frame_geom(T, streams, q);
     const StreamDesc& sd = streams[fg.z];
-    const size_t urow = (size_t)sd.unit_base + 2 * fg.f + gr, gidx = urow * nch + ch;
+    const size_t urow = (size_t)sd.unit_base + T->mode_gr * fg.f + gr, gidx = urow * nch + ch;
     const int targ = granule_budget(nch, fg.mean_bits, gr, q->used0[0], q->used0[1], ch);
     int ov = gr == 0 ? q->in_old[ch] : q->bs_gain0[ch];
     int cs = gr == 0 ? q->in_step[ch] : q->bs_step0[ch];
@@ -1715,11 +1770,11 @@ k_q_search(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ strea
       /* a frame encoded from a guessed in-state also guesses the step gr1's search starts with: 2, what a stationary
        * signal produces (the formula would give 4 whenever the guessed start lies 4 above the landing gain); the value
        * used is recorded, and re-validation re-runs gr1's search only when the true step differs from it */
-      if (gr == 0 && fg.f != 0) cs = 2;
+      if (gr == 0 && fg.f != 0 && T->mode_gr == 2) cs = 2;
       if (lane == 0) {
         q->bs_hash[gr][ch] = h;
         if (gr == 0) { q->bs_gain0[ch] = ov; q->bs_step0[ch] = cs; }
-        else { q->out_old[ch] = ov; q->out_step[ch] = cs; }
+        if (gr == T->mode_gr - 1) { q->out_old[ch] = ov; q->out_step[ch] = cs; }   /* the frame's last granule leaves the out-state */
       }
     } else if (gr == 0) {
       store = ov != q->bs_gain0[ch] || h != q->bs_hash[0][ch];
@@ -1727,8 +1782,9 @@ k_q_search(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ strea
       __syncwarp();
       if (lane == 0) {
         int old = -1;
+        if (T->mode_gr == 1) { q->out_old[ch] = ov; q->out_step[ch] = cs; }   /* LSF: gr0 is the frame's last granule */
         if (store) { q->bs_gain0[ch] = ov; q->bs_step0[ch] = cs; q->bs_hash[0][ch] = h; old = atomicOr(&q->redo, Q_R0(ch)); }
-        else if (step_changed) { q->bs_step0[ch] = cs; old = atomicOr(&q->redo, Q_R1S(ch)); }
+        else if (step_changed && T->mode_gr == 2) { q->bs_step0[ch] = cs; old = atomicOr(&q->redo, Q_R1S(ch)); }
         /* frames with anything left to do go on the short list the remaining kernels of this pass walk */
         if (old == 0) list2[atomicAdd(count2, 1)] = frow;
       }
@@ -1766,7 +1822,7 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
     if (revalidate) QSTAT(14);
     const FrameGeom fg = frame_geom(T, streams, q);
     const StreamDesc& sd = streams[fg.z];
-    const size_t urow = (size_t)sd.unit_base + 2 * fg.f + gr, gidx = urow * nch + ch;
+    const size_t urow = (size_t)sd.unit_base + T->mode_gr * fg.f + gr, gidx = urow * nch + ch;
     const int targ = granule_budget(nch, fg.mean_bits, gr, q->used0[0], q->used0[1], ch);
     const GcPrep* pr = prep + gidx;
     const bool have = pr->have != 0;
@@ -1806,13 +1862,13 @@ k_q_finish(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ strea
     QuantFrameState* q = qs + frow;
     if (revalidate && !(q->redo & (gr == 0 ? Q_R0(ch) : Q_R1(ch)))) continue;
     const StreamDesc& sd = streams[q->stream];
-    const size_t urow = (size_t)sd.unit_base + 2 * q->rel_frame + gr, gidx = urow * nch + ch;
+    const size_t urow = (size_t)sd.unit_base + T->mode_gr * q->rel_frame + gr, gidx = urow * nch + ch;
     short* const ixrow = l3enc + gidx * 576;
     copy_gi_w(&wk->b, &ginfo[gidx]);
     copy_row16_w(wk->ixw, ixrow, 1152);
     if (lane == 0) wk->geo = &T->geo[wk->b.block_type == BT_SHORT ? 1 : 0];
     __syncwarp();
-    best_scalefac_store_w(wk, ws->scfsi, gr == 1 ? &ginfo[gidx - nch] : nullptr, gr);
+    best_scalefac_store_w(wk, ws->scfsi, gr == 1 ? &ginfo[gidx - nch] : nullptr, gr, T->mode_gr);
     best_huffman_divide_w(T, wk);
     copy_gi_w(&ginfo[gidx], &wk->b);
     if (gr == 0) { if (lane == 0) q->used0[ch] = wk->b.part2_3_length + wk->b.part2_length; }
@@ -1845,7 +1901,7 @@ k_q_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams
     if (revalidate) QSTAT(5);
     const FrameGeom fg = frame_geom(T, streams, q);
     const StreamDesc& sd = streams[fg.z];
-    const size_t g0 = ((size_t)sd.unit_base + 2 * fg.f) * nch;       /* first of the frame's 2 * nch granule-channels */
+    const size_t g0 = ((size_t)sd.unit_base + T->mode_gr * fg.f) * nch;   /* first of the frame's mode_gr * nch granule-channels */
     __syncwarp();
 #pragma unroll 1
     for (int i = lane; i < 368; i += 32) ps->bits[i] = 0;
@@ -1853,7 +1909,7 @@ k_q_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams
     __syncwarp();
     int pos = 8 * T->sideinfo_len;
 #pragma unroll 1
-    for (int k = 0; k < 2 * nch; k++) {                              /* gr0ch0, gr0ch1, gr1ch0, gr1ch1 back to back */
+    for (int k = 0; k < T->mode_gr * nch; k++) {                     /* gr0ch0, gr0ch1, gr1ch0, gr1ch1 back to back */
       copy_gi_w(&ps->gi, &ginfo[g0 + k]);
       copy_row16_w(ps->ix, l3enc + (g0 + k) * 576, 1152);
       copy_row16_w(ps->xr, xrq + (g0 + k) * 576, 2304);
@@ -1942,8 +1998,9 @@ struct QuantBuffers {
 #define Q_NCOUNTERS 256
 
 static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_streams, int S, int max_frames, long long F,
-                     const QuantBuffers& B, uint8_t* d_out, cudaStream_t st, cudaEvent_t ev_pass1, int* passes_out,
+                     const QuantBuffers& B, uint8_t* d_out, cudaStream_t st, cudaEvent_t ev_pass1, cudaEvent_t* evq, int* passes_out,
                      std::atomic<long long>* launches) {
+  /* evq[0..8]: before prepare, after prepare, after each of the seven kernels of the first pass (per-kernel timings) */
   static std::mutex attr_mu;
   static bool attr_done[64] = {};
   int dev = 0, sms = 148;
@@ -1978,8 +2035,11 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     k_qstate_init<<<g, 128, 0, st>>>(d_streams, S, B.qs);
     (*launches)++;
   }
-  k_q_prepare<<<grid_for(F * 2 * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.xr, B.ratio, B.bt, B.ath_q, B.qs, B.xrq, B.xrpow,
-                                                                              B.prep, (int)F, fresh_counter());
+  int* const prep_counter = fresh_counter();     /* (may enqueue the counter memset: keep it out of the timed span) */
+  cudaEventRecord(evq[0], st);
+  k_q_prepare<<<grid_for(F * hT.mode_gr * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.xr, B.ratio, B.bt, B.ath_q, B.qs, B.xrq, B.xrpow,
+                                                                              B.prep, (int)F, prep_counter);
+  cudaEventRecord(evq[1], st);
   (*launches)++;
   /* counter[0]: length of the verify list; counter[1]: length of the short list (frames a re-validation pass must touch
    * beyond gr0's search); the task counters start at 2 */
@@ -1988,15 +2048,27 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     const int* l1 = reval ? B.list : nullptr;                   /* all listed frames */
     const int* l2 = reval ? B.list + (F + 1) : nullptr;          /* short list, length on the device */
     const int* c2 = reval ? B.counter + 1 : nullptr;
+    int ei = 2;
+    auto mark = [&]() { if (!reval) cudaEventRecord(evq[ei++], st); };
     k_q_search<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, 0, l1, nullptr, (int)count, reval, fresh_counter(),
                                             B.list + (F + 1), B.counter + 1);
+    mark();
     k_q_outer<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 0, l2, c2, (int)count, reval, fresh_counter());
+    mark();
     k_q_finish<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 0, l2, c2, (int)count, reval, fresh_counter());
-    k_q_search<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, 1, l2, c2, (int)count, reval, fresh_counter(), nullptr, nullptr);
-    k_q_outer<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 1, l2, c2, (int)count, reval, fresh_counter());
-    k_q_finish<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 1, l2, c2, (int)count, reval, fresh_counter());
+    mark();
+    if (hT.mode_gr == 2) {
+      k_q_search<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, 1, l2, c2, (int)count, reval, fresh_counter(), nullptr, nullptr);
+      mark();
+      k_q_outer<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 1, l2, c2, (int)count, reval, fresh_counter());
+      mark();
+      k_q_finish<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 1, l2, c2, (int)count, reval, fresh_counter());
+      mark();
+      (*launches) += 3;
+    } else { mark(); mark(); mark(); }
     k_q_pack<<<gp, Q_THREADS, smem_pack, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, l2, c2, (int)count, reval, fresh_counter(), d_out);
-    (*launches) += 7;
+    mark();
+    (*launches) += 4;
   };
   run_pass(F, 0);
   if (cudaEventRecord(ev_pass1, st) != cudaSuccess) return -100;

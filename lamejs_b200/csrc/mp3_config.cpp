@@ -15,7 +15,10 @@
 
 namespace {
 
-const int kMpeg1Bitrates[15] = {0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320};
+/* Tables.js:494-498: [0] MPEG-2, [1] MPEG-1, [2] MPEG-2.5 */
+const int kBitrates[3][15] = {{0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160},
+                              {0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320},
+                              {0, 8, 16, 24, 32, 40, 48, 56, 64, -1, -1, -1, -1, -1, -1}};
 const int kFullBitrates[17] = {8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320};
 /* optimum_bandwidth() low-pass table, Lame.js:456-464 */
 const int kLowpassHz[17] = {2000, 3700, 3900, 5500, 7000, 7500, 10000, 11000, 13500, 15100, 15600,
@@ -33,13 +36,27 @@ const Preset kPresets[17] = {
     {1, 5.20, 0.98, -6, 9.0, 2, 0, 0},        {1, 5.20, 1.00, -8, 10.0, 1, 0, 0},
     {1, 5.20, 1.00, -10, 12.0, 0, 0, 0}};
 
-const int kSfbLong[3][23] = {
+/* QuantizePVT.js:137-204 sfBandIndex, index = samplerate_index + 3 * version + 6 * (rate < 16 kHz):
+ * 22.05, 24, 16 kHz (MPEG-2); 44.1, 48, 32 kHz (MPEG-1); 11.025, 12, 8 kHz (MPEG-2.5) */
+const int kSfbLong[9][23] = {
+    {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
+    {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 114, 136, 162, 194, 232, 278, 332, 394, 464, 540, 576},
+    {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
     {0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 52, 62, 74, 90, 110, 134, 162, 196, 238, 288, 342, 418, 576},
     {0, 4, 8, 12, 16, 20, 24, 30, 36, 42, 50, 60, 72, 88, 106, 128, 156, 190, 230, 276, 330, 384, 576},
-    {0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 54, 66, 82, 102, 126, 156, 194, 240, 296, 364, 448, 550, 576}};
-const int kSfbShort[3][14] = {{0, 4, 8, 12, 16, 22, 30, 40, 52, 66, 84, 106, 136, 192},
+    {0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 54, 66, 82, 102, 126, 156, 194, 240, 296, 364, 448, 550, 576},
+    {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
+    {0, 6, 12, 18, 24, 30, 36, 44, 54, 66, 80, 96, 116, 140, 168, 200, 238, 284, 336, 396, 464, 522, 576},
+    {0, 12, 24, 36, 48, 60, 72, 88, 108, 132, 160, 192, 232, 280, 336, 400, 476, 566, 568, 570, 572, 574, 576}};
+const int kSfbShort[9][14] = {{0, 4, 8, 12, 18, 24, 32, 42, 56, 74, 100, 132, 174, 192},
+                              {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 136, 180, 192},
+                              {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 134, 174, 192},
+                              {0, 4, 8, 12, 16, 22, 30, 40, 52, 66, 84, 106, 136, 192},
                               {0, 4, 8, 12, 16, 22, 28, 38, 50, 64, 80, 100, 126, 192},
-                              {0, 4, 8, 12, 16, 22, 30, 42, 58, 78, 104, 138, 180, 192}};
+                              {0, 4, 8, 12, 16, 22, 30, 42, 58, 78, 104, 138, 180, 192},
+                              {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 134, 174, 192},
+                              {0, 4, 8, 12, 18, 26, 36, 48, 62, 80, 104, 134, 174, 192},
+                              {0, 8, 16, 24, 36, 52, 72, 96, 124, 160, 162, 164, 166, 192}};
 
 inline int to_i32(double d) {  /* ToInt32 for the finite, in-range values that occur at init */
   return (int)d;
@@ -192,23 +209,33 @@ int mp3_build_tables(int channels, int samplerate, int kbps, Mp3Tables* t) {
   lp = dmin(20500, lp);
   lp = dmin(out_rate / 2.0, lp);
   if (out_rate != samplerate) return -1;               /* would need fill_buffer_resample */
-  switch (samplerate) {
-    case 44100: t->samplerate_index = 0; break;
-    case 48000: t->samplerate_index = 1; break;
-    case 32000: t->samplerate_index = 2; break;
-    default: return -1;                                /* MPEG-2/2.5 */
+  switch (samplerate) {                                /* SmpFrqIndex (Lame.js:369-402) */
+    case 44100: t->version = 1; t->samplerate_index = 0; break;
+    case 48000: t->version = 1; t->samplerate_index = 1; break;
+    case 32000: t->version = 1; t->samplerate_index = 2; break;
+    case 22050: case 11025: t->version = 0; t->samplerate_index = 0; break;
+    case 24000: case 12000: t->version = 0; t->samplerate_index = 1; break;
+    case 16000: case 8000: t->version = 0; t->samplerate_index = 2; break;
+    default: return -1;
   }
   t->samplerate = samplerate;
+  t->mpeg25 = samplerate < 16000;
+  t->mode_gr = samplerate <= 24000 ? 1 : 2;
   {
-    int best = kMpeg1Bitrates[1];
+    /* FindNearestBitrate / BitrateIndex (Lame.js:408-443): below 16 kHz the MPEG-2.5 row is searched */
+    const int* bt = kBitrates[t->mpeg25 ? 2 : t->version];
+    int best = bt[1];
     for (int i = 2; i <= 14; i++)
-      if (abs(kMpeg1Bitrates[i] - kbps) < abs(best - kbps)) best = kMpeg1Bitrates[i];
+      if (bt[i] > 0 && abs(bt[i] - kbps) < abs(best - kbps)) best = bt[i];
     t->kbps = best;
-    for (int i = 1; i <= 14; i++) if (kMpeg1Bitrates[i] == best) t->bitrate_index = i;
+    t->bitrate_index = -1;
+    for (int i = 1; i <= 14; i++) if (bt[i] > 0 && bt[i] == best) { t->bitrate_index = i; break; }
+    if (t->bitrate_index <= 0) return -1;
   }
-  t->sideinfo_len = t->mono ? 21 : 36;
-  t->frac_SpF = (144000 * t->kbps) % samplerate;
-  t->frame_bytes_nopad = (int)((double)(144000 * t->kbps) / samplerate);
+  if (t->version == 1) t->sideinfo_len = t->mono ? 21 : 36;
+  else t->sideinfo_len = t->mono ? 13 : 21;
+  t->frac_SpF = ((t->version + 1) * 72000 * t->kbps) % samplerate;
+  t->frame_bytes_nopad = (int)((double)((t->version + 1) * 72000 * t->kbps) / samplerate);
   const Preset& ps = kPresets[ladder_index(t->kbps)];  /* apply_preset runs on the snapped rate */
   t->noise_shaping = ps.sfscale > 0 ? 2 : 1;
   t->quant_comp = t->quant_comp_short = 9;
@@ -249,8 +276,11 @@ int mp3_build_tables(int channels, int samplerate, int kbps, Mp3Tables* t) {
   }
 
   /* ---- scalefactor band edges, incl. the fractional pseudo bands (Lame.js:1079-1101) ---- */
-  memcpy(t->sfb_l, kSfbLong[t->samplerate_index], sizeof t->sfb_l);
-  memcpy(t->sfb_s, kSfbShort[t->samplerate_index], sizeof t->sfb_s);
+  {
+    const int j = t->samplerate_index + 3 * t->version + 6 * (t->mpeg25 ? 1 : 0);
+    memcpy(t->sfb_l, kSfbLong[j], sizeof t->sfb_l);
+    memcpy(t->sfb_s, kSfbShort[j], sizeof t->sfb_s);
+  }
   for (int i = 0; i < 7; i++) {
     t->psfb21[i] = to_i32(t->sfb_l[21] + i * ((t->sfb_l[22] - t->sfb_l[21]) / 6.0));
     t->psfb12[i] = to_i32(t->sfb_s[12] + i * ((t->sfb_s[13] - t->sfb_s[12]) / 6.0));

@@ -37,7 +37,10 @@ struct Mp3Tables {
   /* ---- scalars ---- */
   int nch, samplerate, kbps, mono;
   int bitrate_index, samplerate_index, sideinfo_len, frac_SpF;
-  int frame_bytes_nopad;          /* floor(144000*kbps/sr) */
+  int frame_bytes_nopad;          /* floor((version + 1) * 72000 * kbps / sr) */
+  int version;                    /* header version bit: 1 = MPEG-1 (32/44.1/48 kHz), 0 = MPEG-2 and MPEG-2.5 (LSF) */
+  int mode_gr;                    /* granules per frame: 2 (MPEG-1) or 1 (LSF); a frame carries 576 * mode_gr samples */
+  int mpeg25;                     /* output rate below 16 kHz: sync word 0xFFE */
   int noise_shaping;              /* 1 or 2 (sfscale) */
   int quant_comp, quant_comp_short;
   int coupled_short_blocks;
@@ -84,8 +87,8 @@ struct Mp3Tables {
   double ixmax_over_istep[MP3_QMAX], cmp01_over_istep[MP3_QMAX];
 };
 
-/* returns 0, or -1 when lamejs itself would fail / needs the resampler or the MPEG-2 path
- * (not built). */
+/* returns 0, or -1 when lamejs itself would fail or would resample (out_samplerate != samplerate, Lame.js:285-364:
+ * SURVEY.md 8(f1) resampler, not built on the GPU) */
 int mp3_build_tables(int channels, int samplerate, int kbps, Mp3Tables* t);
 
 #endif

@@ -47,7 +47,8 @@ bool g_fb_attr_done[MP3_MAX_DEVICES] = {};
 
 struct Config { Mp3Tables host; Mp3Tables* dev; int device; };
 std::map<std::tuple<int, int, int, int>, Config*> g_configs;   /* (device, ch, sr, kbps) */
-std::map<std::tuple<int, int, int>, std::pair<int, int>> g_byte_geom;   /* (ch, sr, kbps) -> frame_bytes_nopad, frac_SpF */
+struct ByteGeom { int frame_bytes_nopad, frac_SpF, mode_gr; };
+std::map<std::tuple<int, int, int>, ByteGeom> g_byte_geom;   /* (ch, sr, kbps) -> byte geometry; frame_bytes_nopad < 0: unsupported */
 
 /* g_mu held.  Makes `dev` current for the calling thread and uploads the constant tables once per device. */
 int ensure_device(int dev) {
@@ -87,13 +88,33 @@ int get_config(int ch, int sr, int kbps, Config** out) {
   return 0;
 }
 
-/* frames produced by encodeBuffer(n samples) + flush()  (Lame.js:1592-1663 + :1393-1443 in closed form) */
-long long frames_for(long long n) {
-  const long long f_enc = n >= 1376 ? (n - 1376) / 1152 + 1 : 0;
-  const long long ste = 576 + n - 1152 * f_enc;
-  long long end_padding = 1152 - (ste % 1152);
-  if (end_padding < 576) end_padding += 1152;
-  return f_enc + (ste + end_padding) / 1152;
+/* frames produced by encodeBuffer(n samples) + flush()  (Lame.js:1592-1663 + :1393-1443 in closed form).
+ * framesize = 576 * mode_gr; a frame is encoded whenever the FIFO holds framesize + 752 samples (calcNeeded, Lame.js:1516);
+ * the FIFO starts with 528 zeros; ENCDELAY + POSTDELAY = 576 + 1152 regardless of the frame size. */
+long long frames_for(long long n, int mode_gr) {
+  const long long fs = 576LL * mode_gr, need = fs + 752;
+  const long long f_enc = 528 + n >= need ? (528 + n - need) / fs + 1 : 0;
+  long long mf_size = 528 + n - fs * f_enc;
+  const long long ste = 576 + n - fs * f_enc;            /* mf_samples_to_encode - POSTDELAY */
+  long long end_padding = fs - (ste % fs);
+  if (end_padding < 576) end_padding += fs;
+  long long frames_left = (ste + end_padding) / fs, frames = f_enc;
+  /* lame_encode_flush feeds zero bunches of min(1152, need - mf_size) samples and counts ONE frame per bunch that completed
+   * any (Lame.js:1416-1443); with 576-sample frames a bunch can complete two, so the loop is replayed, not closed-formed */
+  while (frames_left > 0) {
+    long long bunch = need - mf_size;
+    if (bunch > 1152) bunch = 1152;
+    if (bunch < 1) bunch = 1;
+    int got = 0;
+    while (bunch > 0) {
+      const long long c = bunch < fs ? bunch : fs;
+      bunch -= c; mf_size += c;
+      if (mf_size >= need) { got++; mf_size -= fs; }
+    }
+    frames += got;
+    frames_left -= got > 0 ? 1 : 0;
+  }
+  return frames;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -162,7 +183,7 @@ enum { MP3_MAX_PCM_CHUNKS = 8 };
 struct ThreadCtx {
   int device = -1;
   cudaStream_t st = nullptr, up_st = nullptr;
-  cudaEvent_t ev[8] = {}, ev_in = nullptr, ready[MP3_MAX_PCM_CHUNKS] = {};
+  cudaEvent_t ev[8] = {}, evq[9] = {}, ev_in = nullptr, ready[MP3_MAX_PCM_CHUNKS] = {};
   Workspace ws;
   int16_t* d_pcm = nullptr; size_t d_pcm_cap = 0;
   uint8_t* d_out = nullptr; size_t d_out_cap = 0;
@@ -175,6 +196,7 @@ struct ThreadCtx {
     cudaFree(d_out); d_out = nullptr; d_out_cap = 0;
     cudaFreeHost(h_pin); h_pin = nullptr; h_pin_cap = 0;
     for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : evq) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto& e : ready) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (ev_in) { cudaEventDestroy(ev_in); ev_in = nullptr; }
     if (st) { cudaStreamDestroy(st); st = nullptr; }
@@ -189,6 +211,7 @@ struct ThreadCtx {
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&up_st, cudaStreamNonBlocking));
     for (auto& e : ev) CK(cudaEventCreate(&e));
+    for (auto& e : evq) CK(cudaEventCreate(&e));
     for (auto& e : ready) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
     device = dev;
@@ -229,7 +252,8 @@ bool debug_sync() { static int v = -1; if (v < 0) { const char* e = getenv("MP3B
     }                                                                                       \
   } while (0)
 
-struct Timings { float psy = 0, scan = 0, mask = 0, fb = 0, q1 = 0, qn = 0, total = 0; int passes = 0; };
+struct Timings { float psy = 0, scan = 0, mask = 0, fb = 0, q1 = 0, qn = 0, total = 0; int passes = 0;
+                 float q_prepare = 0, q_search = 0, q_outer = 0, q_finish = 0, q_pack = 0; };
 
 /* Runs the whole pipeline for the streams described in `h_streams` (device pointers already set).
  * d_out: device output buffer.  force_bt: optional host array [units][nch] of block types (debug). */
@@ -268,12 +292,13 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     /* units (relative index, -1 = halo) each upload slice completes, over all streams: the kernel's own rule
      * (k_psy_analysis) evaluated on the host, so that a slice's launch covers only its range of units */
     int u_lo[MP3_MAX_PCM_CHUNKS], u_hi[MP3_MAX_PCM_CHUNKS];
-    for (int j = 0; j < nchunks; j++) { u_lo[j] = 2 * max_frames; u_hi[j] = -1; }
+    const int G = cfg->host.mode_gr;     /* granules ("units") per frame */
+    for (int j = 0; j < nchunks; j++) { u_lo[j] = G * max_frames; u_hi[j] = -1; }
     if (nchunks > 1) {
       for (const auto& sd : h_streams) {
         const long long n = sd.pcm_end - sd.pcm_base;
-        for (int u = -1; u < 2 * sd.nframes; u++) {
-          long long last = 576 * (2LL * sd.frame0 + u) - 224 + 1023 - sd.pcm_base;
+        for (int u = -1; u < G * sd.nframes; u++) {
+          long long last = 576 * ((long long)G * sd.frame0 + u) - 224 + 1023 - sd.pcm_base;
           if (last > n - 1) last = n - 1;
           int mine = 0;
           while (mine < nchunks - 1 && last >= n * (mine + 1) / nchunks) mine++;
@@ -281,7 +306,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
           if (u + 1 > u_hi[mine]) u_hi[mine] = u + 1;
         }
       }
-    } else { u_lo[0] = -1; u_hi[0] = 2 * max_frames; }
+    } else { u_lo[0] = -1; u_hi[0] = G * max_frames; }
     for (int j = 0; j < nchunks; j++) {
       if (arrival) CK(cudaStreamWaitEvent(st, arrival->ready[j], 0));
       if (u_hi[j] <= u_lo[j]) continue;
@@ -290,7 +315,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
       g_launches++;
       DBG("k_psy_analysis");
     }
-    const long long psy_rows = (2 * total_frames + S) * nch;   /* rows unit_base + z + u + 1 of every stream */
+    const long long psy_rows = (G * total_frames + S) * nch;   /* rows unit_base + z + u + 1 of every stream */
     k_psy_loudness<<<(unsigned)((psy_rows + LOUD_ROWS - 1) / LOUD_ROWS), LOUD_ROWS, 0, st>>>(cfg->dev, ws.d_fe, ws.d_psy, psy_rows);
     g_launches++;
     DBG("k_psy_loudness");
@@ -298,7 +323,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   CK(cudaEventRecord(ev[1], st));
   /* K3a: attack pre-pass (parallel) + sequential per-stream scans */
   {
-    dim3 grid((2 * max_frames + 127) / 128, 1, S);
+    dim3 grid((cfg->host.mode_gr * max_frames + 127) / 128, 1, S);
     k_attack_prepass<<<grid, 128, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_scan_in);
     DBG("k_attack_prepass");
     k_stream_scan<<<S, SCAN_THREADS, 0, st>>>(cfg->dev, ws.d_streams, S, ws.d_scan_in, ws.d_bt_final, ws.d_bt_prev, ws.d_ath_psy, ws.d_ath_q, ws.d_scan);
@@ -315,7 +340,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   }
   /* K3b: masking thresholds */
   {
-    dim3 grid(2 * max_frames + 1, 1, S);
+    dim3 grid(cfg->host.mode_gr * max_frames + 1, 1, S);
     k_psy_masking<<<grid, MASK_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_bt_prev, ws.d_ath_psy, ws.d_ratio);
     g_launches++;
     DBG("k_psy_masking");
@@ -324,7 +349,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   /* K1: filterbank + MDCT.  (Running it on a second stream beside K3b was measured: the two kernels slow each other
    * down by exactly what the overlap would save, 0.61 ms either way.) */
   {
-    dim3 grid((2 * max_frames + FB_G - 1) / FB_G, nch, S);
+    dim3 grid((cfg->host.mode_gr * max_frames + FB_G - 1) / FB_G, nch, S);
     const size_t smem = sizeof(double) * FB_PCM_WORDS + sizeof(float) * ((FB_G + 1) * 18 * FB_SLAB_STRIDE);
     {
       std::lock_guard<std::mutex> lk(g_mu);   /* the attribute is per device */
@@ -340,7 +365,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     QuantBuffers qb;
     qb.xr = ws.d_xr; qb.ratio = ws.d_ratio; qb.bt = ws.d_bt_final; qb.ath_q = ws.d_ath_q; qb.qs = ws.d_qstate; qb.ginfo = ws.d_ginfo;
     qb.l3enc = ws.d_l3enc; qb.xrq = ws.d_xrq; qb.xrpow = ws.d_xrpow; qb.prep = ws.d_prep; qb.list = ws.d_dirty; qb.counter = ws.d_counter;
-    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, max_frames, total_frames, qb, d_out, st, ev[5], &passes, &g_launches);
+    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, max_frames, total_frames, qb, d_out, st, ev[5], t_ctx.evq, &passes, &g_launches);
     if (rc) { g_err = "quantizer stage failed: " + std::string(cudaGetErrorString(cudaGetLastError())); return rc; }
   } else {
     CK(cudaEventRecord(ev[5], st));
@@ -358,6 +383,15 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     cudaEventElapsedTime(&tm->qn, ev[5], ev[6]);
     cudaEventElapsedTime(&tm->total, ev[0], ev[6]);
     tm->passes = passes;
+    if (!stop_after_mdct && passes > 0) {
+      cudaEvent_t* q = t_ctx.evq;
+      auto span = [&](int a, int b) { float v = 0; cudaEventElapsedTime(&v, q[a], q[b]); return v; };
+      tm->q_prepare = span(0, 1);
+      tm->q_search = span(1, 2) + span(4, 5);
+      tm->q_outer = span(2, 3) + span(5, 6);
+      tm->q_finish = span(3, 4) + span(6, 7);
+      tm->q_pack = span(7, 8);
+    }
   }
   return 0;
 }
@@ -396,26 +430,40 @@ int mp3b200_set_device(int device) {
   return 0;
 }
 
-int64_t mp3b200_stream_frames(int64_t nsamples) { return frames_for(nsamples); }
+int64_t mp3b200_stream_frames(int64_t nsamples) { return frames_for(nsamples, 2); }
+
+namespace {
+/* the byte geometry of a configuration is three integers; building the full tables costs ~1 ms, so it is done once */
+ByteGeom byte_geom(int channels, int samplerate, int kbps) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto key = std::make_tuple(channels, samplerate, kbps);
+  auto it = g_byte_geom.find(key);
+  if (it != g_byte_geom.end()) return it->second;
+  Mp3Tables* t = new Mp3Tables();
+  const int rc = mp3_build_tables(channels, samplerate, kbps, t);
+  ByteGeom g = rc == 0 ? ByteGeom{t->frame_bytes_nopad, t->frac_SpF, t->mode_gr} : ByteGeom{-1, 0, 2};
+  delete t;
+  g_byte_geom[key] = g;
+  return g;
+}
+}  // namespace
 
 int64_t mp3b200_stream_bytes(int channels, int samplerate, int kbps, int64_t nsamples) {
-  /* the byte geometry of a configuration is two integers; building the full tables costs ~1 ms, so it is done once */
-  std::pair<int, int> geom;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto key = std::make_tuple(channels, samplerate, kbps);
-    auto it = g_byte_geom.find(key);
-    if (it == g_byte_geom.end()) {
-      Mp3Tables* t = new Mp3Tables();
-      const int rc = mp3_build_tables(channels, samplerate, kbps, t);
-      geom = rc == 0 ? std::make_pair(t->frame_bytes_nopad, t->frac_SpF) : std::make_pair(-1, 0);
-      delete t;
-      g_byte_geom[key] = geom;
-    } else geom = it->second;
-  }
-  if (geom.first < 0 || nsamples < 0) return -1;
-  const long long frames = frames_for(nsamples);
-  return frames * geom.first + pad_count(frames - 1, geom.second, samplerate);
+  const ByteGeom g = byte_geom(channels, samplerate, kbps);
+  if (g.frame_bytes_nopad < 0 || nsamples < 0) return -1;
+  const long long frames = frames_for(nsamples, g.mode_gr);
+  return frames * g.frame_bytes_nopad + pad_count(frames - 1, g.frac_SpF, samplerate);
+}
+
+int64_t mp3b200_stream_frames_cfg(int channels, int samplerate, int kbps, int64_t nsamples) {
+  const ByteGeom g = byte_geom(channels, samplerate, kbps);
+  if (g.frame_bytes_nopad < 0 || nsamples < 0) return -1;
+  return frames_for(nsamples, g.mode_gr);
+}
+
+int mp3b200_granules_per_frame(int channels, int samplerate, int kbps) {
+  const ByteGeom g = byte_geom(channels, samplerate, kbps);
+  return g.frame_bytes_nopad < 0 ? -1 : g.mode_gr;
 }
 
 }  // extern "C"
@@ -433,14 +481,14 @@ int encode_streams_device_impl(Config* cfg, int channels, int nstreams, const in
     sd.pcm[0] = d_pcm + pcm_off[s];
     sd.pcm[1] = channels == 2 ? d_pcm + pcm_off[s] + nsamples[s] : sd.pcm[0];
     sd.pcm_base = 0; sd.pcm_end = nsamples[s];
-    sd.frame0 = 0; sd.nframes = (int)frames_for(nsamples[s]);
+    sd.frame0 = 0; sd.nframes = (int)frames_for(nsamples[s], cfg->host.mode_gr);
     sd.unit_base = (int)U; sd.frame_base = (int)F;
     sd.out_base = out_off[s];
     init_stream_state(sd);
-    U += 2LL * sd.nframes; F += sd.nframes;
+    U += (long long)cfg->host.mode_gr * sd.nframes; F += sd.nframes;
   }
   if (nstreams == 0 || F == 0) {            /* empty batch: success, nothing launched */
-    if (timings_ms) for (int i = 0; i < 8; i++) timings_ms[i] = 0.0f;
+    if (timings_ms) for (int i = 0; i < 16; i++) timings_ms[i] = 0.0f;
     return MP3B200_OK;
   }
   Workspace& ws = t_ctx.ws;
@@ -454,6 +502,8 @@ int encode_streams_device_impl(Config* cfg, int channels, int nstreams, const in
   if (timings_ms) {
     timings_ms[0] = tm.psy; timings_ms[1] = tm.scan; timings_ms[2] = tm.mask; timings_ms[3] = tm.fb;
     timings_ms[4] = tm.q1; timings_ms[5] = tm.qn; timings_ms[6] = tm.total; timings_ms[7] = (float)tm.passes;
+    timings_ms[8] = tm.q_prepare; timings_ms[9] = tm.q_search; timings_ms[10] = tm.q_outer; timings_ms[11] = tm.q_finish; timings_ms[12] = tm.q_pack;
+    timings_ms[13] = timings_ms[14] = timings_ms[15] = 0.0f;
   }
   return 0;
 }
@@ -487,7 +537,7 @@ int mp3b200_encode_streams(int channels, int samplerate, int kbps, int nstreams,
     pcm_off[s] = tot_samples;
     tot_samples += nsamples[s] * channels;
     out_off[s] = tot_bytes;
-    const long long b = bytes_for(cfg->host, frames_for(nsamples[s]));
+    const long long b = bytes_for(cfg->host, frames_for(nsamples[s], cfg->host.mode_gr));
     if (cap[s] < b) { g_err = "output buffer too small"; return MP3B200_ERR_BUFFER; }
     out_bytes[s] = b;
     tot_bytes += b;
@@ -536,7 +586,8 @@ int mp3b200_debug_stages(int channels, int samplerate, int kbps, const int16_t* 
   rc = t_ctx.use(cfg->device);
   if (rc) return rc;
   const int nch = cfg->host.nch;
-  const long long F = frames_for(nsamples), U = 2 * F;
+  const int G = cfg->host.mode_gr;
+  const long long F = frames_for(nsamples, G), U = G * F;
   int16_t* d_pcm = nullptr; uint8_t* d_out = nullptr;
   CK(cudaMalloc(&d_pcm, sizeof(int16_t) * (size_t)(nsamples * nch + 8)));
   CK(cudaMemcpy(d_pcm, left, sizeof(int16_t) * nsamples, cudaMemcpyHostToDevice));

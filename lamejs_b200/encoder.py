@@ -39,6 +39,9 @@ def lib():
     L.mp3b200_stream_bytes.argtypes = [c_int, c_int, c_int, c_i64]
     L.mp3b200_stream_frames.restype = c_i64
     L.mp3b200_stream_frames.argtypes = [c_i64]
+    L.mp3b200_stream_frames_cfg.restype = c_i64
+    L.mp3b200_stream_frames_cfg.argtypes = [c_int, c_int, c_int, c_i64]
+    L.mp3b200_granules_per_frame.argtypes = [c_int, c_int, c_int]
     L.mp3b200_encode_streams.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
     L.mp3b200_encode_streams_device.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
     L.mp3b200_debug_stages.argtypes = [c_int, c_int, c_int, vp, vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_i64]
@@ -52,8 +55,16 @@ def _check(rc):
     return rc
 
 
-def stream_frames(nsamples):
-    return int(lib().mp3b200_stream_frames(int(nsamples)))
+def stream_frames(nsamples, channels=None, samplerate=None, kbps=None):
+    """Frames encodeBuffer(nsamples) + flush() produce.  Without a configuration: MPEG-1 (1152-sample frames)."""
+    if samplerate is None:
+        return int(lib().mp3b200_stream_frames(int(nsamples)))
+    return int(lib().mp3b200_stream_frames_cfg(channels, samplerate, kbps, int(nsamples)))
+
+
+def granules_per_frame(channels, samplerate, kbps):
+    """2 for MPEG-1 (32/44.1/48 kHz), 1 for MPEG-2 / 2.5 (8..24 kHz); -1 for configurations the library rejects."""
+    return int(lib().mp3b200_granules_per_frame(channels, samplerate, kbps))
 
 
 def stream_bytes(channels, samplerate, kbps, nsamples):
@@ -163,12 +174,12 @@ def encode_streams(channels, samplerate, kbps, lefts, rights=None):
 
 
 def encode_streams_device(channels, samplerate, kbps, d_pcm_ptr, pcm_off, nsamples, d_out_ptr, out_off):
-    """Device-resident batch (raw device pointers as ints).  Returns the 8 kernel timings (ms)."""
+    """Device-resident batch (raw device pointers as ints).  Returns the 16 timing slots of include/mp3b200.h (ms)."""
     L = lib()
     pcm_off = np.ascontiguousarray(pcm_off, dtype=np.int64)
     nsamples = np.ascontiguousarray(nsamples, dtype=np.int64)
     out_off = np.ascontiguousarray(out_off, dtype=np.int64)
-    tm = np.zeros(8, dtype=np.float32)
+    tm = np.zeros(16, dtype=np.float32)
     _check(L.mp3b200_encode_streams_device(channels, samplerate, kbps, len(nsamples), d_pcm_ptr, pcm_off.ctypes.data,
                                            nsamples.ctypes.data, d_out_ptr, out_off.ctypes.data, tm.ctypes.data))
     return tm
@@ -180,7 +191,10 @@ def debug_stages(channels, samplerate, kbps, left, right=None, force_blocktype=N
     left = np.ascontiguousarray(left, dtype=np.int16)
     right = left if (right is None or channels == 1) else np.ascontiguousarray(right, dtype=np.int16)
     n = len(left)
-    F = stream_frames(n)
+    F = stream_frames(n, channels, samplerate, kbps)
+    G = granules_per_frame(channels, samplerate, kbps)
+    if F < 0 or G < 0:
+        raise Mp3B200Error("unsupported configuration: channels=%d samplerate=%d kbps=%d" % (channels, samplerate, kbps))
     nch = channels
     res = {}
 
@@ -193,16 +207,16 @@ def debug_stages(channels, samplerate, kbps, left, right=None, force_blocktype=N
     fb = None
     if force_blocktype is not None:
         fb = np.ascontiguousarray(force_blocktype, dtype=np.int32)
-        assert fb.shape == (F, 2, nch)
-    p_xr = alloc("xr", (F, 2, nch, 576), np.float32)
-    p_bt = alloc("blocktype", (F, 2, nch), np.int32)
-    p_enl = alloc("en_l", (F, 2, nch, 22), np.float32)
-    p_thl = alloc("thm_l", (F, 2, nch, 22), np.float32)
-    p_ens = alloc("en_s", (F, 2, nch, 13, 3), np.float32)
-    p_ths = alloc("thm_s", (F, 2, nch, 13, 3), np.float32)
+        assert fb.shape == (F, G, nch)
+    p_xr = alloc("xr", (F, G, nch, 576), np.float32)
+    p_bt = alloc("blocktype", (F, G, nch), np.int32)
+    p_enl = alloc("en_l", (F, G, nch, 22), np.float32)
+    p_thl = alloc("thm_l", (F, G, nch, 22), np.float32)
+    p_ens = alloc("en_s", (F, G, nch, 13, 3), np.float32)
+    p_ths = alloc("thm_s", (F, G, nch, 13, 3), np.float32)
     p_ath = alloc("ath_adjust", (F,), np.float64)
-    p_l3 = alloc("l3_enc", (F, 2, nch, 576), np.int32)
-    p_gi = alloc("ginfo", (F, 2, nch, 16), np.int32)
+    p_l3 = alloc("l3_enc", (F, G, nch, 576), np.int32)
+    p_gi = alloc("ginfo", (F, G, nch, 16), np.int32)
     nb = stream_bytes(channels, samplerate, kbps, n)
     if nb < 0:
         raise Mp3B200Error("unsupported configuration: channels=%d samplerate=%d kbps=%d" % (channels, samplerate, kbps))

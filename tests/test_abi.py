@@ -41,7 +41,8 @@ def test_stream_geometry_matches_oracle(M, oracle, n):
 
 def test_config_errors(M):
     assert M.stream_bytes(2, 44100, 64, 1000) == -1       # lamejs would resample to 32 kHz: not built
-    assert M.stream_bytes(2, 22050, 64, 1000) == -1       # MPEG-2
+    assert M.stream_bytes(2, 22050, 64, 1000) == 835      # MPEG-2: 4 frames of 208/209 bytes
+    assert M.stream_bytes(2, 48000, 64, 1000) == -1       # lamejs would resample to 24 kHz
     assert M.stream_bytes(3, 44100, 128, 1000) == -1
     assert M.stream_bytes(2, 44100, 123, 44100) == M.stream_bytes(2, 44100, 128, 44100)   # FindNearestBitrate
 
@@ -67,12 +68,13 @@ def test_product_does_not_reference_oracle():
 
 
 def test_config_matrix_acceptance_and_sizes_match_oracle(M, oracle):
-    """Host logic only: for every MPEG-1 bitrate x mono/stereo x native rate the library accepts exactly the
-    configurations the oracle (lame_init_params restatement) accepts, and predicts the oracle's byte count."""
+    """Host logic only: for every sample rate x bitrate x mono/stereo the library accepts exactly the configurations
+    lamejs encodes at the input rate (MPEG-1, MPEG-2 and MPEG-2.5), and predicts the oracle's byte count -- including
+    the flush quirk that a 1152-sample zero bunch can complete two 576-sample frames (Lame.js:1416-1443)."""
     from synth import make_signal
-    for sr in (32000, 44100, 48000):
+    for sr in (8000, 11025, 12000, 16000, 22050, 24000, 32000, 44100, 48000):
         l, r = make_signal("noise", 2000, sr, 1)
-        for kbps in (32, 40, 48, 56, 64, 80, 96, 112, 123, 128, 160, 192, 224, 256, 320):
+        for kbps in (8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 123, 128, 144, 160, 192, 224, 256, 320):
             for ch in (1, 2):
                 # the product takes the configurations lamejs encodes at the input rate; where lamejs would resample
                 # (oracle.out_samplerate != sr) it answers -1 (documented deviation, include/mp3b200.h)

@@ -23,7 +23,7 @@ out = torch.zeros(nb + 64, dtype=torch.uint8, device="cuda")
 for _ in range(reps):
     tm = M.encode_streams_device(2, 44100, 128, pcm.data_ptr(), [0], [n], out.data_ptr(), [0])
 torch.cuda.synchronize()
-print("timings ms [psy, scan, mask, fb, q1, qn, total, passes]:", [round(float(x), 3) for x in tm])
+print("timings ms [psy, scan, mask, fb, q1, qn, total, passes | prepare, search, outer, finish, pack]:", [round(float(x), 3) for x in tm[:13]])
 import hashlib
 print("sha256:", hashlib.sha256(out[:nb].cpu().numpy().tobytes()).hexdigest()[:16], "lib:", os.environ.get("MP3B200_LIB", "default"))
 print("x realtime:", (M.stream_frames(n) * 1152 / 44100) / (tm[6] / 1000))
