@@ -253,3 +253,47 @@ def test_empty_batch_and_error_paths_keep_the_stream_intact(oracle):
     got += big[:rc].tobytes()
     L.mp3b200_destroy(h)
     assert bytes(got) == ref
+
+
+@pytest.mark.parametrize("kind,ch,sr,kbps,frames", [
+    ("noise", 2, 22050, 64, 80), ("burst", 2, 24000, 96, 100), ("octave", 1, 16000, 32, 80), ("white", 2, 16000, 160, 60),
+    ("burst", 1, 22050, 32, 90), ("noise", 1, 8000, 8, 60), ("burst", 2, 12000, 32, 70), ("sine", 2, 11025, 24, 50),
+    ("silence", 2, 24000, 64, 14)])
+def test_stage_parity_lsf(M, oracle, kind, ch, sr, kbps, frames):
+    """MPEG-2 / MPEG-2.5 (one granule per frame, 576-sample frames, scale_bitcount_lsf, 9/17-byte side info): every stage
+    tap bit-equal to the oracle, which is byte-identical to real lamejs on these configurations (test_lamejs_pin)."""
+    l, r = make_signal(kind, frames * 576 + 211, sr, 23)
+    r = r if ch == 2 else None
+    assert M.granules_per_frame(ch, sr, kbps) == 1
+    F = M.stream_frames(len(l), ch, sr, kbps)
+    ref, _, tr = oracle.encode_stream(ch, sr, kbps, l, r, trace_frames=F + 2)
+    assert len(tr) == F
+    g = M.debug_stages(ch, sr, kbps, l, r, want=("xr", "blocktype", "en_l", "thm_l", "en_s", "thm_s", "ath_adjust", "l3_enc", "ginfo", "bytes"))
+    assert np.array_equal(g["blocktype"], tr["blocktype"][:, :1, :ch])
+    assert np.array_equal(g["ath_adjust"], tr["ath_adjust"])
+    for k in ("xr", "en_l", "thm_l", "en_s", "thm_s"):
+        assert bits_equal(g[k], tr[k][:, :1, :ch]), k
+    assert np.array_equal(g["l3_enc"], tr["l3_enc"][:, :1, :ch])
+    for j, k in enumerate(["global_gain", "part2_3_length", "part2_length", "big_values", "count1", "scalefac_compress"]):
+        assert np.array_equal(g["ginfo"][..., j], tr[k][:, :1, :ch]), k
+    assert g["bytes"].tobytes() == ref
+
+
+def test_lsf_batches_and_handles(M, oracle):
+    """LSF through the batch API (ragged streams) and through live handles with odd chunkings (flush completes two 576-sample
+    frames from one 1152-sample zero bunch, Lame.js:1416-1443)."""
+    for ch, sr, kbps in [(2, 22050, 64), (1, 16000, 24), (2, 8000, 16)]:
+        lens = [0, 1, 575, 576, 800, 1329, 5000, 576 * 40 + 3]
+        sigs = [make_signal("burst" if i % 2 else "noise", n, sr, 70 + i) for i, n in enumerate(lens)]
+        outs = M.encode_streams(ch, sr, kbps, [s[0] for s in sigs], [s[1] for s in sigs] if ch == 2 else None)
+        for n, s, o in zip(lens, sigs, outs):
+            assert o == oracle.encode_stream(ch, sr, kbps, s[0], s[1] if ch == 2 else None)[0], (ch, sr, kbps, n)
+        l, r = make_signal("burst", 576 * 50 + 77, sr, 9)
+        for chunk in (576, 1152, 777, 5000):
+            enc = M.Mp3Encoder(ch, sr, kbps)
+            ref = oracle.OracleEncoder(ch, sr, kbps)
+            for i in range(0, len(l), chunk):
+                assert enc.encodeBuffer(l[i:i + chunk], r[i:i + chunk] if ch == 2 else None) == ref.encode_buffer(l[i:i + chunk], r[i:i + chunk]), (chunk, i)
+            assert enc.flush() == ref.flush()
+            assert enc.flush() == b"" == ref.flush()
+            enc.close(); ref.close()
