@@ -84,7 +84,8 @@ int mp3b200_encode_streams(int channels, int samplerate, int kbps, int nstreams,
  * (optional, 16 floats) receives per-kernel CUDA-event times in ms: [0] psy analysis, [1] scan, [2] masking,
  * [3] filterbank+MDCT, [4] quantizer first pass (all of its kernels), [5] re-validation passes, [6] total, [7] number of
  * quantizer passes; first pass by kernel: [8] k_q_prepare, [9] k_q_search (gr0 + gr1), [10] k_q_outer (gr0 + gr1),
- * [11] k_q_finish (gr0 + gr1), [12] k_q_pack; [13..15] reserved (0).
+ * [11] k_q_finish (gr0 + gr1), [12] k_q_pack, [13] the re-validation folded into the first pass (verify + repaired
+ * searches / rate loops of the few frames whose speculated start did not stand); [14..15] reserved (0).
  * The call runs on a stream of its own that first waits for work already queued on the legacy default stream (where torch /
  * plain CUDA callers produced d_pcm) and returns after that stream has drained. */
 int mp3b200_encode_streams_device(int channels, int samplerate, int kbps, int nstreams, const int16_t* d_pcm,

@@ -300,7 +300,7 @@ __device__ __forceinline__ void mdct_short_dev(f32s* io) {
 __global__ void __launch_bounds__(FB_THREADS, FB_MIN_BLOCKS)
 k_filterbank_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams,
                   const signed char* __restrict__ blocktype, float* __restrict__ xr_out) {
-  const StreamDesc sd = streams[blockIdx.z];
+  const StreamDesc& sd = streams[blockIdx.z];
   const int ch = blockIdx.y;
   const int ngr = sd.nframes * T->mode_gr;
   const int g0 = blockIdx.x * FB_G;                 /* first granule (relative to frame0) of this block */

@@ -1996,11 +1996,11 @@ struct QuantBuffers {
                                      counter[2..Q_NCOUNTERS): task counters, one per launch */
 };
 #define Q_NCOUNTERS 256
+enum { QE_START, QE_PREP, QE_S0, QE_O0, QE_F0, QE_S1, QE_MID, QE_O1, QE_F1, QE_PK, QE_COUNT };   /* timing event slots */
 
 static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_streams, int S, int max_frames, long long F,
-                     const QuantBuffers& B, uint8_t* d_out, cudaStream_t st, cudaEvent_t ev_pass1, cudaEvent_t* evq, int* passes_out,
-                     std::atomic<long long>* launches) {
-  /* evq[0..8]: before prepare, after prepare, after each of the seven kernels of the first pass (per-kernel timings) */
+                     const QuantBuffers& B, uint8_t* d_out, cudaStream_t st, cudaEvent_t ev_pass1, cudaEvent_t* evq, int* evq_pred,
+                     int* passes_out, std::atomic<long long>* launches) {
   static std::mutex attr_mu;
   static bool attr_done[64] = {};
   int dev = 0, sms = 148;
@@ -2035,55 +2035,98 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     k_qstate_init<<<g, 128, 0, st>>>(d_streams, S, B.qs);
     (*launches)++;
   }
+  /* per-kernel timings: mark(slot) records evq[slot] and remembers which event preceded it (the launch order differs
+   * between MPEG-1 and LSF streams); the caller computes span(slot) = evq[slot] - evq[pred[slot]] after the final sync */
+  for (int i = 0; i < QE_COUNT; i++) evq_pred[i] = -1;
+  int last_slot = -1;
+  auto mark = [&](int slot) { cudaEventRecord(evq[slot], st); evq_pred[slot] = last_slot; last_slot = slot; };
   int* const prep_counter = fresh_counter();     /* (may enqueue the counter memset: keep it out of the timed span) */
-  cudaEventRecord(evq[0], st);
+  mark(QE_START);
   k_q_prepare<<<grid_for(F * hT.mode_gr * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.xr, B.ratio, B.bt, B.ath_q, B.qs, B.xrq, B.xrpow,
                                                                               B.prep, (int)F, prep_counter);
-  cudaEventRecord(evq[1], st);
+  mark(QE_PREP);
   (*launches)++;
   /* counter[0]: length of the verify list; counter[1]: length of the short list (frames a re-validation pass must touch
-   * beyond gr0's search); the task counters start at 2 */
-  auto run_pass = [&](long long count, int reval) {
-    const int gq = grid_for(count * nch, Q_BLOCKS_PER_SM), gp = grid_for(count, 8);
-    const int* l1 = reval ? B.list : nullptr;                   /* all listed frames */
-    const int* l2 = reval ? B.list + (F + 1) : nullptr;          /* short list, length on the device */
-    const int* c2 = reval ? B.counter + 1 : nullptr;
-    int ei = 2;
-    auto mark = [&]() { if (!reval) cudaEventRecord(evq[ei++], st); };
-    k_q_search<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, 0, l1, nullptr, (int)count, reval, fresh_counter(),
-                                            B.list + (F + 1), B.counter + 1);
-    mark();
-    k_q_outer<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 0, l2, c2, (int)count, reval, fresh_counter());
-    mark();
-    k_q_finish<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 0, l2, c2, (int)count, reval, fresh_counter());
-    mark();
-    if (hT.mode_gr == 2) {
-      k_q_search<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, 1, l2, c2, (int)count, reval, fresh_counter(), nullptr, nullptr);
-      mark();
-      k_q_outer<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 1, l2, c2, (int)count, reval, fresh_counter());
-      mark();
-      k_q_finish<<<gq, Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 1, l2, c2, (int)count, reval, fresh_counter());
-      mark();
-      (*launches) += 3;
-    } else { mark(); mark(); mark(); }
-    k_q_pack<<<gp, Q_THREADS, smem_pack, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, l2, c2, (int)count, reval, fresh_counter(), d_out);
-    mark();
-    (*launches) += 4;
-  };
-  run_pass(F, 0);
-  if (cudaEventRecord(ev_pass1, st) != cudaSuccess) return -100;
-  int passes = 1;
-  for (;;) {
-    if (cudaMemsetAsync(B.counter, 0, 2 * sizeof(int), st) != cudaSuccess) return -100;
-    k_qstate_verify<<<(int)((F + 255) / 256), 256, 0, st>>>(d_streams, B.qs, F, B.list, B.counter);
+   * beyond gr0's search); the task counters start at 2.  A launch takes its work either from all frames (list == nullptr,
+   * count on the host) or from a list whose length lives on the device (grids are sized for the worst case; persistent
+   * warps leave at once when there is nothing to pull). */
+  int* const list1 = B.list;                     /* frames listed by k_qstate_verify */
+  int* const list2 = B.list + (F + 1);           /* short list built by the re-validating gr0 search */
+  const int gq_all = grid_for(F * nch, Q_BLOCKS_PER_SM), gp_all = grid_for(F, 8);
+  auto search = [&](int gr, const int* list, const int* cptr, long long count, int reval) {
+    k_q_search<<<grid_for(count * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, gr, list, cptr, (int)count,
+                                                                             reval, fresh_counter(), list2, B.counter + 1);
     (*launches)++;
+  };
+  auto outer = [&](int gr, const int* list, const int* cptr, long long count, int reval) {
+    k_q_outer<<<grid_for(count * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, gr, list, cptr, (int)count,
+                                                                            reval, fresh_counter());
+    (*launches)++;
+  };
+  auto finish = [&](int gr, const int* list, const int* cptr, long long count, int reval) {
+    k_q_finish<<<grid_for(count * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, gr, list, cptr, (int)count, reval, fresh_counter());
+    (*launches)++;
+  };
+  auto pack = [&](const int* list, const int* cptr, long long count, int reval) {
+    k_q_pack<<<grid_for(count, 8), Q_THREADS, smem_pack, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, list, cptr, (int)count, reval, fresh_counter(), d_out);
+    (*launches)++;
+  };
+  auto verify = [&]() {
+    cudaMemsetAsync(B.counter, 0, 2 * sizeof(int), st);
+    k_qstate_verify<<<(int)((F + 255) / 256), 256, 0, st>>>(d_streams, B.qs, F, list1, B.counter);
+    (*launches)++;
+  };
+  (void)gq_all; (void)gp_all;
+  const int G = hT.mode_gr;
+  /* ---- first pass, with the first re-validation folded in ----
+   * The out-state of every frame is known as soon as its LAST granule's search has run (it does not depend on the rate
+   * loop of that granule), so the in-state assumptions are verified right there and the few frames whose searches do not
+   * stand are repaired before the big rate-loop / finish / pack launches of the last granule touch them: the repair's
+   * latency chain (a handful of single-warp tasks) is short and those launches then see final data.
+   *   MPEG-1: S0 O0 F0 S1 | verify, S0' (listed), O0' F0' S1' (short list) | O1 F1 PACK
+   *   LSF:    S0          | verify, S0' (listed)                            | O0 F0 PACK */
+  search(0, nullptr, nullptr, F, 0); mark(QE_S0);
+  if (G == 2) {
+    outer(0, nullptr, nullptr, F, 0); mark(QE_O0);
+    finish(0, nullptr, nullptr, F, 0); mark(QE_F0);
+    search(1, nullptr, nullptr, F, 0); mark(QE_S1);
+  }
+  verify();
+  search(0, list1, B.counter, F, 1);
+  if (G == 2) {
+    outer(0, list2, B.counter + 1, F, 1);
+    finish(0, list2, B.counter + 1, F, 1);
+    search(1, list2, B.counter + 1, F, 1);
+  }
+  mark(QE_MID);
+  if (G == 2) {
+    outer(1, nullptr, nullptr, F, 0); mark(QE_O1);
+    finish(1, nullptr, nullptr, F, 0); mark(QE_F1);
+  } else {
+    outer(0, nullptr, nullptr, F, 0); mark(QE_O0);
+    finish(0, nullptr, nullptr, F, 0); mark(QE_F0);
+  }
+  pack(nullptr, nullptr, F, 0); mark(QE_PK);
+  if (cudaEventRecord(ev_pass1, st) != cudaSuccess) return -100;
+  int passes = 2;
+  /* ---- fixed point: a repaired frame may hand its successor a different in-state than the one it was verified with ---- */
+  for (;;) {
+    verify();
     int h_count = 0;
     if (cudaMemcpyAsync(&h_count, B.counter, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -100;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -100;
     if (h_count == 0) break;
-    run_pass(h_count, 1);
+    search(0, list1, nullptr, h_count, 1);
+    outer(0, list2, B.counter + 1, h_count, 1);
+    finish(0, list2, B.counter + 1, h_count, 1);
+    if (G == 2) {
+      search(1, list2, B.counter + 1, h_count, 1);
+      outer(1, list2, B.counter + 1, h_count, 1);
+      finish(1, list2, B.counter + 1, h_count, 1);
+    }
+    pack(list2, B.counter + 1, h_count, 1);
     passes++;
-    if (passes > max_frames + 2) return -100;   /* cannot happen: each pass fixes at least the first dirty frame */
+    if (passes > max_frames + 3) return -100;   /* cannot happen: each pass fixes at least the first dirty frame */
   }
   k_qstate_commit<<<(S + 63) / 64, 64, 0, st>>>(d_streams, S, B.qs);
   (*launches)++;

@@ -183,8 +183,9 @@ enum { MP3_MAX_PCM_CHUNKS = 8 };
 struct ThreadCtx {
   int device = -1;
   cudaStream_t st = nullptr, up_st = nullptr;
-  cudaEvent_t ev[8] = {}, evq[9] = {}, ev_in = nullptr, ready[MP3_MAX_PCM_CHUNKS] = {};
+  cudaEvent_t ev[8] = {}, evq[QE_COUNT] = {}, ev_in = nullptr, ready[MP3_MAX_PCM_CHUNKS] = {};
   Workspace ws;
+  int evq_pred[QE_COUNT] = {};
   int16_t* d_pcm = nullptr; size_t d_pcm_cap = 0;
   uint8_t* d_out = nullptr; size_t d_out_cap = 0;
   uint8_t* h_pin = nullptr; size_t h_pin_cap = 0;       /* pinned host staging */
@@ -253,7 +254,7 @@ bool debug_sync() { static int v = -1; if (v < 0) { const char* e = getenv("MP3B
   } while (0)
 
 struct Timings { float psy = 0, scan = 0, mask = 0, fb = 0, q1 = 0, qn = 0, total = 0; int passes = 0;
-                 float q_prepare = 0, q_search = 0, q_outer = 0, q_finish = 0, q_pack = 0; };
+                 float q_prepare = 0, q_search = 0, q_outer = 0, q_finish = 0, q_pack = 0, q_mid = 0; };
 
 /* Runs the whole pipeline for the streams described in `h_streams` (device pointers already set).
  * d_out: device output buffer.  force_bt: optional host array [units][nch] of block types (debug). */
@@ -365,7 +366,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     QuantBuffers qb;
     qb.xr = ws.d_xr; qb.ratio = ws.d_ratio; qb.bt = ws.d_bt_final; qb.ath_q = ws.d_ath_q; qb.qs = ws.d_qstate; qb.ginfo = ws.d_ginfo;
     qb.l3enc = ws.d_l3enc; qb.xrq = ws.d_xrq; qb.xrpow = ws.d_xrpow; qb.prep = ws.d_prep; qb.list = ws.d_dirty; qb.counter = ws.d_counter;
-    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, max_frames, total_frames, qb, d_out, st, ev[5], t_ctx.evq, &passes, &g_launches);
+    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, max_frames, total_frames, qb, d_out, st, ev[5], t_ctx.evq, t_ctx.evq_pred, &passes, &g_launches);
     if (rc) { g_err = "quantizer stage failed: " + std::string(cudaGetErrorString(cudaGetLastError())); return rc; }
   } else {
     CK(cudaEventRecord(ev[5], st));
@@ -384,13 +385,13 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     cudaEventElapsedTime(&tm->total, ev[0], ev[6]);
     tm->passes = passes;
     if (!stop_after_mdct && passes > 0) {
-      cudaEvent_t* q = t_ctx.evq;
-      auto span = [&](int a, int b) { float v = 0; cudaEventElapsedTime(&v, q[a], q[b]); return v; };
-      tm->q_prepare = span(0, 1);
-      tm->q_search = span(1, 2) + span(4, 5);
-      tm->q_outer = span(2, 3) + span(5, 6);
-      tm->q_finish = span(3, 4) + span(6, 7);
-      tm->q_pack = span(7, 8);
+      auto span = [&](int slot) { float v = 0; const int p = t_ctx.evq_pred[slot]; if (p >= 0) cudaEventElapsedTime(&v, t_ctx.evq[p], t_ctx.evq[slot]); return v; };
+      tm->q_prepare = span(QE_PREP);
+      tm->q_search = span(QE_S0) + span(QE_S1);
+      tm->q_outer = span(QE_O0) + span(QE_O1);
+      tm->q_finish = span(QE_F0) + span(QE_F1);
+      tm->q_pack = span(QE_PK);
+      tm->q_mid = span(QE_MID);
     }
   }
   return 0;
@@ -503,7 +504,7 @@ int encode_streams_device_impl(Config* cfg, int channels, int nstreams, const in
     timings_ms[0] = tm.psy; timings_ms[1] = tm.scan; timings_ms[2] = tm.mask; timings_ms[3] = tm.fb;
     timings_ms[4] = tm.q1; timings_ms[5] = tm.qn; timings_ms[6] = tm.total; timings_ms[7] = (float)tm.passes;
     timings_ms[8] = tm.q_prepare; timings_ms[9] = tm.q_search; timings_ms[10] = tm.q_outer; timings_ms[11] = tm.q_finish; timings_ms[12] = tm.q_pack;
-    timings_ms[13] = timings_ms[14] = timings_ms[15] = 0.0f;
+    timings_ms[13] = tm.q_mid; timings_ms[14] = timings_ms[15] = 0.0f;
   }
   return 0;
 }
