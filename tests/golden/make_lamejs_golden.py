@@ -72,6 +72,32 @@ def run_case(item):
                       nonempty_calls=sum(1 for s in sizes if s))
 
 
+TAP_CASES = {   # name -> (kind, channels, samplerate, kbps, samples, seed): lamejs's own INTERMEDIATES are recorded for these
+    "taps_burst_stereo_128": ("burst", 2, 44100, 128, 60 * 1152 + 5, 31),
+    "taps_white_stereo_48k_320": ("white", 2, 48000, 320, 24 * 1152, 32),
+    "taps_octave_mono_128": ("octave", 1, 44100, 128, 40 * 1152, 33),
+    "taps_burst_mono_22k_32": ("burst", 1, 22050, 32, 80 * 576, 34),
+    "taps_noise_stereo_16k_64": ("noise", 2, 16000, 64, 60 * 576 + 9, 35),
+}
+TAP_KEYS = ["xr", "en_l", "thm_l", "en_s", "thm_s", "blocktype", "ath_adjust", "l3_enc", "global_gain", "part2_3_length", "part2_length",
+            "big_values", "count1", "scalefac_compress"]
+
+
+def tap_hash(a):
+    import numpy as np
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def run_tap_case(item):
+    name, (kind, ch, sr, kbps, n, seed) = item
+    import ref_lamejs as R
+    l, r = make_signal(kind, n, sr, seed)
+    data, taps = R.encode_with_taps(ch, sr, kbps, l, r)
+    return name, dict(kind=kind, channels=ch, samplerate=sr, kbps=kbps, samples=n, seed=seed, bytes=len(data),
+                      sha256=hashlib.sha256(data).hexdigest(), frames=int(taps["xr"].shape[0]), granules=int(taps["xr"].shape[1]),
+                      taps={k: tap_hash(taps[k]) for k in TAP_KEYS})
+
+
 def main():
     import ref_lamejs as R
     assert R.available(), "needs /root/reference and the Qt JS engine of this image"
@@ -82,9 +108,14 @@ def main():
         for name, res in ex.map(run_case, cs.items()):
             out[name] = res
             print(name, res.get("bytes"), res.get("error", ""), flush=True)
+    taps = {}
+    with ProcessPoolExecutor(max_workers=os.cpu_count()) as ex:
+        for name, res in ex.map(run_tap_case, TAP_CASES.items()):
+            taps[name] = res
+            print(name, res["frames"], "frames of intermediates", flush=True)
     meta = {"_generator": "tests/golden/make_lamejs_golden.py", "_engine": "Qt QJSEngine 6.6.3 (libQt6Qml), Math.* = C libm",
             "_reference_commit": json.load(open("/root/reference/.SUBMODULES.json"))["commit"], "_loader": "lame.all.js"}
-    json.dump({"meta": meta, "cases": out}, open(os.path.join(HERE, "lamejs_golden.json"), "w"), indent=1, sort_keys=True)
+    json.dump({"meta": meta, "cases": out, "taps": taps}, open(os.path.join(HERE, "lamejs_golden.json"), "w"), indent=1, sort_keys=True)
     print("wrote", len(out), "fixtures")
 
 

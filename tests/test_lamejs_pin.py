@@ -15,7 +15,9 @@ from synth import make_signal
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-FIX = json.load(open(os.path.join(HERE, "golden", "lamejs_golden.json")))["cases"]
+_GOLD = json.load(open(os.path.join(HERE, "golden", "lamejs_golden.json")))
+FIX = _GOLD["cases"]
+TAPS = _GOLD["taps"]     # lamejs's own intermediates (SHA-256 per array): MDCT spectrum, masking, block types, quantised lines ...
 
 
 def _supported(oracle, c):
@@ -123,3 +125,53 @@ def test_loader_and_libm_independence():
     if os.path.exists(os.path.join(ROOT, "tools", "jsrun", "fdlibm.js")):
         c, _, _ = R.encode(2, 44100, 128, l, r, fdlibm=True)
         assert a == c
+
+
+def _tap_hash(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", sorted(TAPS))
+def test_oracle_intermediates_match_lamejs(oracle, name):
+    """Not only the bytes: the MDCT spectrum, the masking energies / thresholds (float32 bit patterns), block types, ATH
+    adjustment, quantised lines and side info that REAL lamejs held in every frame (recorded through two one-line hooks,
+    tools/jsrun/ref_lamejs.encode_with_taps) equal the oracle's trace bit for bit."""
+    c = TAPS[name]
+    ch, G = c["channels"], c["granules"]
+    l, r = make_signal(c["kind"], c["samples"], c["samplerate"], c["seed"])
+    data, _, tr = oracle.encode_stream(ch, c["samplerate"], c["kbps"], l, r if ch == 2 else None, trace_frames=c["frames"] + 2)
+    assert hashlib.sha256(data).hexdigest() == c["sha256"] and len(tr) == c["frames"]
+    for k, want in c["taps"].items():
+        a = tr[k] if k == "ath_adjust" else tr[k][:, :G, :ch]
+        assert _tap_hash(a) == want, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(TAPS))
+def test_gpu_intermediates_match_lamejs(name):
+    """The CUDA stage taps against lamejs's own intermediates directly (no oracle in between): relative tolerance 0."""
+    import lamejs_b200 as M
+
+    c = TAPS[name]
+    ch = c["channels"]
+    l, r = make_signal(c["kind"], c["samples"], c["samplerate"], c["seed"])
+    g = M.debug_stages(ch, c["samplerate"], c["kbps"], l, r if ch == 2 else None,
+                       want=("xr", "blocktype", "en_l", "thm_l", "en_s", "thm_s", "ath_adjust", "l3_enc", "ginfo", "bytes"))
+    assert hashlib.sha256(g["bytes"].tobytes()).hexdigest() == c["sha256"]
+    gi = {k: g["ginfo"][..., j] for j, k in enumerate(["global_gain", "part2_3_length", "part2_length", "big_values", "count1", "scalefac_compress"])}
+    for k, want in c["taps"].items():
+        a = gi[k] if k in gi else g[k]
+        assert _tap_hash(a) == want, k
+
+
+def test_live_intermediates_on_a_random_input(oracle):
+    R = _engine()
+    if R is None:
+        pytest.skip("no JS engine / reference here (GPU box)")
+    l, r = make_signal("burst", 20 * 1152 + 3, 44100, 4242)
+    data, taps = R.encode_with_taps(2, 44100, 128, l, r)
+    ref, _, tr = oracle.encode_stream(2, 44100, 128, l, r, trace_frames=40)
+    assert data == ref
+    for k in ("xr", "en_l", "thm_l", "en_s", "thm_s", "blocktype", "l3_enc", "global_gain"):
+        assert _tap_hash(taps[k]) == _tap_hash(tr[k][:, :2, :2]), k
+    assert np.array_equal(taps["ath_adjust"], tr["ath_adjust"])
