@@ -322,12 +322,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                         # nvidia-smi needs ~0.3 s to deliver its first sample: start before the warm-up
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = L.mp3b200_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     total_ms, coll_ms, ktimes = 0.0, 0.0, np.zeros(16)
@@ -343,12 +343,17 @@ def main():
             coll_ms += ev_c0.elapsed_time(ev_c1)
         ktimes += tm
     launches = L.mp3b200_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     own_ms = total_ms / args.steps
     t = torch.tensor([total_ms, -total_ms, coll_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t[0].item()) / args.steps
+    # A C2 step lasts ~6 ms and nvidia-smi ticks every 100 ms: keep the same load running (untimed, the same count on every
+    # rank because step_device contains the gather) so that the clock sampler sees several ticks under this load.
+    for _ in range(min(400, int(900.0 / max(ms_per_step, 1e-3))) if ms_per_step < 300 else 0):
+        step_device()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     skew_ms = (float(t[0].item()) + float(t[1].item())) / args.steps        # slowest rank minus fastest rank
     collective_ms = float(t[2].item()) / args.steps
     audio_s = S_global * frames * 1152 / SR

@@ -22,7 +22,10 @@
 #include "mp3_device.cuh"
 #include "mp3_tables.h"
 
-#define PSY_THREADS 256
+#ifndef PSY_THREADS
+#define PSY_THREADS 128     /* 4 warps per (unit, channel): measured 1.30 -> 1.08 ms against 256 (cheaper block barriers,
+                               better-filled rounds); sections written for 256 "virtual threads" loop over them */
+#endif
 #define MASK_THREADS 128
 
 struct PsyUnit {
@@ -143,7 +146,7 @@ __device__ __forceinline__ size_t psy_row(const StreamDesc& sd, int z, int u) { 
 
 /* grid (max_units + 1, nch, nstreams) */
 #ifndef PSY_MIN_BLOCKS
-#define PSY_MIN_BLOCKS 4
+#define PSY_MIN_BLOCKS 10
 #endif
 __global__ void __launch_bounds__(PSY_THREADS, PSY_MIN_BLOCKS)
 k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ out,
@@ -174,17 +177,26 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     if (tid < 9) o->peaks[tid] = 10.0f;
     if (tid == 0) { o->loudness = 0.0f; o->fe_valid = 0; }
     if (tid < 4) o->attack[tid] = 0;
+    {   /* k_psy_loudness streams every row: give it defined line energies (its result for this row is not stored) */
+      float* fg = fe_out + ((size_t)psy_row(sd, z, u) * nch + ch) * 512;
+      for (int j = tid; j < 512; j += PSY_THREADS) fg[j] = 0.0f;
+    }
     return;
   }
 
-  __shared__ double xs[1024];                       /* scaled float32 PCM widened ONCE (HPF reads each sample 21x) */
+  /* xs (the PCM span widened once; the HPF reads each sample 21 times) is dead after the high-pass and the first radix-4
+   * pass; the line / partition energies are first written after the last FHT stage: they share its storage */
+  __shared__ __align__(16) unsigned char s_u[sizeof(double) * 1024];
+  double* const xs = reinterpret_cast<double*>(s_u);
+  f32s* const fe = reinterpret_cast<f32s*>(s_u);                                  /* [513] */
+  f32s (*const fes)[129] = reinterpret_cast<f32s (*)[129]>(s_u + 2064);           /* [3][129] */
+  f32s* const s_max = reinterpret_cast<f32s*>(s_u + 2064 + 1552);                 /* [64] */
+  f32s* const s_avg = s_max + MP3_CBANDS;                                         /* [64] */
+  f32s (*const s_ebs)[MP3_CBANDS] = reinterpret_cast<f32s (*)[MP3_CBANDS]>(s_avg + MP3_CBANDS);   /* [3][64] */
+  static_assert(2064 + 1552 + 2 * 4 * MP3_CBANDS + 3 * 4 * MP3_CBANDS <= (int)sizeof(s_u), "energies must fit the PCM span");
   __shared__ f32s wl[1024 + 64];
   __shared__ f32s wsh[3][256 + 16];
   __shared__ f32s hp[576];
-  __shared__ f32s fe[513];
-  __shared__ f32s fes[3][129];
-  __shared__ f32s s_max[MP3_CBANDS], s_avg[MP3_CBANDS];
-  __shared__ f32s s_ebs[3][MP3_CBANDS];
   __shared__ int s_peak[9];
   if (tid < 9) s_peak[tid] = __float_as_int(1.0f);
 
@@ -206,8 +218,9 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     hp[i] = sum1 + sum2;
   }
   /* windowing + first radix-4 pass of fft_long (FFT.js:185-224): iteration jj writes y[4jj..4jj+3], y[512+4jj..] */
-  if (tid < 128) {
-    const int jj = tid, i = c_fft_rv[jj], x = 4 * jj;
+  for (int vt = tid; vt < 128 + 96; vt += PSY_THREADS) {
+  if (vt < 128) {
+    const int jj = vt, i = c_fft_rv[jj], x = 4 * jj;
     const float* w = T->fft_window;
     double f0, f1, f2, f3, wv;
     f0 = (double)w[i] * (double)xs[i];
@@ -224,9 +237,9 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     wv = (double)w[i + 0x301] * (double)xs[i + 0x301];
     f3 = f2 - wv; f2 = f2 + wv;
     wl[FHT_PAD(x + 512 + 0)] = f0 + f2; wl[FHT_PAD(x + 512 + 2)] = f0 - f2; wl[FHT_PAD(x + 512 + 1)] = f1 + f3; wl[FHT_PAD(x + 512 + 3)] = f1 - f3;
-  } else if (tid < 128 + 96) {
+  } else {
     /* fft_short (FFT.js:140-183): block b, iteration j writes x_real[b][4j..], [128+4j..] */
-    const int q = tid - 128, b = q >> 5, j = q & 31;
+    const int q = vt - 128, b = q >> 5, j = q & 31;
     const int i = c_fft_rv[j << 2], x = 4 * j, k = 192 * (b + 1);
     const float* w = T->fft_window_s;
     const double* bx = xs + i + k;
@@ -245,6 +258,7 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     wv = (double)w[0x3e - i] * (double)bx[0xc1];
     f3 = f2 - wv; f2 = f2 + wv;
     wsh[b][FHT_PAD(x + 128 + 0)] = f0 + f2; wsh[b][FHT_PAD(x + 128 + 2)] = f0 - f2; wsh[b][FHT_PAD(x + 128 + 1)] = f1 + f3; wsh[b][FHT_PAD(x + 128 + 3)] = f1 - f3;
+  }
   }
   __syncthreads();
 
@@ -277,15 +291,16 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   __syncthreads();
 
   const int npl = T->npart_l, nps = T->npart_s;
-  if (tid < npl) {                                   /* calc_energy (PsyModel.js:906-928) */
+  for (int vt = tid; vt < 256; vt += PSY_THREADS) {
+  if (vt < npl) {                                    /* calc_energy (PsyModel.js:906-928) */
     double ebb = 0, m = 0;
-    const int l0 = T->line0_l[tid], l1 = T->line0_l[tid + 1];
+    const int l0 = T->line0_l[vt], l1 = T->line0_l[vt + 1];
     for (int j = l0; j < l1; j++) { const double el = fe[j]; ebb += el; if (m < el) m = el; }
-    o->eb_l[tid] = (float)ebb;
-    s_max[tid] = m;
-    s_avg[tid] = ebb * (double)T->rnumlines_l[tid];
-  } else if (tid >= 64 && tid < 64 + 3 * 64) {       /* short partition energies (compute_masking_s :740-750) */
-    const int q = tid - 64, sb = q >> 6, b = q & 63;
+    o->eb_l[vt] = (float)ebb;
+    s_max[vt] = m;
+    s_avg[vt] = ebb * (double)T->rnumlines_l[vt];
+  } else if (vt >= 64 && vt < 64 + 3 * 64) {         /* short partition energies (compute_masking_s :740-750) */
+    const int q = vt - 64, sb = q >> 6, b = q & 63;
     if (b < nps) {
       double ebb = 0;
       const int l0 = T->line0_s[b], l1 = T->line0_s[b + 1];
@@ -293,6 +308,7 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
       s_ebs[sb][b] = ebb;
       o->eb_s[sb][b] = (float)ebb;
     }
+  }
   }
   /* psycho_loudness_approx is one ordered 512-term sum: k_psy_loudness does it with a thread per unit instead of
    * stalling this block on a single lane; hand it the line energies */
@@ -304,8 +320,9 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   if (tid == 9) o->fe_valid = 1;
   __syncthreads();
 
-  if (tid < npl) {                                   /* calc_mask_index_l (PsyModel.js:930-992) */
-    const int b = tid;
+  for (int vt = tid; vt < 256; vt += PSY_THREADS) {
+  if (vt < npl) {                                    /* calc_mask_index_l (PsyModel.js:930-992) */
+    const int b = vt;
     const int lo = b > 0 ? b - 1 : b, hi = b < npl - 1 ? b + 1 : b;
     double a = 0; double m = 0; int lines = 0;
     for (int q = lo; q <= hi; q++) {
@@ -321,8 +338,8 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
       if (k > 8) k = 8;
     }
     o->mask_idx[b] = (unsigned char)k;
-  } else if (tid >= 64 && tid < 64 + 3 * 64) {       /* short spreading sums (compute_masking_s :753-761) */
-    const int q = tid - 64, sb = q >> 6, b = q & 63;
+  } else if (vt >= 64 && vt < 64 + 3 * 64) {         /* short spreading sums (compute_masking_s :753-761) */
+    const int q = vt - 64, sb = q >> 6, b = q & 63;
     if (b < nps) {
       int kk = T->s3lo_s[b];
       int j = T->s3off_s[b];
@@ -331,6 +348,7 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
       while (kk <= T->s3hi_s[b]) { ecb += (double)T->s3_ss[j] * (double)s_ebs[sb][kk]; ++j; ++kk; }
       o->ecb_s[sb][b] = ecb;
     }
+  }
   }
 }
 

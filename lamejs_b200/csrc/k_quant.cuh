@@ -545,6 +545,7 @@ __device__ __noinline__ bool scale_bitcount_w(GranuleInfoDev* gi) {
     const int pt = pretab_of(lane);
     const bool ok = !in || scalefac[lane] >= pt;
     if (__all_sync(Q_FULL, ok)) {
+      __syncwarp();
       if (in) scalefac[lane] -= pt;
       if (lane == 0) gi->preflag = 1;
       __syncwarp();
@@ -991,6 +992,7 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, const 
       if (!(fabs((double)wk->xr[j]) < ath21)) keep = j;
     }
     keep = wmax(keep);
+    __syncwarp();                                   /* every lane's reads above are done before anyone clears lines */
 #pragma unroll 1
     for (int j = keep + 1 + lane; j < 576; j += 32) wk->xr[j] = 0.0f;
   } else if (lane == 0) {
@@ -1998,7 +2000,7 @@ struct QuantBuffers {
 #define Q_NCOUNTERS 256
 enum { QE_START, QE_PREP, QE_S0, QE_O0, QE_F0, QE_S1, QE_MID, QE_O1, QE_F1, QE_PK, QE_COUNT };   /* timing event slots */
 
-static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_streams, int S, int max_frames, long long F,
+static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_streams, int S, int nstreams_with_frames, int max_frames, long long F,
                      const QuantBuffers& B, uint8_t* d_out, cudaStream_t st, cudaEvent_t ev_pass1, cudaEvent_t* evq, int* evq_pred,
                      int* passes_out, std::atomic<long long>* launches) {
   static std::mutex attr_mu;
@@ -2078,6 +2080,9 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
   };
   (void)gq_all; (void)gp_all;
   const int G = hT.mode_gr;
+  /* every stream contributes at most its first frame of this launch (a live encoder advancing one frame per call): all
+   * in-states are the true ones, nothing is speculated, nothing to verify -- no extra launches, no host round trip */
+  const bool speculated = F > nstreams_with_frames;
   /* ---- first pass, with the first re-validation folded in ----
    * The out-state of every frame is known as soon as its LAST granule's search has run (it does not depend on the rate
    * loop of that granule), so the in-state assumptions are verified right there and the few frames whose searches do not
@@ -2091,12 +2096,14 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     finish(0, nullptr, nullptr, F, 0); mark(QE_F0);
     search(1, nullptr, nullptr, F, 0); mark(QE_S1);
   }
-  verify();
-  search(0, list1, B.counter, F, 1);
-  if (G == 2) {
-    outer(0, list2, B.counter + 1, F, 1);
-    finish(0, list2, B.counter + 1, F, 1);
-    search(1, list2, B.counter + 1, F, 1);
+  if (speculated) {
+    verify();
+    search(0, list1, B.counter, F, 1);
+    if (G == 2) {
+      outer(0, list2, B.counter + 1, F, 1);
+      finish(0, list2, B.counter + 1, F, 1);
+      search(1, list2, B.counter + 1, F, 1);
+    }
   }
   mark(QE_MID);
   if (G == 2) {
@@ -2110,7 +2117,7 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
   if (cudaEventRecord(ev_pass1, st) != cudaSuccess) return -100;
   int passes = 2;
   /* ---- fixed point: a repaired frame may hand its successor a different in-state than the one it was verified with ---- */
-  for (;;) {
+  for (; speculated;) {
     verify();
     int h_count = 0;
     if (cudaMemcpyAsync(&h_count, B.counter, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -100;

@@ -275,9 +275,11 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   int max_frames = 0;
   long long total_frames = 0;          /* rows actually used this launch (the workspace may be larger) */
   int scan_rows = 0;
+  int streams_with_frames = 0;
   for (auto& s : h_streams) {
     max_frames = s.nframes > max_frames ? s.nframes : max_frames;
     total_frames += s.nframes;
+    streams_with_frames += s.nframes > 0 ? 1 : 0;
     s.scan_base = scan_rows;
     scan_rows += (s.nframes + SCAN_FRAMES - 1) / SCAN_FRAMES;
   }
@@ -366,7 +368,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     QuantBuffers qb;
     qb.xr = ws.d_xr; qb.ratio = ws.d_ratio; qb.bt = ws.d_bt_final; qb.ath_q = ws.d_ath_q; qb.qs = ws.d_qstate; qb.ginfo = ws.d_ginfo;
     qb.l3enc = ws.d_l3enc; qb.xrq = ws.d_xrq; qb.xrpow = ws.d_xrpow; qb.prep = ws.d_prep; qb.list = ws.d_dirty; qb.counter = ws.d_counter;
-    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, max_frames, total_frames, qb, d_out, st, ev[5], t_ctx.evq, t_ctx.evq_pred, &passes, &g_launches);
+    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, streams_with_frames, max_frames, total_frames, qb, d_out, st, ev[5], t_ctx.evq, t_ctx.evq_pred, &passes, &g_launches);
     if (rc) { g_err = "quantizer stage failed: " + std::string(cudaGetErrorString(cudaGetLastError())); return rc; }
   } else {
     CK(cudaEventRecord(ev[5], st));
