@@ -321,7 +321,31 @@ k_filterbank_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict_
   const int scale_applied = T->scale_applied;
   const double scale = T->scale;
   const int span = 576 * gcount + 1055;
-  for (int j = tid; j < span; j += FB_THREADS) pcm[fb_pad(j)] = (double)load_pcm(sd, ch, lo + j, scale_applied, scale);
+  {
+    /* 8 independent Int16 loads per thread in flight (one dependent load per iteration left this phase, a third of the
+     * kernel's samples in the round-2 profile, waiting for HBM latency) */
+    const int16_t* __restrict__ pbuf = sd.pcm[ch];
+    const long long pbase = sd.pcm_base, pend = sd.pcm_end;
+#pragma unroll 1
+    for (int j0 = tid; j0 < span; j0 += FB_THREADS * 8) {
+      short v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int j = j0 + k * FB_THREADS;
+        const long long i = lo + j;
+        v[k] = (j < span && i >= 0 && i < pend) ? __ldg(&pbuf[i - pbase]) : (short)0;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int j = j0 + k * FB_THREADS;
+        if (j < span) {
+          float f = (float)v[k];                       /* load_pcm: Float32(Int16 * scale) */
+          if (scale_applied) f = (float)((double)f * scale);
+          pcm[fb_pad(j)] = (double)f;
+        }
+      }
+    }
+  }
   if (tid < 32) s_amp[c_sb_order[tid]] = T->amp_filter[tid];
   if (tid < gcount) s_bt[tid] = blocktype[(size_t)(sd.unit_base + g0 + tid) * 2 + ch];
   __syncthreads();

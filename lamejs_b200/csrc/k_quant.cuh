@@ -763,8 +763,12 @@ __device__ __noinline__ void copy_gi_w(GranuleInfoDev* dst, const GranuleInfoDev
   const int* s = reinterpret_cast<const int*>(src);
   int* d = reinterpret_cast<int*>(dst);
   __syncwarp();                                   /* earlier readers of *dst are done */
-#pragma unroll 1
-  for (int i = LANE; i < n; i += 32) d[i] = s[i];
+  static_assert(sizeof(GranuleInfoDev) / 4 <= 96, "three rounds");
+  int v[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { const int i = LANE + 32 * k; if (i < n) v[k] = s[i]; }   /* loads in flight together (HBM rows) */
+#pragma unroll
+  for (int k = 0; k < 3; k++) { const int i = LANE + 32 * k; if (i < n) d[i] = v[k]; }
   __syncwarp();
 }
 __device__ __noinline__ void copy_ix_w(short* dst, const short* src) {
@@ -967,13 +971,25 @@ __device__ __noinline__ bool gc_prepare_w(const Mp3Tables* T, GcWork* wk, const 
   /* band geometry: constant per block type; short blocks are reordered band-major on the way in */
   const Mp3Geo* geo = &T->geo[is_short ? 1 : 0];
   if (lane == 0) wk->geo = geo;
-  if (!is_short) {
-#pragma unroll 1
-    for (int q = lane; q < 144; q += 32)             /* rows are 2304 B apart: 16-byte vectors */
-      reinterpret_cast<float4*>(wk->xr)[q] = __ldg(reinterpret_cast<const float4*>(xr_g) + q);
-  } else {
-#pragma unroll 3
-    for (int i = lane; i < 576; i += 32) wk->xr[__ldg(&geo->reorder[i])] = xr_g[i];
+  {
+    /* the whole row in flight before any of it is used (rows are 2304 B apart: 16-byte vectors); short blocks are scattered
+     * to the quantizer's band-major line order */
+    float4 v[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) { const int q = lane + 32 * k; if (q < 144) v[k] = __ldg(reinterpret_cast<const float4*>(xr_g) + q); }
+    if (!is_short) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) { const int q = lane + 32 * k; if (q < 144) reinterpret_cast<float4*>(wk->xr)[q] = v[k]; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const int q = lane + 32 * k;
+        if (q < 144) {
+          const short* ro = geo->reorder + 4 * q;
+          wk->xr[__ldg(ro + 0)] = v[k].x; wk->xr[__ldg(ro + 1)] = v[k].y; wk->xr[__ldg(ro + 2)] = v[k].z; wk->xr[__ldg(ro + 3)] = v[k].w;
+        }
+      }
+    }
   }
   __syncwarp();
   /* analog silence in the pseudo bands above sfb21 / sfb12 (Quantize.js:147-202): walking down from the top line, lines
@@ -1670,9 +1686,12 @@ __device__ __forceinline__ void gi_init_w(GranuleInfoDev* gi, const GcPrep* __re
 }
 __device__ __forceinline__ void copy_row16_w(void* dst, const void* src, int nbytes) {   /* 16-byte vectors, coalesced */
   __syncwarp();
-  const int n = nbytes >> 4;
-#pragma unroll 1
-  for (int i = LANE; i < n; i += 32) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(src)[i];
+  const int n = nbytes >> 4;                       /* 144 (a 576-float row) or 72 (a 576-short row) */
+  int4 v[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) { const int i = LANE + 32 * k; if (i < n) v[k] = reinterpret_cast<const int4*>(src)[i]; }   /* all loads in flight */
+#pragma unroll
+  for (int k = 0; k < 5; k++) { const int i = LANE + 32 * k; if (i < n) reinterpret_cast<int4*>(dst)[i] = v[k]; }
   __syncwarp();
 }
 struct FrameGeom { int z, f, padding, frame_bytes, mean_bits; long long kabs; };
