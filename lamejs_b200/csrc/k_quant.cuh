@@ -21,6 +21,7 @@
  */
 #ifndef MP3B200_K_QUANT_CUH
 #define MP3B200_K_QUANT_CUH
+#include <stddef.h>
 #include "mp3_device.cuh"
 #include "mp3_tables.h"
 #include "k_psy.cuh"
@@ -58,6 +59,7 @@ struct QuantFrameState {
 #define Q_R1(ch) (16 << (ch))
 #define Q_R0_ANY 3
 #define Q_R1_ANY 48
+#define Q_R1S_ANY 12
 /* what the prepare kernel hands to the search / rate-loop kernels besides the xr and xrpow rows */
 struct GcPrep { float xmin[MP3_SFBMAX]; int have, mnz, block_type; double xrpow_max; };
 
@@ -129,7 +131,6 @@ static int quant_upload_constants() {
 
 /* ---- per-warp working set (shared memory) ---------------------------------------------------------------- */
 struct __align__(16) GcWork {
-  float xr[576];                 /* gi.xr after short-block reorder and analog-silence zeroing */
   float xrpow[576];
   short ixw[576];                /* the one quantised-line buffer: cod_info_w.l3_enc; cod_info.l3_enc (best so far) is
                                     either this buffer (best_here) or parked in global memory at ixg */
@@ -143,13 +144,20 @@ struct __align__(16) GcWork {
   short nstart[MP3_SFBMAX], nlen[MP3_SFBMAX];
   int scratch[8];
   double dscratch[4];
+  float xr[576];                 /* gi.xr after short-block reorder and analog-silence zeroing.  LAST member: the search and
+                                    finish kernels never touch it and leave it out of their shared-memory footprint */
 };
 /* everything one warp (= one granule-channel task) keeps in shared memory */
 struct __align__(16) WarpShared {
-  GcWork wk;
   double ath[6];                  /* analog-silence thresholds of the pseudo bands (psfb21 or psfb12) of this gc */
   int scfsi[4];
+  GcWork wk;                      /* last, so that wk.xr is the tail of the struct */
 };
+/* per-warp stride of the kernels that do not use wk.xr */
+#define Q_STRIDE_NOXR ((int)((offsetof(WarpShared, wk) + offsetof(GcWork, xr) + 15) & ~(size_t)15))
+#ifndef Q_SLIM_BLOCKS
+#define Q_SLIM_BLOCKS 9           /* blocks per SM of the slim kernels (shared memory allows 10) */
+#endif
 
 #define LANE (threadIdx.x & 31)
 /* -DQ_STATS: call counters for tuning (tools/profile_run.py prints them); absent from the product build */
@@ -1663,9 +1671,10 @@ __device__ __forceinline__ int next_task(int* counter) {
   if (LANE == 0) t = atomicAdd(counter, 1);
   return __shfl_sync(Q_FULL, t, 0);
 }
+template <int STRIDE = (int)sizeof(WarpShared)>
 __device__ __forceinline__ WarpShared* warp_shared() {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  return reinterpret_cast<WarpShared*>(smem_raw) + (threadIdx.x >> 5);
+  return reinterpret_cast<WarpShared*>(smem_raw + (threadIdx.x >> 5) * STRIDE);
 }
 /* init_outer_loop's scalar part (Quantize.js:204-260) for the search / rate-loop kernels, from what k_q_prepare kept */
 __device__ __forceinline__ void gi_init_w(GranuleInfoDev* gi, const GcPrep* __restrict__ pr) {
@@ -1747,12 +1756,12 @@ k_q_prepare(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stre
  * gr0 started.  If gr0 lands on the recorded gain with the same cod_info fingerprint, its bytes and the bits it spent stand;
  * gr1's search is then re-run only if its start step changed, and stands if it lands on the recorded gain too.  Whatever
  * does not stand is flagged in q->redo for the rate-loop and pack kernels of this pass. */
-__global__ void __launch_bounds__(Q_THREADS, Q_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(Q_THREADS, Q_SLIM_BLOCKS)
 k_q_search(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs,
            GranuleInfoDev* __restrict__ ginfo, short* __restrict__ l3enc, const float* __restrict__ xrpow_g,
            const GcPrep* __restrict__ prep, int gr, const int* __restrict__ list, const int* __restrict__ count_ptr, int count_direct,
            int revalidate, int* __restrict__ counter, int* __restrict__ list2, int* __restrict__ count2) {
-  WarpShared* ws = warp_shared();
+  WarpShared* ws = warp_shared<Q_STRIDE_NOXR>();
   GcWork* wk = &ws->wk;
   const int lane = LANE, nch = T->nch;
   const int ntasks = (count_ptr ? *count_ptr : count_direct) * nch;
@@ -1839,8 +1848,11 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
     const int wi = t / nch, ch = t - wi * nch;
     const int frow = list ? list[wi] : wi;
     QuantFrameState* q = qs + frow;
-    if (revalidate && !(q->redo & (gr == 0 ? Q_R0(ch) : Q_R1(ch)))) continue;
-    if (revalidate) QSTAT(14);
+    /* revalidate: 0 every listed frame; 1 only what the re-validating searches flagged; 2 every channel of the listed
+     * (short-list) frames; -1 all frames except the short-list ones (their last granule is redone on the repair stream) */
+    if (revalidate == 1 && !(q->redo & (gr == 0 ? Q_R0(ch) : Q_R1(ch)))) continue;
+    if (revalidate == -1 && (q->redo & (Q_R0_ANY | Q_R1S_ANY))) continue;
+    if (revalidate > 0) QSTAT(14);
     const FrameGeom fg = frame_geom(T, streams, q);
     const StreamDesc& sd = streams[fg.z];
     const size_t urow = (size_t)sd.unit_base + T->mode_gr * fg.f + gr, gidx = urow * nch + ch;
@@ -1868,11 +1880,11 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
 /* ---- iteration_finish_one (Quantize.js:1059-1078) of granule `gr`: best_scalefac_store (+ scfsi in gr1) and
  * best_huffman_divide.  Needs only the quantised lines and the side info; its 25 KB of code stay out of the rate loop's
  * instruction-cache footprint. ---- */
-__global__ void __launch_bounds__(Q_THREADS, Q_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(Q_THREADS, Q_SLIM_BLOCKS)
 k_q_finish(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs,
            GranuleInfoDev* __restrict__ ginfo, short* __restrict__ l3enc, int gr, const int* __restrict__ list,
            const int* __restrict__ count_ptr, int count_direct, int revalidate, int* __restrict__ counter) {
-  WarpShared* ws = warp_shared();
+  WarpShared* ws = warp_shared<Q_STRIDE_NOXR>();
   GcWork* wk = &ws->wk;
   const int lane = LANE, nch = T->nch;
   const int ntasks = (count_ptr ? *count_ptr : count_direct) * nch;
@@ -1881,7 +1893,8 @@ k_q_finish(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ strea
     const int wi = t / nch, ch = t - wi * nch;
     const int frow = list ? list[wi] : wi;
     QuantFrameState* q = qs + frow;
-    if (revalidate && !(q->redo & (gr == 0 ? Q_R0(ch) : Q_R1(ch)))) continue;
+    if (revalidate == 1 && !(q->redo & (gr == 0 ? Q_R0(ch) : Q_R1(ch)))) continue;
+    if (revalidate == -1 && (q->redo & (Q_R0_ANY | Q_R1S_ANY))) continue;
     const StreamDesc& sd = streams[q->stream];
     const size_t urow = (size_t)sd.unit_base + T->mode_gr * q->rel_frame + gr, gidx = urow * nch + ch;
     short* const ixrow = l3enc + gidx * 576;
@@ -2017,24 +2030,26 @@ struct QuantBuffers {
                                      counter[2..Q_NCOUNTERS): task counters, one per launch */
 };
 #define Q_NCOUNTERS 256
+#define Q_REPAIR_BLOCKS 16
 enum { QE_START, QE_PREP, QE_S0, QE_O0, QE_F0, QE_S1, QE_MID, QE_O1, QE_F1, QE_PK, QE_COUNT };   /* timing event slots */
 
 static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_streams, int S, int nstreams_with_frames, int max_frames, long long F,
-                     const QuantBuffers& B, uint8_t* d_out, cudaStream_t st, cudaEvent_t ev_pass1, cudaEvent_t* evq, int* evq_pred,
-                     int* passes_out, std::atomic<long long>* launches) {
+                     const QuantBuffers& B, uint8_t* d_out, cudaStream_t st_main, cudaStream_t st_repair, cudaEvent_t ev_fork, cudaEvent_t ev_join,
+                     cudaEvent_t ev_pass1, cudaEvent_t* evq, int* evq_pred, int* passes_out, std::atomic<long long>* launches) {
+  cudaStream_t st = st_main;       /* the launch helpers below use `st`; the repair chain temporarily points it at st_repair */
   static std::mutex attr_mu;
   static bool attr_done[64] = {};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const size_t smem = sizeof(WarpShared) * Q_WARPS, smem_pack = sizeof(PackShared) * Q_WARPS;
+  const size_t smem = sizeof(WarpShared) * Q_WARPS, smem_slim = (size_t)Q_STRIDE_NOXR * Q_WARPS, smem_pack = sizeof(PackShared) * Q_WARPS;
   {
     std::lock_guard<std::mutex> lk(attr_mu);
     if (dev < 64 && !attr_done[dev]) {            /* the attribute is per device */
       if (cudaFuncSetAttribute(k_q_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
-      if (cudaFuncSetAttribute(k_q_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
+      if (cudaFuncSetAttribute(k_q_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slim) != cudaSuccess) return -100;
       if (cudaFuncSetAttribute(k_q_outer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
-      if (cudaFuncSetAttribute(k_q_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -100;
+      if (cudaFuncSetAttribute(k_q_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slim) != cudaSuccess) return -100;
       if (cudaFuncSetAttribute(k_q_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pack) != cudaSuccess) return -100;
       attr_done[dev] = true;
     }
@@ -2075,17 +2090,18 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
   int* const list2 = B.list + (F + 1);           /* short list built by the re-validating gr0 search */
   const int gq_all = grid_for(F * nch, Q_BLOCKS_PER_SM), gp_all = grid_for(F, 8);
   auto search = [&](int gr, const int* list, const int* cptr, long long count, int reval) {
-    k_q_search<<<grid_for(count * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, gr, list, cptr, (int)count,
+    k_q_search<<<grid_for(count * nch, Q_SLIM_BLOCKS), Q_THREADS, smem_slim, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, gr, list, cptr, (int)count,
                                                                              reval, fresh_counter(), list2, B.counter + 1);
     (*launches)++;
   };
+  int reserve_blocks = 0;          /* blocks left free for the repair stream while it runs beside the main stream */
   auto outer = [&](int gr, const int* list, const int* cptr, long long count, int reval) {
-    k_q_outer<<<grid_for(count * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, gr, list, cptr, (int)count,
+    k_q_outer<<<max(1, grid_for(count * nch, Q_BLOCKS_PER_SM) - reserve_blocks), Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, gr, list, cptr, (int)count,
                                                                             reval, fresh_counter());
     (*launches)++;
   };
   auto finish = [&](int gr, const int* list, const int* cptr, long long count, int reval) {
-    k_q_finish<<<grid_for(count * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, gr, list, cptr, (int)count, reval, fresh_counter());
+    k_q_finish<<<max(1, grid_for(count * nch, Q_SLIM_BLOCKS) - reserve_blocks), Q_THREADS, smem_slim, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, gr, list, cptr, (int)count, reval, fresh_counter());
     (*launches)++;
   };
   auto pack = [&](const int* list, const int* cptr, long long count, int reval) {
@@ -2115,19 +2131,38 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     finish(0, nullptr, nullptr, F, 0); mark(QE_F0);
     search(1, nullptr, nullptr, F, 0); mark(QE_S1);
   }
+  bool forked = false;
   if (speculated) {
     verify();
     search(0, list1, B.counter, F, 1);
     if (G == 2) {
-      outer(0, list2, B.counter + 1, F, 1);
-      finish(0, list2, B.counter + 1, F, 1);
-      search(1, list2, B.counter + 1, F, 1);
+      /* The few short-list frames are repaired on a second stream -- gr0 rate loop, finish, gr1 search, then their whole gr1
+       * (single-warp tasks: ~0.3 ms of pure latency) -- while the main stream runs the gr1 rate loop of all other frames. */
+      int* const c0 = fresh_counter(); int* const c1 = fresh_counter(); int* const c2 = fresh_counter();
+      int* const c3 = fresh_counter(); int* const c4 = fresh_counter();
+      cudaEventRecord(ev_fork, st_main);
+      cudaStreamWaitEvent(st_repair, ev_fork, 0);
+      /* the main stream's persistent grid would occupy every block slot for a millisecond: it leaves Q_REPAIR_BLOCKS slots
+       * free (1.5 % of its warps) and the repair kernels never ask for more (the short list holds a handful of frames) */
+      const int gq = Q_REPAIR_BLOCKS, gs = Q_REPAIR_BLOCKS;
+      const int* cp = B.counter + 1;
+      k_q_outer<<<gq, Q_THREADS, smem, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 0, list2, cp, (int)F, 1, c0);
+      k_q_finish<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 0, list2, cp, (int)F, 1, c1);
+      k_q_search<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, 1, list2, cp, (int)F, 1, c2, list2, B.counter + 1);
+      k_q_outer<<<gq, Q_THREADS, smem, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 1, list2, cp, (int)F, 2, c3);
+      k_q_finish<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 1, list2, cp, (int)F, 2, c4);
+      cudaEventRecord(ev_join, st_repair);
+      (*launches) += 5;
+      forked = true;
     }
   }
   mark(QE_MID);
   if (G == 2) {
-    outer(1, nullptr, nullptr, F, 0); mark(QE_O1);
-    finish(1, nullptr, nullptr, F, 0); mark(QE_F1);
+    reserve_blocks = forked ? Q_REPAIR_BLOCKS : 0;
+    outer(1, nullptr, nullptr, F, forked ? -1 : 0); mark(QE_O1);
+    finish(1, nullptr, nullptr, F, forked ? -1 : 0); mark(QE_F1);
+    reserve_blocks = 0;
+    if (forked) cudaStreamWaitEvent(st_main, ev_join, 0);
   } else {
     outer(0, nullptr, nullptr, F, 0); mark(QE_O0);
     finish(0, nullptr, nullptr, F, 0); mark(QE_F0);

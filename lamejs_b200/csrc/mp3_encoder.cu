@@ -182,8 +182,8 @@ struct Workspace {
 enum { MP3_MAX_PCM_CHUNKS = 8 };
 struct ThreadCtx {
   int device = -1;
-  cudaStream_t st = nullptr, up_st = nullptr;
-  cudaEvent_t ev[8] = {}, evq[QE_COUNT] = {}, ev_in = nullptr, ready[MP3_MAX_PCM_CHUNKS] = {};
+  cudaStream_t st = nullptr, up_st = nullptr, aux_st = nullptr;   /* main, PCM upload, quantizer repair chain */
+  cudaEvent_t ev[8] = {}, evq[QE_COUNT] = {}, ev_in = nullptr, ev_fork = nullptr, ev_join = nullptr, ready[MP3_MAX_PCM_CHUNKS] = {};
   Workspace ws;
   int evq_pred[QE_COUNT] = {};
   int16_t* d_pcm = nullptr; size_t d_pcm_cap = 0;
@@ -200,6 +200,9 @@ struct ThreadCtx {
     for (auto& e : evq) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto& e : ready) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (ev_in) { cudaEventDestroy(ev_in); ev_in = nullptr; }
+    if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
+    if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
+    if (aux_st) { cudaStreamDestroy(aux_st); aux_st = nullptr; }
     if (st) { cudaStreamDestroy(st); st = nullptr; }
     if (up_st) { cudaStreamDestroy(up_st); up_st = nullptr; }
     device = -1;
@@ -215,6 +218,13 @@ struct ThreadCtx {
     for (auto& e : evq) CK(cudaEventCreate(&e));
     for (auto& e : ready) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    {
+      int lo = 0, hi = 0;                  /* the repair chain is latency critical: highest priority */
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&aux_st, cudaStreamNonBlocking, hi));
+    }
     device = dev;
     return 0;
   }
@@ -368,7 +378,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     QuantBuffers qb;
     qb.xr = ws.d_xr; qb.ratio = ws.d_ratio; qb.bt = ws.d_bt_final; qb.ath_q = ws.d_ath_q; qb.qs = ws.d_qstate; qb.ginfo = ws.d_ginfo;
     qb.l3enc = ws.d_l3enc; qb.xrq = ws.d_xrq; qb.xrpow = ws.d_xrpow; qb.prep = ws.d_prep; qb.list = ws.d_dirty; qb.counter = ws.d_counter;
-    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, streams_with_frames, max_frames, total_frames, qb, d_out, st, ev[5], t_ctx.evq, t_ctx.evq_pred, &passes, &g_launches);
+    int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, streams_with_frames, max_frames, total_frames, qb, d_out, st, t_ctx.aux_st, t_ctx.ev_fork, t_ctx.ev_join, ev[5], t_ctx.evq, t_ctx.evq_pred, &passes, &g_launches);
     if (rc) { g_err = "quantizer stage failed: " + std::string(cudaGetErrorString(cudaGetLastError())); return rc; }
   } else {
     CK(cudaEventRecord(ev[5], st));
