@@ -465,7 +465,7 @@ __global__ void k_attack_prepass(const Mp3Tables* __restrict__ T, const StreamDe
  * guesses are checked against the predecessor's out-state, and only wrong chunks are redone until nothing changes.
  * The result equals the sequential scan exactly; the worst case degenerates to it.  One block per stream. */
 #define SCAN_FRAMES 16
-#define SCAN_THREADS 256      /* the chunk inputs are preloaded into registers: 256 threads leave room for them */
+#define SCAN_THREADS 1024
 struct ScanChunk { int fsm_in, fsm_out, dirty_fsm, dirty_ath; double ath_in[2], ath_out[2]; };
 
 __device__ __forceinline__ int fsm_pack(int la0, int la1, int o0, int o1) { return la0 | (la1 << 2) | (o0 << 4) | (o1 << 6); }
@@ -476,14 +476,18 @@ __device__ void scan_fsm_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, 
   int la[2] = {ck->fsm_in & 3, (ck->fsm_in >> 2) & 3};
   int old[2] = {(ck->fsm_in >> 4) & 3, (ck->fsm_in >> 6) & 3};
   const int G = T->mode_gr;
-  /* all inputs of the chunk in flight first: the walk below is a serial recurrence, and one dependent L2 round trip per
-   * step (64 of them) was most of the scan's time */
-  unsigned avs[2 * SCAN_FRAMES][2];
+  /* all inputs of the chunk in flight first (the walk below is a serial recurrence, and one dependent L2 round trip per
+   * step -- 64 of them -- was most of the scan's time); packed to 4 bits per (unit, channel) so that 1024 threads fit */
+  unsigned pk[(2 * SCAN_FRAMES) / 4] = {};           /* unit k: bits 8(k&3)..+3 channel 0, +4..+7 channel 1 */
 #pragma unroll
   for (int k = 0; k < 2 * SCAN_FRAMES; k++) {
     const int u = G * f0 + k;
 #pragma unroll
-    for (int ch = 0; ch < 2; ch++) avs[k][ch] = (u < G * f1 && ch < nch) ? sin[psy_row(sd, z, u) * nch + ch].attack4 : 0u;
+    for (int ch = 0; ch < 2; ch++) {
+      const unsigned av = (u < G * f1 && ch < nch) ? sin[psy_row(sd, z, u) * nch + ch].attack4 : 0u;
+      const unsigned nib = (av & 1u) | ((av >> 7) & 2u) | ((av >> 14) & 4u) | ((av >> 21) & 8u);   /* the four 0/1 bytes */
+      pk[k >> 2] |= nib << (8 * (k & 3) + 4 * ch);
+    }
   }
 #pragma unroll
   for (int k = 0; k < 2 * SCAN_FRAMES; k++) {
@@ -493,8 +497,8 @@ __device__ void scan_fsm_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, 
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
       if (ch >= nch) break;
-      const unsigned av = avs[k][ch];
-      int a0 = av & 0xff, a1 = (av >> 8) & 0xff, a2 = (av >> 16) & 0xff, a3 = (av >> 24) & 0xff;
+      const unsigned nib = (pk[k >> 2] >> (8 * (k & 3) + 4 * ch)) & 15u;
+      int a0 = nib & 1, a1 = (nib >> 1) & 1, a2 = (nib >> 2) & 1, a3 = (nib >> 3) & 1;
       if (a0 != 0 && la[ch] != 0) a0 = 0;
       if (la[ch] == 3 || (a0 + a1 + a2 + a3) != 0) {
         uselong[ch] = 0;
@@ -529,34 +533,34 @@ __device__ void scan_ath_chunk(const Mp3Tables* T, const StreamDesc& sd, int z, 
   double adjust = ck->ath_in[0], limit = ck->ath_in[1];
   const double sens = T->aa_sensitivity_p;
   const int G = T->mode_gr;
-  /* the loudness values the chunk needs, loaded up front (independent loads) */
-  float ld[SCAN_FRAMES][4];
+  /* the loudness sums the chunk needs, loaded up front (independent loads) and reduced to one double per frame */
+  double mp[SCAN_FRAMES];
 #pragma unroll
   for (int k = 0; k < SCAN_FRAMES; k++) {
     const int f = f0 + k;
-    const bool in = f < f1;
-    const ScanIn* r0 = sin + psy_row(sd, z, G * f - 1) * nch;
-    const ScanIn* r1 = sin + psy_row(sd, z, G * f) * nch;
-    ld[k][0] = in ? r0[0].loudness : 0.0f;
-    ld[k][1] = (in && nch == 2) ? r0[1].loudness : 0.0f;
-    ld[k][2] = (in && G == 2) ? r1[0].loudness : 0.0f;
-    ld[k][3] = (in && G == 2 && nch == 2) ? r1[1].loudness : 0.0f;
+    double max_pow = 0.0;
+    if (f < f1) {
+      /* loudness_sq[gr][ch] is the loudness of the unit BEFORE call G f + gr (one-call delay, PsyModel.js:321-322) */
+      const ScanIn* r0 = sin + psy_row(sd, z, G * f - 1) * nch;
+      max_pow = (double)r0[0].loudness;
+      if (nch == 2) max_pow += (double)r0[1].loudness;
+      else max_pow += max_pow;
+      if (G == 2) {                                   /* Encoder.js:187: the second granule only exists in MPEG-1 */
+        const ScanIn* r1 = sin + psy_row(sd, z, G * f) * nch;
+        double gr2_max = (double)r1[0].loudness;
+        if (nch == 2) gr2_max += (double)r1[1].loudness;
+        else gr2_max += gr2_max;
+        max_pow = js_dmax(max_pow, gr2_max);
+      }
+    }
+    mp[k] = max_pow;
   }
 #pragma unroll
   for (int k = 0; k < SCAN_FRAMES; k++) {
     const int f = f0 + k;
     if (f >= f1) break;
     ath_psy[sd.frame_base + f] = adjust;
-    /* loudness_sq[gr][ch] is the loudness of the unit BEFORE call G f + gr (one-call delay, PsyModel.js:321-322) */
-    double max_pow = (double)ld[k][0];
-    if (nch == 2) max_pow += (double)ld[k][1];
-    else max_pow += max_pow;
-    if (G == 2) {                                     /* Encoder.js:187: the second granule only exists in MPEG-1 */
-      double gr2_max = (double)ld[k][2];
-      if (nch == 2) gr2_max += (double)ld[k][3];
-      else gr2_max += gr2_max;
-      max_pow = js_dmax(max_pow, gr2_max);
-    }
+    double max_pow = mp[k];
     max_pow *= 0.5;
     max_pow *= sens;
     if (max_pow > 0.03125) {
@@ -683,18 +687,8 @@ k_psy_masking(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ st
   __shared__ f32s s_thr_s[2][3][MP3_CBANDS + 2];
   __shared__ PsyRatioDev s_out[2];
   const int npl = T->npart_l, nps = T->npart_s;
-  /* this unit's analysis rows (both channels) are staged once with coalesced 16-byte loads: the spreading / conversion loops
-   * below index them per partition (they were dependent L1/L2 loads); of the previous unit only ecb_s is read, in place */
-  __shared__ __align__(16) PsyUnit s_pu[2];
-  static_assert(sizeof(PsyUnit) % 16 == 0, "PsyUnit rows are copied as 16-byte vectors");
-  {
-    const int4* src = reinterpret_cast<const int4*>(psy + psy_row(sd, z, u) * nch);
-    int4* dst = reinterpret_cast<int4*>(s_pu);
-    constexpr int PER = (int)sizeof(PsyUnit) / 16;
-    for (int i = tid; i < nch * PER; i += MASK_THREADS) dst[i] = src[i];
-  }
-  __syncthreads();
-  const PsyUnit* pu = (ch < nch) ? &s_pu[ch] : nullptr;
+  /* (staging these rows in shared memory was measured: 238 -> 257 us, the extra barrier costs more than the L1 hits) */
+  const PsyUnit* pu = (ch < nch) ? psy + psy_row(sd, z, u) * nch + ch : nullptr;
   const PsyUnit* pp = (ch < nch) ? psy + psy_row(sd, z, u - 1) * nch + ch : nullptr;
   const double ath_adjust = ath_psy[sd.frame_base + u / T->mode_gr];
 

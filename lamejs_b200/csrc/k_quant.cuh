@@ -144,7 +144,7 @@ struct __align__(16) GcWork {
   short nstart[MP3_SFBMAX], nlen[MP3_SFBMAX];
   int scratch[8];
   double dscratch[4];
-  float xr[576];                 /* gi.xr after short-block reorder and analog-silence zeroing.  LAST member: the search and
+  __align__(16) float xr[576];   /* gi.xr after short-block reorder and analog-silence zeroing.  LAST member: the search and
                                     finish kernels never touch it and leave it out of their shared-memory footprint */
 };
 /* everything one warp (= one granule-channel task) keeps in shared memory */
@@ -155,6 +155,8 @@ struct __align__(16) WarpShared {
 };
 /* per-warp stride of the kernels that do not use wk.xr */
 #define Q_STRIDE_NOXR ((int)((offsetof(WarpShared, wk) + offsetof(GcWork, xr) + 15) & ~(size_t)15))
+static_assert((offsetof(WarpShared, wk) + offsetof(GcWork, xr)) % 16 == 0 && (offsetof(WarpShared, wk) + offsetof(GcWork, xrpow)) % 16 == 0 &&
+              (offsetof(WarpShared, wk) + offsetof(GcWork, ixw)) % 16 == 0 && sizeof(WarpShared) % 16 == 0, "rows are moved as 16-byte vectors");
 #ifndef Q_SLIM_BLOCKS
 #define Q_SLIM_BLOCKS 9           /* blocks per SM of the slim kernels (shared memory allows 10) */
 #endif
@@ -175,6 +177,9 @@ __device__ unsigned long long g_qstats[16];
 #endif
 #ifndef Q_CB_UNROLL
 #define Q_CB_UNROLL 1
+#endif
+#ifndef Q_CN_UNROLL
+#define Q_CN_UNROLL 1
 #endif
 #ifndef Q_HELPER
 #define Q_HELPER __forceinline__
@@ -502,7 +507,7 @@ __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const 
         const double step = (double)T->pow20[s + MP3_QMAX2];
         int j = wk->nstart[sfb];
         noise = 0;
-#pragma unroll 1
+Q_UNROLL(Q_CN_UNROLL)
         for (int l = wk->nlen[sfb]; l > 0; l--, j += 2) {          /* j is even: one 64-bit and one 32-bit load per pair */
           const float2 x = *reinterpret_cast<const float2*>(&wk->xr[j]);
           const unsigned q = *reinterpret_cast<const unsigned*>(&ix[j]);
@@ -1993,19 +1998,29 @@ __global__ void k_qstate_init(const StreamDesc* __restrict__ streams, int nstrea
 }
 
 /* compare each frame's assumed in-state with its predecessor's out-state; append mismatches to the work list */
+/* predict_step (LSF, first verification only): the predecessor's out-step was computed from ITS guessed start; the step it
+ * will have once it is re-searched from its true start (its own predecessor's gain) is (start - gain >= 4) ? 4 : 2 if its gain
+ * stands -- hand that to the successor right away instead of discovering it one pass later.  A wrong prediction is caught by
+ * the next verification like any other wrong guess. */
 __global__ void k_qstate_verify(const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs, long long nframes,
-                                int* __restrict__ list, int* __restrict__ counter) {
+                                int* __restrict__ list, int* __restrict__ counter, int predict_step) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nframes) return;
   QuantFrameState* q = qs + r;
   if (q->rel_frame == 0) return;
   const QuantFrameState* p = q - 1;
+  int pstep[2] = {p->out_step[0], p->out_step[1]};
+  if (predict_step && p->rel_frame != 0) {
+    const QuantFrameState* pp = p - 1;
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) pstep[c] = (pp->out_old[c] - p->out_old[c] >= 4) ? 4 : 2;
+  }
   bool same = true;
 #pragma unroll 1
-  for (int c = 0; c < 2; c++) if (q->in_old[c] != p->out_old[c] || q->in_step[c] != p->out_step[c]) same = false;
+  for (int c = 0; c < 2; c++) if (q->in_old[c] != p->out_old[c] || q->in_step[c] != pstep[c]) same = false;
   if (!same) {
 #pragma unroll 1
-    for (int c = 0; c < 2; c++) { q->in_old[c] = p->out_old[c]; q->in_step[c] = p->out_step[c]; }
+    for (int c = 0; c < 2; c++) { q->in_old[c] = p->out_old[c]; q->in_step[c] = pstep[c]; }
     q->redo = 0;
     list[atomicAdd(counter, 1)] = (int)r;
   }
@@ -2108,9 +2123,9 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     k_q_pack<<<grid_for(count, 8), Q_THREADS, smem_pack, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, list, cptr, (int)count, reval, fresh_counter(), d_out);
     (*launches)++;
   };
-  auto verify = [&]() {
+  auto verify = [&](int predict_step = 0) {
     cudaMemsetAsync(B.counter, 0, 2 * sizeof(int), st);
-    k_qstate_verify<<<(int)((F + 255) / 256), 256, 0, st>>>(d_streams, B.qs, F, list1, B.counter);
+    k_qstate_verify<<<(int)((F + 255) / 256), 256, 0, st>>>(d_streams, B.qs, F, list1, B.counter, predict_step);
     (*launches)++;
   };
   (void)gq_all; (void)gp_all;
@@ -2133,7 +2148,7 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
   }
   bool forked = false;
   if (speculated) {
-    verify();
+    verify(G == 1 ? 1 : 0);
     search(0, list1, B.counter, F, 1);
     if (G == 2) {
       /* The few short-list frames are repaired on a second stream -- gr0 rate loop, finish, gr1 search, then their whole gr1
