@@ -179,7 +179,7 @@ __device__ unsigned long long g_qstats[16];
 #define Q_CB_UNROLL 1
 #endif
 #ifndef Q_CN_UNROLL
-#define Q_CN_UNROLL 1
+#define Q_CN_UNROLL 2          /* calc_noise band chain: A/B 1 / 2 / 4 -> k_q_outer 2.27 / 2.18 / 2.19 ms (C2) */
 #endif
 #ifndef Q_HELPER
 #define Q_HELPER __forceinline__
@@ -1765,7 +1765,8 @@ __global__ void __launch_bounds__(Q_THREADS, Q_SLIM_BLOCKS)
 k_q_search(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs,
            GranuleInfoDev* __restrict__ ginfo, short* __restrict__ l3enc, const float* __restrict__ xrpow_g,
            const GcPrep* __restrict__ prep, int gr, const int* __restrict__ list, const int* __restrict__ count_ptr, int count_direct,
-           int revalidate, int* __restrict__ counter, int* __restrict__ list2, int* __restrict__ count2) {
+           int revalidate, int* __restrict__ counter, int* __restrict__ list2, int* __restrict__ count2,
+           int* __restrict__ list3, int* __restrict__ count3) {
   WarpShared* ws = warp_shared<Q_STRIDE_NOXR>();
   GcWork* wk = &ws->wk;
   const int lane = LANE, nch = T->nch;
@@ -1775,7 +1776,10 @@ k_q_search(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ strea
     const int wi = t / nch, ch = t - wi * nch;
     const int frow = list ? list[wi] : wi;
     QuantFrameState* q = qs + frow;
+    /* revalidate: 0 first pass; 1 re-validation (gr1: channels whose start step changed, both channels when gr0 was redone);
+     * 3 = gr1 of the frames whose gr0 stands (the frames with a redone gr0 are on the repair list, handled on its stream) */
     const int flags = revalidate ? q->redo : 0;
+    if (revalidate == 3 && (flags & Q_R0_ANY)) continue;
     if (revalidate && gr == 1 && !(flags & (Q_R0_ANY | Q_R1S(ch)))) continue;
     const FrameGeom fg = frame_geom(T, streams, q);
     const StreamDesc& sd = streams[fg.z];
@@ -1818,8 +1822,10 @@ k_q_search(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ strea
       if (lane == 0) {
         int old = -1;
         if (T->mode_gr == 1) { q->out_old[ch] = ov; q->out_step[ch] = cs; }   /* LSF: gr0 is the frame's last granule */
-        if (store) { q->bs_gain0[ch] = ov; q->bs_step0[ch] = cs; q->bs_hash[0][ch] = h; old = atomicOr(&q->redo, Q_R0(ch)); }
-        else if (step_changed && T->mode_gr == 2) { q->bs_step0[ch] = cs; old = atomicOr(&q->redo, Q_R1S(ch)); }
+        if (store) {
+          q->bs_gain0[ch] = ov; q->bs_step0[ch] = cs; q->bs_hash[0][ch] = h; old = atomicOr(&q->redo, Q_R0(ch));
+          if ((old & Q_R0_ANY) == 0) list3[atomicAdd(count3, 1)] = frow;     /* repair list: gr0 must be redone (a handful) */
+        } else if (step_changed && T->mode_gr == 2) { q->bs_step0[ch] = cs; old = atomicOr(&q->redo, Q_R1S(ch)); }
         /* frames with anything left to do go on the short list the remaining kernels of this pass walk */
         if (old == 0) list2[atomicAdd(count2, 1)] = frow;
       }
@@ -1854,9 +1860,9 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
     const int frow = list ? list[wi] : wi;
     QuantFrameState* q = qs + frow;
     /* revalidate: 0 every listed frame; 1 only what the re-validating searches flagged; 2 every channel of the listed
-     * (short-list) frames; -1 all frames except the short-list ones (their last granule is redone on the repair stream) */
+     * frames; -1 all frames except those on the repair list (gr0 redone: their gr1 runs on the repair stream) */
     if (revalidate == 1 && !(q->redo & (gr == 0 ? Q_R0(ch) : Q_R1(ch)))) continue;
-    if (revalidate == -1 && (q->redo & (Q_R0_ANY | Q_R1S_ANY))) continue;
+    if (revalidate == -1 && (q->redo & Q_R0_ANY)) continue;
     if (revalidate > 0) QSTAT(14);
     const FrameGeom fg = frame_geom(T, streams, q);
     const StreamDesc& sd = streams[fg.z];
@@ -1899,7 +1905,7 @@ k_q_finish(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ strea
     const int frow = list ? list[wi] : wi;
     QuantFrameState* q = qs + frow;
     if (revalidate == 1 && !(q->redo & (gr == 0 ? Q_R0(ch) : Q_R1(ch)))) continue;
-    if (revalidate == -1 && (q->redo & (Q_R0_ANY | Q_R1S_ANY))) continue;
+    if (revalidate == -1 && (q->redo & Q_R0_ANY)) continue;
     const StreamDesc& sd = streams[q->stream];
     const size_t urow = (size_t)sd.unit_base + T->mode_gr * q->rel_frame + gr, gidx = urow * nch + ch;
     short* const ixrow = l3enc + gidx * 576;
@@ -2073,7 +2079,7 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
   const int nch = hT.nch;
   int next_counter = Q_NCOUNTERS;                 /* forces the first memset */
   auto fresh_counter = [&]() -> int* {            /* a zeroed task counter for the next launch */
-    if (next_counter >= Q_NCOUNTERS) { cudaMemsetAsync(B.counter + 2, 0, sizeof(int) * (Q_NCOUNTERS - 2), st); next_counter = 2; }
+    if (next_counter >= Q_NCOUNTERS) { cudaMemsetAsync(B.counter + 3, 0, sizeof(int) * (Q_NCOUNTERS - 3), st); next_counter = 3; }
     return B.counter + next_counter++;
   };
   auto grid_for = [&](long long tasks, int per_sm) -> int {   /* persistent blocks, never more than the tasks need */
@@ -2102,11 +2108,12 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
    * count on the host) or from a list whose length lives on the device (grids are sized for the worst case; persistent
    * warps leave at once when there is nothing to pull). */
   int* const list1 = B.list;                     /* frames listed by k_qstate_verify */
-  int* const list2 = B.list + (F + 1);           /* short list built by the re-validating gr0 search */
+  int* const list2 = B.list + (F + 1);           /* short list built by the re-validating gr0 search: any flag */
+  int* const list3 = B.list + 2 * (F + 1);       /* repair list: frames whose gr0 must be redone */
   const int gq_all = grid_for(F * nch, Q_BLOCKS_PER_SM), gp_all = grid_for(F, 8);
   auto search = [&](int gr, const int* list, const int* cptr, long long count, int reval) {
     k_q_search<<<grid_for(count * nch, Q_SLIM_BLOCKS), Q_THREADS, smem_slim, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, gr, list, cptr, (int)count,
-                                                                             reval, fresh_counter(), list2, B.counter + 1);
+                                                                             reval, fresh_counter(), list2, B.counter + 1, list3, B.counter + 2);
     (*launches)++;
   };
   int reserve_blocks = 0;          /* blocks left free for the repair stream while it runs beside the main stream */
@@ -2124,7 +2131,7 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     (*launches)++;
   };
   auto verify = [&](int predict_step = 0) {
-    cudaMemsetAsync(B.counter, 0, 2 * sizeof(int), st);
+    cudaMemsetAsync(B.counter, 0, 3 * sizeof(int), st);
     k_qstate_verify<<<(int)((F + 255) / 256), 256, 0, st>>>(d_streams, B.qs, F, list1, B.counter, predict_step);
     (*launches)++;
   };
@@ -2151,21 +2158,26 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     verify(G == 1 ? 1 : 0);
     search(0, list1, B.counter, F, 1);
     if (G == 2) {
-      /* The few short-list frames are repaired on a second stream -- gr0 rate loop, finish, gr1 search, then their whole gr1
-       * (single-warp tasks: ~0.3 ms of pure latency) -- while the main stream runs the gr1 rate loop of all other frames. */
+      /* gr1's search of the frames whose gr0 stands but whose start step changed (a third of the frames on C2; cheap with
+       * the whole machine): afterwards every frame but the repair list is ready for gr1's rate loop */
+      search(1, list2, B.counter + 1, F, 3);
+      /* The repair list (frames whose gr0 search did not stand: a handful) is redone on a second stream -- gr0 rate loop,
+       * finish, gr1 search, then their whole gr1: single-warp tasks, ~0.3 ms of pure latency -- while the main stream
+       * runs the gr1 rate loop of all other frames. */
       int* const c0 = fresh_counter(); int* const c1 = fresh_counter(); int* const c2 = fresh_counter();
       int* const c3 = fresh_counter(); int* const c4 = fresh_counter();
       cudaEventRecord(ev_fork, st_main);
       cudaStreamWaitEvent(st_repair, ev_fork, 0);
       /* the main stream's persistent grid would occupy every block slot for a millisecond: it leaves Q_REPAIR_BLOCKS slots
-       * free (1.5 % of its warps) and the repair kernels never ask for more (the short list holds a handful of frames) */
+       * free (1.5 % of its warps) and the repair kernels never ask for more */
       const int gq = Q_REPAIR_BLOCKS, gs = Q_REPAIR_BLOCKS;
-      const int* cp = B.counter + 1;
-      k_q_outer<<<gq, Q_THREADS, smem, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 0, list2, cp, (int)F, 1, c0);
-      k_q_finish<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 0, list2, cp, (int)F, 1, c1);
-      k_q_search<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, 1, list2, cp, (int)F, 1, c2, list2, B.counter + 1);
-      k_q_outer<<<gq, Q_THREADS, smem, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 1, list2, cp, (int)F, 2, c3);
-      k_q_finish<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 1, list2, cp, (int)F, 2, c4);
+      const int* cp = B.counter + 2;
+      k_q_outer<<<gq, Q_THREADS, smem, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 0, list3, cp, (int)F, 1, c0);
+      k_q_finish<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 0, list3, cp, (int)F, 1, c1);
+      k_q_search<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, 1, list3, cp, (int)F, 1, c2, list2, B.counter + 1,
+                                                          list3, B.counter + 2);
+      k_q_outer<<<gq, Q_THREADS, smem, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 1, list3, cp, (int)F, 2, c3);
+      k_q_finish<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 1, list3, cp, (int)F, 2, c4);
       cudaEventRecord(ev_join, st_repair);
       (*launches) += 5;
       forked = true;

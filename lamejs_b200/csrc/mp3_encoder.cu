@@ -169,7 +169,7 @@ struct Workspace {
     CK(cudaMalloc(&d_xrq, sizeof(float) * (size_t)U * nch * 576));
     CK(cudaMalloc(&d_xrpow, sizeof(float) * (size_t)U * nch * 576));
     CK(cudaMalloc(&d_prep, sizeof(GcPrep) * (size_t)U * nch));
-    CK(cudaMalloc(&d_dirty, sizeof(int) * 2 * (size_t)(F + 1)));
+    CK(cudaMalloc(&d_dirty, sizeof(int) * 3 * (size_t)(F + 1)));
     CK(cudaMalloc(&d_counter, sizeof(int) * Q_NCOUNTERS));
     CK(cudaMalloc(&d_scan, sizeof(ScanChunk) * (size_t)(F / SCAN_FRAMES + S + 1)));
     return 0;
