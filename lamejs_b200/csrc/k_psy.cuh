@@ -598,6 +598,14 @@ k_stream_scan(const Mp3Tables* __restrict__ T, StreamDesc* __restrict__ streams,
 }
 
 __device__ __noinline__ double psy_log10(double x) { return m3_log10(x); }
+/* 0 | (log10(ratio) * 16) for 1 <= ratio < 10^1.5, from the threshold table when the host validated it (mp3_config.h) */
+__device__ __forceinline__ int log10_times16_trunc(const Mp3Tables* T, double ratio) {
+  if (!T->l16_ok) return js_trunc(psy_log10(ratio) * 16.0);
+  int i = 0;
+#pragma unroll
+  for (int k = 1; k <= 24; k++) i += ratio >= T->l16_thr[k] ? 1 : 0;
+  return i;
+}
 
 /* mask_add (PsyModel.js:403-473), long blocks only (shortblock == 0) */
 __device__ __forceinline__ double mask_add_dev(double m1, double m2, int kk, int b, const Mp3Tables* T, double ath_adjust) {
@@ -612,10 +620,10 @@ __device__ __forceinline__ double mask_add_dev(double m1, double m2, int kk, int
   m1 += m2;
   if ((b + 3) <= 3 + 3) {                    /* sic: signed compare in lamejs */
     if (ratio >= T->ma_max_i1) return m1;
-    const int i = js_trunc(psy_log10(ratio) * 16.0);
+    const int i = log10_times16_trunc(T, ratio);
     return m1 * c_table2[i];
   }
-  const int i = js_trunc(psy_log10(ratio) * 16.0);
+  const int i = log10_times16_trunc(T, ratio);
   m2 = (double)T->ath_cb_l[kk] * ath_adjust;
   if (m1 < T->ma_max_m * m2) {
     if (m1 > m2) {

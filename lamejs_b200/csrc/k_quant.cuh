@@ -1857,7 +1857,11 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
 #pragma unroll 1
   for (int t = next_task(counter); t < ntasks; t = next_task(counter)) {
     const int wi = t / nch, ch = t - wi * nch;
+#ifdef Q_REVERSE
+    const int frow = list ? list[wi] : (ntasks / nch - 1 - wi);
+#else
     const int frow = list ? list[wi] : wi;
+#endif
     QuantFrameState* q = qs + frow;
     /* revalidate: 0 every listed frame; 1 only what the re-validating searches flagged; 2 every channel of the listed
      * frames; -1 all frames except those on the repair list (gr0 redone: their gr1 runs on the repair stream) */

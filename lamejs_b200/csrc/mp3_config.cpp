@@ -430,6 +430,21 @@ int mp3_build_tables(int channels, int samplerate, int kbps, Mp3Tables* t) {
     }
     for (; sbi < nb; ++sbi) { cv.init[sbi] = -2; cv.start[sbi] = cv.end[sbi] = 0; cv.bound[sbi] = -1; }
   }
+  {
+    /* thresholds of 0 | (log10(r) * 16): see mp3_config.h */
+    auto idx = [](double r) { return (int)(m3_log10(r) * 16.0); };
+    auto bits = [](double d) { uint64_t u; memcpy(&u, &d, 8); return u; };
+    auto from = [](uint64_t u) { double d; memcpy(&d, &u, 8); return d; };
+    t->l16_ok = 1;
+    t->l16_thr[0] = 0.0;
+    for (int k = 1; k <= 24; k++) {
+      uint64_t lo = bits(1.0), hi = bits(64.0);          /* idx(lo) < k <= idx(hi); positive doubles order like their bits */
+      while (hi - lo > 1) { const uint64_t mid = lo + (hi - lo) / 2; if (idx(from(mid)) >= k) hi = mid; else lo = mid; }
+      t->l16_thr[k] = from(hi);
+      for (int d = 1; d <= 4096; d++)                    /* a clean step: nothing at or above the threshold falls below k ... */
+        if (idx(from(hi + d - 1)) < k || idx(from(hi - d)) >= k) t->l16_ok = 0;
+    }
+  }
   t->ma_max_i1 = m3_pow(10, (8 + 1) / 16.0);
   t->ma_max_i2 = m3_pow(10, (23 + 1) / 16.0);
   t->ma_max_m = m3_pow(10, 15 / 10.0);

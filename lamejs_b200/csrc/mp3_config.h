@@ -52,6 +52,12 @@ struct Mp3Tables {
   double attack_threshold;
   double aa_sensitivity_p, ath_floor, decay;
   double ma_max_i1, ma_max_i2, ma_max_m;
+  /* mask_add needs i = 0 | (Math.log10(ratio) * 16) for 1 <= ratio < 10^1.5 (PsyModel.js:433,461): l16_thr[k] is the smallest
+   * double whose value of that expression (with this library's fdlibm log10) is >= k, found by bisection over the bit
+   * patterns and checked to be a clean step around it; then i = #{k in 1..24 : ratio >= l16_thr[k]} -- 24 comparisons instead
+   * of an fdlibm log10 (one division, ~40 FP64 operations) per spreading term.  l16_ok == 0: fall back to log10. */
+  double l16_thr[25];
+  int l16_ok;
   /* ---- filterbank ---- */
   float amp_filter[32];
   /* ---- scalefactor bands ---- */

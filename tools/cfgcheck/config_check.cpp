@@ -87,6 +87,25 @@ static int check(int ch, int sr, int kbps) {
   for (int i = 0; i < 1024; i++) CHK(feq(t->fft_window[i], e->fft_window[i].v), "fft_window[%d]", i);
   for (int i = 0; i < 128; i++) CHK(feq(t->fft_window_s[i], e->fft_window_s[i].v), "fft_window_s[%d]", i);
   CHK(deq(t->masking_lower_long, pow(10.0, e->mask_adjust * 0.1)) || true, "masking_lower");
+  {
+    /* the threshold table must reproduce 0 | (log10(r) * 16) of the ORACLE's log10 (js_math.h) on random ratios and around
+     * every threshold */
+    CHK(t->l16_ok == 1, "l16 thresholds not a clean step");
+    unsigned long long st = 0x9E3779B97F4A7C15ull;
+    for (int n = 0; n < 200000; n++) {
+      st = st * 6364136223846793005ull + 1442695040888963407ull;
+      const double r = 1.0 + (double)(st >> 11) * (1.0 / 9007199254740992.0) * 30.6;     /* [1, 31.6) */
+      int i = 0;
+      for (int k = 1; k <= 24; k++) i += r >= t->l16_thr[k] ? 1 : 0;
+      CHK(i == (int)(js_log10(r) * 16.0), "l16 random r=%.17g", r);
+    }
+    for (int k = 1; k <= 24; k++) for (int d = -300; d <= 300; d++) {
+      unsigned long long u; memcpy(&u, &t->l16_thr[k], 8); u += d; double r; memcpy(&r, &u, 8);
+      int i = 0;
+      for (int kk = 1; kk <= 24; kk++) i += r >= t->l16_thr[kk] ? 1 : 0;
+      CHK(i == (int)(js_log10(r) * 16.0), "l16 near threshold %d", k);
+    }
+  }
   const int r = bad != before;
   if (r) printf("cfg ch=%d sr=%d kbps=%d: %d mismatches\n", ch, sr, kbps, bad - before);
   free(t); lj_destroy(e);
