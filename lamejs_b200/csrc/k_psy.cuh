@@ -74,13 +74,16 @@ static int psy_upload_constants() {
 /* ---- one butterfly task of an FHT stage (FFT.js:31-115), fz float32 in shared memory ------------------- */
 /* one pad word per 16 floats: the stage-0/1 butterflies stride 16 / 64 floats across lanes (first profile: 116 M bank conflicts) */
 #define FHT_PAD(i) ((i) + ((i) >> 4))
-__device__ __forceinline__ void fht_task(f32s* fz, int n, int stage, int task, const double* __restrict__ tw, const int* tw_off) {
+/* Stage `stage` (k1 = 4, 16, 64, 256) of an n-point transform consists of n / (8 k1) groups of kx = k1 / 2 tasks: task i = 0
+ * does the group's two twiddle-free butterflies (at the group base and at base + kx), task i = 1..kx-1 the butterfly pair
+ * (base + i, base + k1 - i).  Tasks per stage: n / 8 -- 128 for the 1024-point, 32 for a 256-point transform -- and group /
+ * index follow from the task number by shifts (stage is a compile-time constant after unrolling). */
+__device__ __forceinline__ void fht_task(f32s* fz, int stage, int task, const double* __restrict__ tw, const int* tw_off) {
   const int k1 = 4 << (2 * stage);          /* 4,16,64,256 */
   const int kx = k1 >> 1, k2 = k1 << 1, k3 = k2 + k1, k4 = k2 << 1;
-  const int groups = n / k4;
-  if (task < 2 * groups) {
-    const int g = task >> 1;
-    if ((task & 1) == 0) {
+  const int g = task >> (2 * stage + 1), i = task & (kx - 1);
+  if (i == 0) {
+    {
       const int fi = g * k4;
       double f0, f1, f2, f3;
       f1 = fz[FHT_PAD(fi + 0)] - fz[FHT_PAD(fi + k1)];
@@ -91,7 +94,8 @@ __device__ __forceinline__ void fht_task(f32s* fz, int n, int stage, int task, c
       fz[FHT_PAD(fi + 0)] = f0 + f2;
       fz[FHT_PAD(fi + k3)] = f1 - f3;
       fz[FHT_PAD(fi + k1)] = f1 + f3;
-    } else {
+    }
+    {
       const int gi = g * k4 + kx;
       double f0, f1, f2, f3;
       f1 = fz[FHT_PAD(gi + 0)] - fz[FHT_PAD(gi + k1)];
@@ -105,8 +109,6 @@ __device__ __forceinline__ void fht_task(f32s* fz, int n, int stage, int task, c
     }
     return;
   }
-  const int q = task - 2 * groups;
-  const int g = q / (kx - 1), i = 1 + q - g * (kx - 1);
   const double* e = tw + 4 * (tw_off[stage] + i);
   const double c1 = e[0], s1 = e[1], c2 = e[2], s2 = e[3];
   const int fi = g * k4 + i, gi = g * k4 + k1 - i;
@@ -135,10 +137,6 @@ __device__ __forceinline__ void fht_task(f32s* fz, int n, int stage, int task, c
   fz[FHT_PAD(gi + 0)] = g0 + a;
   fz[FHT_PAD(fi + k3)] = f1 - b;
   fz[FHT_PAD(fi + k1)] = f1 + b;
-}
-__device__ __forceinline__ int fht_tasks(int n, int stage) {
-  const int k1 = 4 << (2 * stage), kx = k1 >> 1, k4 = k1 << 2;
-  return (n / k4) * (kx + 1);
 }
 
 /* psy row of (stream z, relative unit u >= -1): unit_base + z + u + 1 */
@@ -286,13 +284,14 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   /* 9 sub-block peaks of the high-passed signal (PsyModel.js:1125-1132): max(1, |hp|) over 64 samples each; the
    * values are non-negative float32, whose order is the order of their bit patterns */
   for (int i = tid; i < 576; i += PSY_THREADS) atomicMax(&s_peak[i >> 6], __float_as_int(fabsf(hp[i].v)));
-  /* FHT stages: long transform (4 stages) and the three short ones (3 stages) share the loop */
+  /* FHT stages: 128 tasks per stage for the long transform (4 stages), 32 for each short one (3 stages); task numbers map to
+   * butterflies by shifts (the earlier enumeration needed integer divisions: 16 % of this kernel's instructions) */
+#pragma unroll
   for (int stage = 0; stage < 4; stage++) {
-    const int tl = fht_tasks(1024, stage);
-    const int tsn = stage < 3 ? fht_tasks(256, stage) : 0;
-    for (int t = tid; t < tl + 3 * tsn; t += PSY_THREADS) {
-      if (t < tl) fht_task(wl, 1024, stage, t, T->tw, T->tw_off);
-      else { const int q = t - tl; fht_task(wsh[q / tsn], 256, stage, q % tsn, T->tw, T->tw_off); }
+    const int nt = 128 + (stage < 3 ? 96 : 0);
+    for (int t = tid; t < nt; t += PSY_THREADS) {
+      if (t < 128) fht_task(wl, stage, t, T->tw, T->tw_off);
+      else fht_task(wsh[(t - 128) >> 5], stage, (t - 128) & 31, T->tw, T->tw_off);
     }
     __syncthreads();
   }
