@@ -71,6 +71,24 @@ static int psy_upload_constants() {
   return 0;
 }
 
+/* Float32 cell of the FHT work arrays.  Reading widens float32 -> double; the hardware conversion runs on the XU pipe, which
+ * the round-2 profile shows 52 % busy (the limiter of k_psy_analysis), while the integer pipe idles.  PSY_ALU_WIDEN widens with
+ * integer operations instead -- exact for zero and normal numbers; FHT data are products and sums of window x Int16 samples,
+ * never subnormal, infinite or NaN (>= 1e-16 in magnitude or exactly 0).  Writing rounds with the hardware conversion. */
+struct f32w {
+  float v;
+  __device__ __forceinline__ operator double() const {
+#ifdef PSY_ALU_WIDEN
+    const unsigned u = __float_as_uint(v);
+    const unsigned hi = (u & 0x7fffffffu) ? ((u & 0x80000000u) | (((u >> 3) & 0x0fffffffu) + 0x38000000u)) : u;
+    return __hiloint2double((int)hi, (int)(u << 29));
+#else
+    return (double)v;
+#endif
+  }
+  __device__ __forceinline__ f32w& operator=(double d) { v = (float)d; return *this; }
+};
+
 /* ---- one butterfly task of an FHT stage (FFT.js:31-115), fz float32 in shared memory ------------------- */
 /* one pad word per 16 floats: the stage-0/1 butterflies stride 16 / 64 floats across lanes (first profile: 116 M bank conflicts) */
 #define FHT_PAD(i) ((i) + ((i) >> 4))
@@ -78,7 +96,7 @@ static int psy_upload_constants() {
  * does the group's two twiddle-free butterflies (at the group base and at base + kx), task i = 1..kx-1 the butterfly pair
  * (base + i, base + k1 - i).  Tasks per stage: n / 8 -- 128 for the 1024-point, 32 for a 256-point transform -- and group /
  * index follow from the task number by shifts (stage is a compile-time constant after unrolling). */
-__device__ __forceinline__ void fht_task(f32s* fz, int stage, int task, const double* __restrict__ tw, const int* tw_off) {
+__device__ __forceinline__ void fht_task(f32w* fz, int stage, int task, const double* __restrict__ tw, const int* tw_off) {
   const int k1 = 4 << (2 * stage);          /* 4,16,64,256 */
   const int kx = k1 >> 1, k2 = k1 << 1, k3 = k2 + k1, k4 = k2 << 1;
   const int g = task >> (2 * stage + 1), i = task & (kx - 1);
@@ -192,8 +210,8 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   f32s* const s_avg = s_max + MP3_CBANDS;                                         /* [64] */
   f32s (*const s_ebs)[MP3_CBANDS] = reinterpret_cast<f32s (*)[MP3_CBANDS]>(s_avg + MP3_CBANDS);   /* [3][64] */
   static_assert(2064 + 1552 + 2 * 4 * MP3_CBANDS + 3 * 4 * MP3_CBANDS <= (int)sizeof(s_u), "energies must fit the PCM span");
-  __shared__ f32s wl[1024 + 64];
-  __shared__ f32s wsh[3][256 + 16];
+  __shared__ f32w wl[1024 + 64];
+  __shared__ f32w wsh[3][256 + 16];
   __shared__ f32s hp[576];
   __shared__ int s_peak[9];
   if (tid < 9) s_peak[tid] = __float_as_int(1.0f);

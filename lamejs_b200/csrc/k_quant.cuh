@@ -179,7 +179,8 @@ __device__ unsigned long long g_qstats[16];
 #define Q_CB_UNROLL 1
 #endif
 #ifndef Q_FUSE_FINISH
-#define Q_FUSE_FINISH 1
+#define Q_FUSE_FINISH 0         /* finish tasks inside the rate-loop launch (fills its tail): measured 2.58 vs 2.42 ms for
+                                  rate loop + finish on C2 -- the bigger kernel spills and re-pollutes the I-cache; kept as a knob */
 #endif
 #ifndef Q_CN_UNROLL
 #define Q_CN_UNROLL 2          /* calc_noise band chain: A/B 1 / 2 / 4 -> k_q_outer 2.27 / 2.18 / 2.19 ms (C2) */
@@ -1927,6 +1928,7 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
    * on iteration_finish_one of the same granule instead of idling through the kernel's tail (a rate loop lasts ~0.25 ms).
    * Finish task t waits for rate-loop task t (same numbering, same skip rules); every rate-loop task has been pulled by a
    * resident warp by then, so the wait always ends.  Rows written by other SMs during this kernel are read through L2. ---- */
+#if Q_FUSE_FINISH
   if (counter2 == nullptr) return;
 #pragma unroll 1
   for (int t = next_task(counter2); t < ntasks; t = next_task(counter2)) {
@@ -1954,6 +1956,9 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
     if (gr == 0) { if (lane == 0) q->used0[ch] = wk->b.part2_3_length + wk->b.part2_length; }
     else if (lane < 4) q->scfsi[ch][lane] = ws->scfsi[lane];
   }
+#else
+  (void)counter2;
+#endif
 }
 
 /* ---- iteration_finish_one (Quantize.js:1059-1078) of granule `gr`: best_scalefac_store (+ scfsi in gr1) and
