@@ -1280,10 +1280,7 @@ struct DivScratch {
 };
 static_assert(sizeof(DivScratch) <= 576 * sizeof(float), "DivScratch must fit into the xrpow array");
 
-/* per-band statistics of the pairs below big_values; returns the number of bands (a partial last band counts).
- * The pairs are walked 32 at a time, one per lane; lanes whose pairs lie in the same band form a group (__match_any), the
- * group's integer sums / maximum come from masked warp reductions and its first lane adds them to the band's row.  (The first
- * version gave every (band, class) to one lane, which then walked the band alone: the 76-line band set the time.) */
+/* per-band statistics of the pairs below big_values; returns the number of bands (a partial last band counts) */
 __device__ __noinline__ int band_stats_w(const Mp3Tables* T, const short* ix, int bigv, DivScratch* ds) {
   const int lane = LANE;
   const unsigned* w32 = reinterpret_cast<const unsigned*>(ix);
@@ -1292,33 +1289,34 @@ __device__ __noinline__ int band_stats_w(const Mp3Tables* T, const short* ix, in
   const int nb = (B < 22 && T->sfb_l[B] < bigv) ? B + 1 : B;      /* band B = [sfb_l[B], big_values) if not empty */
   __syncwarp();
 #pragma unroll 1
-  for (int t = lane; t < 23 * 7; t += 32) { (&ds->ab[0][0])[t] = 0u; (&ds->cc[0][0])[t] = 0; }
-  if (lane < 23) { ds->bmax[lane] = 0; ds->nesc[lane] = 0; }
-  __syncwarp();
-  const unsigned char* __restrict__ band_of = T->geo[0].sfb_of_line;
-  const int np = bigv >> 1;
+  for (int b = lane; b < nb; b += 32) {
+    const int lo = T->sfb_l[b] >> 1, hi = (b < B ? T->sfb_l[b + 1] : bigv) >> 1;
+    unsigned m = 0, ne = 0;
 #pragma unroll 1
-  for (int p0 = 0; p0 < np; p0 += 32) {
-    const int p = p0 + lane;
-    const bool in = p < np;
-    const unsigned w = in ? w32[p] : 0u;
-    const int b = in ? (int)band_of[2 * p] : 31;                 /* idle lanes: a band number no pair has */
-    const unsigned grp = __match_any_sync(Q_FULL, b);
-    const bool lead = in && (__ffs(grp) - 1) == lane;
-    const unsigned x = w & 0xffffu, y = w >> 16;
-    const unsigned mx = __reduce_max_sync(grp, max(x, y));
-    const unsigned ne = __reduce_add_sync(grp, (unsigned)(x > 14u) + (unsigned)(y > 14u));
-    if (lead) { ds->bmax[b] = (unsigned short)max((unsigned)ds->bmax[b], mx); ds->nesc[b] = (unsigned short)(ds->nesc[b] + ne); }
-    const unsigned idx = min(x, 15u) * 16 + min(y, 15u);
-#pragma unroll
-    for (int c = 0; c < 7; c++) {                                /* classes below the band's own are never read later */
-      const unsigned v = in ? __ldg(&g_cat_tab[c][idx]) : 0u;
-      const unsigned ab = __reduce_add_sync(grp, (v & 0x7ffu) | (((v >> 11) & 0x7ffu) << 16));
-      const unsigned cc = __reduce_add_sync(grp, v >> 22);
-      if (lead) { ds->ab[b][c] += ab; ds->cc[b][c] = (unsigned short)(ds->cc[b][c] + cc); }
-    }
-    __syncwarp();
+    for (int p = lo; p < hi; p++) { const unsigned w = w32[p]; m = __vmaxu2(m, w); ne += ((w & 0xffffu) > 14u) + ((w >> 16) > 14u); }
+    ds->bmax[b] = (unsigned short)max(m & 0xffffu, m >> 16);
+    ds->nesc[b] = (unsigned short)ne;
   }
+  __syncwarp();
+#pragma unroll 1
+  for (int t = lane; t < nb * 7; t += 32) {                       /* one (band, class) task per lane and round */
+    const int b = t / 7, c = t - 7 * b;
+    const int mx = ds->bmax[b];
+    const int lowc = mx <= 1 ? 0 : (mx <= 3 ? mx - 1 : (mx <= 5 ? 3 : (mx <= 7 ? 4 : (mx <= 15 ? 5 : 6))));
+    if (c < lowc) continue;
+    const unsigned int* tab = g_cat_tab[c];
+    const int lo = T->sfb_l[b] >> 1, hi = (b < B ? T->sfb_l[b + 1] : bigv) >> 1;
+    unsigned sa = 0, sb = 0, sc = 0;
+#pragma unroll 1
+    for (int p = lo; p < hi; p++) {
+      const unsigned w = w32[p];
+      const unsigned v = __ldg(&tab[min(w & 0xffffu, 15u) * 16 + min(w >> 16, 15u)]);
+      sa += v & 0x7ffu; sb += (v >> 11) & 0x7ffu; sc += v >> 22;
+    }
+    ds->ab[b][c] = sa | (sb << 16);
+    ds->cc[b][c] = (unsigned short)sc;
+  }
+  __syncwarp();
   return nb;
 }
 
