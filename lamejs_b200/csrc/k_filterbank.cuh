@@ -1,19 +1,20 @@
-/* k_filterbank.cuh -- K1: 32-band polyphase analysis + MDCT + alias reduction, G granules per block.
+/* k_filterbank.cuh -- K1a: 32-band polyphase analysis, K1b: MDCT + alias reduction.
  *
  * Replaces lamejs NewMDCT.mdct_sub48 (reference src/js/NewMDCT.js:1053-1161) with its callees
  * window_subband (:534-914), mdct_long (:981-1051), mdct_short (:927-979).
  *
  * Parallel decomposition:
- *   phase 0  stage the block's PCM span in shared memory as double holding the scaled float32 value (coalesced
- *            Int16 loads; the f32->f64 widening each of the 16 taps per sample would need is paid once -- the
- *            first profile showed the conversion (XU) pipe, not FP64, as the busiest unit; one pad word per 32
- *            samples so that the stride-32 window taps hit distinct banks)
- *   phase 1  one thread per (granule slab, time slot): a full window_subband -- 512-tap folded window in
- *            double, 32-point butterfly network in registers -- writes 32 subband samples
- *   phase 2  one thread per (granule, subband): block-type windowing + 36->18 / 3x(12->6) MDCT
- *   phase 3  alias-reduction butterflies across subband boundaries, then coalesced store of xr
- * The previous granule's subband slab (the 50% MDCT overlap lamejs keeps in gfc.sb_sample) is recomputed
- * from PCM: 1/G redundant work instead of a cross-block dependency.
+ *   k_subband_analysis (needs PCM only; runs beside the psy analysis / under the per-stream scan)
+ *     phase 0  stage the block's PCM span in shared memory as double holding the scaled float32 value (coalesced
+ *              Int16 loads; the f32->f64 widening each of the 16 taps per sample would need is paid once -- the
+ *              first profile showed the conversion (XU) pipe, not FP64, as the busiest unit; one pad word per 32
+ *              samples so that the stride-32 window taps hit distinct banks)
+ *     phase 1  one thread per (granule slab, time slot): a full window_subband -- 512-tap folded window in
+ *              double, 32-point butterfly network in registers -- writes 32 subband samples; slabs go to HBM
+ *              (lamejs keeps them in gfc.sb_sample: the MDCT overlaps each granule with its predecessor)
+ *   k_mdct (needs the block types)
+ *     phase 2  one thread per (granule, subband): block-type windowing + 36->18 / 3x(12->6) MDCT
+ *     phase 3  alias-reduction butterflies across subband boundaries, then coalesced store of xr
  * Every arithmetic statement keeps the reference's operand order; doubles with float32 store points.
  */
 #ifndef MP3B200_K_FILTERBANK_CUH
@@ -292,35 +293,40 @@ __device__ __forceinline__ void mdct_short_dev(f32s* io) {
   }
 }
 
-/* grid: (ceil(max_granules / FB_G), nch, nstreams); block: FB_THREADS.
- * blocktype: int8 [granule row][2]; xr_out: float [granule row][nch][576]. */
+/* ---- K1a: polyphase analysis of FB_SLABS granules per block -> subband slabs in HBM ----
+ * A slab (18 time slots x 32 subbands, float32: lamejs gfc.sb_sample) depends on PCM only, so this kernel is launched at
+ * the start of the pipeline on a side stream: its blocks fill the SMs the psy analysis has left and the whole machine while the
+ * per-stream scan (one block per stream) decides the block types.  Slab rows use the psy row numbering (one leading row per
+ * stream for granule -1, the MDCT overlap of the first granule): row = unit_base + z + u + 1.
+ * grid: (ceil((max_granules + 1) / FB_SLABS), nch, nstreams); block: FB_THREADS. */
 #ifndef FB_MIN_BLOCKS
 #define FB_MIN_BLOCKS 3
 #endif
+#define FB_SLABS (FB_G + 1)
 __global__ void __launch_bounds__(FB_THREADS, FB_MIN_BLOCKS)
-k_filterbank_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams,
-                  const signed char* __restrict__ blocktype, float* __restrict__ xr_out) {
-  const StreamDesc& sd = streams[blockIdx.z];
+k_subband_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, float* __restrict__ slab_out) {
+  const int z = blockIdx.z;
+  const StreamDesc& sd = streams[z];
   const int ch = blockIdx.y;
   const int ngr = sd.nframes * T->mode_gr;
-  const int g0 = blockIdx.x * FB_G;                 /* first granule (relative to frame0) of this block */
-  if (g0 >= ngr) return;
-  const int gcount = min(FB_G, ngr - g0);
-  const long long c0 = (long long)T->mode_gr * sd.frame0 + g0;   /* absolute granule index */
+  const int u0 = (int)blockIdx.x * FB_SLABS - 1;    /* first granule (relative to frame0) of this block, -1 = overlap row */
+  if (u0 >= ngr) return;
+  const int scount = min(FB_SLABS, ngr - u0);
+  const long long cs = (long long)T->mode_gr * sd.frame0 + u0;   /* absolute granule index of slab 0 */
   const int nch = T->nch;
 
   extern __shared__ double smem_d[];
-  double* pcm = smem_d;                             /* FB_PCM_WORDS doubles, later reused as xr[FB_G][576] float32 */
-  f32s* slab = reinterpret_cast<f32s*>(smem_d + FB_PCM_WORDS);   /* [FB_G+1][18][33] */
+  double* pcm = smem_d;                             /* FB_PCM_WORDS doubles */
+  f32s* slab = reinterpret_cast<f32s*>(smem_d + FB_PCM_WORDS);   /* [FB_SLABS][18][33] */
   __shared__ float s_amp[32];                       /* amp_filter by subband-array position */
-  __shared__ int s_bt[FB_G];
 
   const int tid = threadIdx.x;
-  /* ---- phase 0: stage PCM.  sample j of the span is stream sample lo + j ---- */
-  const long long lo = 576 * c0 - 1104;
+  /* ---- phase 0: stage PCM.  sample j of the span is stream sample lo + j; slab s, time slot j has its window origin
+   * (reference wkPos) at stream sample 576 (cs + s) - 242 + 32 j = span index 576 s + 286 + 32 j ---- */
+  const long long lo = 576 * (cs + 1) - 1104;
   const int scale_applied = T->scale_applied;
   const double scale = T->scale;
-  const int span = 576 * gcount + 1055;
+  const int span = 576 * (scount - 1) + 1055;
   {
     /* 8 independent Int16 loads per thread in flight (one dependent load per iteration left this phase, a third of the
      * kernel's samples in the round-2 profile, waiting for HBM latency) */
@@ -339,20 +345,18 @@ k_filterbank_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict_
       for (int k = 0; k < 8; k++) {
         const int j = j0 + k * FB_THREADS;
         if (j < span) {
-          float f = (float)v[k];                       /* load_pcm: Float32(Int16 * scale) */
-          if (scale_applied) f = (float)((double)f * scale);
-          pcm[fb_pad(j)] = (double)f;
+          double d = (double)(int)v[k];                /* load_pcm: Float32(Int16 * scale); unscaled: one conversion */
+          if (scale_applied) d = (double)(float)(d * scale);
+          pcm[fb_pad(j)] = d;
         }
       }
     }
   }
   if (tid < 32) s_amp[c_sb_order[tid]] = T->amp_filter[tid];
-  if (tid < gcount) s_bt[tid] = blocktype[(size_t)(sd.unit_base + g0 + tid) * 2 + ch];
   __syncthreads();
 
-  /* ---- phase 1: subband analysis.  slab s = granule c0-1+s; time slot j; window origin (reference
-   * wkPos) = stream sample 576*c - 242 + 32*j  ->  span index 576*s + 286 + 32*j ---- */
-  for (int w = tid; w < (gcount + 1) * 18; w += FB_THREADS) {
+  /* ---- phase 1: subband analysis, thread = (slab, time slot) ---- */
+  for (int w = tid; w < scount * 18; w += FB_THREADS) {
     const int s = w / 18, j = w - s * 18;
     f32s a[32];
     window_subband_dev(pcm, 576 * s + 286 + 32 * j, a);
@@ -368,55 +372,92 @@ k_filterbank_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict_
     }
   }
   __syncthreads();
+  /* coalesced store: slab rows are 576 consecutive floats [slot][subband] */
+  float* const dst = slab_out + (((size_t)sd.unit_base + z + u0 + 1) * nch + ch) * 576;
+  for (int w = tid; w < scount * 576; w += FB_THREADS) {
+    const int s = w / 576, r = w - s * 576;
+    dst[(size_t)s * nch * 576 + r] = slab[(s * 18 + (r >> 5)) * FB_SLAB_STRIDE + (r & 31)].v;
+  }
+}
 
-  /* ---- phase 2: windowing + MDCT, thread = (granule g, band) ---- */
-  f32s* xr = reinterpret_cast<f32s*>(pcm);          /* [FB_G][576] */
-  for (int w = tid; w < gcount * 32; w += FB_THREADS) {
-    const int g = w >> 5, band = w & 31;
-    const int type = s_bt[g];
-    const int ob = c_sb_order[band];
-    const f32s* band0 = slab + (g * 18) * FB_SLAB_STRIDE + ob;        /* previous granule */
-    const f32s* band1 = slab + ((g + 1) * 18) * FB_SLAB_STRIDE + ob;  /* current granule */
-#define B0(k) band0[(k) * FB_SLAB_STRIDE]
-#define B1(k) band1[(k) * FB_SLAB_STRIDE]
-    f32s* o = xr + g * 576 + band * 18;
-    if ((double)s_amp[ob] < 1e-12) {
+/* ---- K1b: block-type windowing + MDCT + alias reduction from the slabs (needs the block types, i.e. the scan) ----
+ * thread = (granule, subband); a warp reads one 128-byte line of the previous and of the current slab per time slot.
+ * grid: (ceil(max_granules / FB_G), nch, nstreams); block: FB_G * 32.
+ * blocktype: int8 [granule row][2]; xr_out: float [granule row][nch][576]. */
+__global__ void __launch_bounds__(FB_G * 32)
+k_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, const float* __restrict__ slab_in,
+       const signed char* __restrict__ blocktype, float* __restrict__ xr_out) {
+  const int z = blockIdx.z;
+  const StreamDesc& sd = streams[z];
+  const int ch = blockIdx.y;
+  const int ngr = sd.nframes * T->mode_gr;
+  const int g0 = blockIdx.x * FB_G;                 /* first granule (relative to frame0) of this block */
+  if (g0 >= ngr) return;
+  const int gcount = min(FB_G, ngr - g0);
+  const int nch = T->nch;
+  __shared__ f32s xr[FB_G * 576];
+  __shared__ float s_amp[32];
+  __shared__ int s_bt[FB_G];
+  const int tid = threadIdx.x;
+  if (tid < 32) s_amp[c_sb_order[tid]] = T->amp_filter[tid];
+  if (tid < gcount) s_bt[tid] = blocktype[(size_t)(sd.unit_base + g0 + tid) * 2 + ch];
+  __syncthreads();
+
+  /* ---- windowing + MDCT ---- */
+  {
+    const int g = tid >> 5, band = tid & 31;
+    if (g < gcount) {
+      const int type = s_bt[g];
+      const int ob = c_sb_order[band];
+      f32s* o = xr + g * 576 + band * 18;
+      if ((double)s_amp[ob] < 1e-12) {
 #pragma unroll
-      for (int k = 0; k < 18; k++) o[k] = 0.0;
-    } else if (type == BT_SHORT) {
-      f32s io[18];
+        for (int k = 0; k < 18; k++) o[k] = 0.0;
+      } else {
+        /* slab row of granule g0 + g - 1 (previous) and g0 + g (current): rows unit_base + z + (g0 + g), + 1 */
+        const float* p0 = slab_in + (((size_t)sd.unit_base + z + g0 + g) * nch + ch) * 576 + ob;
+        const float* p1 = p0 + (size_t)nch * 576;
+        float b0[18], b1[18];
 #pragma unroll
-      for (int k = -3; k < 0; k++) {                 /* NewMDCT.js:1098-1112, static indices after unrolling */
-        const double wv = WS(k + 3);
-        io[k * 3 + 9] = B0(9 + k) * wv - B0(8 - k);
-        io[k * 3 + 18] = B0(14 - k) * wv + B0(15 + k);
-        io[k * 3 + 10] = B0(15 + k) * wv - B0(14 - k);
-        io[k * 3 + 19] = B1(2 - k) * wv + B1(3 + k);
-        io[k * 3 + 11] = B1(3 + k) * wv - B1(2 - k);
-        io[k * 3 + 20] = B1(8 - k) * wv + B1(9 + k);
-      }
-      mdct_short_dev(io);
+        for (int k = 0; k < 18; k++) { b0[k] = __ldg(p0 + 32 * k); b1[k] = __ldg(p1 + 32 * k); }   /* 36 loads in flight */
+#define B0(k) ((double)b0[(k)])
+#define B1(k) ((double)b1[(k)])
+        if (type == BT_SHORT) {
+          f32s io[18];
 #pragma unroll
-      for (int k = 0; k < 18; k++) o[k] = (double)io[k];
-    } else {
-      f32s work[18];
+          for (int k = -3; k < 0; k++) {                 /* NewMDCT.js:1098-1112, static indices after unrolling */
+            const double wv = WS(k + 3);
+            io[k * 3 + 9] = B0(9 + k) * wv - B0(8 - k);
+            io[k * 3 + 18] = B0(14 - k) * wv + B0(15 + k);
+            io[k * 3 + 10] = B0(15 + k) * wv - B0(14 - k);
+            io[k * 3 + 19] = B1(2 - k) * wv + B1(3 + k);
+            io[k * 3 + 11] = B1(3 + k) * wv - B1(2 - k);
+            io[k * 3 + 20] = B1(8 - k) * wv + B1(9 + k);
+          }
+          mdct_short_dev(io);
 #pragma unroll
-      for (int k = -9; k < 0; k++) {
-        double a, b;
-        a = MWIN(type, k + 27) * B1(k + 9) + MWIN(type, k + 36) * B1(8 - k);
-        b = MWIN(type, k + 9) * B0(k + 9) - MWIN(type, k + 18) * B0(8 - k);
-        work[k + 9] = a - b * WS(3 + k + 9);
-        work[k + 18] = a * WS(3 + k + 9) + b;
-      }
-      mdct_long_dev(o, work);
-    }
+          for (int k = 0; k < 18; k++) o[k] = (double)io[k];
+        } else {
+          f32s work[18];
+#pragma unroll
+          for (int k = -9; k < 0; k++) {
+            double a, b;
+            a = MWIN(type, k + 27) * B1(k + 9) + MWIN(type, k + 36) * B1(8 - k);
+            b = MWIN(type, k + 9) * B0(k + 9) - MWIN(type, k + 18) * B0(8 - k);
+            work[k + 9] = a - b * WS(3 + k + 9);
+            work[k + 18] = a * WS(3 + k + 9) + b;
+          }
+          mdct_long_dev(o, work);
+        }
 #undef B0
 #undef B1
+      }
+    }
   }
   __syncthreads();
 
-  /* ---- phase 3: alias reduction (NewMDCT.js:1133-1154): boundary `band` couples lines 18*band-1-k, 18*band+k ---- */
-  for (int w = tid; w < gcount * 31 * 8; w += FB_THREADS) {
+  /* ---- alias reduction (NewMDCT.js:1133-1154): boundary `band` couples lines 18*band-1-k, 18*band+k ---- */
+  for (int w = tid; w < gcount * 31 * 8; w += FB_G * 32) {
     const int g = w / 248, r = w - g * 248;
     const int band = 1 + (r >> 3), k = r & 7;
     if (s_bt[g] == BT_SHORT) continue;
@@ -428,7 +469,7 @@ k_filterbank_mdct(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict_
     e[k] = bd;
   }
   __syncthreads();
-  for (int w = tid; w < gcount * 576; w += FB_THREADS) {
+  for (int w = tid; w < gcount * 576; w += FB_G * 32) {
     const int g = w / 576, i = w - g * 576;
     xr_out[((size_t)(sd.unit_base + g0 + g) * nch + ch) * 576 + i] = xr[w].v;
   }

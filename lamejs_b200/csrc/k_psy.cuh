@@ -8,8 +8,8 @@
  * lamejs runs one psy call per granule ("unit" c, analysing stream samples [576c-224, 576c+800)) and carries
  * state from call to call.  Here the work is split by what it depends on:
  *   k_psy_analysis   pure function of PCM: fs/4 HPF + 9 sub-block peaks, 1024-pt and 3x256-pt FHT, line
- *                    energies, partition energies / tonality index, short-block spreading sums, the ordered 512-term
- *                    loudness sum (psycho_loudness_approx) on the one thread that owns no partition
+ *                    energies, partition energies / tonality index, short-block spreading sums
+ *   k_psy_loudness   the 512-term ordered loudness sum of every unit, one thread each (psycho_loudness_approx)
  *   k_attack_prepass pure function of two consecutive units: attack candidates (before the lastAttacks FSM)
  *   k_stream_scan    the only sequential part: per stream, the attack / block-type FSM and the ATH-adjust IIR
  *   k_psy_masking    long-block spreading with mask_add (needs ATH.adjust), short thresholds (need the previous
@@ -36,7 +36,7 @@ struct PsyUnit {
   float loudness;                   /* psycho_loudness_approx */
   unsigned char mask_idx[MP3_CBANDS];
   unsigned char attack[4];          /* pre-FSM ns_attacks[0..3] */
-  unsigned char pad_;
+  unsigned char fe_valid;           /* this launch wrote the row's line energies: k_psy_loudness owns `loudness` */
 };
 struct PsyRatioDev { float en_l[22], thm_l[22], en_s[13][3], thm_s[13][3]; };
 
@@ -84,10 +84,10 @@ struct f32w {
     return __hiloint2double((int)hi, (int)(u << 29));
 #else
     return (double)v;
-#endif
   }
   __device__ __forceinline__ f32w& operator=(double d) { v = (float)d; return *this; }
 };
+#endif
 
 /* ---- one butterfly task of an FHT stage (FFT.js:31-115), fz float32 in shared memory ------------------- */
 /* one pad word per 16 floats: the stage-0/1 butterflies stride 16 / 64 floats across lanes (first profile: 116 M bank conflicts) */
@@ -166,7 +166,7 @@ __device__ __forceinline__ size_t psy_row(const StreamDesc& sd, int z, int u) { 
 #endif
 __global__ void __launch_bounds__(PSY_THREADS, PSY_MIN_BLOCKS)
 k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ out,
-               int chunk, int nchunks, int u_base) {
+               float* __restrict__ fe_out, int chunk, int nchunks, int u_base) {
   const int z = blockIdx.z;
   const StreamDesc& sd = streams[z];
   const int u = (int)blockIdx.x + u_base;             /* relative unit, -1 = halo */
@@ -191,8 +191,12 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     for (int i = tid; i < 3 * MP3_CBANDS; i += PSY_THREADS) { (&o->ecb_s[0][0])[i] = 1.0; (&o->eb_s[0][0])[i] = 0.0f; }
     if (tid < MP3_CBANDS) { o->eb_l[tid] = 0.0f; o->mask_idx[tid] = 0; }
     if (tid < 9) o->peaks[tid] = 10.0f;
-    if (tid == 0) o->loudness = 0.0f;
+    if (tid == 0) { o->loudness = 0.0f; o->fe_valid = 0; }
     if (tid < 4) o->attack[tid] = 0;
+    {   /* k_psy_loudness streams every row: give it defined line energies (its result for this row is not stored) */
+      float* fg = fe_out + ((size_t)psy_row(sd, z, u) * nch + ch) * 512;
+      for (int j = tid; j < 512; j += PSY_THREADS) fg[j] = 0.0f;
+    }
     return;
   }
 
@@ -231,9 +235,10 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     for (int k = 0; k < NB; k++) {
       const int j = tid + k * PSY_THREADS;
       if (j < 1024) {
-        float f = (float)v[k];                         /* load_pcm: Float32(Int16 * scale) */
-        if (scale_applied) f = (float)((double)f * scale);
-        xs[j] = (double)f;
+        /* load_pcm: Float32(Int16 * scale); without a scale the Int16 widens to double in one conversion */
+        double d = (double)(int)v[k];
+        if (scale_applied) d = (double)(float)(d * scale);
+        xs[j] = d;
       }
     }
   }
@@ -344,17 +349,14 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     }
   }
   }
-  /* psycho_loudness_approx (PsyModel.js:241-249): loudness = sum_i energy[i] * eql_w[i] -- one ORDERED 512-term double sum --
-   * scaled by 1 / (14752^2 * 512).  The last thread of the block owns no partition in either of the two partition phases
-   * (its virtual threads 127 and 255 are partition 63 of a short sub-block: never a real one), so it walks the chain there,
-   * half in each phase, while the others work: the line energies never leave the SM (they used to go through HBM to a
-   * separate kernel: 82 MB per 10 k frames). */
-  double loud = 0.0;
-  if (tid == PSY_THREADS - 1) {
-#pragma unroll 4
-    for (int i = 0; i < 256; ++i) loud += (double)fe[i] * (double)T->eql_w[i];
+  /* psycho_loudness_approx is one ordered 512-term sum: k_psy_loudness does it with a thread per unit instead of
+   * stalling this block on a single lane; hand it the line energies */
+  {
+    float* fg = fe_out + ((size_t)psy_row(sd, z, u) * nch + ch) * 512;
+    for (int j = tid; j < 512; j += PSY_THREADS) fg[j] = fe[j].v;
   }
   if (tid < 9) o->peaks[tid] = __int_as_float(s_peak[tid]);
+  if (tid == 9) o->fe_valid = 1;
   __syncthreads();
 
   for (int vt = tid; vt < 256; vt += PSY_THREADS) {
@@ -387,11 +389,40 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     }
   }
   }
-  if (tid == PSY_THREADS - 1) {
+}
+
+/* psycho_loudness_approx (PsyModel.js:241-249): loudness = sum_i energy[i] * eql_w[i] (ordered, in double) scaled by
+ * 1 / (14752^2 * 512).  One thread per (unit, channel) row owns the ordered sum; the 128 rows of a block are streamed
+ * through shared memory in 32-column tiles so that the HBM reads are whole 128-byte lines.
+ * grid (ceil(rows / 128)), rows = all (unit+halo, channel) rows of the batch; `valid` marks rows K2 filled. */
+#define LOUD_ROWS 128
+__global__ void __launch_bounds__(LOUD_ROWS)
+k_psy_loudness(const Mp3Tables* __restrict__ T, const float* __restrict__ fe_in, PsyUnit* __restrict__ out, long long nrows) {
+  __shared__ float tile[LOUD_ROWS][33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long row0 = (long long)blockIdx.x * LOUD_ROWS;
+  double lp = 0.0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 512; c0 += 32) {
+    {
+      float v[32];                                   /* all 32 row segments of this warp in flight before any is used */
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
+        const long long row = row0 + warp + k * (LOUD_ROWS / 32);
+        v[k] = row < nrows ? __ldcs(&fe_in[row * 512 + c0 + lane]) : 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < 32; k++) tile[warp + k * (LOUD_ROWS / 32)][lane] = v[k];
+    }
+    __syncthreads();
 #pragma unroll 4
-    for (int i = 256; i < 512; ++i) loud += (double)fe[i] * (double)T->eql_w[i];
-    loud *= (1. / (14752. * 14752.) / 512);
-    o->loudness = (float)loud;
+    for (int i = 0; i < 32; ++i) lp += (double)tile[tid][i] * (double)T->eql_w[c0 + i];
+    __syncthreads();
+  }
+  const long long row = row0 + tid;
+  if (row < nrows && out[row].fe_valid) {
+    lp *= (1. / (14752. * 14752.) / 512);
+    out[row].loudness = (float)lp;
   }
 }
 
@@ -545,6 +576,11 @@ k_stream_scan(const Mp3Tables* __restrict__ T, StreamDesc* __restrict__ streams,
               const ScanIn* __restrict__ sin, signed char* __restrict__ bt_final,
               signed char* __restrict__ bt_prev, double* __restrict__ ath_psy, double* __restrict__ ath_q,
               ScanChunk* __restrict__ scratch) {
+  /* The scan is one block per stream -- with a single long stream the machine idles for its 0.17 ms.  The subband analysis
+   * (k_subband_analysis, needs PCM only) is launched behind it as a programmatic dependent: as soon as every scan block is
+   * resident it may start and take the rest of the machine.  (On a side stream it either fought the psy analysis for SMs or
+   * kept this 1024-thread block, which needs a whole SM's registers, waiting until it had drained: both measured.) */
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int z = blockIdx.x;
   if (z >= nstreams) return;
   const StreamDesc& sd = streams[z];

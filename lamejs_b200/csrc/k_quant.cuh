@@ -162,6 +162,10 @@ static_assert((offsetof(WarpShared, wk) + offsetof(GcWork, xr)) % 16 == 0 && (of
 #endif
 
 #define LANE (threadIdx.x & 31)
+#ifdef Q_TASKSTAT
+/* tuning builds: per rate-loop task {clocks >> 6, gr, max_nonzero_coeff, block type, gain in, bits in, target bits, gain out} */
+__device__ int g_taskstat[1 << 16][8];
+#endif
 /* -DQ_STATS: call counters for tuning (tools/profile_run.py prints them); absent from the product build */
 #ifdef Q_STATS
 __device__ unsigned long long g_qstats[16];
@@ -1908,6 +1912,10 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
     if (lane == 0) { wk->geo = &T->geo[pr->block_type == BT_SHORT ? 1 : 0]; wk->ixg = ixrow; }
     copy_gi_w(&wk->b, &ginfo[gidx]);
     copy_row16_w(wk->ixw, ixrow, 1152);
+#ifdef Q_TASKSTAT
+    const long long ts_t0 = clock64();
+    const int ts_gain = wk->b.global_gain, ts_bits = wk->b.part2_3_length;
+#endif
     if (have) {
       copy_row16_w(wk->xr, xrq + gidx * 576, 2304);
       copy_row16_w(wk->xrpow, xrpow_g + gidx * 576, 2304);
@@ -1916,6 +1924,13 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
       __syncwarp();
       outer_loop_w(T, wk, targ);
     }
+#ifdef Q_TASKSTAT
+    if (lane == 0 && revalidate <= 0 && gidx < (1u << 16)) {
+      int* r = g_taskstat[gidx];
+      r[0] = (int)((clock64() - ts_t0) >> 6); r[1] = gr; r[2] = wk->b.max_nonzero_coeff; r[3] = wk->b.block_type;
+      r[4] = ts_gain; r[5] = ts_bits; r[6] = targ; r[7] = wk->b.global_gain;
+    }
+#endif
     copy_gi_w(&ginfo[gidx], &wk->b);
     copy_row16_w(ixrow, wk->ixw, 1152);
     if (done) {                                   /* publish: rows first, then the flag */

@@ -126,8 +126,10 @@ struct Workspace {
   signed char* d_bt_final = nullptr;      /* [units][2] final block type used by MDCT + quantizer */
   signed char* d_bt_prev = nullptr;       /* [units][2] blocktype_old seen by the masking of this granule */
   float* d_xr = nullptr;                  /* [units][nch][576] */
+  float* d_slab = nullptr;                /* [units + nstreams][nch][18][32] subband samples (gfc.sb_sample), psy row numbering */
   PsyUnit* d_psy = nullptr;               /* [units + nstreams][nch]  (one halo unit per stream in front) */
   ScanIn* d_scan_in = nullptr;            /* [units + nstreams][nch] attack candidates + loudness for the scans */
+  float* d_fe = nullptr;                  /* [units + nstreams][nch][512] long-FFT line energies (loudness input) */
   PsyRatioDev* d_ratio = nullptr;         /* [units + nstreams][nch]  masking of unit c (used by granule c+1) */
   double* d_ath_psy = nullptr;            /* [frames] ATH.adjust seen by the psy calls of the frame */
   double* d_ath_q = nullptr;              /* [frames] ATH.adjust after adjust_ATH (quantizer) */
@@ -144,7 +146,7 @@ struct Workspace {
   ScanChunk* d_scan = nullptr;            /* [frames / SCAN_FRAMES + nstreams] */
   ~Workspace() { release(); }
   void release() {
-    cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_psy); cudaFree(d_scan_in); d_scan_in = nullptr;
+    cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_slab); d_slab = nullptr; cudaFree(d_psy); cudaFree(d_fe); d_fe = nullptr; cudaFree(d_scan_in); d_scan_in = nullptr;
     cudaFree(d_ratio); cudaFree(d_ath_psy); cudaFree(d_ath_q); cudaFree(d_qstate); cudaFree(d_ginfo);
     cudaFree(d_l3enc); cudaFree(d_xrq); d_xrq = nullptr; cudaFree(d_xrpow); d_xrpow = nullptr; cudaFree(d_prep); d_prep = nullptr; cudaFree(d_done); d_done = nullptr; cudaFree(d_dirty); cudaFree(d_counter); cudaFree(d_scan); d_scan = nullptr;
     d_streams = nullptr; d_bt_final = d_bt_prev = nullptr; d_xr = nullptr; d_psy = nullptr; d_ratio = nullptr;
@@ -157,7 +159,9 @@ struct Workspace {
     CK(cudaMalloc(&d_bt_final, (size_t)U * 2 + 16));
     CK(cudaMalloc(&d_bt_prev, (size_t)U * 2 + 16));
     CK(cudaMalloc(&d_xr, sizeof(float) * (size_t)U * nch * 576));
+    CK(cudaMalloc(&d_slab, sizeof(float) * (size_t)(U + S) * nch * 576));
     CK(cudaMalloc(&d_psy, sizeof(PsyUnit) * (size_t)(U + S) * nch));
+    CK(cudaMalloc(&d_fe, sizeof(float) * 512 * (size_t)(U + S) * nch));
     CK(cudaMalloc(&d_scan_in, sizeof(ScanIn) * (size_t)(U + S) * nch));
     CK(cudaMalloc(&d_ratio, sizeof(PsyRatioDev) * (size_t)(U + S) * nch));
     CK(cudaMalloc(&d_ath_psy, sizeof(double) * (size_t)(F + 1)));
@@ -327,10 +331,14 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
       if (arrival) CK(cudaStreamWaitEvent(st, arrival->ready[j], 0));
       if (u_hi[j] <= u_lo[j]) continue;
       dim3 gridj(u_hi[j] - u_lo[j], nch, S);
-      k_psy_analysis<<<gridj, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, j, nchunks, u_lo[j]);
+      k_psy_analysis<<<gridj, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_fe, j, nchunks, u_lo[j]);
       g_launches++;
       DBG("k_psy_analysis");
     }
+    const long long psy_rows = (G * total_frames + S) * nch;   /* rows unit_base + z + u + 1 of every stream */
+    k_psy_loudness<<<(unsigned)((psy_rows + LOUD_ROWS - 1) / LOUD_ROWS), LOUD_ROWS, 0, st>>>(cfg->dev, ws.d_fe, ws.d_psy, psy_rows);
+    g_launches++;
+    DBG("k_psy_loudness");
   }
   CK(cudaEventRecord(ev[1], st));
   /* K3a: attack pre-pass (parallel) + sequential per-stream scans */
@@ -341,6 +349,25 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     k_stream_scan<<<S, SCAN_THREADS, 0, st>>>(cfg->dev, ws.d_streams, S, ws.d_scan_in, ws.d_bt_final, ws.d_bt_prev, ws.d_ath_psy, ws.d_ath_q, ws.d_scan);
     g_launches += 2;
     DBG("k_stream_scan");
+    /* K1a: subband analysis, programmatic dependent of the scan (reads nothing the scan writes; see k_stream_scan) */
+    {
+      const int G = cfg->host.mode_gr;
+      const size_t smem = sizeof(double) * FB_PCM_WORDS + sizeof(float) * (FB_SLABS * 18 * FB_SLAB_STRIDE);
+      {
+        std::lock_guard<std::mutex> lk(g_mu);   /* the attribute is per device */
+        if (!g_fb_attr_done[cfg->device]) { CK(cudaFuncSetAttribute(k_subband_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g_fb_attr_done[cfg->device] = true; }
+      }
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3((G * max_frames + 1 + FB_SLABS - 1) / FB_SLABS, nch, S);
+      lc.blockDim = dim3(FB_THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = at; lc.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&lc, k_subband_analysis, (const Mp3Tables*)cfg->dev, (const StreamDesc*)ws.d_streams, ws.d_slab));
+      g_launches++;
+      DBG("k_subband_analysis");
+    }
   }
   CK(cudaEventRecord(ev[2], st));
   if (force_bt) {   /* debug: override block decision for the filterbank */
@@ -358,18 +385,12 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
     DBG("k_psy_masking");
   }
   CK(cudaEventRecord(ev[3], st));
-  /* K1: filterbank + MDCT.  (Running it on a second stream beside K3b was measured: the two kernels slow each other
-   * down by exactly what the overlap would save, 0.61 ms either way.) */
+  /* K1b: MDCT from the slabs and the block types */
   {
     dim3 grid((cfg->host.mode_gr * max_frames + FB_G - 1) / FB_G, nch, S);
-    const size_t smem = sizeof(double) * FB_PCM_WORDS + sizeof(float) * ((FB_G + 1) * 18 * FB_SLAB_STRIDE);
-    {
-      std::lock_guard<std::mutex> lk(g_mu);   /* the attribute is per device */
-      if (!g_fb_attr_done[cfg->device]) { CK(cudaFuncSetAttribute(k_filterbank_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g_fb_attr_done[cfg->device] = true; }
-    }
-    k_filterbank_mdct<<<grid, FB_THREADS, smem, st>>>(cfg->dev, ws.d_streams, ws.d_bt_final, ws.d_xr);
+    k_mdct<<<grid, FB_G * 32, 0, st>>>(cfg->dev, ws.d_streams, ws.d_slab, ws.d_bt_final, ws.d_xr);
     g_launches++;
-    DBG("k_filterbank_mdct");
+    DBG("k_mdct");
   }
   CK(cudaEventRecord(ev[4], st));
   int passes = 0;
@@ -666,3 +687,10 @@ int mp3b200_debug_stages(int channels, int samplerate, int kbps, const int16_t* 
 }  // extern "C"
 
 #include "mp3_handle.inc"
+
+#ifdef Q_TASKSTAT
+extern "C" int mp3b200_debug_taskstat(int* out, int rows) {
+  if (rows > (1 << 16)) rows = 1 << 16;
+  return cudaMemcpyFromSymbol(out, g_taskstat, sizeof(int) * 8 * (size_t)rows) == cudaSuccess ? 0 : -1;
+}
+#endif
