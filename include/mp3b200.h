@@ -81,8 +81,8 @@ int mp3b200_encode_streams(int channels, int samplerate, int kbps, int nstreams,
 /* Device-resident variant for benchmarking kernel throughput: d_pcm is ONE device allocation holding, per
  * stream s, nsamples[s] Int16 of the left channel at sample offset pcm_off[s] and (stereo) the right channel at
  * pcm_off[s] + nsamples[s].  d_out is a device buffer; stream s is written at out_off[s].  `timings_ms`
- * (optional, 16 floats) receives per-kernel CUDA-event times in ms: [0] psy analysis, [1] scan, [2] masking,
- * [3] filterbank+MDCT, [4] quantizer first pass (all of its kernels), [5] re-validation passes, [6] total, [7] number of
+ * (optional, 16 floats) receives per-kernel CUDA-event times in ms: [0] psy analysis + loudness, [1] attack pre-pass + per-stream
+ * scan with the subband analysis (polyphase filterbank) running beside it, [2] masking, [3] MDCT, [4] quantizer first pass (all of its kernels), [5] re-validation passes, [6] total, [7] number of
  * quantizer passes; first pass by kernel: [8] k_q_prepare, [9] k_q_search (gr0 + gr1), [10] k_q_outer (gr0 + gr1),
  * [11] k_q_finish (gr0 + gr1), [12] k_q_pack, [13] the re-validation folded into the first pass (verify + repaired
  * searches / rate loops of the few frames whose speculated start did not stand); [14..15] reserved (0).

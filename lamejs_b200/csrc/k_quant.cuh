@@ -2216,16 +2216,17 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     (*launches)++;
   };
   /* rate loop + finish of one granule in ONE launch: the finish tasks fill the rate loop's tail (see k_q_outer) */
-  auto outer_finish = [&](int gr, long long count, int reval) {
+  auto outer_finish = [&](int gr, long long count, int reval, int slot_o, int slot_f) {
 #if Q_FUSE_FINISH
     int* const ca = fresh_counter(); int* const cb = fresh_counter();
     const int epoch = ++(*B.epoch);
     k_q_outer<<<max(1, grid_for(count * nch, Q_BLOCKS_PER_SM) - reserve_blocks), Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, gr, nullptr, nullptr, (int)count,
                                                                             reval, ca, cb, B.done, epoch);
     (*launches)++;
+    mark(slot_o); mark(slot_f);
 #else
-    outer(gr, nullptr, nullptr, count, reval);
-    finish(gr, nullptr, nullptr, count, reval);
+    outer(gr, nullptr, nullptr, count, reval); mark(slot_o);
+    finish(gr, nullptr, nullptr, count, reval); mark(slot_f);
 #endif
   };
   auto pack = [&](const int* list, const int* cptr, long long count, int reval) {
@@ -2251,7 +2252,7 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
    *   LSF:    S0          | verify, S0' (listed)                            | O0 F0 PACK */
   search(0, nullptr, nullptr, F, 0); mark(QE_S0);
   if (G == 2) {
-    outer_finish(0, F, 0); mark(QE_O0); mark(QE_F0);
+    outer_finish(0, F, 0, QE_O0, QE_F0);
     search(1, nullptr, nullptr, F, 0); mark(QE_S1);
   }
   bool forked = false;
@@ -2287,11 +2288,11 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
   mark(QE_MID);
   if (G == 2) {
     reserve_blocks = forked ? Q_REPAIR_BLOCKS : 0;
-    outer_finish(1, F, forked ? -1 : 0); mark(QE_O1); mark(QE_F1);
+    outer_finish(1, F, forked ? -1 : 0, QE_O1, QE_F1);
     reserve_blocks = 0;
     if (forked) cudaStreamWaitEvent(st_main, ev_join, 0);
   } else {
-    outer_finish(0, F, 0); mark(QE_O0); mark(QE_F0);
+    outer_finish(0, F, 0, QE_O0, QE_F0);
   }
   pack(nullptr, nullptr, F, 0); mark(QE_PK);
   if (cudaEventRecord(ev_pass1, st) != cudaSuccess) return -100;

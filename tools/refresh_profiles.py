@@ -9,7 +9,7 @@ for src, dst in (("bench.json", "bench.json"), ("bench_ref.json", "bench_referen
     if os.path.exists(os.path.join(G, src)): shutil.copy(os.path.join(G, src), os.path.join(P, "%s_%s" % (tag, dst)))
 tj = os.path.join(P, "r01_kernel_traffic.json")
 out = json.load(open(tj))
-names = {"k_quantize_pack": "quantize_pack", "k_psy_analysis": "psy", "k_filterbank_mdct": "filterbank_mdct", "k_psy_masking": "psy_masking"}
+names = {"k_quantize_pack": "quantize_pack", "k_psy_analysis": "psy", "k_subband_analysis": "subband_analysis", "k_mdct": "mdct", "k_psy_masking": "psy_masking"}
 for k, n in names.items():
     rep = os.path.join(G, "prof_%s.ncu-rep" % k)
     if not os.path.exists(rep) or (len(sys.argv) > 2 and k not in sys.argv[2:]): continue
