@@ -103,56 +103,61 @@ __device__ __forceinline__ void window_subband_dev(const double* __restrict__ x,
 #undef X1
 #undef X2
   {
+    /* Statements of the form a[i] = a[j] +- a[k] (one addition of two float32 values, rounded to float32) are done in
+     * float32: rounding the exact sum to 53 and then to 24 bits equals rounding it to 24 bits directly (53 >= 2 * 24 + 2),
+     * so the result is the reference's, without two widenings, a double addition and a narrowing.  Everything that chains two
+     * operations in double before the store stays in double. */
     double xr;
-    xr = a[28] - a[0]; a[0] += a[28]; a[28] = xr * EW(wp + -2 * 18 + 7);
-    xr = a[29] - a[1]; a[1] += a[29]; a[29] = xr * EW(wp + -2 * 18 + 7);
-    xr = a[26] - a[2]; a[2] += a[26]; a[26] = xr * EW(wp + -4 * 18 + 7);
-    xr = a[27] - a[3]; a[3] += a[27]; a[27] = xr * EW(wp + -4 * 18 + 7);
-    xr = a[24] - a[4]; a[4] += a[24]; a[24] = xr * EW(wp + -6 * 18 + 7);
-    xr = a[25] - a[5]; a[5] += a[25]; a[25] = xr * EW(wp + -6 * 18 + 7);
-    xr = a[22] - a[6]; a[6] += a[22]; a[22] = xr * SQRT2_D;
-    xr = a[23] - a[7]; a[7] += a[23]; a[23] = xr * SQRT2_D - a[7];
-    a[7] -= a[6];
-    a[22] -= a[7];
-    a[23] -= a[22];
-    xr = a[6]; a[6] = a[31] - xr; a[31] = a[31] + xr;
-    xr = a[7]; a[7] = a[30] - xr; a[30] = a[30] + xr;
-    xr = a[22]; a[22] = a[15] - xr; a[15] = a[15] + xr;
-    xr = a[23]; a[23] = a[14] - xr; a[14] = a[14] + xr;
-    xr = a[20] - a[8]; a[8] += a[20]; a[20] = xr * EW(wp + -10 * 18 + 7);
-    xr = a[21] - a[9]; a[9] += a[21]; a[21] = xr * EW(wp + -10 * 18 + 7);
-    xr = a[18] - a[10]; a[10] += a[18]; a[18] = xr * EW(wp + -12 * 18 + 7);
-    xr = a[19] - a[11]; a[11] += a[19]; a[19] = xr * EW(wp + -12 * 18 + 7);
-    xr = a[16] - a[12]; a[12] += a[16]; a[16] = xr * EW(wp + -14 * 18 + 7);
-    xr = a[17] - a[13]; a[13] += a[17]; a[17] = xr * EW(wp + -14 * 18 + 7);
-    xr = -a[20] + a[24]; a[20] += a[24]; a[24] = xr * EW(wp + -12 * 18 + 7);
-    xr = -a[21] + a[25]; a[21] += a[25]; a[25] = xr * EW(wp + -12 * 18 + 7);
-    xr = a[4] - a[8]; a[4] += a[8]; a[8] = xr * EW(wp + -12 * 18 + 7);
-    xr = a[5] - a[9]; a[5] += a[9]; a[9] = xr * EW(wp + -12 * 18 + 7);
-    xr = a[0] - a[12]; a[0] += a[12]; a[12] = xr * EW(wp + -4 * 18 + 7);
-    xr = a[1] - a[13]; a[1] += a[13]; a[13] = xr * EW(wp + -4 * 18 + 7);
-    xr = a[16] - a[28]; a[16] += a[28]; a[28] = xr * EW(wp + -4 * 18 + 7);
-    xr = -a[17] + a[29]; a[17] += a[29]; a[29] = xr * EW(wp + -4 * 18 + 7);
-    xr = SQRT2_D * (a[2] - a[10]); a[2] += a[10]; a[10] = xr;
-    xr = SQRT2_D * (a[3] - a[11]); a[3] += a[11]; a[11] = xr;
-    xr = SQRT2_D * (-a[18] + a[26]); a[18] += a[26]; a[26] = xr - a[18];
-    xr = SQRT2_D * (-a[19] + a[27]); a[19] += a[27]; a[27] = xr - a[19];
-    xr = a[2]; a[19] -= a[3]; a[3] -= xr; a[2] = a[31] - xr; a[31] += xr;
-    xr = a[3]; a[11] -= a[19]; a[18] -= xr; a[3] = a[30] - xr; a[30] += xr;
-    xr = a[18]; a[27] -= a[11]; a[19] -= xr; a[18] = a[15] - xr; a[15] += xr;
-    xr = a[19]; a[10] -= xr; a[19] = a[14] - xr; a[14] += xr;
-    xr = a[10]; a[11] -= xr; a[10] = a[23] - xr; a[23] += xr;
-    xr = a[11]; a[26] -= xr; a[11] = a[22] - xr; a[22] += xr;
-    xr = a[26]; a[27] -= xr; a[26] = a[7] - xr; a[7] += xr;
-    xr = a[27]; a[27] = a[6] - xr; a[6] += xr;
-    xr = SQRT2_D * (a[0] - a[4]); a[0] += a[4]; a[4] = xr;
-    xr = SQRT2_D * (a[1] - a[5]); a[1] += a[5]; a[5] = xr;
-    xr = SQRT2_D * (a[16] - a[20]); a[16] += a[20]; a[20] = xr;
-    xr = SQRT2_D * (a[17] - a[21]); a[17] += a[21]; a[21] = xr;
-    xr = -SQRT2_D * (a[8] - a[12]); a[8] += a[12]; a[12] = xr - a[8];
-    xr = -SQRT2_D * (a[9] - a[13]); a[9] += a[13]; a[13] = xr - a[9];
-    xr = -SQRT2_D * (a[25] - a[29]); a[25] += a[29]; a[29] = xr - a[25];
-    xr = -SQRT2_D * (a[24] + a[28]); a[24] -= a[28]; a[28] = xr - a[24];
+    float xf;
+    xr = a[28] - a[0]; a[0].v = __fadd_rn(a[0].v, a[28].v); a[28] = xr * EW(wp + -2 * 18 + 7);
+    xr = a[29] - a[1]; a[1].v = __fadd_rn(a[1].v, a[29].v); a[29] = xr * EW(wp + -2 * 18 + 7);
+    xr = a[26] - a[2]; a[2].v = __fadd_rn(a[2].v, a[26].v); a[26] = xr * EW(wp + -4 * 18 + 7);
+    xr = a[27] - a[3]; a[3].v = __fadd_rn(a[3].v, a[27].v); a[27] = xr * EW(wp + -4 * 18 + 7);
+    xr = a[24] - a[4]; a[4].v = __fadd_rn(a[4].v, a[24].v); a[24] = xr * EW(wp + -6 * 18 + 7);
+    xr = a[25] - a[5]; a[5].v = __fadd_rn(a[5].v, a[25].v); a[25] = xr * EW(wp + -6 * 18 + 7);
+    xr = a[22] - a[6]; a[6].v = __fadd_rn(a[6].v, a[22].v); a[22] = xr * SQRT2_D;
+    xr = a[23] - a[7]; a[7].v = __fadd_rn(a[7].v, a[23].v); a[23] = xr * SQRT2_D - a[7];
+    a[7].v = __fsub_rn(a[7].v, a[6].v);
+    a[22].v = __fsub_rn(a[22].v, a[7].v);
+    a[23].v = __fsub_rn(a[23].v, a[22].v);
+    xf = a[6].v; a[6].v = __fsub_rn(a[31].v, xf); a[31].v = __fadd_rn(a[31].v, xf);
+    xf = a[7].v; a[7].v = __fsub_rn(a[30].v, xf); a[30].v = __fadd_rn(a[30].v, xf);
+    xf = a[22].v; a[22].v = __fsub_rn(a[15].v, xf); a[15].v = __fadd_rn(a[15].v, xf);
+    xf = a[23].v; a[23].v = __fsub_rn(a[14].v, xf); a[14].v = __fadd_rn(a[14].v, xf);
+    xr = a[20] - a[8]; a[8].v = __fadd_rn(a[8].v, a[20].v); a[20] = xr * EW(wp + -10 * 18 + 7);
+    xr = a[21] - a[9]; a[9].v = __fadd_rn(a[9].v, a[21].v); a[21] = xr * EW(wp + -10 * 18 + 7);
+    xr = a[18] - a[10]; a[10].v = __fadd_rn(a[10].v, a[18].v); a[18] = xr * EW(wp + -12 * 18 + 7);
+    xr = a[19] - a[11]; a[11].v = __fadd_rn(a[11].v, a[19].v); a[19] = xr * EW(wp + -12 * 18 + 7);
+    xr = a[16] - a[12]; a[12].v = __fadd_rn(a[12].v, a[16].v); a[16] = xr * EW(wp + -14 * 18 + 7);
+    xr = a[17] - a[13]; a[13].v = __fadd_rn(a[13].v, a[17].v); a[17] = xr * EW(wp + -14 * 18 + 7);
+    xr = -a[20] + a[24]; a[20].v = __fadd_rn(a[20].v, a[24].v); a[24] = xr * EW(wp + -12 * 18 + 7);
+    xr = -a[21] + a[25]; a[21].v = __fadd_rn(a[21].v, a[25].v); a[25] = xr * EW(wp + -12 * 18 + 7);
+    xr = a[4] - a[8]; a[4].v = __fadd_rn(a[4].v, a[8].v); a[8] = xr * EW(wp + -12 * 18 + 7);
+    xr = a[5] - a[9]; a[5].v = __fadd_rn(a[5].v, a[9].v); a[9] = xr * EW(wp + -12 * 18 + 7);
+    xr = a[0] - a[12]; a[0].v = __fadd_rn(a[0].v, a[12].v); a[12] = xr * EW(wp + -4 * 18 + 7);
+    xr = a[1] - a[13]; a[1].v = __fadd_rn(a[1].v, a[13].v); a[13] = xr * EW(wp + -4 * 18 + 7);
+    xr = a[16] - a[28]; a[16].v = __fadd_rn(a[16].v, a[28].v); a[28] = xr * EW(wp + -4 * 18 + 7);
+    xr = -a[17] + a[29]; a[17].v = __fadd_rn(a[17].v, a[29].v); a[29] = xr * EW(wp + -4 * 18 + 7);
+    xr = SQRT2_D * (a[2] - a[10]); a[2].v = __fadd_rn(a[2].v, a[10].v); a[10] = xr;
+    xr = SQRT2_D * (a[3] - a[11]); a[3].v = __fadd_rn(a[3].v, a[11].v); a[11] = xr;
+    xr = SQRT2_D * (-a[18] + a[26]); a[18].v = __fadd_rn(a[18].v, a[26].v); a[26] = xr - a[18];
+    xr = SQRT2_D * (-a[19] + a[27]); a[19].v = __fadd_rn(a[19].v, a[27].v); a[27] = xr - a[19];
+    xf = a[2].v; a[19].v = __fsub_rn(a[19].v, a[3].v); a[3].v = __fsub_rn(a[3].v, xf); a[2].v = __fsub_rn(a[31].v, xf); a[31].v = __fadd_rn(a[31].v, xf);
+    xf = a[3].v; a[11].v = __fsub_rn(a[11].v, a[19].v); a[18].v = __fsub_rn(a[18].v, xf); a[3].v = __fsub_rn(a[30].v, xf); a[30].v = __fadd_rn(a[30].v, xf);
+    xf = a[18].v; a[27].v = __fsub_rn(a[27].v, a[11].v); a[19].v = __fsub_rn(a[19].v, xf); a[18].v = __fsub_rn(a[15].v, xf); a[15].v = __fadd_rn(a[15].v, xf);
+    xf = a[19].v; a[10].v = __fsub_rn(a[10].v, xf); a[19].v = __fsub_rn(a[14].v, xf); a[14].v = __fadd_rn(a[14].v, xf);
+    xf = a[10].v; a[11].v = __fsub_rn(a[11].v, xf); a[10].v = __fsub_rn(a[23].v, xf); a[23].v = __fadd_rn(a[23].v, xf);
+    xf = a[11].v; a[26].v = __fsub_rn(a[26].v, xf); a[11].v = __fsub_rn(a[22].v, xf); a[22].v = __fadd_rn(a[22].v, xf);
+    xf = a[26].v; a[27].v = __fsub_rn(a[27].v, xf); a[26].v = __fsub_rn(a[7].v, xf); a[7].v = __fadd_rn(a[7].v, xf);
+    xf = a[27].v; a[27].v = __fsub_rn(a[6].v, xf); a[6].v = __fadd_rn(a[6].v, xf);
+    xr = SQRT2_D * (a[0] - a[4]); a[0].v = __fadd_rn(a[0].v, a[4].v); a[4] = xr;
+    xr = SQRT2_D * (a[1] - a[5]); a[1].v = __fadd_rn(a[1].v, a[5].v); a[5] = xr;
+    xr = SQRT2_D * (a[16] - a[20]); a[16].v = __fadd_rn(a[16].v, a[20].v); a[20] = xr;
+    xr = SQRT2_D * (a[17] - a[21]); a[17].v = __fadd_rn(a[17].v, a[21].v); a[21] = xr;
+    xr = -SQRT2_D * (a[8] - a[12]); a[8].v = __fadd_rn(a[8].v, a[12].v); a[12] = xr - a[8];
+    xr = -SQRT2_D * (a[9] - a[13]); a[9].v = __fadd_rn(a[9].v, a[13].v); a[13] = xr - a[9];
+    xr = -SQRT2_D * (a[25] - a[29]); a[25].v = __fadd_rn(a[25].v, a[29].v); a[29] = xr - a[25];
+    xr = -SQRT2_D * (a[24] + a[28]); a[24].v = __fsub_rn(a[24].v, a[28].v); a[28] = xr - a[24];
     xr = a[24] - a[16]; a[24] = xr;
     xr = a[20] - xr; a[20] = xr;
     xr = a[28] - xr; a[28] = xr;
@@ -181,22 +186,22 @@ __device__ __forceinline__ void window_subband_dev(const double* __restrict__ x,
     xr = a[13] - xr; a[13] = xr;
     xr = a[28] - xr; a[28] = xr;
     xr = a[29] - xr; a[29] = xr;
-    xr = a[0]; a[0] += a[31]; a[31] -= xr;
-    xr = a[1]; a[1] += a[30]; a[30] -= xr;
-    xr = a[16]; a[16] += a[15]; a[15] -= xr;
-    xr = a[17]; a[17] += a[14]; a[14] -= xr;
-    xr = a[8]; a[8] += a[23]; a[23] -= xr;
-    xr = a[9]; a[9] += a[22]; a[22] -= xr;
-    xr = a[24]; a[24] += a[7]; a[7] -= xr;
-    xr = a[25]; a[25] += a[6]; a[6] -= xr;
-    xr = a[4]; a[4] += a[27]; a[27] -= xr;
-    xr = a[5]; a[5] += a[26]; a[26] -= xr;
-    xr = a[20]; a[20] += a[11]; a[11] -= xr;
-    xr = a[21]; a[21] += a[10]; a[10] -= xr;
-    xr = a[12]; a[12] += a[19]; a[19] -= xr;
-    xr = a[13]; a[13] += a[18]; a[18] -= xr;
-    xr = a[28]; a[28] += a[3]; a[3] -= xr;
-    xr = a[29]; a[29] += a[2]; a[2] -= xr;
+    xf = a[0].v; a[0].v = __fadd_rn(a[0].v, a[31].v); a[31].v = __fsub_rn(a[31].v, xf);
+    xf = a[1].v; a[1].v = __fadd_rn(a[1].v, a[30].v); a[30].v = __fsub_rn(a[30].v, xf);
+    xf = a[16].v; a[16].v = __fadd_rn(a[16].v, a[15].v); a[15].v = __fsub_rn(a[15].v, xf);
+    xf = a[17].v; a[17].v = __fadd_rn(a[17].v, a[14].v); a[14].v = __fsub_rn(a[14].v, xf);
+    xf = a[8].v; a[8].v = __fadd_rn(a[8].v, a[23].v); a[23].v = __fsub_rn(a[23].v, xf);
+    xf = a[9].v; a[9].v = __fadd_rn(a[9].v, a[22].v); a[22].v = __fsub_rn(a[22].v, xf);
+    xf = a[24].v; a[24].v = __fadd_rn(a[24].v, a[7].v); a[7].v = __fsub_rn(a[7].v, xf);
+    xf = a[25].v; a[25].v = __fadd_rn(a[25].v, a[6].v); a[6].v = __fsub_rn(a[6].v, xf);
+    xf = a[4].v; a[4].v = __fadd_rn(a[4].v, a[27].v); a[27].v = __fsub_rn(a[27].v, xf);
+    xf = a[5].v; a[5].v = __fadd_rn(a[5].v, a[26].v); a[26].v = __fsub_rn(a[26].v, xf);
+    xf = a[20].v; a[20].v = __fadd_rn(a[20].v, a[11].v); a[11].v = __fsub_rn(a[11].v, xf);
+    xf = a[21].v; a[21].v = __fadd_rn(a[21].v, a[10].v); a[10].v = __fsub_rn(a[10].v, xf);
+    xf = a[12].v; a[12].v = __fadd_rn(a[12].v, a[19].v); a[19].v = __fsub_rn(a[19].v, xf);
+    xf = a[13].v; a[13].v = __fadd_rn(a[13].v, a[18].v); a[18].v = __fsub_rn(a[18].v, xf);
+    xf = a[28].v; a[28].v = __fadd_rn(a[28].v, a[3].v); a[3].v = __fsub_rn(a[3].v, xf);
+    xf = a[29].v; a[29].v = __fadd_rn(a[29].v, a[2].v); a[2].v = __fsub_rn(a[2].v, xf);
   }
 }
 
