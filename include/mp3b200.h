@@ -60,6 +60,25 @@ int mp3b200_encode_batch(mp3b200_encoder* const* handles, const int16_t* const* 
                          const int* nsamples, uint8_t* const* out, const int* cap, int nstreams, int* out_bytes);
 int mp3b200_flush_batch(mp3b200_encoder* const* handles, uint8_t* const* out, const int* cap, int nstreams, int* out_bytes);
 
+/* ---- encoder state: checkpoint / resume, and one stream cut into segments ----------------------------
+ * lamejs keeps an Mp3Encoder's state in JS objects (gfc.*: ATH adjust, block-type FSM, OldValue / CurrentStep, the previous
+ * granule's masking, mfbuf); a JS caller checkpoints by keeping the object alive.  Here the state is a blob:
+ *   export_state  writes everything the handle carries between calls (scalars, the previous unit's masking row from device
+ *                 memory, the PCM tail later frames still read, FIFO accounting); buf == NULL returns the size.  Two handles
+ *                 that encoded the same frames from the same samples export identical bytes.
+ *   import_state  makes a handle of the same configuration continue exactly where the exporting one stood.
+ *   seek          positions a FRESH handle at frame `frame` >= 1 with the sequential state of a stream start: the start of
+ *                 a warm-up.  A segment encoder seeks W frames before its first frame, encodes them (discarding the bytes)
+ *                 and compares its state with the predecessor segment's exported end state: equal blobs prove its frames are
+ *                 the ones a single encoder would produce; otherwise it imports the predecessor's state and encodes again
+ *                 (lamejs_b200/sharding.py encode_stream_segments).  `hist`: the stream samples
+ *                 [max(0, frame*framesize - 1104), frame*framesize + 224), framesize = 576 * granules per frame; feeding
+ *                 continues with sample frame*framesize + 224.
+ * Return MP3B200_OK / bytes written, or a negative error (wrong configuration -2, buffer -1, handle -3). */
+int mp3b200_export_state(mp3b200_encoder* h, void* buf, int cap);
+int mp3b200_import_state(mp3b200_encoder* h, const void* buf, int len);
+int mp3b200_seek(mp3b200_encoder* h, int64_t frame, const int16_t* left_hist, const int16_t* right_hist, int nhist);
+
 /* ---- batch extension (same semantics, many independent streams per launch sequence) -------------------
  * Equivalent to, for each stream s: e = new Mp3Encoder(ch, sr, kbps); bytes = e.encodeBuffer(L_s, R_s) ++
  * e.flush().  This is the throughput path (a JS caller would loop over encoders, worker-example/worker.js). */

@@ -35,6 +35,9 @@ def lib():
     L.mp3b200_encode_batch.argtypes = [vp, vp, vp, vp, vp, vp, c_int, vp]
     L.mp3b200_flush_batch.argtypes = [vp, vp, vp, c_int, vp]
     L.mp3b200_destroy.restype = None
+    L.mp3b200_export_state.argtypes = [vp, vp, c_int]
+    L.mp3b200_import_state.argtypes = [vp, vp, c_int]
+    L.mp3b200_seek.argtypes = [vp, c_i64, vp, vp, c_int]
     L.mp3b200_stream_bytes.restype = c_i64
     L.mp3b200_stream_bytes.argtypes = [c_int, c_int, c_int, c_i64]
     L.mp3b200_stream_frames.restype = c_i64
@@ -100,6 +103,24 @@ class Mp3Encoder:
 
     # pythonic aliases
     encode_buffer = encodeBuffer
+
+    # ---- state: checkpoint / resume and segment encoding (include/mp3b200.h "encoder state") ----
+    def export_state(self):
+        n = _check(self._L.mp3b200_export_state(self._h, None, 0))
+        buf = np.empty(n, dtype=np.uint8)
+        n = _check(self._L.mp3b200_export_state(self._h, buf.ctypes.data, n))
+        return buf[:n].tobytes()
+
+    def import_state(self, blob):
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        _check(self._L.mp3b200_import_state(self._h, buf.ctypes.data, len(buf)))
+
+    def seek(self, frame, left_hist, right_hist=None):
+        """fresh encoder -> frame `frame` of a stream with start-of-stream sequential state; *_hist = samples
+        [max(0, frame*framesize-1104), frame*framesize+224)"""
+        left_hist = np.ascontiguousarray(left_hist, dtype=np.int16)
+        right_hist = left_hist if (self.channels == 1 or right_hist is None) else np.ascontiguousarray(right_hist, dtype=np.int16)
+        _check(self._L.mp3b200_seek(self._h, int(frame), left_hist.ctypes.data, right_hist.ctypes.data, len(left_hist)))
 
     def close(self):
         if self._h:
