@@ -9,7 +9,7 @@
  * state from call to call.  Here the work is split by what it depends on:
  *   k_psy_analysis   pure function of PCM: fs/4 HPF + 9 sub-block peaks, 1024-pt and 3x256-pt FHT, line
  *                    energies, partition energies / tonality index, short-block spreading sums
- *   k_psy_loudness   the 512-term ordered loudness sum of every unit, one thread each (psycho_loudness_approx)
+ *                    (and the ordered 512-term loudness sum, psycho_loudness_approx: terms in parallel, additions on one thread)
  *   k_attack_prepass pure function of two consecutive units: attack candidates (before the lastAttacks FSM)
  *   k_stream_scan    the only sequential part: per stream, the attack / block-type FSM and the ATH-adjust IIR
  *   k_psy_masking    long-block spreading with mask_add (needs ATH.adjust), short thresholds (need the previous
@@ -36,7 +36,7 @@ struct PsyUnit {
   float loudness;                   /* psycho_loudness_approx */
   unsigned char mask_idx[MP3_CBANDS];
   unsigned char attack[4];          /* pre-FSM ns_attacks[0..3] */
-  unsigned char fe_valid;           /* this launch wrote the row's line energies: k_psy_loudness owns `loudness` */
+  unsigned char pad_;
 };
 struct PsyRatioDev { float en_l[22], thm_l[22], en_s[13][3], thm_s[13][3]; };
 
@@ -166,7 +166,7 @@ __device__ __forceinline__ size_t psy_row(const StreamDesc& sd, int z, int u) { 
 #endif
 __global__ void __launch_bounds__(PSY_THREADS, PSY_MIN_BLOCKS)
 k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ out,
-               float* __restrict__ fe_out, int chunk, int nchunks, int u_base) {
+               int chunk, int nchunks, int u_base) {
   const int z = blockIdx.z;
   const StreamDesc& sd = streams[z];
   const int u = (int)blockIdx.x + u_base;             /* relative unit, -1 = halo */
@@ -191,12 +191,8 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     for (int i = tid; i < 3 * MP3_CBANDS; i += PSY_THREADS) { (&o->ecb_s[0][0])[i] = 1.0; (&o->eb_s[0][0])[i] = 0.0f; }
     if (tid < MP3_CBANDS) { o->eb_l[tid] = 0.0f; o->mask_idx[tid] = 0; }
     if (tid < 9) o->peaks[tid] = 10.0f;
-    if (tid == 0) { o->loudness = 0.0f; o->fe_valid = 0; }
+    if (tid == 0) o->loudness = 0.0f;
     if (tid < 4) o->attack[tid] = 0;
-    {   /* k_psy_loudness streams every row: give it defined line energies (its result for this row is not stored) */
-      float* fg = fe_out + ((size_t)psy_row(sd, z, u) * nch + ch) * 512;
-      for (int j = tid; j < 512; j += PSY_THREADS) fg[j] = 0.0f;
-    }
     return;
   }
 
@@ -210,9 +206,19 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   f32s* const s_avg = s_max + MP3_CBANDS;                                         /* [64] */
   f32s (*const s_ebs)[MP3_CBANDS] = reinterpret_cast<f32s (*)[MP3_CBANDS]>(s_avg + MP3_CBANDS);   /* [3][64] */
   static_assert(2064 + 1552 + 2 * 4 * MP3_CBANDS + 3 * 4 * MP3_CBANDS <= (int)sizeof(s_u), "energies must fit the PCM span");
+  /* psycho_loudness_approx (PsyModel.js:241-249) is ONE ordered 512-term double sum per unit.  Its terms energy[i] * eql_w[i]
+   * are computed by the threads that produce the energies (double products, 2 x 256 of them parked in shared memory that is
+   * dead by then: the high-pass output and the tail of the PCM span); the thread that owns no partition then only walks the
+   * additions -- an 8-cycle step instead of the 60-cycle load / convert / multiply / add step that stalled the block when
+   * the whole sum sat on one thread (measured: 0.81 -> 1.09 ms) -- half in each of the two partition phases. */
+  constexpr int PROD_HI_OFF = 2064 + 1552 + 2 * 4 * MP3_CBANDS + 3 * 4 * MP3_CBANDS;
+  static_assert(PROD_HI_OFF % 8 == 0 && PROD_HI_OFF + 256 * 8 <= (int)sizeof(s_u), "second half of the loudness terms");
+  double* const prod_hi = reinterpret_cast<double*>(s_u + PROD_HI_OFF);                /* terms 256..511 */
   __shared__ f32w wl[1024 + 64];
   __shared__ f32w wsh[3][256 + 16];
-  __shared__ f32s hp[576];
+  __shared__ __align__(8) f32s hp[576];
+  double* const prod_lo = reinterpret_cast<double*>(hp);                               /* terms 0..255 (hp is dead by then) */
+  static_assert(sizeof(f32s) * 576 >= 256 * 8, "first half of the loudness terms");
   __shared__ int s_peak[9];
   if (tid < 9) s_peak[tid] = __float_as_int(1.0f);
 
@@ -318,9 +324,12 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
   /* line energies (PsyModel.js:278-298) */
   for (int j = tid; j < 512; j += PSY_THREADS) {
     const double re = wl[FHT_PAD(512 - j)], im = wl[FHT_PAD(512 + j)];
-    fe[512 - j] = (re * re + im * im) * 0.5;
+    f32s e; e = (re * re + im * im) * 0.5;
+    fe[512 - j] = (double)e;
+    const int k = 512 - j;                              /* 1..512; the loudness sum runs over 0..511 */
+    if (k < 512) { const double p = (double)e * (double)T->eql_w[k]; if (k < 256) prod_lo[k] = p; else prod_hi[k - 256] = p; }
   }
-  if (tid == 0) { f32s t0; t0 = (double)wl[0]; t0 *= (double)t0; fe[0] = (double)t0; }
+  if (tid == 0) { f32s t0; t0 = (double)wl[0]; t0 *= (double)t0; fe[0] = (double)t0; prod_lo[0] = (double)t0 * (double)T->eql_w[0]; }
   for (int t = tid; t < 3 * 128; t += PSY_THREADS) {
     const int b = t >> 7, j = t & 127;
     const double re = wsh[b][FHT_PAD(128 - j)], im = wsh[b][FHT_PAD(128 + j)];
@@ -349,14 +358,12 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     }
   }
   }
-  /* psycho_loudness_approx is one ordered 512-term sum: k_psy_loudness does it with a thread per unit instead of
-   * stalling this block on a single lane; hand it the line energies */
-  {
-    float* fg = fe_out + ((size_t)psy_row(sd, z, u) * nch + ch) * 512;
-    for (int j = tid; j < 512; j += PSY_THREADS) fg[j] = fe[j].v;
+  double loud = 0.0;
+  if (tid == PSY_THREADS - 1) {
+#pragma unroll 8
+    for (int i = 0; i < 256; ++i) loud += prod_lo[i];
   }
   if (tid < 9) o->peaks[tid] = __int_as_float(s_peak[tid]);
-  if (tid == 9) o->fe_valid = 1;
   __syncthreads();
 
   for (int vt = tid; vt < 256; vt += PSY_THREADS) {
@@ -389,45 +396,14 @@ k_psy_analysis(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ s
     }
   }
   }
-}
-
-/* psycho_loudness_approx (PsyModel.js:241-249): loudness = sum_i energy[i] * eql_w[i] (ordered, in double) scaled by
- * 1 / (14752^2 * 512).  One thread per (unit, channel) row owns the ordered sum; the 128 rows of a block are streamed
- * through shared memory in 32-column tiles so that the HBM reads are whole 128-byte lines.
- * grid (ceil(rows / 128)), rows = all (unit+halo, channel) rows of the batch; `valid` marks rows K2 filled. */
-#define LOUD_ROWS 128
-__global__ void __launch_bounds__(LOUD_ROWS)
-k_psy_loudness(const Mp3Tables* __restrict__ T, const float* __restrict__ fe_in, PsyUnit* __restrict__ out, long long nrows) {
-  __shared__ float tile[LOUD_ROWS][33];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long row0 = (long long)blockIdx.x * LOUD_ROWS;
-  double lp = 0.0;
-#pragma unroll 1
-  for (int c0 = 0; c0 < 512; c0 += 32) {
-    {
-      float v[32];                                   /* all 32 row segments of this warp in flight before any is used */
-#pragma unroll
-      for (int k = 0; k < 32; k++) {
-        const long long row = row0 + warp + k * (LOUD_ROWS / 32);
-        v[k] = row < nrows ? __ldcs(&fe_in[row * 512 + c0 + lane]) : 0.0f;
-      }
-#pragma unroll
-      for (int k = 0; k < 32; k++) tile[warp + k * (LOUD_ROWS / 32)][lane] = v[k];
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) lp += (double)tile[tid][i] * (double)T->eql_w[c0 + i];
-    __syncthreads();
-  }
-  const long long row = row0 + tid;
-  if (row < nrows && out[row].fe_valid) {
-    lp *= (1. / (14752. * 14752.) / 512);
-    out[row].loudness = (float)lp;
+  if (tid == PSY_THREADS - 1) {
+#pragma unroll 8
+    for (int i = 0; i < 256; ++i) loud += prod_hi[i];
+    loud *= (1. / (14752. * 14752.) / 512);
+    o->loudness = (float)loud;
   }
 }
 
-/* ---- attack candidates: needs peaks of unit u and u-1 (PsyModel.js:1105-1181) -------------------------- */
-/* what the sequential scans read per (unit, channel), packed densely: a PsyUnit is 2.6 KB, the scans need 8 bytes of it */
 struct ScanIn { unsigned attack4; float loudness; };
 
 __global__ void k_attack_prepass(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, PsyUnit* __restrict__ psy,

@@ -129,7 +129,6 @@ struct Workspace {
   float* d_slab = nullptr;                /* [units + nstreams][nch][18][32] subband samples (gfc.sb_sample), psy row numbering */
   PsyUnit* d_psy = nullptr;               /* [units + nstreams][nch]  (one halo unit per stream in front) */
   ScanIn* d_scan_in = nullptr;            /* [units + nstreams][nch] attack candidates + loudness for the scans */
-  float* d_fe = nullptr;                  /* [units + nstreams][nch][512] long-FFT line energies (loudness input) */
   PsyRatioDev* d_ratio = nullptr;         /* [units + nstreams][nch]  masking of unit c (used by granule c+1) */
   double* d_ath_psy = nullptr;            /* [frames] ATH.adjust seen by the psy calls of the frame */
   double* d_ath_q = nullptr;              /* [frames] ATH.adjust after adjust_ATH (quantizer) */
@@ -146,7 +145,7 @@ struct Workspace {
   ScanChunk* d_scan = nullptr;            /* [frames / SCAN_FRAMES + nstreams] */
   ~Workspace() { release(); }
   void release() {
-    cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_slab); d_slab = nullptr; cudaFree(d_psy); cudaFree(d_fe); d_fe = nullptr; cudaFree(d_scan_in); d_scan_in = nullptr;
+    cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_slab); d_slab = nullptr; cudaFree(d_psy); cudaFree(d_scan_in); d_scan_in = nullptr;
     cudaFree(d_ratio); cudaFree(d_ath_psy); cudaFree(d_ath_q); cudaFree(d_qstate); cudaFree(d_ginfo);
     cudaFree(d_l3enc); cudaFree(d_xrq); d_xrq = nullptr; cudaFree(d_xrpow); d_xrpow = nullptr; cudaFree(d_prep); d_prep = nullptr; cudaFree(d_done); d_done = nullptr; cudaFree(d_dirty); cudaFree(d_counter); cudaFree(d_scan); d_scan = nullptr;
     d_streams = nullptr; d_bt_final = d_bt_prev = nullptr; d_xr = nullptr; d_psy = nullptr; d_ratio = nullptr;
@@ -161,7 +160,6 @@ struct Workspace {
     CK(cudaMalloc(&d_xr, sizeof(float) * (size_t)U * nch * 576));
     CK(cudaMalloc(&d_slab, sizeof(float) * (size_t)(U + S) * nch * 576));
     CK(cudaMalloc(&d_psy, sizeof(PsyUnit) * (size_t)(U + S) * nch));
-    CK(cudaMalloc(&d_fe, sizeof(float) * 512 * (size_t)(U + S) * nch));
     CK(cudaMalloc(&d_scan_in, sizeof(ScanIn) * (size_t)(U + S) * nch));
     CK(cudaMalloc(&d_ratio, sizeof(PsyRatioDev) * (size_t)(U + S) * nch));
     CK(cudaMalloc(&d_ath_psy, sizeof(double) * (size_t)(F + 1)));
@@ -331,14 +329,10 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
       if (arrival) CK(cudaStreamWaitEvent(st, arrival->ready[j], 0));
       if (u_hi[j] <= u_lo[j]) continue;
       dim3 gridj(u_hi[j] - u_lo[j], nch, S);
-      k_psy_analysis<<<gridj, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, ws.d_fe, j, nchunks, u_lo[j]);
+      k_psy_analysis<<<gridj, PSY_THREADS, 0, st>>>(cfg->dev, ws.d_streams, ws.d_psy, j, nchunks, u_lo[j]);
       g_launches++;
       DBG("k_psy_analysis");
     }
-    const long long psy_rows = (G * total_frames + S) * nch;   /* rows unit_base + z + u + 1 of every stream */
-    k_psy_loudness<<<(unsigned)((psy_rows + LOUD_ROWS - 1) / LOUD_ROWS), LOUD_ROWS, 0, st>>>(cfg->dev, ws.d_fe, ws.d_psy, psy_rows);
-    g_launches++;
-    DBG("k_psy_loudness");
   }
   CK(cudaEventRecord(ev[1], st));
   /* K3a: attack pre-pass (parallel) + sequential per-stream scans */
