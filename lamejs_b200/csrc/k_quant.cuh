@@ -182,10 +182,6 @@ __device__ unsigned long long g_qstats[16];
 #ifndef Q_CB_UNROLL
 #define Q_CB_UNROLL 1
 #endif
-#ifndef Q_FUSE_FINISH
-#define Q_FUSE_FINISH 0         /* finish tasks inside the rate-loop launch (fills its tail): measured 2.58 vs 2.42 ms for
-                                  rate loop + finish on C2 -- the bigger kernel spills and re-pollutes the I-cache; kept as a knob */
-#endif
 #ifndef Q_CN_UNROLL
 #define Q_CN_UNROLL 2          /* calc_noise band chain: A/B 1 / 2 / 4 -> k_q_outer 2.27 / 2.18 / 2.19 ms (C2) */
 #endif
@@ -788,20 +784,6 @@ __device__ __noinline__ void copy_gi_w(GranuleInfoDev* dst, const GranuleInfoDev
   int v[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) { const int i = LANE + 32 * k; if (i < n) v[k] = s[i]; }   /* loads in flight together (HBM rows) */
-#pragma unroll
-  for (int k = 0; k < 3; k++) { const int i = LANE + 32 * k; if (i < n) d[i] = v[k]; }
-  __syncwarp();
-}
-/* same, reading *src from L2 (ld.global.cg): for rows another SM wrote during this kernel (fused finish phase) */
-__device__ __noinline__ void copy_gi_cg_w(GranuleInfoDev* dst, const GranuleInfoDev* src) {
-  const int n = sizeof(GranuleInfoDev) / 4;
-  const int* s = reinterpret_cast<const int*>(src);
-  int* d = reinterpret_cast<int*>(dst);
-  __syncwarp();                                   /* earlier readers of *dst are done */
-  static_assert(sizeof(GranuleInfoDev) / 4 <= 96, "three rounds");
-  int v[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) { const int i = LANE + 32 * k; if (i < n) v[k] = __ldcg(&s[i]); }   /* loads in flight together (HBM rows) */
 #pragma unroll
   for (int k = 0; k < 3; k++) { const int i = LANE + 32 * k; if (i < n) d[i] = v[k]; }
   __syncwarp();
@@ -1730,16 +1712,6 @@ __device__ __forceinline__ void copy_row16_w(void* dst, const void* src, int nby
   for (int k = 0; k < 5; k++) { const int i = LANE + 32 * k; if (i < n) reinterpret_cast<int4*>(dst)[i] = v[k]; }
   __syncwarp();
 }
-__device__ __forceinline__ void copy_row16_cg_w(void* dst, const void* src, int nbytes) {   /* the same through L2 only */
-  __syncwarp();
-  const int n = nbytes >> 4;
-  int4 v[5];
-#pragma unroll
-  for (int k = 0; k < 5; k++) { const int i = LANE + 32 * k; if (i < n) v[k] = __ldcg(reinterpret_cast<const int4*>(src) + i); }
-#pragma unroll
-  for (int k = 0; k < 5; k++) { const int i = LANE + 32 * k; if (i < n) reinterpret_cast<int4*>(dst)[i] = v[k]; }
-  __syncwarp();
-}
 struct FrameGeom { int z, f, padding, frame_bytes, mean_bits; long long kabs; };
 __device__ __forceinline__ FrameGeom frame_geom(const Mp3Tables* T, const StreamDesc* streams, const QuantFrameState* q) {
   FrameGeom g;
@@ -1881,8 +1853,7 @@ __global__ void __launch_bounds__(Q_THREADS, Q_BLOCKS_PER_SM)
 k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs,
           GranuleInfoDev* __restrict__ ginfo, short* __restrict__ l3enc, const float* __restrict__ xrq,
           const float* __restrict__ xrpow_g, const GcPrep* __restrict__ prep, int gr, const int* __restrict__ list,
-          const int* __restrict__ count_ptr, int count_direct, int revalidate, int* __restrict__ counter,
-          int* __restrict__ counter2, int* __restrict__ done, int epoch) {
+          const int* __restrict__ count_ptr, int count_direct, int revalidate, int* __restrict__ counter) {
   WarpShared* ws = warp_shared();
   GcWork* wk = &ws->wk;
   const int lane = LANE, nch = T->nch;
@@ -1933,47 +1904,7 @@ k_q_outer(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stream
 #endif
     copy_gi_w(&ginfo[gidx], &wk->b);
     copy_row16_w(ixrow, wk->ixw, 1152);
-    if (done) {                                   /* publish: rows first, then the flag */
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) atomicExch(&done[gidx], epoch);
-    }
   }
-  /* ---- fused finish phase (counter2 != nullptr): when the rate-loop tasks are all handed out, the warps that run dry start
-   * on iteration_finish_one of the same granule instead of idling through the kernel's tail (a rate loop lasts ~0.25 ms).
-   * Finish task t waits for rate-loop task t (same numbering, same skip rules); every rate-loop task has been pulled by a
-   * resident warp by then, so the wait always ends.  Rows written by other SMs during this kernel are read through L2. ---- */
-#if Q_FUSE_FINISH
-  if (counter2 == nullptr) return;
-#pragma unroll 1
-  for (int t = next_task(counter2); t < ntasks; t = next_task(counter2)) {
-    const int wi = t / nch, ch = t - wi * nch;
-#ifdef Q_REVERSE
-    const int frow = list ? list[wi] : (ntasks / nch - 1 - wi);
-#else
-    const int frow = list ? list[wi] : wi;
-#endif
-    QuantFrameState* q = qs + frow;
-    if (revalidate == 1 && !(q->redo & (gr == 0 ? Q_R0(ch) : Q_R1(ch)))) continue;
-    if (revalidate == -1 && (q->redo & Q_R0_ANY)) continue;
-    const StreamDesc& sd = streams[q->stream];
-    const size_t urow = (size_t)sd.unit_base + T->mode_gr * q->rel_frame + gr, gidx = urow * nch + ch;
-    if (lane == 0) { while (atomicAdd(&done[gidx], 0) != epoch) __nanosleep(256); }
-    __syncwarp();
-    short* const ixrow = l3enc + gidx * 576;
-    copy_gi_cg_w(&wk->b, &ginfo[gidx]);
-    copy_row16_cg_w(wk->ixw, ixrow, 1152);
-    if (lane == 0) wk->geo = &T->geo[wk->b.block_type == BT_SHORT ? 1 : 0];
-    __syncwarp();
-    best_scalefac_store_w(wk, ws->scfsi, gr == 1 ? &ginfo[gidx - nch] : nullptr, gr, T->mode_gr);
-    best_huffman_divide_w(T, wk);
-    copy_gi_w(&ginfo[gidx], &wk->b);
-    if (gr == 0) { if (lane == 0) q->used0[ch] = wk->b.part2_3_length + wk->b.part2_length; }
-    else if (lane < 4) q->scfsi[ch][lane] = ws->scfsi[lane];
-  }
-#else
-  (void)counter2;
-#endif
 }
 
 /* ---- iteration_finish_one (Quantize.js:1059-1078) of granule `gr`: best_scalefac_store (+ scfsi in gr1) and
@@ -2135,7 +2066,6 @@ __global__ void k_qstate_commit(StreamDesc* __restrict__ streams, int nstreams, 
 struct QuantBuffers {
   const float* xr; const PsyRatioDev* ratio; const signed char* bt; const double* ath_q;
   QuantFrameState* qs; GranuleInfoDev* ginfo; short* l3enc; float* xrq; float* xrpow; GcPrep* prep;
-  int* done; int* epoch;          /* fused finish phase: per granule-channel completion flags (device), launch epoch (host) */
   int* list; int* counter;        /* list: 2 x (frames + 1) entries (verify list, short list); counter[0..1]: their lengths;
                                      counter[2..Q_NCOUNTERS): task counters, one per launch */
 };
@@ -2212,22 +2142,15 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
   };
   auto outer = [&](int gr, const int* list, const int* cptr, long long count, int reval) {
     k_q_outer<<<max(1, grid_for(count * nch, Q_BLOCKS_PER_SM) - reserve_blocks), Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, gr, list, cptr, (int)count,
-                                                                            reval, fresh_counter(), nullptr, nullptr, 0);
+                                                                            reval, fresh_counter());
     (*launches)++;
   };
-  /* rate loop + finish of one granule in ONE launch: the finish tasks fill the rate loop's tail (see k_q_outer) */
+  /* rate loop, then the finish phase of one granule.  (Both in one launch, the finish tasks filling the rate loop's tail behind
+   * per-row completion flags, and the finish kernel as a programmatic dependent launch were measured: slower, the tail's few
+   * very long tasks lose the SMs they have to themselves -- profiles/r02_summary.md.) */
   auto outer_finish = [&](int gr, long long count, int reval, int slot_o, int slot_f) {
-#if Q_FUSE_FINISH
-    int* const ca = fresh_counter(); int* const cb = fresh_counter();
-    const int epoch = ++(*B.epoch);
-    k_q_outer<<<max(1, grid_for(count * nch, Q_BLOCKS_PER_SM) - reserve_blocks), Q_THREADS, smem, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, gr, nullptr, nullptr, (int)count,
-                                                                            reval, ca, cb, B.done, epoch);
-    (*launches)++;
-    mark(slot_o); mark(slot_f);
-#else
     outer(gr, nullptr, nullptr, count, reval); mark(slot_o);
     finish(gr, nullptr, nullptr, count, reval); mark(slot_f);
-#endif
   };
   auto pack = [&](const int* list, const int* cptr, long long count, int reval) {
     k_q_pack<<<grid_for(count, 8), Q_THREADS, smem_pack, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, list, cptr, (int)count, reval, fresh_counter(), d_out);
@@ -2274,11 +2197,11 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
        * free (1.5 % of its warps) and the repair kernels never ask for more */
       const int gq = Q_REPAIR_BLOCKS, gs = Q_REPAIR_BLOCKS;
       const int* cp = B.counter + 2;
-      k_q_outer<<<gq, Q_THREADS, smem, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 0, list3, cp, (int)F, 1, c0, nullptr, nullptr, 0);
+      k_q_outer<<<gq, Q_THREADS, smem, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 0, list3, cp, (int)F, 1, c0);
       k_q_finish<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 0, list3, cp, (int)F, 1, c1);
       k_q_search<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrpow, B.prep, 1, list3, cp, (int)F, 1, c2, list2, B.counter + 1,
                                                           list3, B.counter + 2);
-      k_q_outer<<<gq, Q_THREADS, smem, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 1, list3, cp, (int)F, 2, c3, nullptr, nullptr, 0);
+      k_q_outer<<<gq, Q_THREADS, smem, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, B.xrpow, B.prep, 1, list3, cp, (int)F, 2, c3);
       k_q_finish<<<gs, Q_THREADS, smem_slim, st_repair>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, 1, list3, cp, (int)F, 2, c4);
       cudaEventRecord(ev_join, st_repair);
       (*launches) += 5;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small workloads for compute-sanitizer (racecheck / memcheck / initcheck): transient bursts (block switching), 320 kbps
-white noise (long rate loops), an MPEG-2 stream, live handles.  Every result is checked against the oracle."""
+white noise (long rate loops), an MPEG-2 stream, live handles, state export / import / seek.  Every result is checked against the oracle."""
 import os
 import sys
 
@@ -25,5 +25,17 @@ for ch, sr, kbps, kind, n in cases:
     enc.close()
     ok = got == O.encode_stream(ch, sr, kbps, l, r if ch == 2 else None, chunk=1152)[0]
     bad += 0 if ok else 1
-print("sanitize_run: %d cases, %d mismatches" % (len(cases) * 4, bad))
+    # encoder state: checkpoint / resume in the middle, and the stream cut into three frame ranges with a warm-up
+    from lamejs_b200 import sharding
+    fs = 576 * M.granules_per_frame(ch, sr, kbps)
+    want = O.encode_stream(ch, sr, kbps, l, r if ch == 2 else None)[0]
+    a = M.Mp3Encoder(ch, sr, kbps)
+    got = a.encodeBuffer(l[:n // 2], r[:n // 2] if ch == 2 else None)
+    blob = a.export_state(); a.close()
+    b = M.Mp3Encoder(ch, sr, kbps); b.import_state(blob)
+    got += b.encodeBuffer(l[n // 2:], r[n // 2:] if ch == 2 else None) + b.flush(); b.close()
+    bad += 0 if got == want else 1
+    got, _ = sharding.encode_stream_segments_local(lambda: M.Mp3Encoder(ch, sr, kbps), l, r if ch == 2 else None, fs, 3, 4)
+    bad += 0 if got == want else 1
+print("sanitize_run: %d cases, %d mismatches" % (len(cases) * 6, bad))
 sys.exit(1 if bad else 0)
