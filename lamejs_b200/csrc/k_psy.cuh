@@ -1,4 +1,4 @@
-/* k_psy.cuh -- K2 / K2b / K3pre / K3a / K3b: psycho-acoustic model (lamejs L3psycho_anal_ns) as five kernels.
+/* k_psy.cuh -- K2 / K3pre / K3a / K3b: psycho-acoustic model (lamejs L3psycho_anal_ns) as four kernels.
  *
  * Reference: src/js/PsyModel.js L3psycho_anal_ns :1000-1383 with compute_ffts :251-324, mask_add :403-473,
  * calc_interchannel_masking :525-543, convert_partition2scalefac_s/_l :644-734, compute_masking_s :736-782,
