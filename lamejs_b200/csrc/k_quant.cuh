@@ -514,10 +514,10 @@ __device__ __noinline__ void calc_noise_w(const Mp3Tables* T, GcWork* wk, const 
 Q_UNROLL(Q_CN_UNROLL)
         for (int l = wk->nlen[sfb]; l > 0; l--, j += 2) {          /* j is even: one 64-bit and one 32-bit load per pair */
           const float2 x = *reinterpret_cast<const float2*>(&wk->xr[j]);
-          const unsigned q = *reinterpret_cast<const unsigned*>(&ix[j]);
-          double temp;
-          temp = fabs((double)x.x) - (double)__ldg(&T->pow43[q & 0xffffu]) * step; noise += temp * temp;
-          temp = fabs((double)x.y) - (double)__ldg(&T->pow43[q >> 16]) * step; noise += temp * temp;
+          const unsigned q0 = reinterpret_cast<const unsigned short*>(ix)[j], q1 = reinterpret_cast<const unsigned short*>(ix)[j + 1];
+          double temp;                             /* (two 16-bit loads: the index is ready without shift / mask / 64-bit add) */
+          temp = fabs((double)x.x) - (double)__ldg(&T->pow43[q0]) * step; noise += temp * temp;
+          temp = fabs((double)x.y) - (double)__ldg(&T->pow43[q1]) * step; noise += temp * temp;
         }
         wk->pn_step[sfb] = s;
         { f32s t; t = noise; wk->pn_noise[sfb] = t.v; }
@@ -1479,8 +1479,10 @@ __device__ Q_HELPER void put_bits(unsigned int* buf, int pos, unsigned int val, 
 }
 
 /* main data of one gc, starting at bit `pos` of the frame buffer; returns nothing (lengths are already known) */
+/* sign of line i of the spectrum the quantizer saw (xr < 0), from the 576-bit mask k_q_prepare keeps per granule-channel */
+#define QNEG(i) (((neg[(i) >> 5] >> ((i) & 31)) & 1u) != 0u)
 __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, unsigned int* buf, const GranuleInfoDev* gi, const short* ixq,
-                                       const float* xrq, int pos) {
+                                       const unsigned* neg, int pos) {
   const int lane = LANE;
   /* scalefactors (writeMainData, BitStream.js:609-625): serial, <= 36 values */
   if (lane == 0 && T->mode_gr == 1) {
@@ -1540,13 +1542,13 @@ __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, unsigned int* buf, co
       int cbits = 0, xbits = 0;
       unsigned ext = 0;
       int x1 = ixq[i], x2 = ixq[i + 1];
-      if (x1 != 0) { if (xrq[i] < 0.0f) ext++; cbits--; }
+      if (x1 != 0) { if (QNEG(i)) ext++; cbits--; }
       if (tb > 15) {
         if (x1 > 14) { ext |= (unsigned)(x1 - 15) << 1; xbits = linbits; x1 = 15; }
         if (x2 > 14) { ext <<= linbits; ext |= (unsigned)(x2 - 15); xbits += linbits; x2 = 15; }
         xlen = 16;
       }
-      if (x2 != 0) { ext <<= 1; if (xrq[i + 1] < 0.0f) ext++; cbits--; }
+      if (x2 != 0) { ext <<= 1; if (QNEG(i + 1)) ext++; cbits--; }
       const int idx = x1 * xlen + x2;
       xbits -= cbits;
       cbits += __ldg(&g_huff_len[c_huff_off[tb] + idx]);
@@ -1578,10 +1580,10 @@ __device__ __noinline__ void pack_gc_w(const Mp3Tables* T, unsigned int* buf, co
     for (int q = q0; q < q1; q++) {
       const int i = bigv + 4 * q;
       int huffbits = 0, p = 0;
-      if (ixq[i] != 0) { p += 8; if (xrq[i] < 0.0f) huffbits++; }
-      if (ixq[i + 1] != 0) { p += 4; huffbits *= 2; if (xrq[i + 1] < 0.0f) huffbits++; }
-      if (ixq[i + 2] != 0) { p += 2; huffbits *= 2; if (xrq[i + 2] < 0.0f) huffbits++; }
-      if (ixq[i + 3] != 0) { p++; huffbits *= 2; if (xrq[i + 3] < 0.0f) huffbits++; }
+      if (ixq[i] != 0) { p += 8; if (QNEG(i)) huffbits++; }
+      if (ixq[i + 1] != 0) { p += 4; huffbits *= 2; if (QNEG(i + 1)) huffbits++; }
+      if (ixq[i + 2] != 0) { p += 2; huffbits *= 2; if (QNEG(i + 2)) huffbits++; }
+      if (ixq[i + 3] != 0) { p++; huffbits *= 2; if (QNEG(i + 3)) huffbits++; }
       const int len = __ldg(&g_huff_len[c_huff_off[tb] + p]);
       if (pass == 0) mybits += len;
       else { put_bits(buf, at, (unsigned)huffbits + __ldg(&g_huff_code[c_huff_off[tb] + p]), len); at += len; }
@@ -1727,7 +1729,8 @@ __device__ __forceinline__ FrameGeom frame_geom(const Mp3Tables* T, const Stream
 __global__ void __launch_bounds__(Q_THREADS, Q_BLOCKS_PER_SM)
 k_q_prepare(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, const float* __restrict__ xr,
             const PsyRatioDev* __restrict__ ratio, const signed char* __restrict__ bt_final, const double* __restrict__ ath_q,
-            const QuantFrameState* __restrict__ qs, float* __restrict__ xrq, float* __restrict__ xrpow_g, GcPrep* __restrict__ prep,
+            const QuantFrameState* __restrict__ qs, float* __restrict__ xrq, float* __restrict__ xrpow_g, unsigned* __restrict__ neg_g,
+            GcPrep* __restrict__ prep,
             int nframes, int* __restrict__ counter) {
   WarpShared* ws = warp_shared();
   GcWork* wk = &ws->wk;
@@ -1750,6 +1753,12 @@ k_q_prepare(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ stre
     __syncwarp();
     const bool have = gc_prepare_w(T, wk, ws->ath, xr + gidx * 576, bt, rt, ath_adjust);
     copy_row16_w(xrq + gidx * 576, wk->xr, 2304);
+    {   /* the packer needs only the signs: 18 words instead of the 2304-byte row */
+      unsigned mine = 0;
+#pragma unroll 1
+      for (int k = 0; k < 18; k++) { const unsigned m = __ballot_sync(Q_FULL, wk->xr[lane + 32 * k] < 0.0f); if (lane == k) mine = m; }
+      if (lane < 18) neg_g[gidx * 18 + lane] = mine;
+    }
     copy_row16_w(xrpow_g + gidx * 576, wk->xrpow, 2304);
     GcPrep* pr = prep + gidx;
 #pragma unroll 1
@@ -1944,13 +1953,13 @@ k_q_finish(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ strea
 struct __align__(16) PackShared {
   unsigned int bits[368];         /* frame bit buffer (<= 1441 bytes), filled with shared-memory atomic ORs */
   short ix[576];
-  float xr[576];                  /* only the signs are read */
+  unsigned neg[20];               /* sign mask of the spectrum (18 words used) */
   GranuleInfoDev gi;
   int scfsi[8];
 };
 __global__ void __launch_bounds__(Q_THREADS)
 k_q_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams, QuantFrameState* __restrict__ qs,
-         const GranuleInfoDev* __restrict__ ginfo, const short* __restrict__ l3enc, const float* __restrict__ xrq,
+         const GranuleInfoDev* __restrict__ ginfo, const short* __restrict__ l3enc, const unsigned* __restrict__ neg_g,
          const int* __restrict__ list, const int* __restrict__ count_ptr, int count_direct, int revalidate,
          int* __restrict__ counter, uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1976,8 +1985,9 @@ k_q_pack(const Mp3Tables* __restrict__ T, const StreamDesc* __restrict__ streams
     for (int k = 0; k < T->mode_gr * nch; k++) {                     /* gr0ch0, gr0ch1, gr1ch0, gr1ch1 back to back */
       copy_gi_w(&ps->gi, &ginfo[g0 + k]);
       copy_row16_w(ps->ix, l3enc + (g0 + k) * 576, 1152);
-      copy_row16_w(ps->xr, xrq + (g0 + k) * 576, 2304);
-      pack_gc_w(T, ps->bits, &ps->gi, ps->ix, ps->xr, pos);
+      if (lane < 18) ps->neg[lane] = neg_g[(g0 + k) * 18 + lane];
+      __syncwarp();
+      pack_gc_w(T, ps->bits, &ps->gi, ps->ix, ps->neg, pos);
       pos += ps->gi.part2_3_length + ps->gi.part2_length;
       __syncwarp();
     }
@@ -2065,7 +2075,7 @@ __global__ void k_qstate_commit(StreamDesc* __restrict__ streams, int nstreams, 
 /* device buffers of the quantizer stage (owned by the Workspace) */
 struct QuantBuffers {
   const float* xr; const PsyRatioDev* ratio; const signed char* bt; const double* ath_q;
-  QuantFrameState* qs; GranuleInfoDev* ginfo; short* l3enc; float* xrq; float* xrpow; GcPrep* prep;
+  QuantFrameState* qs; GranuleInfoDev* ginfo; short* l3enc; float* xrq; float* xrpow; unsigned* neg; GcPrep* prep;
   int* list; int* counter;        /* list: 2 x (frames + 1) entries (verify list, short list); counter[0..1]: their lengths;
                                      counter[2..Q_NCOUNTERS): task counters, one per launch */
 };
@@ -2118,7 +2128,7 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
   auto mark = [&](int slot) { cudaEventRecord(evq[slot], st); evq_pred[slot] = last_slot; last_slot = slot; };
   int* const prep_counter = fresh_counter();     /* (may enqueue the counter memset: keep it out of the timed span) */
   mark(QE_START);
-  k_q_prepare<<<grid_for(F * hT.mode_gr * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.xr, B.ratio, B.bt, B.ath_q, B.qs, B.xrq, B.xrpow,
+  k_q_prepare<<<grid_for(F * hT.mode_gr * nch, Q_BLOCKS_PER_SM), Q_THREADS, smem, st>>>(dT, d_streams, B.xr, B.ratio, B.bt, B.ath_q, B.qs, B.xrq, B.xrpow, B.neg,
                                                                               B.prep, (int)F, prep_counter);
   mark(QE_PREP);
   (*launches)++;
@@ -2153,7 +2163,7 @@ static int quant_run(const Mp3Tables* dT, const Mp3Tables& hT, StreamDesc* d_str
     finish(gr, nullptr, nullptr, count, reval); mark(slot_f);
   };
   auto pack = [&](const int* list, const int* cptr, long long count, int reval) {
-    k_q_pack<<<grid_for(count, 8), Q_THREADS, smem_pack, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.xrq, list, cptr, (int)count, reval, fresh_counter(), d_out);
+    k_q_pack<<<grid_for(count, 9), Q_THREADS, smem_pack, st>>>(dT, d_streams, B.qs, B.ginfo, B.l3enc, B.neg, list, cptr, (int)count, reval, fresh_counter(), d_out);
     (*launches)++;
   };
   auto verify = [&](int predict_step = 0) {

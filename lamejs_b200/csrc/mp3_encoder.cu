@@ -137,6 +137,7 @@ struct Workspace {
   short* d_l3enc = nullptr;               /* [units][nch][576] quantised lines of a gc: after the search, parked best, final */
   float* d_xrq = nullptr;                 /* [units][nch][576] xr as the quantizer sees it (reordered, analog silence zeroed) */
   float* d_xrpow = nullptr;               /* [units][nch][576] |xr|^(3/4) */
+  unsigned* d_neg = nullptr;              /* [units][nch][18] sign mask of d_xrq (what the packer needs of it) */
   GcPrep* d_prep = nullptr;               /* [units][nch] xmin + scalars of the prepared granule-channel */
   int* d_dirty = nullptr;                 /* [frames] work list for re-quantization passes */
   int* d_counter = nullptr;               /* [4] */
@@ -145,7 +146,7 @@ struct Workspace {
   void release() {
     cudaFree(d_streams); cudaFree(d_bt_final); cudaFree(d_bt_prev); cudaFree(d_xr); cudaFree(d_slab); d_slab = nullptr; cudaFree(d_psy); cudaFree(d_scan_in); d_scan_in = nullptr;
     cudaFree(d_ratio); cudaFree(d_ath_psy); cudaFree(d_ath_q); cudaFree(d_qstate); cudaFree(d_ginfo);
-    cudaFree(d_l3enc); cudaFree(d_xrq); d_xrq = nullptr; cudaFree(d_xrpow); d_xrpow = nullptr; cudaFree(d_prep); d_prep = nullptr; cudaFree(d_dirty); cudaFree(d_counter); cudaFree(d_scan); d_scan = nullptr;
+    cudaFree(d_l3enc); cudaFree(d_xrq); d_xrq = nullptr; cudaFree(d_xrpow); d_xrpow = nullptr; cudaFree(d_neg); d_neg = nullptr; cudaFree(d_prep); d_prep = nullptr; cudaFree(d_dirty); cudaFree(d_counter); cudaFree(d_scan); d_scan = nullptr;
     d_streams = nullptr; d_bt_final = d_bt_prev = nullptr; d_xr = nullptr; d_psy = nullptr; d_ratio = nullptr;
     d_ath_psy = d_ath_q = nullptr; d_qstate = nullptr; d_ginfo = nullptr; d_l3enc = nullptr; d_dirty = nullptr; d_counter = nullptr;
   }
@@ -168,6 +169,7 @@ struct Workspace {
     CK(cudaMalloc(&d_l3enc, sizeof(short) * (size_t)U * nch * 576));
     CK(cudaMalloc(&d_xrq, sizeof(float) * (size_t)U * nch * 576));
     CK(cudaMalloc(&d_xrpow, sizeof(float) * (size_t)U * nch * 576));
+    CK(cudaMalloc(&d_neg, sizeof(unsigned) * (size_t)U * nch * 18));
     CK(cudaMalloc(&d_prep, sizeof(GcPrep) * (size_t)U * nch));
     CK(cudaMalloc(&d_dirty, sizeof(int) * 3 * (size_t)(F + 1)));
     CK(cudaMalloc(&d_counter, sizeof(int) * Q_NCOUNTERS));
@@ -387,7 +389,7 @@ int run_pipeline(Config* cfg, Workspace& ws, std::vector<StreamDesc>& h_streams,
   if (!stop_after_mdct) {
     QuantBuffers qb;
     qb.xr = ws.d_xr; qb.ratio = ws.d_ratio; qb.bt = ws.d_bt_final; qb.ath_q = ws.d_ath_q; qb.qs = ws.d_qstate; qb.ginfo = ws.d_ginfo;
-    qb.l3enc = ws.d_l3enc; qb.xrq = ws.d_xrq; qb.xrpow = ws.d_xrpow; qb.prep = ws.d_prep; qb.list = ws.d_dirty; qb.counter = ws.d_counter;
+    qb.l3enc = ws.d_l3enc; qb.xrq = ws.d_xrq; qb.xrpow = ws.d_xrpow; qb.neg = ws.d_neg; qb.prep = ws.d_prep; qb.list = ws.d_dirty; qb.counter = ws.d_counter;
     int rc = quant_run(cfg->dev, cfg->host, ws.d_streams, S, streams_with_frames, max_frames, total_frames, qb, d_out, st, t_ctx.aux_st, t_ctx.ev_fork, t_ctx.ev_join, ev[5], t_ctx.evq, t_ctx.evq_pred, &passes, &g_launches);
     if (rc) { g_err = "quantizer stage failed: " + std::string(cudaGetErrorString(cudaGetLastError())); return rc; }
   } else {
