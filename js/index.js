@@ -21,6 +21,9 @@ const lib = ffi.Library(process.env.MP3B200_LIB || 'libmp3b200', {
   mp3b200_encode: ['int', [voidPtr, 'pointer', 'pointer', 'int', 'pointer', 'int']],
   mp3b200_flush: ['int', [voidPtr, 'pointer', 'int']],
   mp3b200_destroy: ['void', [voidPtr]],
+  mp3b200_export_state: ['int', [voidPtr, 'pointer', 'int']],
+  mp3b200_import_state: ['int', [voidPtr, 'pointer', 'int']],
+  mp3b200_seek: ['int', [voidPtr, 'int64', 'pointer', 'pointer', 'int']],
   mp3b200_last_error: ['string', []],
 });
 
@@ -53,6 +56,25 @@ function Mp3Encoder(channels, samplerate, kbps) {
     const n = lib.mp3b200_flush(h, buf, buf.length);
     if (n < 0) throw new Error('mp3b200_flush failed (' + n + '): ' + lib.mp3b200_last_error());
     return new Int8Array(buf.subarray(0, n));
+  };
+
+  // ---- beyond lamejs: the encoder state as a blob (checkpoint / resume; segment workers, see INTEGRATION.md) ----
+  this.exportState = function () {
+    const n = lib.mp3b200_export_state(h, ref.NULL, 0);
+    if (n < 0) throw new Error('mp3b200_export_state failed (' + n + '): ' + lib.mp3b200_last_error());
+    const blob = Buffer.alloc(n);
+    const m = lib.mp3b200_export_state(h, blob, n);
+    if (m < 0) throw new Error('mp3b200_export_state failed (' + m + '): ' + lib.mp3b200_last_error());
+    return blob.subarray(0, m);
+  };
+  this.importState = function (blob) {
+    const rc = lib.mp3b200_import_state(h, blob, blob.length);
+    if (rc !== 0) throw new Error('mp3b200_import_state failed (' + rc + '): ' + lib.mp3b200_last_error());
+  };
+  this.seek = function (frame, leftHist, rightHist) {
+    if (channels === 1 || !rightHist) rightHist = leftHist;
+    const rc = lib.mp3b200_seek(h, frame, asBuf(leftHist), asBuf(rightHist), leftHist.length);
+    if (rc !== 0) throw new Error('mp3b200_seek failed (' + rc + '): ' + lib.mp3b200_last_error());
   };
 
   this.close = function () { lib.mp3b200_destroy(h); };
