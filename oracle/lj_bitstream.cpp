@@ -309,12 +309,16 @@ void lj_format_bitstream(LjEnc* e) {
   if (e->hdr_pending) { e->bs_byteidx++; putheader_bits(e); e->bs_byteidx--; }
 }
 
-int lj_copy_buffer(LjEnc* e, uint8_t* out, int cap) {
+int lj_copy_buffer(LjEnc* e, uint8_t* out, int cap, int mp3data) {
   int minimum = e->bs_byteidx + 1;
   if (minimum <= 0) return 0;
   if (cap != 0 && minimum > cap) return -1;
   memcpy(out, e->bs_buf, minimum);
   e->bs_byteidx = -1;
   e->bs_bitidx = 0;
+  if (mp3data != 0) {              /* BitStream.js:924-935: music CRC and byte count of real frame data */
+    lj_update_music_crc(e, out, minimum);
+    if (minimum > 0) e->nBytesWritten += minimum;
+  }
   return minimum;
 }

@@ -97,6 +97,13 @@ struct LjEnc {
   uint8_t hdr_buf[40]; int hdr_ptr; int hdr_pending;
   /* trace */
   LjFrameTrace* trace; int trace_cap, trace_n;
+  /* Xing / LAME tag state (VBRSeekInfo.js, LameInternalFlags.js:170; lj_vbrtag.cpp).  nMusicCRC and nBytesWritten are
+   * maintained by copy_buffer on every call whether or not a tag is written (BitStream.js:924-935). */
+  int nMusicCRC; long long nBytesWritten;
+  int bWriteVbrTag, vbr_TotalFrameSize, vbr_nframes, vbr_sum, vbr_seen, vbr_want, vbr_pos;
+  int vbr_bag[400];
+  int encoder_padding;             /* gfp.encoder_padding, set by lame_encode_flush (Lame.js:1412) */
+  double lowpass_final;            /* gfp.lowpassfreq after lame_init_params (Lame.js:884-896) */
 };
 
 /* lj_init.cpp */
@@ -114,5 +121,8 @@ void lj_iteration_loop(LjEnc* e, double pe[2][2], PsyRatio ratio[2][2]);
 int  lj_getframebits(const LjEnc* e);
 /* lj_bitstream.cpp */
 void lj_format_bitstream(LjEnc* e);
-int  lj_copy_buffer(LjEnc* e, uint8_t* out, int cap);
+int  lj_copy_buffer(LjEnc* e, uint8_t* out, int cap, int mp3data);
+/* lj_vbrtag.cpp */
+void lj_update_music_crc(LjEnc* e, const uint8_t* buf, int size);
+void lj_add_vbr_frame(LjEnc* e);
 #endif

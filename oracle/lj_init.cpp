@@ -188,6 +188,7 @@ int lj_init_params(LjEnc* e, int channels, int samplerate, int kbps) {
   e->out_samplerate = optimum_samplefreq(js_toint32(lowpassfreq), e->in_samplerate);
   lowpassfreq = js_min(20500, lowpassfreq);
   lowpassfreq = js_min(e->out_samplerate / 2.0, lowpassfreq);
+  e->lowpass_final = lowpassfreq;
   switch (e->out_samplerate) {   /* SmpFrqIndex (Lame.js:369-402): version 1 = MPEG-1, 0 = MPEG-2 and MPEG-2.5 */
     case 44100: e->version = 1; e->samplerate_index = 0; break;
     case 48000: e->version = 1; e->samplerate_index = 1; break;
@@ -404,7 +405,8 @@ static int encode_mp3_frame(LjEnc* e, uint8_t* mp3buf, int mp3buf_size) {
   }
   lj_iteration_loop(e, pe, masking_LR);
   lj_format_bitstream(e);
-  int mp3count = lj_copy_buffer(e, mp3buf, mp3buf_size);
+  int mp3count = lj_copy_buffer(e, mp3buf, mp3buf_size, 1);
+  lj_add_vbr_frame(e);             /* Encoder.js:640-641 */
   if (tracing) {
     for (int gr = 0; gr < 2; gr++) for (int ch = 0; ch < e->channels_out; ch++) {
       const GrInfo& gi = e->tt[gr][ch];
@@ -509,7 +511,7 @@ static int fill_buffer_resample(LjEnc* e, F32* outbuf, int outbufPos, int desire
 static int encode_buffer_sample(LjEnc* e, F32* in0, F32* in1, int in_n, double nsamples, uint8_t* mp3buf, int mp3buf_size) {
   int mp3size = 0;
   if (nsamples == 0) return 0;
-  int mp3out = lj_copy_buffer(e, mp3buf, mp3buf_size);
+  int mp3out = lj_copy_buffer(e, mp3buf, mp3buf_size, 0);   /* tags written into the bitstream (Lame.js:1541) */
   if (mp3out < 0) return mp3out;
   mp3buf += mp3out; mp3size += mp3out;
   if (bs_NEQ(e->scale, 0) && bs_NEQ(e->scale, 1.0)) {
@@ -614,6 +616,7 @@ int lj_flush(LjEnc* e, uint8_t* out, int cap) {
   if (e->in_samplerate != e->out_samplerate) samples_to_encode += 16. * e->out_samplerate / e->in_samplerate;
   double end_padding = e->framesize - fmod(samples_to_encode, (double)e->framesize);
   if (end_padding < 576) end_padding += e->framesize;
+  e->encoder_padding = js_toint32(end_padding);
   double frames_left = (samples_to_encode + end_padding) / e->framesize;
   while (frames_left > 0 && imp3 >= 0) {
     double bunch = mf_needed - e->mf_size;
@@ -634,7 +637,7 @@ int lj_flush(LjEnc* e, uint8_t* out, int cap) {
   e->ResvSize = 0; e->main_data_begin = 0;
   int remaining = cap - mp3count;
   if (cap == 0) remaining = 0;
-  imp3 = lj_copy_buffer(e, out, remaining);
+  imp3 = lj_copy_buffer(e, out, remaining, 1);
   if (imp3 < 0) return imp3;
   mp3count += imp3;
   return mp3count;

@@ -72,6 +72,15 @@ def lib():
         L.lj_set_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.lj_trace_count.argtypes = [ctypes.c_void_p]
         L.lj_query_out_samplerate.argtypes = [ctypes.c_int] * 3
+        L.lj_enable_vbr_tag.argtypes = [ctypes.c_void_p]
+        L.lj_music_crc.argtypes = [ctypes.c_void_p]
+        L.lj_bytes_written.argtypes = [ctypes.c_void_p]
+        L.lj_bytes_written.restype = ctypes.c_longlong
+        L.lj_vbr_frames.argtypes = [ctypes.c_void_p]
+        L.lj_encoder_padding.argtypes = [ctypes.c_void_p]
+        L.lj_get_lametag_frame.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.lj_crc16.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int]
+        L.lj_wav_read_header.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
         assert L.lj_trace_size() == TRACE_DTYPE.itemsize, (L.lj_trace_size(), TRACE_DTYPE.itemsize)
         _lib = L
     return _lib
@@ -85,12 +94,13 @@ def out_samplerate(channels, samplerate, kbps):
 class OracleEncoder:
     """Mirror of lamejs.Mp3Encoder (src/js/index.js:66-136) backed by the C++ restatement."""
 
-    def __init__(self, channels, samplerate, kbps, trace_frames=0):
+    def __init__(self, channels, samplerate, kbps, trace_frames=0, write_vbr_tag=False):
         self.L = lib()
         self.h = self.L.lj_create(channels, samplerate, kbps)
         if not self.h:
             raise ValueError("unsupported configuration")
         self.channels = channels
+        self.tag_on = bool(write_vbr_tag) and self.L.lj_enable_vbr_tag(self.h) == 1   # gfp.bWriteVbrTag (InitVbrTag may refuse)
         self.trace = None
         if trace_frames:
             self.trace = np.zeros(trace_frames, dtype=TRACE_DTYPE)
@@ -117,6 +127,25 @@ class OracleEncoder:
 
     def traces(self):
         return self.trace[: self.L.lj_trace_count(self.h)]
+
+    # gfc.nMusicCRC / VBR_seek_table.nBytesWritten: kept by copy_buffer on every call (BitStream.js:924-935)
+    def music_crc(self):
+        return self.L.lj_music_crc(self.h)
+
+    def bytes_written(self):
+        return self.L.lj_bytes_written(self.h)
+
+    def vbr_frames(self):
+        return self.L.lj_vbr_frames(self.h)
+
+    def encoder_padding(self):
+        return self.L.lj_encoder_padding(self.h)
+
+    def lametag_frame(self):
+        """VBRTag.getLameTagFrame: b'' when the tag is off."""
+        buf = np.zeros(2880, dtype=np.uint8)
+        k = self.L.lj_get_lametag_frame(self.h, buf.ctypes.data, 2880)
+        return buf[:k].tobytes()
 
     def close(self):
         if self.h:
@@ -146,3 +175,43 @@ def encode_stream(channels, samplerate, kbps, left, right=None, chunk=None, trac
     tr = enc.traces().copy() if trace_frames else None
     enc.close()
     return bytes(out), sizes, tr
+
+
+def crc16(data, crc=0):
+    """CRC-16 of VBRTag.js:547-556 (reflected 0xA001, start value `crc`)."""
+    a = np.frombuffer(bytes(data), dtype=np.uint8)
+    return lib().lj_crc16(a.ctypes.data if len(a) else None, len(a), crc)
+
+
+def wav_read_header(data):
+    """WavHeader.readHeader (index.js:154-193): dict, None (`return undefined`), or raises like the reference throws."""
+    a = np.frombuffer(bytes(data), dtype=np.uint8)
+    out = (ctypes.c_longlong * 4)()
+    rc = lib().lj_wav_read_header(a.ctypes.data if len(a) else None, len(a), out)
+    if rc == 0:
+        return None
+    if rc == -1:
+        raise ValueError("extended fmt chunk not implemented")
+    if rc == -2:
+        raise IndexError("read past the end of the buffer")
+    return {"dataOffset": out[0], "dataLen": out[1], "channels": out[2], "sampleRate": out[3]}
+
+
+def encode_stream_tagged(channels, samplerate, kbps, left, right=None, chunk=None):
+    """Like encode_stream with gfp.bWriteVbrTag = true: the first call's bytes start with the placeholder frame
+    (InitVbrTag); returns (bytes, per-call sizes, info) with info = tag frame, music CRC, byte / frame counts, padding."""
+    enc = OracleEncoder(channels, samplerate, kbps, write_vbr_tag=True)
+    out, sizes = bytearray(), []
+    n = len(left)
+    step = chunk or max(n, 1)
+    for i in range(0, n, step):
+        b = enc.encode_buffer(left[i : i + step], None if right is None else right[i : i + step])
+        sizes.append(len(b))
+        out += b
+    b = enc.flush()
+    sizes.append(len(b))
+    out += b
+    info = {"tag_on": enc.tag_on, "tag": enc.lametag_frame(), "music_crc": enc.music_crc(), "bytes_written": enc.bytes_written(),
+            "frames": enc.vbr_frames(), "encoder_padding": enc.encoder_padding()}
+    enc.close()
+    return bytes(out), sizes, info
