@@ -111,6 +111,46 @@ int mp3b200_encode_streams_device(int channels, int samplerate, int kbps, int ns
                                   const int64_t* pcm_off, const int64_t* nsamples, uint8_t* d_out,
                                   const int64_t* out_off, float* timings_ms);
 
+/* ---- container / metadata step after the path ------------------------------------------------------
+ * lamejs carries LAME's Xing / Info / LAME tag writer (src/js/VBRTag.js) and keeps its two inputs up to date on every
+ * Mp3Encoder call -- gfc.nMusicCRC and VBR_seek_table.nBytesWritten (BitStream.js:924-935) -- but switches the writer off
+ * (index.js:107: gfp.bWriteVbrTag = false).  Here the writer can be switched on.  Semantics are LAME's (VBRTag.java, which
+ * VBRTag.js transliterates): with the tag on, the first bytes an encoder hands out are an all-zero frame of the stream's own
+ * bitrate (InitVbrTag); after flush() mp3b200_get_lametag_frame returns the finished frame, which the caller writes over
+ * that placeholder (lame_get_lametag_frame / putVbrTag).  The CRC-16 over all audio bytes is computed on the GPU
+ * (k_music_crc, lamejs_b200/csrc/k_tag.cuh) from the bytes where the packer left them.
+ *   set_write_vbr_tag   gfp.bWriteVbrTag, before the first sample.  Returns 1 (on), 0 (off: asked to, or InitVbrTag refused
+ *                       because the frame cannot hold side info + 156 bytes, VBRTag.js:508-513), negative on error.
+ *   get_lametag_frame   VBRTag.getLameTagFrame (VBRTag.js:829-923): 0 when the tag is off or no frame has been encoded;
+ *                       the size needed when `cap` is too small (or buf NULL); else writes that many bytes and returns it.
+ *   music_crc / bytes_written   gfc.nMusicCRC / nBytesWritten so far (-1 with the tag off: the accumulators are idle then).
+ *   lametag_size        the tag frame's size for a configuration (0: does not fit; negative: rejected configuration).
+ *   lametag_build       the same frame from numbers instead of a handle (pure host arithmetic, no device needed): for callers
+ *                       that encode one stream in segments and combine counts and CRCs themselves.
+ *   encode_streams_tagged   mp3b200_encode_streams with the tag on: out[s] = finished tag frame ++ audio frames
+ *                       (cap[s] >= mp3b200_stream_bytes + mp3b200_lametag_size); one k_music_crc launch for the batch. */
+int mp3b200_set_write_vbr_tag(mp3b200_encoder* h, int on);
+int mp3b200_get_lametag_frame(mp3b200_encoder* h, uint8_t* buf, int cap);
+int mp3b200_music_crc(mp3b200_encoder* h);
+int64_t mp3b200_bytes_written(mp3b200_encoder* h);
+int mp3b200_lametag_size(int channels, int samplerate, int kbps);
+int mp3b200_lametag_build(int channels, int samplerate, int kbps, int64_t nframes, int64_t music_bytes, int music_crc,
+                          int encoder_padding, uint8_t* buf, int cap);
+int mp3b200_encode_streams_tagged(int channels, int samplerate, int kbps, int nstreams, const int16_t* const* left,
+                                  const int16_t* const* right, const int64_t* nsamples, uint8_t* const* out,
+                                  const int64_t* cap, int64_t* out_bytes);
+
+/* Test / bench tap of k_music_crc: CRC-16 (VBRTag.js:547-556, start 0) of the ranges [off[i], off[i] + len[i]) of a DEVICE
+ * buffer; `ms` (optional) receives the CUDA-event time of one launch sequence incl. its 4-byte-per-range read-back. */
+int mp3b200_debug_music_crc(const uint8_t* d_buf, const int64_t* off, const int64_t* len, int nranges, uint32_t* crc, float* ms);
+
+/* Replaces `lamejs.WavHeader.readHeader(dataView)` (src/js/index.js:154-193): the RIFF/WAVE front-end lamejs ships for its
+ * examples.  Returns 1 and fills `out`; 0 where the reference returns undefined (not RIFF / not WAVE / "fmt " not first);
+ * -1 where it throws 'extended fmt chunk not implemented' (fmt length other than 16 or 18); -2 where its DataView read runs
+ * past the buffer (RangeError).  Pure host code, no device needed.  PCM starts at data + data_offset. */
+typedef struct mp3b200_wav_header { int64_t data_offset, data_len; int32_t channels; uint32_t sample_rate; } mp3b200_wav_header;
+int mp3b200_wav_read_header(const uint8_t* data, int64_t len, mp3b200_wav_header* out);
+
 /* ---- stage taps for parity tests (one stream, whole-stream semantics) -----------------------------------
  * Run the pipeline for one stream given host PCM and copy intermediate results back.  Any output pointer may be
  * NULL.  Shapes ([F] = mp3b200_stream_frames(n)):

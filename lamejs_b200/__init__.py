@@ -8,4 +8,4 @@
 (reference: zhuker/lamejs src/js/index.js:66-136).  All computation happens in libmp3b200.so on the GPU; the
 module raises if the library or a CUDA device is missing -- there is no CPU fallback.
 """
-from .encoder import Mp3Encoder, encode_batch, flush_batch, encode_streams, encode_streams_device, debug_stages, lib, stream_bytes, stream_frames, granules_per_frame, Mp3B200Error  # noqa: F401
+from .encoder import Mp3Encoder, WavHeader, lametag_size, lametag_build, encode_streams_tagged, debug_music_crc, encode_batch, flush_batch, encode_streams, encode_streams_device, debug_stages, lib, stream_bytes, stream_frames, granules_per_frame, Mp3B200Error  # noqa: F401

@@ -6,9 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmp3b200.so")
-SOURCES = ["mp3_encoder.cu", "mp3_config.cpp"]
+SOURCES = ["mp3_encoder.cu", "mp3_config.cpp", "mp3_tag.cpp"]
 DEPS = SOURCES + ["mp3_config.h", "mp3_device.cuh", "mp3_math.cuh", "mp3_tables.h", "k_filterbank.cuh", "k_psy.cuh",
-                  "k_quant.cuh", "mp3_handle.inc", "../../include/mp3b200.h"]
+                  "k_quant.cuh", "k_tag.cuh", "mp3_tag.h", "mp3_handle.inc", "../../include/mp3b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # bit-exactness contract: no FMA contraction, IEEE div/sqrt, no flush-to-zero (DESIGN.md "numerics")

@@ -487,3 +487,34 @@ int mp3_build_tables(int channels, int samplerate, int kbps, Mp3Tables* t) {
   }
   return 0;
 }
+
+/* The tag's view of a configuration: lowpassfreq as lame_init_params leaves it (Lame.js:838-896), the preset's safejoint
+ * bit (Presets.js:262-263), and the "non optimal settings" rule of putLameVBR (VBRTag.js:722-731), which for Mp3Encoder
+ * reduces to: reservoir disabled below 320 kbps, or a source rate of 32 kHz and below. */
+int mp3_tag_params(int channels, int samplerate, int kbps, Mp3TagParams* p) {
+  memset(p, 0, sizeof *p);
+  Mp3Tables* t = new Mp3Tables();
+  const int rc = mp3_build_tables(channels, samplerate, kbps, t);
+  if (rc == 0) {
+    p->version = t->version; p->mpeg25 = t->mpeg25; p->samplerate = t->samplerate; p->kbps = t->kbps; p->mono = t->mono;
+    p->bitrate_index = t->bitrate_index; p->samplerate_index = t->samplerate_index; p->sideinfo_len = t->sideinfo_len;
+    p->frame_bytes = t->frame_bytes_nopad;
+    p->fits = p->frame_bytes >= p->sideinfo_len + 156 && p->frame_bytes <= 2880;
+    double lowpass = kLowpassHz[ladder_index(kbps)];            /* the unsnapped rate, like mp3_build_tables */
+    if (t->mono) lowpass *= 1.5;
+    double lp = (double)to_i32(lowpass);
+    if (2 * lp > samplerate) lp = samplerate / 2.0;
+    lp = dmin(20500, lp);
+    lp = dmin(samplerate / 2.0, lp);
+    const double lb = lp / 100.0 + .5;
+    p->lowpass_byte = to_i32(lb > 255 ? 255 : lb);
+    p->quality_byte = 100 - 10 * 4 - 3;
+    const Preset& ps = kPresets[ladder_index(t->kbps)];
+    p->flags_byte = 4 + (1 << 4) + ((ps.safejoint ? 1 : 0) << 5);
+    const int source_class = samplerate <= 32000 ? 0 : samplerate == 48000 ? 2 : samplerate > 48000 ? 3 : 1;
+    const int non_optimal = (t->kbps < 320 || samplerate <= 32000) ? 1 : 0;
+    p->misc_byte = t->noise_shaping + ((t->mono ? 0 : 1) << 2) + (non_optimal << 5) + (source_class << 6);
+  }
+  delete t;
+  return rc;
+}

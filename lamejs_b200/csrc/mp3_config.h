@@ -93,6 +93,20 @@ struct Mp3Tables {
   double ixmax_over_istep[MP3_QMAX], cmp01_over_istep[MP3_QMAX];
 };
 
+/* What the Xing / Info / LAME tag frame says about a configuration (reference src/js/VBRTag.js:281-364,558-802): the
+ * values `lame_init_params` leaves in gfp / gfc for the fields of the tag.  Host only; not part of Mp3Tables. */
+struct Mp3TagParams {
+  int version, mpeg25, samplerate, kbps, mono;
+  int bitrate_index, samplerate_index, sideinfo_len;
+  int frame_bytes;                /* VBR_seek_table.TotalFrameSize: (version + 1) * 72000 * kbps / samplerate, integer quotient */
+  int fits;                       /* InitVbrTag keeps the tag only if the frame holds side info + 156 bytes (VBRTag.js:508-513) */
+  int lowpass_byte;               /* trunc(min(255, lowpassfreq / 100 + .5)) */
+  int quality_byte;               /* 100 - 10 * VBR_q - quality = 57 (VBR_q 4, quality 3) */
+  int flags_byte;                 /* ATHtype | nspsytune << 4 | safejoint << 5 */
+  int misc_byte;                  /* noise_shaping | stereo mode << 2 | non-optimal << 5 | source rate class << 6 */
+};
+int mp3_tag_params(int channels, int samplerate, int kbps, Mp3TagParams* p);
+
 /* returns 0, or -1 when lamejs itself would fail or would resample (out_samplerate != samplerate, Lame.js:285-364:
  * SURVEY.md 8(f1) resampler, not built on the GPU) */
 int mp3_build_tables(int channels, int samplerate, int kbps, Mp3Tables* t);

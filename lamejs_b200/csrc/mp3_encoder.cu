@@ -23,6 +23,8 @@
 #include "k_filterbank.cuh"
 #include "k_psy.cuh"
 #include "k_quant.cuh"
+#include "k_tag.cuh"
+#include "mp3_tag.h"
 
 namespace {
 
@@ -191,6 +193,7 @@ struct ThreadCtx {
   int16_t* d_pcm = nullptr; size_t d_pcm_cap = 0;
   uint8_t* d_out = nullptr; size_t d_out_cap = 0;
   uint8_t* h_pin = nullptr; size_t h_pin_cap = 0;       /* pinned host staging */
+  long long* d_crc_ranges = nullptr; unsigned* d_crc = nullptr; int crc_cap = 0;   /* music CRC: [2][cap] offsets / lengths, [cap] results */
   void release() {
     if (device < 0) return;
     cudaSetDevice(device);
@@ -198,6 +201,7 @@ struct ThreadCtx {
     cudaFree(d_pcm); d_pcm = nullptr; d_pcm_cap = 0;
     cudaFree(d_out); d_out = nullptr; d_out_cap = 0;
     cudaFreeHost(h_pin); h_pin = nullptr; h_pin_cap = 0;
+    cudaFree(d_crc_ranges); d_crc_ranges = nullptr; cudaFree(d_crc); d_crc = nullptr; crc_cap = 0;
     for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto& e : evq) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto& e : ready) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -242,6 +246,14 @@ struct ThreadCtx {
     cudaFree(d_out); d_out = nullptr; d_out_cap = 0;
     CK(cudaMalloc(&d_out, bytes));
     d_out_cap = bytes;
+    return 0;
+  }
+  int need_crc(int ranges) {
+    if (crc_cap >= ranges) return 0;
+    cudaFree(d_crc_ranges); d_crc_ranges = nullptr; cudaFree(d_crc); d_crc = nullptr; crc_cap = 0;
+    CK(cudaMalloc(&d_crc_ranges, sizeof(long long) * 2 * (size_t)ranges));
+    CK(cudaMalloc(&d_crc, sizeof(unsigned) * (size_t)ranges));
+    crc_cap = ranges;
     return 0;
   }
   int need_pin(size_t bytes) {
@@ -673,6 +685,175 @@ int mp3b200_debug_stages(int channels, int samplerate, int kbps, const int16_t* 
     }
   }
   cudaFree(d_pcm); cudaFree(d_out);
+  return rc;
+}
+
+}  // extern "C"
+
+/* ---- container / metadata step: music CRC on the device, tag frames on the host ---- */
+namespace {
+CrcTables g_crc_host;                              /* byte table + zero-byte powers (k_tag.cuh), built once */
+bool g_crc_host_ready = false;
+CrcTables* g_crc_dev[MP3_MAX_DEVICES] = {};        /* per device copy */
+
+const CrcTables& crc_host() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_crc_host_ready) { crc_host_tables(&g_crc_host); g_crc_host_ready = true; }
+  return g_crc_host;
+}
+
+/* CRC-16 (start 0) of the byte ranges [off[i], off[i] + len[i]) of d_buf, one k_music_crc launch per 65535 ranges, on the
+ * calling thread's stream behind whatever wrote the bytes.  crc[i] is valid when the call returns. */
+int music_crc_ranges(int device, const uint8_t* d_buf, const std::vector<long long>& off, const std::vector<long long>& len, std::vector<unsigned>& crc) {
+  const int R = (int)off.size();
+  crc.assign((size_t)R, 0u);
+  if (R == 0) return 0;
+  const CrcTables& ht = crc_host();
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_crc_dev[device]) {
+      CK(cudaMalloc(&g_crc_dev[device], sizeof(CrcTables)));
+      CK(cudaMemcpy(g_crc_dev[device], &ht, sizeof(CrcTables), cudaMemcpyHostToDevice));
+    }
+  }
+  ThreadCtx& sc = t_ctx;
+  int rc = sc.need_crc(R);
+  if (rc) return rc;
+  std::vector<long long> ranges((size_t)2 * R);
+  long long longest = 0;
+  for (int i = 0; i < R; i++) { ranges[i] = off[i]; ranges[(size_t)R + i] = len[i]; longest = len[i] > longest ? len[i] : longest; }
+  CK(cudaMemcpyAsync(sc.d_crc_ranges, ranges.data(), sizeof(long long) * ranges.size(), cudaMemcpyHostToDevice, sc.st));
+  CK(cudaMemsetAsync(sc.d_crc, 0, sizeof(unsigned) * (size_t)R, sc.st));
+  if (longest > 0) {
+    const long long pieces = (longest + CRC_PIECE_BYTES - 1) / CRC_PIECE_BYTES;
+    for (int r0 = 0; r0 < R; r0 += 65535) {
+      const int nr = R - r0 < 65535 ? R - r0 : 65535;
+      dim3 grid((unsigned)((pieces + CRC_WARPS - 1) / CRC_WARPS), (unsigned)nr);
+      k_music_crc<<<grid, CRC_WARPS * 32, 0, sc.st>>>(d_buf, sc.d_crc_ranges + r0, sc.d_crc_ranges + R + r0, g_crc_dev[device], sc.d_crc + r0);
+      g_launches++;
+    }
+  }
+  CK(cudaMemcpyAsync(crc.data(), sc.d_crc, sizeof(unsigned) * (size_t)R, cudaMemcpyDeviceToHost, sc.st));
+  CK(cudaStreamSynchronize(sc.st));
+  CK(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int mp3b200_wav_read_header(const uint8_t* data, int64_t len, mp3b200_wav_header* out) {
+  if (!out || len < 0 || (len > 0 && !data)) return MP3B200_ERR_HANDLE;
+  long long off = 0, dl = 0; int ch = 0; unsigned sr = 0;
+  const int rc = mp3_wav_read_header(data, len, &off, &dl, &ch, &sr);
+  out->data_offset = off; out->data_len = dl; out->channels = ch; out->sample_rate = sr;
+  return rc;
+}
+
+/* CRC-16 of byte ranges of a DEVICE buffer (test / bench tap of k_music_crc): crc[i] for [off[i], off[i] + len[i]);
+ * ms (optional) = CUDA-event time of the launch(es) on the library's stream, tables already resident. */
+int mp3b200_debug_music_crc(const uint8_t* d_buf, const int64_t* off, const int64_t* len, int nranges, uint32_t* crc, float* ms) {
+  if (nranges < 0 || (nranges > 0 && (!d_buf || !off || !len || !crc))) return MP3B200_ERR_HANDLE;
+  int dev = 0;
+  { std::lock_guard<std::mutex> lk(g_mu); dev = g_device; int rc = ensure_device(dev); if (rc) return rc; }
+  int rc = t_ctx.use(dev);
+  if (rc) return rc;
+  std::vector<long long> o(off, off + nranges), l(len, len + nranges);
+  std::vector<unsigned> c;
+  CK(cudaEventRecord(t_ctx.ev_in, cudaStreamLegacy));
+  CK(cudaStreamWaitEvent(t_ctx.st, t_ctx.ev_in, 0));
+  rc = music_crc_ranges(dev, d_buf, o, l, c);              /* first call: uploads the tables */
+  if (rc) return rc;
+  if (ms) {
+    CK(cudaEventRecord(t_ctx.ev[0], t_ctx.st));
+    rc = music_crc_ranges(dev, d_buf, o, l, c);
+    if (rc) return rc;
+    CK(cudaEventRecord(t_ctx.ev[1], t_ctx.st));
+    CK(cudaEventSynchronize(t_ctx.ev[1]));
+    CK(cudaEventElapsedTime(ms, t_ctx.ev[0], t_ctx.ev[1]));
+  }
+  for (int i = 0; i < nranges; i++) crc[i] = c[i];
+  return 0;
+}
+
+int mp3b200_lametag_size(int channels, int samplerate, int kbps) {
+  Mp3TagParams p;
+  if (mp3_tag_params(channels, samplerate, kbps, &p) != 0) return MP3B200_ERR_CONFIG;
+  return p.fits ? p.frame_bytes : 0;
+}
+
+int mp3b200_lametag_build(int channels, int samplerate, int kbps, int64_t nframes, int64_t music_bytes, int music_crc, int encoder_padding,
+                          uint8_t* buf, int cap) {
+  Mp3TagParams p;
+  if (mp3_tag_params(channels, samplerate, kbps, &p) != 0) { g_err = "unsupported configuration"; return MP3B200_ERR_CONFIG; }
+  if (!p.fits || nframes <= 0) return 0;
+  if (!buf || cap < p.frame_bytes) return p.frame_bytes;              /* like getLameTagFrame: the size it needs */
+  Mp3SeekBag* bag = new Mp3SeekBag();
+  bag->reset();
+  bag->add_frames(nframes, p.kbps);
+  const int n = mp3_tag_frame(p, *bag, music_bytes, (unsigned)music_crc, encoder_padding, buf);
+  delete bag;
+  return n;
+}
+
+int mp3b200_encode_streams_tagged(int channels, int samplerate, int kbps, int nstreams, const int16_t* const* left,
+                                  const int16_t* const* right, const int64_t* nsamples, uint8_t* const* out,
+                                  const int64_t* cap, int64_t* out_bytes) {
+  if (nstreams < 0) { g_err = "negative stream count"; return MP3B200_ERR_HANDLE; }
+  Config* cfg;
+  int rc = get_config(channels, samplerate, kbps, &cfg);
+  if (rc) return rc;
+  Mp3TagParams p;
+  if (mp3_tag_params(channels, samplerate, kbps, &p) != 0) { g_err = "unsupported configuration"; return MP3B200_ERR_CONFIG; }
+  const int tfs = p.fits ? p.frame_bytes : 0;
+  std::vector<int64_t> pcm_off(nstreams), out_off(nstreams);
+  std::vector<long long> frames(nstreams), audio(nstreams);
+  long long tot_samples = 0, tot_bytes = 0;
+  for (int s = 0; s < nstreams; s++) {
+    pcm_off[s] = tot_samples; tot_samples += nsamples[s] * channels;
+    out_off[s] = tot_bytes;
+    frames[s] = frames_for(nsamples[s], cfg->host.mode_gr);
+    audio[s] = bytes_for(cfg->host, frames[s]);
+    if (cap[s] < audio[s] + tfs) { g_err = "output buffer too small"; return MP3B200_ERR_BUFFER; }
+    out_bytes[s] = audio[s] + tfs;
+    tot_bytes += audio[s];
+  }
+  if (nstreams == 0) return MP3B200_OK;
+  rc = t_ctx.use(cfg->device);
+  if (rc) return rc;
+  rc = t_ctx.need_pcm((size_t)tot_samples + 8);
+  if (rc) return rc;
+  rc = t_ctx.need_out((size_t)tot_bytes + 8);
+  if (rc) return rc;
+  for (int s = 0; s < nstreams; s++) {
+    if (nsamples[s] <= 0) continue;
+    CK(cudaMemcpyAsync(t_ctx.d_pcm + pcm_off[s], left[s], sizeof(int16_t) * nsamples[s], cudaMemcpyHostToDevice, t_ctx.up_st));
+    if (channels == 2)
+      CK(cudaMemcpyAsync(t_ctx.d_pcm + pcm_off[s] + nsamples[s], (right && right[s]) ? right[s] : left[s], sizeof(int16_t) * nsamples[s], cudaMemcpyHostToDevice, t_ctx.up_st));
+  }
+  PcmArrival arr;
+  arr.chunks = 1; arr.ready = t_ctx.ready;
+  CK(cudaEventRecord(t_ctx.ready[0], t_ctx.up_st));
+  rc = encode_streams_device_impl(cfg, channels, nstreams, t_ctx.d_pcm, pcm_off.data(), nsamples, t_ctx.d_out, out_off.data(), nullptr, &arr);
+  if (rc) return rc;
+  /* the music CRC of every stream, where the bytes are */
+  std::vector<long long> off(out_off.begin(), out_off.end());
+  std::vector<unsigned> crc;
+  rc = music_crc_ranges(cfg->device, t_ctx.d_out, off, audio, crc);
+  if (rc) return rc;
+  Mp3SeekBag* bag = new Mp3SeekBag();
+  for (int s = 0; s < nstreams; s++) {
+    int wrote = 0;
+    if (tfs > 0 && frames[s] > 0) {
+      bag->reset();
+      bag->add_frames(frames[s], p.kbps);
+      wrote = mp3_tag_frame(p, *bag, audio[s], crc[s], mp3_encoder_padding(nsamples[s], cfg->host.mode_gr), out[s]);
+    }
+    out_bytes[s] = audio[s] + wrote;
+    if (audio[s] > 0 && cudaMemcpyAsync(out[s] + wrote, t_ctx.d_out + out_off[s], (size_t)audio[s], cudaMemcpyDeviceToHost, t_ctx.st) != cudaSuccess) rc = MP3B200_ERR_CUDA;
+  }
+  delete bag;
+  if (cudaStreamSynchronize(t_ctx.st) != cudaSuccess) rc = MP3B200_ERR_CUDA;
   return rc;
 }
 

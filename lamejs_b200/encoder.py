@@ -47,6 +47,16 @@ def lib():
     L.mp3b200_granules_per_frame.argtypes = [c_int, c_int, c_int]
     L.mp3b200_encode_streams.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
     L.mp3b200_encode_streams_device.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    L.mp3b200_set_write_vbr_tag.argtypes = [vp, c_int]
+    L.mp3b200_get_lametag_frame.argtypes = [vp, vp, c_int]
+    L.mp3b200_music_crc.argtypes = [vp]
+    L.mp3b200_bytes_written.argtypes = [vp]
+    L.mp3b200_bytes_written.restype = c_i64
+    L.mp3b200_lametag_size.argtypes = [c_int, c_int, c_int]
+    L.mp3b200_lametag_build.argtypes = [c_int, c_int, c_int, c_i64, c_i64, c_int, c_int, vp, c_int]
+    L.mp3b200_encode_streams_tagged.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    L.mp3b200_wav_read_header.argtypes = [vp, c_i64, vp]
+    L.mp3b200_debug_music_crc.argtypes = [vp, vp, vp, c_int, vp, vp]
     L.mp3b200_debug_stages.argtypes = [c_int, c_int, c_int, vp, vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_i64]
     _lib = L
     return L
@@ -74,15 +84,70 @@ def stream_bytes(channels, samplerate, kbps, nsamples):
     return int(lib().mp3b200_stream_bytes(channels, samplerate, kbps, int(nsamples)))
 
 
-class Mp3Encoder:
-    """Drop-in for lamejs.Mp3Encoder(channels, samplerate, kbps) (src/js/index.js:66-136)."""
+class WavHeader:
+    """lamejs.WavHeader (src/js/index.js:138-193): dataOffset, dataLen, channels, sampleRate."""
 
-    def __init__(self, channels=1, samplerate=44100, kbps=128):
+    def __init__(self):
+        self.dataOffset = self.dataLen = self.channels = self.sampleRate = 0
+
+    class _C(ctypes.Structure):
+        _fields_ = [("data_offset", ctypes.c_int64), ("data_len", ctypes.c_int64), ("channels", ctypes.c_int32), ("sample_rate", ctypes.c_uint32)]
+
+    @staticmethod
+    def readHeader(data):
+        """WavHeader.readHeader(dataView): a WavHeader, None where the reference returns undefined; raises ValueError where it
+        throws 'extended fmt chunk not implemented', IndexError where its DataView read leaves the buffer (RangeError)."""
+        a = np.frombuffer(bytes(data), dtype=np.uint8)
+        c = WavHeader._C()
+        rc = lib().mp3b200_wav_read_header(a.ctypes.data if len(a) else None, len(a), ctypes.byref(c))
+        if rc == 0:
+            return None
+        if rc == -1:
+            raise ValueError("extended fmt chunk not implemented")
+        if rc != 1:
+            raise IndexError("read past the end of the buffer")
+        w = WavHeader()
+        w.dataOffset, w.dataLen, w.channels, w.sampleRate = c.data_offset, c.data_len, c.channels, c.sample_rate
+        return w
+
+
+def lametag_size(channels, samplerate, kbps):
+    """Size of the Xing / Info / LAME tag frame of a configuration (0: InitVbrTag would switch the tag off)."""
+    return _check(lib().mp3b200_lametag_size(channels, samplerate, kbps))
+
+
+def lametag_build(channels, samplerate, kbps, nframes, music_bytes, music_crc, encoder_padding):
+    """The tag frame from numbers (no device needed): VBRTag.getLameTagFrame for a CBR stream of `nframes` frames."""
+    buf = np.zeros(2880, dtype=np.uint8)
+    n = _check(lib().mp3b200_lametag_build(channels, samplerate, kbps, int(nframes), int(music_bytes), int(music_crc), int(encoder_padding),
+                                           buf.ctypes.data, 2880))
+    return buf[:n].tobytes()
+
+
+class Mp3Encoder:
+    """Drop-in for lamejs.Mp3Encoder(channels, samplerate, kbps) (src/js/index.js:66-136).  `write_vbr_tag=True` is
+    gfp.bWriteVbrTag (index.js:107 sets it false): the stream then starts with a placeholder frame, and `lametag_frame()`
+    after flush() returns the finished Info / LAME tag frame to write over it."""
+
+    def __init__(self, channels=1, samplerate=44100, kbps=128, write_vbr_tag=False):
         self._L = lib()
         self._h = ctypes.c_void_p()
         self.channels = channels
         rc = self._L.mp3b200_create(channels, samplerate, kbps, ctypes.byref(self._h))
         _check(rc)
+        self.tag_on = bool(write_vbr_tag) and _check(self._L.mp3b200_set_write_vbr_tag(self._h, 1)) == 1
+        self._tag_room = lametag_size(channels, samplerate, kbps) if self.tag_on else 0
+
+    def lametag_frame(self):
+        buf = np.zeros(2880, dtype=np.uint8)
+        n = _check(self._L.mp3b200_get_lametag_frame(self._h, buf.ctypes.data, 2880))
+        return buf[:n].tobytes()
+
+    def music_crc(self):
+        return int(self._L.mp3b200_music_crc(self._h))
+
+    def bytes_written(self):
+        return int(self._L.mp3b200_bytes_written(self._h))
 
     def encodeBuffer(self, left, right=None):
         left = np.ascontiguousarray(left, dtype=np.int16)
@@ -90,13 +155,13 @@ class Mp3Encoder:
             right = left
         right = np.ascontiguousarray(right, dtype=np.int16)
         assert len(left) == len(right)
-        cap = int(1.25 * len(left) + 7200)     # index.js:114,124
+        cap = int(1.25 * len(left) + 7200) + self._tag_room     # index.js:114,124
         buf = np.empty(cap, dtype=np.uint8)
         n = _check(self._L.mp3b200_encode(self._h, left.ctypes.data, right.ctypes.data, len(left), buf.ctypes.data, cap))
         return buf[:n].tobytes()
 
     def flush(self):
-        cap = 7200 + 8 * 1441
+        cap = 7200 + 8 * 1441 + self._tag_room
         buf = np.empty(cap, dtype=np.uint8)
         n = _check(self._L.mp3b200_flush(self._h, buf.ctypes.data, cap))
         return buf[:n].tobytes()
@@ -192,6 +257,38 @@ def encode_streams(channels, samplerate, kbps, lefts, rights=None):
     got = np.zeros(S, dtype=np.int64)
     _check(L.mp3b200_encode_streams(channels, samplerate, kbps, S, lp, rp, ns.ctypes.data, op, caps.ctypes.data, got.ctypes.data))
     return [o[: int(g)].tobytes() for o, g in zip(outs, got)]
+
+
+def encode_streams_tagged(channels, samplerate, kbps, lefts, rights=None):
+    """encode_streams with gfp.bWriteVbrTag on: every returned stream starts with its finished Info / LAME tag frame (frame
+    and byte counts, seek table, encoder delay / padding, CRC-16 of the audio bytes computed on the GPU)."""
+    L = lib()
+    S = len(lefts)
+    if S == 0:
+        return []
+    lefts = [np.ascontiguousarray(x, dtype=np.int16) for x in lefts]
+    rights = lefts if (rights is None or channels == 1) else [np.ascontiguousarray(x, dtype=np.int16) for x in rights]
+    ns = np.array([len(x) for x in lefts], dtype=np.int64)
+    room = lametag_size(channels, samplerate, kbps)
+    nb = [stream_bytes(channels, samplerate, kbps, int(n)) + room for n in ns]
+    outs = [np.empty(b, dtype=np.uint8) for b in nb]
+    lp = (ctypes.c_void_p * S)(*[x.ctypes.data for x in lefts])
+    rp = (ctypes.c_void_p * S)(*[x.ctypes.data for x in rights])
+    op = (ctypes.c_void_p * S)(*[x.ctypes.data for x in outs])
+    caps = np.array(nb, dtype=np.int64)
+    got = np.zeros(S, dtype=np.int64)
+    _check(L.mp3b200_encode_streams_tagged(channels, samplerate, kbps, S, lp, rp, ns.ctypes.data, op, caps.ctypes.data, got.ctypes.data))
+    return [o[: int(g)].tobytes() for o, g in zip(outs, got)]
+
+
+def debug_music_crc(d_buf_ptr, offsets, lengths, timed=False):
+    """k_music_crc on byte ranges of a device buffer (raw pointer as int): list of CRC-16 values (+ ms if `timed`)."""
+    off = np.ascontiguousarray(offsets, dtype=np.int64)
+    ln = np.ascontiguousarray(lengths, dtype=np.int64)
+    crc = np.zeros(len(off), dtype=np.uint32)
+    ms = ctypes.c_float(0)
+    _check(lib().mp3b200_debug_music_crc(d_buf_ptr, off.ctypes.data, ln.ctypes.data, len(off), crc.ctypes.data, ctypes.byref(ms) if timed else None))
+    return ([int(c) for c in crc], float(ms.value)) if timed else [int(c) for c in crc]
 
 
 def encode_streams_device(channels, samplerate, kbps, d_pcm_ptr, pcm_off, nsamples, d_out_ptr, out_off):
