@@ -140,6 +140,29 @@ int mp3b200_encode_streams_tagged(int channels, int samplerate, int kbps, int ns
                                   const int16_t* const* right, const int64_t* nsamples, uint8_t* const* out,
                                   const int64_t* cap, int64_t* out_bytes);
 
+/* ID3 tags.  lamejs carries only a stub (index.js:56-64) and switches the automatic tags off (index.js:109);
+ * the writer is the Java original's, src/main/java/mp3/ID3Tag.java: lame_get_id3v2_tag :961-1102 (ID3v2.3, ISO-8859-1 text
+ * frames TSSE TIT2 TPE1 TALB TYER COMM TRCK TCON TLEN, optional padding), lame_get_id3v1_tag :1141-1189 (128 bytes, v1.1 when a
+ * track is set).  Fields are Latin-1 strings, NULL or "" = not set (the id3tag_set_* calls, applied in the order of the struct);
+ * `genre` is a number 0..147 or a name of ID3Tag.java:56-89.  Both return the tag size written, the size needed when `cap` is
+ * smaller, 0 when the reference writes no such tag (v2: nothing asks for it and every field fits version 1; v1: nothing set, or
+ * V2_ONLY), negative for a malformed year / track / genre.  The version 2 tag goes in front of the stream (and of the Info / LAME
+ * tag frame), the version 1 tag behind it.  Pure host code. */
+#define MP3B200_ID3_ADD_V2 2     /* id3tag_add_v2 */
+#define MP3B200_ID3_V1_ONLY 4    /* id3tag_v1_only */
+#define MP3B200_ID3_V2_ONLY 8    /* id3tag_v2_only */
+#define MP3B200_ID3_SPACE_V1 16  /* id3tag_space_v1: pad version 1 fields with spaces */
+#define MP3B200_ID3_PAD_V2 32    /* id3tag_set_pad(padding), 128 bytes if padding <= 0 */
+typedef struct mp3b200_id3tag {
+  const char *title, *artist, *album, *year, *comment, *track, *genre;
+  int flags, padding;
+  int64_t num_samples;           /* gfp.num_samples for the TLEN frame; -1 = unknown (no TLEN) */
+  int samplerate;
+} mp3b200_id3tag;
+int mp3b200_id3v2_tag(const mp3b200_id3tag* t, uint8_t* buf, int cap);
+int mp3b200_id3v1_tag(const mp3b200_id3tag* t, uint8_t* buf, int cap);
+const char* mp3b200_id3_genre_name(int index);
+
 /* Test / bench tap of k_music_crc: CRC-16 (VBRTag.js:547-556, start 0) of the ranges [off[i], off[i] + len[i]) of a DEVICE
  * buffer; `ms` (optional) receives the CUDA-event time of one launch sequence incl. its 4-byte-per-range read-back. */
 int mp3b200_debug_music_crc(const uint8_t* d_buf, const int64_t* off, const int64_t* len, int nranges, uint32_t* crc, float* ms);

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmp3b200.so")
-SOURCES = ["mp3_encoder.cu", "mp3_config.cpp", "mp3_tag.cpp"]
+SOURCES = ["mp3_encoder.cu", "mp3_config.cpp", "mp3_tag.cpp", "mp3_id3.cpp"]
 DEPS = SOURCES + ["mp3_config.h", "mp3_device.cuh", "mp3_math.cuh", "mp3_tables.h", "k_filterbank.cuh", "k_psy.cuh",
                   "k_quant.cuh", "k_tag.cuh", "mp3_tag.h", "mp3_handle.inc", "../../include/mp3b200.h"]
 NVCC_FLAGS = [

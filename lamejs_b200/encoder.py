@@ -111,6 +111,45 @@ class WavHeader:
         return w
 
 
+class _Id3C(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_char_p) for k in ("title", "artist", "album", "year", "comment", "track", "genre")] + \
+               [("flags", ctypes.c_int), ("padding", ctypes.c_int), ("num_samples", ctypes.c_int64), ("samplerate", ctypes.c_int)]
+
+
+ID3_ADD_V2, ID3_V1_ONLY, ID3_V2_ONLY, ID3_SPACE_V1, ID3_PAD_V2 = 2, 4, 8, 16, 32
+
+
+def _id3_struct(fields, flags, padding, num_samples, samplerate):
+    c = _Id3C()
+    for k in ("title", "artist", "album", "year", "comment", "track", "genre"):
+        v = fields.get(k)
+        setattr(c, k, None if v is None else str(v).encode("latin-1"))
+    c.flags, c.padding, c.num_samples, c.samplerate = flags, padding, num_samples, samplerate
+    return c
+
+
+def id3v2_tag(flags=0, padding=0, num_samples=-1, samplerate=0, **fields):
+    """ID3v2.3 tag (ID3Tag.java lame_get_id3v2_tag): title / artist / album / year / comment / track / genre as Latin-1 text;
+    b'' when the reference would write none."""
+    L = lib()
+    L.mp3b200_id3v2_tag.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    c = _id3_struct(fields, flags, padding, num_samples, samplerate)
+    n = _check(L.mp3b200_id3v2_tag(ctypes.byref(c), None, 0))
+    buf = np.zeros(max(n, 1), dtype=np.uint8)
+    n = _check(L.mp3b200_id3v2_tag(ctypes.byref(c), buf.ctypes.data, n))
+    return buf[:n].tobytes()
+
+
+def id3v1_tag(flags=0, **fields):
+    """ID3v1 / v1.1 tag (ID3Tag.java lame_get_id3v1_tag): 128 bytes, or b'' when nothing is set."""
+    L = lib()
+    L.mp3b200_id3v1_tag.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    c = _id3_struct(fields, flags, 0, -1, 0)
+    buf = np.zeros(128, dtype=np.uint8)
+    n = _check(L.mp3b200_id3v1_tag(ctypes.byref(c), buf.ctypes.data, 128))
+    return buf[:n].tobytes()
+
+
 def lametag_size(channels, samplerate, kbps):
     """Size of the Xing / Info / LAME tag frame of a configuration (0: InitVbrTag would switch the tag off)."""
     return _check(lib().mp3b200_lametag_size(channels, samplerate, kbps))
