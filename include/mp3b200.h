@@ -140,6 +140,23 @@ int mp3b200_encode_streams_tagged(int channels, int samplerate, int kbps, int ns
                                   const int16_t* const* right, const int64_t* nsamples, uint8_t* const* out,
                                   const int64_t* cap, int64_t* out_bytes);
 
+/* The rest of VBRTag.js's surface:
+ *   put_vbr_tag     putVbrTag (VBRTag.js:937-965) on a stream held in memory: writes the finished frame over the placeholder,
+ *                   behind an ID3v2 tag if the stream starts with one (skipId3v2; the port's inverted test is not reproduced).
+ *                   0 ok / nothing to write, -1 like the reference (no frame counted yet, empty or too short stream).
+ *   get_vbr_tag     getVbrTag (VBRTag.js:375-470): the reader side -- frame / byte counts, seek table, quality, encoder delay
+ *                   and padding from the first frame of any Xing / Info tagged stream.  1 ok, 0 no tag (reference: null), -2
+ *                   buffer too short.  Pure host code.
+ *   crc16_combine   CRC-16 of A || B from crc(A), crc(B) and |B| (the rule k_music_crc and the handles use): lets callers that
+ *                   encode one stream as segments on several GPUs put one tag on the joined stream. */
+typedef struct mp3b200_vbr_tag_data {
+  int32_t h_id, samprate, flags, frames, bytes, vbr_scale, headersize, enc_delay, enc_padding;
+  uint8_t toc[100];
+} mp3b200_vbr_tag_data;
+int mp3b200_put_vbr_tag(mp3b200_encoder* h, uint8_t* stream, int64_t len);
+int mp3b200_get_vbr_tag(const uint8_t* frame, int64_t len, mp3b200_vbr_tag_data* out);
+int mp3b200_crc16_combine(int crc_a, int crc_b, int64_t len_b);
+
 /* ID3 tags.  lamejs carries only a stub (index.js:56-64) and switches the automatic tags off (index.js:109);
  * the writer is the Java original's, src/main/java/mp3/ID3Tag.java: lame_get_id3v2_tag :961-1102 (ID3v2.3, ISO-8859-1 text
  * frames TSSE TIT2 TPE1 TALB TYER COMM TRCK TCON TLEN, optional padding), lame_get_id3v1_tag :1141-1189 (128 bytes, v1.1 when a

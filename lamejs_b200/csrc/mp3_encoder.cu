@@ -776,6 +776,21 @@ int mp3b200_debug_music_crc(const uint8_t* d_buf, const int64_t* off, const int6
   return 0;
 }
 
+int mp3b200_get_vbr_tag(const uint8_t* frame, int64_t len, mp3b200_vbr_tag_data* out) {
+  if (!out || len < 0 || (len > 0 && !frame)) return MP3B200_ERR_HANDLE;
+  Mp3VbrTagData t;
+  const int rc = mp3_tag_parse(frame, len, &t);
+  out->h_id = t.h_id; out->samprate = t.samprate; out->flags = t.flags; out->frames = t.frames; out->bytes = t.bytes;
+  out->vbr_scale = t.vbr_scale; out->headersize = t.headersize; out->enc_delay = t.enc_delay; out->enc_padding = t.enc_padding;
+  memcpy(out->toc, t.toc, 100);
+  return rc;
+}
+
+int mp3b200_crc16_combine(int crc_a, int crc_b, int64_t len_b) {
+  if (len_b < 0) return MP3B200_ERR_HANDLE;
+  return (int)crc_append((unsigned)crc_a & 0xffffu, (unsigned)crc_b & 0xffffu, (unsigned long long)len_b, crc_host().pow);
+}
+
 int mp3b200_lametag_size(int channels, int samplerate, int kbps) {
   Mp3TagParams p;
   if (mp3_tag_params(channels, samplerate, kbps, &p) != 0) return MP3B200_ERR_CONFIG;

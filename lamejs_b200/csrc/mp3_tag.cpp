@@ -149,3 +149,46 @@ int mp3_wav_read_header(const uint8_t* d, long long n, long long* data_offset, l
   *data_offset = pos + 8;
   return 1;
 }
+
+/* getVbrTag (VBRTag.js:375-470): what a decoder reads back from the first frame of a stream.  Returns 1 and fills `t`,
+ * 0 when the frame carries no "Xing" / "Info" magic (the reference returns null), -2 when the buffer ends first. */
+int mp3_tag_parse(const uint8_t* buf, long long n, Mp3VbrTagData* t) {
+  static const int bitrates[2][16] = {{0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160, -1},
+                                      {0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, -1}};
+  static const int rates[3][4] = {{22050, 24000, 16000, -1}, {44100, 48000, 32000, -1}, {11025, 12000, 8000, -1}};
+  memset(t, 0, sizeof *t);
+  if (n < 4) return -2;
+  const int id = (buf[1] >> 3) & 1, sr_index = (buf[2] >> 2) & 3, mode = (buf[3] >> 6) & 3;
+  const int kbps = bitrates[id][(buf[2] >> 4) & 0xf];
+  t->samprate = ((buf[1] >> 4) == 0xE) ? rates[2][sr_index] : rates[id][sr_index];      /* 0xFFE sync: MPEG-2.5 */
+  long long p = id ? (mode != 3 ? 32 + 4 : 17 + 4) : (mode != 3 ? 17 + 4 : 9 + 4);     /* behind the side info */
+  if (p + 8 > n) return -2;
+  if (memcmp(buf + p, "Xing", 4) != 0 && memcmp(buf + p, "Info", 4) != 0) return 0;
+  p += 4;
+  t->h_id = id;
+  auto be32 = [&](long long at) { return (int)(((unsigned)buf[at] << 24) | ((unsigned)buf[at + 1] << 16) | ((unsigned)buf[at + 2] << 8) | buf[at + 3]); };
+  const int flags = t->flags = be32(p);
+  p += 4;
+  if (flags & 1) { if (p + 4 > n) return -2; t->frames = be32(p); p += 4; }
+  if (flags & 2) { if (p + 4 > n) return -2; t->bytes = be32(p); p += 4; }
+  if (flags & 4) { if (p + 100 > n) return -2; memcpy(t->toc, buf + p, 100); p += 100; }
+  t->vbr_scale = -1;
+  if (flags & 8) { if (p + 4 > n) return -2; t->vbr_scale = be32(p); p += 4; }
+  t->headersize = t->samprate > 0 ? ((id + 1) * 72000 * kbps) / t->samprate : 0;
+  p += 21;
+  if (p + 3 > n) return -2;
+  int delay = (buf[p] << 4) + (buf[p + 1] >> 4);
+  int padding = ((buf[p + 1] & 0x0F) << 8) + buf[p + 2];
+  if (delay < 0 || delay > 3000) delay = -1;        /* an old Xing header without the LAME extension */
+  if (padding < 0 || padding > 3000) padding = -1;
+  t->enc_delay = delay; t->enc_padding = padding;
+  return 1;
+}
+
+/* skipId3v2 (VBRTag.js:804-827): size of an ID3v2 tag at the head of a stream, 0 if there is none.  The port's test is
+ * inverted (`if (!...startsWith("ID3"))`, VBRTag.js:811 = VBRTag.java:833: it would read a "size" out of audio bytes when
+ * there is NO tag); LAME's meaning is restated. */
+long long mp3_skip_id3v2(const uint8_t* s, long long n) {
+  if (n < 10 || memcmp(s, "ID3", 3) != 0) return 0;
+  return (((long long)(s[6] & 0x7f) << 21) | ((s[7] & 0x7f) << 14) | ((s[8] & 0x7f) << 7) | (s[9] & 0x7f)) + 10;
+}

@@ -21,4 +21,8 @@ int mp3_tag_frame(const Mp3TagParams& p, const Mp3SeekBag& bag, long long music_
 int mp3_encoder_padding(long long nsamples, int mode_gr);
 /* WavHeader.readHeader: 1 ok, 0 `return undefined`, -1 throws 'extended fmt chunk not implemented', -2 DataView RangeError */
 int mp3_wav_read_header(const uint8_t* d, long long n, long long* data_offset, long long* data_len, int* channels, unsigned* sample_rate);
+/* VBRTagData (reference src/main/java/mp3/VBRTagData.java; `new VBRTagData()` in VBRTag.js:376) */
+struct Mp3VbrTagData { int h_id, samprate, flags, frames, bytes, vbr_scale, headersize, enc_delay, enc_padding; unsigned char toc[100]; };
+int mp3_tag_parse(const uint8_t* buf, long long n, Mp3VbrTagData* t);
+long long mp3_skip_id3v2(const uint8_t* stream, long long n);
 #endif

@@ -150,6 +150,34 @@ def id3v1_tag(flags=0, **fields):
     return buf[:n].tobytes()
 
 
+class _VbrTagC(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ("h_id", "samprate", "flags", "frames", "bytes", "vbr_scale", "headersize", "enc_delay", "enc_padding")] + \
+               [("toc", ctypes.c_uint8 * 100)]
+
+
+def get_vbr_tag(frame):
+    """VBRTag.getVbrTag: dict of the Xing / Info tag fields in the first frame of a stream, or None when there is no tag."""
+    a = np.frombuffer(bytes(frame), dtype=np.uint8)
+    c = _VbrTagC()
+    L = lib()
+    L.mp3b200_get_vbr_tag.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    rc = L.mp3b200_get_vbr_tag(a.ctypes.data if len(a) else None, len(a), ctypes.byref(c))
+    if rc == 0:
+        return None
+    if rc != 1:
+        raise IndexError("frame too short")
+    d = {k: int(getattr(c, k)) for k, _ in _VbrTagC._fields_[:-1]}
+    d["toc"] = bytes(c.toc)
+    return d
+
+
+def crc16_combine(crc_a, crc_b, len_b):
+    """CRC-16 of A || B from crc(A), crc(B), len(B) (VBRTag.js:547-556 is linear over GF(2))."""
+    L = lib()
+    L.mp3b200_crc16_combine.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64]
+    return _check(L.mp3b200_crc16_combine(int(crc_a), int(crc_b), int(len_b)))
+
+
 def lametag_size(channels, samplerate, kbps):
     """Size of the Xing / Info / LAME tag frame of a configuration (0: InitVbrTag would switch the tag off)."""
     return _check(lib().mp3b200_lametag_size(channels, samplerate, kbps))
@@ -184,6 +212,13 @@ class Mp3Encoder:
 
     def music_crc(self):
         return int(self._L.mp3b200_music_crc(self._h))
+
+    def put_vbr_tag(self, stream):
+        """VBRTag.putVbrTag on a stream held in a bytearray / writable uint8 array: the finished frame over the placeholder
+        (behind an ID3v2 tag if the stream starts with one).  Returns 0, or -1 like the reference."""
+        a = np.frombuffer(stream, dtype=np.uint8)
+        self._L.mp3b200_put_vbr_tag.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+        return int(self._L.mp3b200_put_vbr_tag(self._h, a.ctypes.data if len(a) else None, len(a)))
 
     def bytes_written(self):
         return int(self._L.mp3b200_bytes_written(self._h))

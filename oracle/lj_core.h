@@ -2,15 +2,19 @@
  *
  * TEST INFRASTRUCTURE.  The oracle is a single-threaded CPU restatement of
  * zhuker/lamejs (src/js, commit 582bbba) for the Mp3Encoder configuration
- * (CBR, mode STEREO/MONO, quality 3, no reservoir, no VBR tag; reference
- * src/js/index.js:66-136).  It is the parity checker for the CUDA product and
+ * (CBR, mode STEREO/MONO, quality 3, no reservoir; reference src/js/index.js:66-136),
+ * plus the Xing / Info / LAME tag writer Mp3Encoder leaves switched off (lj_vbrtag.cpp).  It is the parity checker for the CUDA product and
  * the timed CPU baseline.  Nothing in the product links or imports it.
  *
- * PARITY UNPINNED: the reference holds no golden vectors (src/js/Tests.js
- * compares nothing) and no JS engine exists in the build image, so this
- * restatement could not be checked against lamejs output.  It is pinned only
- * by derivable known answers (tests/test_oracle_kat.py) and by decoding its output
- * with an independent ISO 11172-3 decoder (tests/test_oracle_decode.py).
+ * PINNED against the reference itself: the unmodified lamejs sources run in the
+ * build image under Qt's QJSEngine (tools/jsrun/); tests/test_lamejs_pin.py checks
+ * this restatement byte for byte against 306 lamejs-made fixtures (every sample
+ * rate x bitrate x channel count, long streams, odd chunkings, the resampling
+ * configurations) and against lamejs's own per-frame intermediates;
+ * tests/test_tag_oracle.py does the same for the tag / CRC / WAV-header row.
+ * Older, independent checks remain: derivable known answers
+ * (tests/test_oracle_kat.py) and an ISO 11172-3 decoder round trip
+ * (tests/test_oracle_decode.py).
  *
  * Arithmetic model: every JS local is an IEEE double; a
  * store into a Float32Array rounds to float32 (RNE), a store into an

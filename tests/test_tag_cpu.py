@@ -131,3 +131,33 @@ def test_wav_header_random_bytes_agree_with_the_oracle(oracle):
         assert (w is None) == (want is None)
         if w is not None:
             assert {"dataOffset": w.dataOffset, "dataLen": w.dataLen, "channels": w.channels, "sampleRate": w.sampleRate} == want
+
+
+def test_get_vbr_tag_reads_back_what_the_writer_wrote(oracle):
+    """getVbrTag (VBRTag.js:375-470) on the oracle's frames: every rate class and channel mode"""
+    for ch, sr, kbps, frames in [(2, 44100, 128, 30), (1, 44100, 128, 5), (2, 48000, 320, 450), (1, 24000, 64, 12), (2, 22050, 64, 12), (1, 8000, 24, 9), (2, 11025, 32, 9)]:
+        info = _oracle_tag(oracle, ch, sr, kbps, frames, 77)
+        assert info["tag_on"]
+        d = M.get_vbr_tag(info["tag"])
+        assert d["flags"] == 15 and d["frames"] == info["frames"] and d["bytes"] == info["bytes_written"] + len(info["tag"])
+        assert d["samprate"] == sr and d["h_id"] == (1 if sr >= 32000 else 0) and d["headersize"] == len(info["tag"])
+        assert d["vbr_scale"] == 57 and d["enc_delay"] == 576 and d["enc_padding"] == info["encoder_padding"]
+        x = {True: {1: 21, 2: 36}, False: {1: 13, 2: 21}}[sr >= 32000][ch]
+        assert d["toc"] == info["tag"][x + 16:x + 116]
+    plain = oracle.encode_stream(2, 44100, 128, *make_signal("noise", 4000, 44100, seed=1))[0]
+    assert M.get_vbr_tag(plain[:417]) is None
+    with pytest.raises(IndexError):
+        M.get_vbr_tag(info["tag"][:20])
+
+
+def test_crc16_combine(oracle):
+    rng = np.random.default_rng(8)
+    a = rng.integers(0, 256, 9000).astype(np.uint8).tobytes()
+    for cut in (0, 1, 417, 4180, 8999, 9000):
+        assert M.crc16_combine(oracle.crc16(a[:cut]), oracle.crc16(a[cut:]), len(a) - cut) == oracle.crc16(a)
+    # three segments, as a segment-sharded stream would be combined on rank 0
+    parts = [a[:3000], a[3000:7000], a[7000:]]
+    c = 0
+    for p in parts:
+        c = M.crc16_combine(c, oracle.crc16(p), len(p))
+    assert c == oracle.crc16(a)

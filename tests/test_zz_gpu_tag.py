@@ -140,3 +140,21 @@ def test_c2_stream_crc_and_tag(M, oracle):
     assert int.from_bytes(tag[x + 152:x + 154], "big") == oracle.crc16(audio)
     assert int.from_bytes(tag[x + 154:x + 156], "big") == oracle.crc16(tag[:x + 154])
     assert tag == M.lametag_build(2, 44100, 128, 10001, len(audio), oracle.crc16(audio), int.from_bytes(tag[x + 142:x + 144], "big") & 0xFFF)
+
+
+def test_put_vbr_tag_in_memory(M, oracle):
+    """putVbrTag: the finished frame lands over the placeholder -- at offset 0, or behind an ID3v2 tag"""
+    l, r = make_signal("octave", 20 * 1152, 48000, seed=12)
+    for head in (b"", M.id3v2_tag(flags=M.ID3_ADD_V2, title="put", artist="vbr", num_samples=len(l), samplerate=48000)):
+        enc = M.Mp3Encoder(2, 48000, 160, write_vbr_tag=True)
+        stream = bytearray(head + enc.encodeBuffer(l, r) + enc.flush())
+        tag = enc.lametag_frame()
+        assert enc.put_vbr_tag(stream) == 0
+        assert bytes(stream[:len(head)]) == head and bytes(stream[len(head):len(head) + len(tag)]) == tag
+        d = M.get_vbr_tag(stream[len(head):len(head) + len(tag)])
+        assert d["frames"] == M.stream_frames(len(l), 2, 48000, 160) and d["bytes"] == len(stream) - len(head)
+        assert bytes(stream[len(head) + len(tag):]) == oracle.encode_stream(2, 48000, 160, l, r)[0]
+        enc.close()
+    e = M.Mp3Encoder(2, 48000, 160, write_vbr_tag=True)
+    assert e.put_vbr_tag(bytearray(1000)) == -1          # nothing encoded yet
+    e.close()
