@@ -13,10 +13,10 @@ extern const int lj_slen1_tab[16];
 extern const int lj_slen2_tab[16];
 
 static void putheader_bits(LjEnc* e) {
-  memcpy(e->bs_buf + e->bs_byteidx, e->hdr_buf, e->sideinfo_len);
+  memcpy(e->bs_buf + e->bs_byteidx, e->header[e->w_ptr].buf, e->sideinfo_len);
   e->bs_byteidx += e->sideinfo_len;
   e->bs_totbit += e->sideinfo_len * 8;
-  e->hdr_pending = 0;
+  e->w_ptr = (e->w_ptr + 1) & 255;
 }
 
 static void putbits2(LjEnc* e, int val, int j) {
@@ -25,7 +25,7 @@ static void putbits2(LjEnc* e, int val, int j) {
     if (e->bs_bitidx == 0) {
       e->bs_bitidx = 8;
       e->bs_byteidx++;
-      if (e->hdr_pending) putheader_bits(e); /* header[w_ptr].write_timing == totbit */
+      if (e->header[e->w_ptr].write_timing == e->bs_totbit) putheader_bits(e);
       e->bs_buf[e->bs_byteidx] = 0;
     }
     k = j < e->bs_bitidx ? j : e->bs_bitidx;
@@ -36,7 +36,7 @@ static void putbits2(LjEnc* e, int val, int j) {
   }
 }
 
-static void drain_into_ancillary(LjEnc* e, int remainingBits) {
+static void drain_into_ancillary(LjEnc* e, double remainingBits) {
   if (remainingBits >= 8) { putbits2(e, 0x4c, 8); remainingBits -= 8; }
   if (remainingBits >= 8) { putbits2(e, 0x41, 8); remainingBits -= 8; }
   if (remainingBits >= 8) { putbits2(e, 0x4d, 8); remainingBits -= 8; }
@@ -50,24 +50,25 @@ static void drain_into_ancillary(LjEnc* e, int remainingBits) {
     }
   }
   for (; remainingBits >= 1; remainingBits -= 1) {
-    putbits2(e, 0 /* ancillary_flag never toggles with disable_reservoir */, 1);
+    putbits2(e, e->ancillary_flag, 1);
+    e->ancillary_flag ^= (!e->disable_reservoir ? 1 : 0);
   }
 }
 
 static void writeheader(LjEnc* e, int val, int j) {
-  int ptr = e->hdr_ptr;
+  int ptr = e->header[e->h_ptr].ptr;
   while (j > 0) {
     int k = j < 8 - (ptr & 7) ? j : 8 - (ptr & 7);
     j -= k;
-    e->hdr_buf[ptr >> 3] |= (uint8_t)(((val >> j)) << (8 - (ptr & 7) - k));
+    e->header[e->h_ptr].buf[ptr >> 3] |= (uint8_t)(((val >> j)) << (8 - (ptr & 7) - k));
     ptr += k;
   }
-  e->hdr_ptr = ptr;
+  e->header[e->h_ptr].ptr = ptr;
 }
 
-static void encodeSideInfo2(LjEnc* e) {
-  e->hdr_ptr = 0;
-  memset(e->hdr_buf, 0, e->sideinfo_len);
+static void encodeSideInfo2(LjEnc* e, int bitsPerFrame) {
+  e->header[e->h_ptr].ptr = 0;
+  memset(e->header[e->h_ptr].buf, 0, e->sideinfo_len);
   writeheader(e, e->out_samplerate < 16000 ? 0xffe : 0xfff, 12);   /* MPEG-2.5 sync word */
   writeheader(e, e->version, 1);
   writeheader(e, 4 - 3, 2);
@@ -76,13 +77,13 @@ static void encodeSideInfo2(LjEnc* e) {
   writeheader(e, e->samplerate_index, 2);
   writeheader(e, e->padding, 1);
   writeheader(e, 0, 1);                        /* extension */
-  writeheader(e, e->mode_mono ? 3 : 0, 2);     /* MPEGMode ordinal: STEREO 0, MONO 3 */
+  writeheader(e, e->mode_mono ? 3 : (e->mode_joint ? 1 : 0), 2);     /* MPEGMode ordinal: STEREO 0, JOINT_STEREO 1, MONO 3 */
   writeheader(e, e->mode_ext, 2);
   writeheader(e, 0, 1);                        /* copyright */
   writeheader(e, 1, 1);                        /* original */
   writeheader(e, 0, 2);                        /* emphasis */
   if (e->version == 1) {
-  writeheader(e, e->main_data_begin, 9);
+  writeheader(e, js_toint32(e->main_data_begin), 9);        /* `val >> j` on a JS number: ToInt32 */
   if (e->channels_out == 2) writeheader(e, 0, 3);
   else writeheader(e, 0, 5);
   for (int ch = 0; ch < e->channels_out; ch++)
@@ -123,7 +124,7 @@ static void encodeSideInfo2(LjEnc* e) {
   }
   } else {
     /* MPEG-2 / 2.5 (BitStream.js:352-404): one granule, 9-bit scalefac_compress, no preflag bit, no scfsi */
-    writeheader(e, e->main_data_begin, 8);
+    writeheader(e, js_toint32(e->main_data_begin), 8);
     writeheader(e, 0, e->channels_out);          /* private_bits */
     for (int ch = 0; ch < e->channels_out; ch++) {
       GrInfo* gi = &e->tt[0][ch];
@@ -157,7 +158,11 @@ static void encodeSideInfo2(LjEnc* e) {
       writeheader(e, gi->count1table_select, 1);
     }
   }
-  e->hdr_pending = 1;
+  {
+    int old = e->h_ptr;
+    e->h_ptr = (old + 1) & 255;
+    e->header[e->h_ptr].write_timing = e->header[old].write_timing + bitsPerFrame;
+  }
 }
 
 static int huffman_coder_count1(LjEnc* e, const GrInfo* gi) {
@@ -295,18 +300,44 @@ static int writeMainData(LjEnc* e) {
   return tot_bits;
 }
 
+/* BitStream.js:708-755 */
+static double compute_flushbits(LjEnc* e) {
+  int first_ptr = e->w_ptr, last_ptr = e->h_ptr - 1;
+  if (last_ptr == -1) last_ptr = 255;
+  double flushbits = e->header[last_ptr].write_timing - e->bs_totbit;
+  if (flushbits >= 0) {
+    int remaining_headers = 1 + last_ptr - first_ptr;
+    if (last_ptr < first_ptr) remaining_headers = 1 + last_ptr - first_ptr + 256;
+    flushbits -= remaining_headers * 8 * e->sideinfo_len;
+  }
+  flushbits += lj_getframebits(e);
+  return flushbits;
+}
+
+/* BitStream.js:757-776 (ReplayGain / peak parts are off) */
+void lj_flush_bitstream(LjEnc* e) {
+  double flushbits = compute_flushbits(e);
+  if (flushbits < 0) return;
+  drain_into_ancillary(e, flushbits);
+  e->ResvSize = 0;
+  e->main_data_begin = 0;
+}
+
 void lj_format_bitstream(LjEnc* e) {
   int bitsPerFrame = lj_getframebits(e);
   drain_into_ancillary(e, e->resvDrain_pre);
-  encodeSideInfo2(e);
-  int bits = 8 * e->sideinfo_len;
+  encodeSideInfo2(e, bitsPerFrame);
+  double bits = 8 * e->sideinfo_len;
   bits += writeMainData(e);
   drain_into_ancillary(e, e->resvDrain_post);
   bits += e->resvDrain_post;
   e->main_data_begin += (bitsPerFrame - bits) / 8;
-  /* if the frame held no main-data and no stuffing bits the header is still pending; cannot happen
-   * (sideinfo < frame) but keep the byte stream well-defined */
-  if (e->hdr_pending) { e->bs_byteidx++; putheader_bits(e); e->bs_byteidx--; }
+  /* BitStream.js:851-884: consistency checks; on a mismatch the reference prints and re-bases ResvSize */
+  if ((e->main_data_begin * 8) != e->ResvSize) e->ResvSize = e->main_data_begin * 8;
+  if (e->bs_totbit > 1000000000) {
+    for (int i = 0; i < 256; ++i) e->header[i].write_timing -= e->bs_totbit;
+    e->bs_totbit = 0;
+  }
 }
 
 int lj_copy_buffer(LjEnc* e, uint8_t* out, int cap, int mp3data) {

@@ -37,7 +37,7 @@ struct LjEnc {
   int sideinfo_len;
   F32 sb_sample[2][2][18][SBLIMIT];
   F32 amp_filter[32];
-  int ResvSize, ResvMax;
+  double ResvSize, ResvMax;      /* JS numbers (Reservoir.js): integers as long as the reservoir is off */
   int sfb_l[SBMAX_l + 1], sfb_s[SBMAX_s + 1], psfb21[PSFB21 + 1], psfb12[PSFB12 + 1];
   /* psy tables */
   F32 minval_l[CBANDS], minval_s[CBANDS];
@@ -71,7 +71,7 @@ struct LjEnc {
       ath_cb_s[CBANDS], ath_eql_w[BLKSIZE / 2];
   /* side info */
   GrInfo tt[2][2];
-  int main_data_begin, resvDrain_pre, resvDrain_post;
+  double main_data_begin, resvDrain_pre, resvDrain_post;   /* JS numbers: `/ 8` is not an integer division (Reservoir.js:283, BitStream.js:849) */
   int scfsi[2][4];
   /* resampler (Lame.js:1691-1843): per-call state exactly as lamejs keeps it */
   double resample_ratio;
@@ -94,7 +94,10 @@ struct LjEnc {
   /* bitstream (BitStream.js closure state, one frame at a time) */
   uint8_t bs_buf[16384 + 131072];
   int bs_totbit, bs_byteidx, bs_bitidx;
-  uint8_t hdr_buf[40]; int hdr_ptr; int hdr_pending;
+  /* gfc.header[MAX_HEADER_BUF] ring (LameInternalFlags.js, BitStream.js:96-101,218-229,407-419) */
+  struct LjHeader { int write_timing; int ptr; uint8_t buf[40]; } header[256];
+  int h_ptr, w_ptr;
+  int ancillary_flag;
   /* trace */
   LjFrameTrace* trace; int trace_cap, trace_n;
   /* Xing / LAME tag state (VBRSeekInfo.js, LameInternalFlags.js:170; lj_vbrtag.cpp).  nMusicCRC and nBytesWritten are
@@ -102,6 +105,8 @@ struct LjEnc {
   int nMusicCRC; long long nBytesWritten;
   int bWriteVbrTag, vbr_TotalFrameSize, vbr_nframes, vbr_sum, vbr_seen, vbr_want, vbr_pos;
   int vbr_bag[400];
+  /* modes Mp3Encoder does not reach: gfp.disable_reservoir (index.js:108 sets it), gfp.mode == JOINT_STEREO */
+  int disable_reservoir, mode_joint;
   int encoder_padding;             /* gfp.encoder_padding, set by lame_encode_flush (Lame.js:1412) */
   double lowpass_final;            /* gfp.lowpassfreq after lame_init_params (Lame.js:884-896) */
 };
@@ -121,6 +126,7 @@ void lj_iteration_loop(LjEnc* e, double pe[2][2], PsyRatio ratio[2][2]);
 int  lj_getframebits(const LjEnc* e);
 /* lj_bitstream.cpp */
 void lj_format_bitstream(LjEnc* e);
+void lj_flush_bitstream(LjEnc* e);
 int  lj_copy_buffer(LjEnc* e, uint8_t* out, int cap, int mp3data);
 /* lj_vbrtag.cpp */
 void lj_update_music_crc(LjEnc* e, const uint8_t* buf, int size);

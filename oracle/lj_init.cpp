@@ -160,6 +160,7 @@ int lj_init_params(LjEnc* e, int channels, int samplerate, int kbps) {
   /* lame_init_old defaults that matter */
   e->num_channels = channels; e->in_samplerate = samplerate; e->brate = kbps;
   e->quality = 3;
+  e->disable_reservoir = 1;      /* index.js:108 */
   e->OldValue[0] = e->OldValue[1] = 180;
   e->CurrentStep[0] = e->CurrentStep[1] = 4;
   e->masking_lower = 1;
@@ -225,7 +226,8 @@ int lj_init_params(LjEnc* e, int channels, int samplerate, int kbps) {
     if (e->bitrate_index <= 0) return -1;
   }
   /* bitstream init */
-  e->bs_byteidx = -1; e->bs_bitidx = 0; e->bs_totbit = 0; e->hdr_pending = 0;
+  e->bs_byteidx = -1; e->bs_bitidx = 0; e->bs_totbit = 0;
+  e->h_ptr = e->w_ptr = 0; e->header[0].write_timing = 0;      /* init_bit_stream_w (BitStream.js:1012-1020) */
   /* sfb tables (Lame.js:1079-1101; QuantizePVT.js:137-204) */
   {
     /* QuantizePVT.js:137-204 sfBandIndex: 22.05, 24, 16 kHz (MPEG-2); 44.1, 48, 32 kHz (MPEG-1); 11.025, 12, 8 kHz (MPEG-2.5) */
@@ -595,6 +597,13 @@ int lj_query_out_samplerate(int channels, int samplerate, int kbps) {
   free(e->s3_ll); free(e->s3_ss); free(e);
   return r;
 }
+/* gfp.disable_reservoir = false (index.js:108 sets it true): a per-frame switch (Reservoir.js:158,217; BitStream.js:208),
+ * so it can be flipped on a fresh encoder.  SURVEY.md 8(f2), oracle only. */
+int lj_enable_reservoir(LjEnc* e) {
+  if (!e || e->frameNum != 0) return -1;
+  e->disable_reservoir = 0;
+  return 0;
+}
 void lj_destroy(LjEnc* e) { if (e) { free(e->s3_ll); free(e->s3_ss); free(e->blackfilt); free(e->inb[0]); free(e->inb[1]); free(e); } }
 
 /* index.js:117-130 + Lame.js:1490-1514.  Returns bytes written or a negative lame error. */
@@ -633,8 +642,7 @@ int lj_flush(LjEnc* e, uint8_t* out, int cap) {
   }
   e->mf_samples_to_encode = 0;
   if (imp3 < 0) return imp3;
-  /* flush_bitstream: with the reservoir disabled flushbits == 0 (BitStream.js:757-815) */
-  e->ResvSize = 0; e->main_data_begin = 0;
+  lj_flush_bitstream(e);                  /* BitStream.js:757-815; with the reservoir disabled flushbits == 0 */
   int remaining = cap - mp3count;
   if (cap == 0) remaining = 0;
   imp3 = lj_copy_buffer(e, out, remaining, 1);

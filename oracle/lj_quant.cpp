@@ -128,7 +128,11 @@ void lj_iteration_init(LjEnc* e) {
 static double ResvFrameBegin(LjEnc* e) {
   int frameLength = lj_getframebits(e);
   double mean_bits = (frameLength - e->sideinfo_len * 8) / (double)e->mode_gr;
-  e->ResvMax = 0; /* disable_reservoir */
+  const int resvLimit = (8 * 256) * e->mode_gr - 8;        /* main_data_begin has 9 bits in MPEG-1, 8 in MPEG-2 */
+  const int maxmp3buf = 8 * 1440;                          /* brate <= 320, !strict_ISO (Reservoir.js:129-152) */
+  e->ResvMax = maxmp3buf - frameLength;
+  if (e->ResvMax > resvLimit) e->ResvMax = resvLimit;
+  if (e->ResvMax < 0 || e->disable_reservoir) e->ResvMax = 0;
   e->resvDrain_pre = 0;
   return mean_bits;
 }
@@ -147,7 +151,7 @@ static double ResvMaxBits(LjEnc* e, double mean_bits, double* targ, int cbr) {
   } else {
     add_bits = 0;
     e->substep_shaping &= 0x7f;
-    /* disable_reservoir: no build-up subtraction */
+    if (!e->disable_reservoir && 0 == (e->substep_shaping & 1)) *targ -= .1 * mean_bits;   /* build the reservoir up */
   }
   double extra_bits = (ResvSize < (e->ResvMax * 6) / 10.0 ? ResvSize : (e->ResvMax * 6) / 10.0);
   extra_bits -= add_bits;
@@ -156,16 +160,17 @@ static double ResvMaxBits(LjEnc* e, double mean_bits, double* targ, int cbr) {
 }
 
 static void ResvFrameEnd(LjEnc* e, double mean_bits) {
-  int over_bits;
-  e->ResvSize = js_toint32(e->ResvSize + mean_bits * e->mode_gr);
-  int stuffingBits = 0;
+  double over_bits;
+  e->ResvSize += mean_bits * e->mode_gr;
+  double stuffingBits = 0;
   e->resvDrain_post = 0;
   e->resvDrain_pre = 0;
-  if ((over_bits = e->ResvSize % 8) != 0) stuffingBits += over_bits;
+  if ((over_bits = fmod(e->ResvSize, 8)) != 0) stuffingBits += over_bits;
   over_bits = (e->ResvSize - stuffingBits) - e->ResvMax;
   if (over_bits > 0) stuffingBits += over_bits;
   {
-    int mdb_bytes = (e->main_data_begin * 8 < stuffingBits ? e->main_data_begin * 8 : stuffingBits) / 8;
+    /* Math.min(...) / 8 on JS numbers: not an integer division (Java's is), so main_data_begin can hold eighths */
+    double mdb_bytes = js_min(e->main_data_begin * 8, stuffingBits) / 8;
     e->resvDrain_pre += 8 * mdb_bytes;
     stuffingBits -= 8 * mdb_bytes;
     e->ResvSize -= 8 * mdb_bytes;

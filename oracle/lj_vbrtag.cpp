@@ -142,12 +142,13 @@ static void setLameTagFrameHeader(const LjEnc* e, uint8_t* buffer) {
   }
 }
 
-/* putbits_noheaders(val, 8) for byte-aligned data (BitStream.js:140-163); header write_timing moves with it, which with one
- * pending header per frame and no reservoir has no effect on the bytes */
+/* putbits_noheaders(val, 8) for byte-aligned data (BitStream.js:140-163) + add_dummy_byte's shift of every header's
+ * write_timing (BitStream.js:817-826) */
 static void add_dummy_byte(LjEnc* e, int val) {
   e->bs_byteidx++;
   e->bs_buf[e->bs_byteidx] = (uint8_t)val;
   e->bs_totbit += 8;
+  for (int i = 0; i < 256; ++i) e->header[i].write_timing += 8;      /* BitStream.js:823-824 */
 }
 
 extern "C" {
