@@ -117,12 +117,13 @@ int  lj_init_params(LjEnc* e, int channels, int samplerate, int kbps);
 void lj_mdct_sub48(LjEnc* e, const F32* w0, const F32* w1);
 /* lj_psy.cpp */
 int  lj_psycho_anal_ns(LjEnc* e, const F32* buf0, const F32* buf1, int bufPos, int gr_out,
-                       PsyRatio masking_ratio[2][2], double* percep_entropy, F32* energy, int* blocktype_d);
+                       PsyRatio masking_ratio[2][2], PsyRatio masking_MS_ratio[2][2], double* percep_entropy,
+                       double* percep_MS_entropy, F32* energy, int* blocktype_d);
 void lj_psymodel_init(LjEnc* e);
 double lj_ATHformula(double f, const LjEnc* e);
 /* lj_quant.cpp */
 void lj_iteration_init(LjEnc* e);
-void lj_iteration_loop(LjEnc* e, double pe[2][2], PsyRatio ratio[2][2]);
+void lj_iteration_loop(LjEnc* e, double pe[2][2], const double* ms_ener_ratio, PsyRatio ratio[2][2]);
 int  lj_getframebits(const LjEnc* e);
 /* lj_bitstream.cpp */
 void lj_format_bitstream(LjEnc* e);

@@ -355,9 +355,10 @@ static void encode_frame_init(LjEnc* e) {
 
 /* Encoder.js:388-659 */
 static int encode_mp3_frame(LjEnc* e, uint8_t* mp3buf, int mp3buf_size) {
-  PsyRatio masking_LR[2][2];
+  PsyRatio masking_LR[2][2], masking_MS[2][2];
   F32 tot_ener[2][4];
-  double pe[2][2] = {{0., 0.}, {0., 0.}};
+  double pe[2][2] = {{0., 0.}, {0., 0.}}, pe_MS[2][2] = {{0., 0.}, {0., 0.}};
+  double ms_ener_ratio[2] = {.5, .5};
   LjFrameTrace tr; /* filled progressively when tracing */
   bool tracing = e->trace && e->trace_n < e->trace_cap;
   if (tracing) memset(&tr, 0, sizeof tr);
@@ -369,8 +370,12 @@ static int encode_mp3_frame(LjEnc* e, uint8_t* mp3buf, int mp3buf_size) {
   int blocktype[2];
   for (int gr = 0; gr < e->mode_gr; gr++) {
     int bufpPos = 576 + gr * 576 - FFTOFFSET;
-    int ret = lj_psycho_anal_ns(e, e->mfbuf[0], e->mfbuf[1], bufpPos, gr, masking_LR, pe[gr], tot_ener[gr], blocktype);
+    int ret = lj_psycho_anal_ns(e, e->mfbuf[0], e->mfbuf[1], bufpPos, gr, masking_LR, masking_MS, pe[gr], pe_MS[gr], tot_ener[gr], blocktype);
     if (ret != 0) return -4;
+    if (e->mode_joint) {                       /* Encoder.js:482-486 */
+      ms_ener_ratio[gr] = tot_ener[gr][2] + tot_ener[gr][3];
+      if (ms_ener_ratio[gr] > 0) ms_ener_ratio[gr] = tot_ener[gr][3] / ms_ener_ratio[gr];
+    }
     for (int ch = 0; ch < e->channels_out; ch++) {
       e->tt[gr][ch].block_type = blocktype[ch];
       e->tt[gr][ch].mixed_block_flag = 0;
@@ -379,12 +384,24 @@ static int encode_mp3_frame(LjEnc* e, uint8_t* mp3buf, int mp3buf_size) {
   adjust_ATH(e);
   lj_mdct_sub48(e, e->mfbuf[0], e->mfbuf[1]);
   e->mode_ext = 0; /* MPG_MD_LR_LR */
+  if (e->mode_joint) {                         /* Encoder.js:524-561: M/S when its perceptual entropy is not higher and the block types agree */
+    double sum_pe_MS = 0., sum_pe_LR = 0.;
+    for (int gr = 0; gr < e->mode_gr; gr++)
+      for (int ch = 0; ch < e->channels_out; ch++) { sum_pe_MS += pe_MS[gr][ch]; sum_pe_LR += pe[gr][ch]; }
+    if (sum_pe_MS <= 1.00 * sum_pe_LR) {
+      const GrInfo* gi0 = e->tt[0];
+      const GrInfo* gi1 = e->tt[e->mode_gr - 1];
+      if (gi0[0].block_type == gi0[1].block_type && gi1[0].block_type == gi1[1].block_type) e->mode_ext = 2; /* MPG_MD_MS_LR */
+    }
+  }
+  PsyRatio (*masking)[2] = e->mode_ext == 2 ? masking_MS : masking_LR;
+  double (*pe_use)[2] = e->mode_ext == 2 ? pe_MS : pe;
 
   if (tracing) {
     for (int gr = 0; gr < 2; gr++) for (int ch = 0; ch < e->channels_out; ch++) {
       for (int i = 0; i < 576; i++) tr.xr[gr][ch][i] = e->tt[gr][ch].xr[i].v;
-      for (int sb = 0; sb < SBMAX_l; sb++) { tr.en_l[gr][ch][sb] = masking_LR[gr][ch].en.l[sb].v; tr.thm_l[gr][ch][sb] = masking_LR[gr][ch].thm.l[sb].v; }
-      for (int sb = 0; sb < SBMAX_s; sb++) for (int b = 0; b < 3; b++) { tr.en_s[gr][ch][sb][b] = masking_LR[gr][ch].en.s[sb][b].v; tr.thm_s[gr][ch][sb][b] = masking_LR[gr][ch].thm.s[sb][b].v; }
+      for (int sb = 0; sb < SBMAX_l; sb++) { tr.en_l[gr][ch][sb] = masking[gr][ch].en.l[sb].v; tr.thm_l[gr][ch][sb] = masking[gr][ch].thm.l[sb].v; }
+      for (int sb = 0; sb < SBMAX_s; sb++) for (int b = 0; b < 3; b++) { tr.en_s[gr][ch][sb][b] = masking[gr][ch].en.s[sb][b].v; tr.thm_s[gr][ch][sb][b] = masking[gr][ch].thm.s[sb][b].v; }
       tr.blocktype[gr][ch] = e->tt[gr][ch].block_type;
     }
     tr.ath_adjust = e->ath_adjust;
@@ -396,16 +413,16 @@ static int encode_mp3_frame(LjEnc* e, uint8_t* mp3buf, int mp3buf_size) {
   {
     for (int i = 0; i < 18; i++) e->pefirbuf[i] = e->pefirbuf[i + 1];
     double f = 0.0;
-    for (int gr = 0; gr < e->mode_gr; gr++) for (int ch = 0; ch < e->channels_out; ch++) f += pe[gr][ch];
+    for (int gr = 0; gr < e->mode_gr; gr++) for (int ch = 0; ch < e->channels_out; ch++) f += pe_use[gr][ch];
     e->pefirbuf[18] = f;
     static const double fircoef[9] = {-0.0207887 * 5, -0.0378413 * 5, -0.0432472 * 5, -0.031183 * 5, 7.79609e-18 * 5,
                                       0.0467745 * 5, 0.10091 * 5, 0.151365 * 5, 0.187098 * 5};
     f = e->pefirbuf[9];
     for (int i = 0; i < 9; i++) f += (e->pefirbuf[i] + e->pefirbuf[18 - i]) * fircoef[i];
     f = (670 * 5 * e->mode_gr * e->channels_out) / f;
-    for (int gr = 0; gr < e->mode_gr; gr++) for (int ch = 0; ch < e->channels_out; ch++) pe[gr][ch] *= f;
+    for (int gr = 0; gr < e->mode_gr; gr++) for (int ch = 0; ch < e->channels_out; ch++) pe_use[gr][ch] *= f;
   }
-  lj_iteration_loop(e, pe, masking_LR);
+  lj_iteration_loop(e, pe_use, ms_ener_ratio, masking);
   lj_format_bitstream(e);
   int mp3count = lj_copy_buffer(e, mp3buf, mp3buf_size, 1);
   lj_add_vbr_frame(e);             /* Encoder.js:640-641 */
@@ -599,6 +616,14 @@ int lj_query_out_samplerate(int channels, int samplerate, int kbps) {
 }
 /* gfp.disable_reservoir = false (index.js:108 sets it true): a per-frame switch (Reservoir.js:158,217; BitStream.js:208),
  * so it can be flipped on a fresh encoder.  SURVEY.md 8(f2), oracle only. */
+/* gfp.mode = JOINT_STEREO (index.js:104 fixes STEREO): lame_init_params derives the same parameters for both modes
+ * (Lame.js:755-766,1310-1315); the difference is per frame -- four psycho-acoustic channels, the M/S decision, ms_convert and
+ * reduce_side, the mode bits of the header.  SURVEY.md 8(f2), oracle only. */
+int lj_enable_joint_stereo(LjEnc* e) {
+  if (!e || e->frameNum != 0 || e->channels_out != 2) return -1;
+  e->mode_joint = 1;
+  return 0;
+}
 int lj_enable_reservoir(LjEnc* e) {
   if (!e || e->frameNum != 0) return -1;
   e->disable_reservoir = 0;

@@ -197,11 +197,27 @@ static double psycho_loudness_approx(const F32* energy, const LjEnc* e) {
   return loudness_power;
 }
 
-static void compute_ffts(LjEnc* e, F32* fftenergy, F32 fftenergy_s[3][HBLKSIZE_s], F32* wsamp_l,
-                         F32 wsamp_s[3][BLKSIZE_s], int gr_out, int chn, const F32* buffer, int bufPos) {
-  /* chn < 2 always (no joint stereo) */
-  fft_long(e, wsamp_l, buffer, bufPos);
-  fft_short(e, wsamp_s, buffer, bufPos);
+static void compute_ffts(LjEnc* e, F32* fftenergy, F32 fftenergy_s[3][HBLKSIZE_s], F32 (*wsamp_L)[BLKSIZE],
+                         F32 (*wsamp_S)[3][BLKSIZE_s], int gr_out, int chn, const F32* const* buffers, int bufPos) {
+  F32* wsamp_l = wsamp_L[chn & 1];
+  F32 (*wsamp_s)[BLKSIZE_s] = wsamp_S[chn & 1];
+  if (chn < 2) {
+    fft_long(e, wsamp_l, buffers[chn], bufPos);
+    fft_short(e, wsamp_s, buffers[chn], bufPos);
+  } else if (chn == 2) {
+    /* FFT data for mid and side channel is derived from L & R (PsyModel.js:258-275) */
+    for (int j = BLKSIZE - 1; j >= 0; --j) {
+      double l = wsamp_L[0][j], r = wsamp_L[1][j];
+      wsamp_L[0][j] = (l + r) * LJ_SQRT2 * 0.5;
+      wsamp_L[1][j] = (l - r) * LJ_SQRT2 * 0.5;
+    }
+    for (int b = 2; b >= 0; --b)
+      for (int j = BLKSIZE_s - 1; j >= 0; --j) {
+        double l = wsamp_S[0][b][j], r = wsamp_S[1][b][j];
+        wsamp_S[0][b][j] = (l + r) * LJ_SQRT2 * 0.5;
+        wsamp_S[1][b][j] = (l - r) * LJ_SQRT2 * 0.5;
+      }
+  }
   fftenergy[0] = wsamp_l[0];
   fftenergy[0] *= fftenergy[0];
   for (int j = BLKSIZE / 2 - 1; j >= 0; --j) {
@@ -223,9 +239,11 @@ static void compute_ffts(LjEnc* e, F32* fftenergy, F32 fftenergy_s[3][HBLKSIZE_s
     for (int j = 11; j < HBLKSIZE; j++) totalenergy += fftenergy[j];
     e->tot_ener[chn] = totalenergy;
   }
-  /* athaa_loudapprox == 2 */
-  e->loudness_sq[gr_out][chn] = e->loudness_sq_save[chn];
-  e->loudness_sq_save[chn] = psycho_loudness_approx(fftenergy, e);
+  /* athaa_loudapprox == 2; no loudness for mid / side */
+  if (chn < 2) {
+    e->loudness_sq[gr_out][chn] = e->loudness_sq_save[chn];
+    e->loudness_sq_save[chn] = psycho_loudness_approx(fftenergy, e);
+  }
 }
 
 static double mask_add(double m1, double m2, int kk, int b, const LjEnc* e, int shortblock) {
@@ -479,8 +497,70 @@ static const double fircoef[10] = {-8.65163e-18 * 2, -0.00851586 * 2, -6.74764e-
                                    -3.36639e-17 * 2, -0.0438162 * 2, -1.54175e-17 * 2, 0.0931738 * 2,
                                    -5.52212e-17 * 2, -0.313819 * 2};
 
+/* PsyModel.js:548-585 */
+static void msfix1(LjEnc* e) {
+  for (int sb = 0; sb < SBMAX_l; sb++) {
+    if (e->thm[0].l[sb] > 1.58 * e->thm[1].l[sb] || e->thm[1].l[sb] > 1.58 * e->thm[0].l[sb]) continue;
+    double mld = e->mld_l[sb] * e->en[3].l[sb];
+    double rmid = js_max(e->thm[2].l[sb], js_min(e->thm[3].l[sb], mld));
+    mld = e->mld_l[sb] * e->en[2].l[sb];
+    double rside = js_max(e->thm[3].l[sb], js_min(e->thm[2].l[sb], mld));
+    e->thm[2].l[sb] = rmid;
+    e->thm[3].l[sb] = rside;
+  }
+  for (int sb = 0; sb < SBMAX_s; sb++)
+    for (int sblock = 0; sblock < 3; sblock++) {
+      if (e->thm[0].s[sb][sblock] > 1.58 * e->thm[1].s[sb][sblock] || e->thm[1].s[sb][sblock] > 1.58 * e->thm[0].s[sb][sblock]) continue;
+      double mld = e->mld_s[sb] * e->en[3].s[sb][sblock];
+      double rmid = js_max(e->thm[2].s[sb][sblock], js_min(e->thm[3].s[sb][sblock], mld));
+      mld = e->mld_s[sb] * e->en[2].s[sb][sblock];
+      double rside = js_max(e->thm[3].s[sb][sblock], js_min(e->thm[2].s[sb][sblock], mld));
+      e->thm[2].s[sb][sblock] = rmid;
+      e->thm[3].s[sb][sblock] = rside;
+    }
+}
+
+/* PsyModel.js:591-640 */
+static void ns_msfix(LjEnc* e, double msfix, double athadjust) {
+  double msfix2 = msfix;
+  double athlower = js_pow(10, athadjust);
+  msfix *= 2.0;
+  msfix2 *= 2.0;
+  for (int sb = 0; sb < SBMAX_l; sb++) {
+    double thmLR, thmM, thmS, ath;
+    ath = (e->ath_cb_l[e->bm_l[sb]]) * athlower;
+    thmLR = js_min(js_max(e->thm[0].l[sb], ath), js_max(e->thm[1].l[sb], ath));
+    thmM = js_max(e->thm[2].l[sb], ath);
+    thmS = js_max(e->thm[3].l[sb], ath);
+    if (thmLR * msfix < thmM + thmS) {
+      double f = thmLR * msfix2 / (thmM + thmS);
+      thmM *= f;
+      thmS *= f;
+    }
+    e->thm[2].l[sb] = js_min(thmM, e->thm[2].l[sb]);
+    e->thm[3].l[sb] = js_min(thmS, e->thm[3].l[sb]);
+  }
+  athlower *= ((double)BLKSIZE_s / BLKSIZE);
+  for (int sb = 0; sb < SBMAX_s; sb++)
+    for (int sblock = 0; sblock < 3; sblock++) {
+      double thmLR, thmM, thmS, ath;
+      ath = (e->ath_cb_s[e->bm_s[sb]]) * athlower;
+      thmLR = js_min(js_max(e->thm[0].s[sb][sblock], ath), js_max(e->thm[1].s[sb][sblock], ath));
+      thmM = js_max(e->thm[2].s[sb][sblock], ath);
+      thmS = js_max(e->thm[3].s[sb][sblock], ath);
+      if (thmLR * msfix < thmM + thmS) {
+        double f = thmLR * msfix / (thmM + thmS);
+        thmM *= f;
+        thmS *= f;
+      }
+      e->thm[2].s[sb][sblock] = js_min(e->thm[2].s[sb][sblock], thmM);
+      e->thm[3].s[sb][sblock] = js_min(e->thm[3].s[sb][sblock], thmS);
+    }
+}
+
 int lj_psycho_anal_ns(LjEnc* e, const F32* buf0, const F32* buf1, int bufPos, int gr_out,
-                      PsyRatio masking_ratio[2][2], double* percep_entropy, F32* energy, int* blocktype_d) {
+                      PsyRatio masking_ratio[2][2], PsyRatio masking_MS_ratio[2][2], double* percep_entropy,
+                      double* percep_MS_entropy, F32* energy, int* blocktype_d) {
   const F32* buffer[2] = {buf0, buf1};
   static thread_local F32 wsamp_L[2][BLKSIZE];
   static thread_local F32 wsamp_S[2][3][BLKSIZE_s];
@@ -493,6 +573,7 @@ int lj_psycho_anal_ns(LjEnc* e, const F32* buf0, const F32* buf1, int bufPos, in
   const int NSFIRLEN = 21;
 
   numchn = e->channels_out;
+  if (e->mode_joint) numchn = 4;           /* chn 2 and 3 = mid and side (PsyModel.js:1031-1034) */
   pcfact = e->ResvMax == 0 ? 0 : ((double)e->ResvSize) / e->ResvMax * 0.5;
 
   for (chn = 0; chn < e->channels_out; chn++) {
@@ -510,6 +591,10 @@ int lj_psycho_anal_ns(LjEnc* e, const F32* buf0, const F32* buf1, int bufPos, in
     }
     masking_ratio[gr_out][chn].en = e->en[chn];
     masking_ratio[gr_out][chn].thm = e->thm[chn];
+    if (numchn > 2) {
+      masking_MS_ratio[gr_out][chn].en = e->en[chn + 2];
+      masking_MS_ratio[gr_out][chn].thm = e->thm[chn + 2];
+    }
   }
 
   for (chn = 0; chn < numchn; chn++) {
@@ -527,6 +612,13 @@ int lj_psycho_anal_ns(LjEnc* e, const F32* buf0, const F32* buf1, int bufPos, in
       en_subshort[i] = e->last_en_subshort[chn][i + 6];
       attack_intensity[i] = en_subshort[i] / e->last_en_subshort[chn][i + 4];
       en_short[0] += en_subshort[i];
+    }
+    if (chn == 2) {
+      for (i = 0; i < 576; i++) {
+        double l = ns_hpfsmpl[0][i], r = ns_hpfsmpl[1][i];
+        ns_hpfsmpl[0][i] = l + r;
+        ns_hpfsmpl[1][i] = l - r;
+      }
     }
     {
       const F32* pf = ns_hpfsmpl[chn & 1];
@@ -567,10 +659,11 @@ int lj_psycho_anal_ns(LjEnc* e, const F32* buf0, const F32* buf1, int bufPos, in
       if (ns_attacks[2] != 0 && ns_attacks[1] != 0) ns_attacks[2] = 0;
       if (ns_attacks[3] != 0 && ns_attacks[2] != 0) ns_attacks[3] = 0;
     }
-    uselongblock[chn] = ns_uselongblock;
+    if (chn < 2) uselongblock[chn] = ns_uselongblock;
+    else if (ns_uselongblock == 0) uselongblock[0] = uselongblock[1] = 0;
     energy[chn] = e->tot_ener[chn];
 
-    compute_ffts(e, fftenergy, fftenergy_s, wsamp_L[chn & 1], wsamp_S[chn & 1], gr_out, chn, buffer[chn], bufPos);
+    compute_ffts(e, fftenergy, fftenergy_s, wsamp_L, wsamp_S, gr_out, chn, buffer, bufPos);
     calc_energy(e, fftenergy, eb_l, max, avg);
     calc_mask_index_l(e, max, avg, mask_idx_l);
     for (sblock = 0; sblock < 3; sblock++) {
@@ -626,12 +719,25 @@ int lj_psycho_anal_ns(LjEnc* e, const F32* buf0, const F32* buf1, int bufPos, in
   if (!e->mode_mono) {
     if (e->interChRatio > 0.0) calc_interchannel_masking(e, e->interChRatio);
   }
+  if (e->mode_joint) {
+    msfix1(e);
+    double msfix = e->msfix;
+    if (fabs(msfix) > 0.0) ns_msfix(e, msfix, e->ATHlower * e->ath_adjust);
+  }
   block_type_set(e, uselongblock, blocktype_d, blocktype);
   for (chn = 0; chn < numchn; chn++) {
-    int type = blocktype_d[chn];
-    const PsyRatio* mr = &masking_ratio[gr_out][chn];
-    if (type == SHORT_TYPE) percep_entropy[chn] = pecalc_s(mr, e->masking_lower);
-    else percep_entropy[chn] = pecalc_l(mr, e->masking_lower);
+    if (chn > 1) {
+      int type = NORM_TYPE;
+      if (blocktype_d[0] == SHORT_TYPE || blocktype_d[1] == SHORT_TYPE) type = SHORT_TYPE;
+      const PsyRatio* mr = &masking_MS_ratio[gr_out][chn - 2];
+      if (type == SHORT_TYPE) percep_MS_entropy[chn - 2] = pecalc_s(mr, e->masking_lower);
+      else percep_MS_entropy[chn - 2] = pecalc_l(mr, e->masking_lower);
+    } else {
+      int type = blocktype_d[chn];
+      const PsyRatio* mr = &masking_ratio[gr_out][chn];
+      if (type == SHORT_TYPE) percep_entropy[chn] = pecalc_s(mr, e->masking_lower);
+      else percep_entropy[chn] = pecalc_l(mr, e->masking_lower);
+    }
   }
   return 0;
 }

@@ -181,7 +181,7 @@ static void ResvFrameEnd(LjEnc* e, double mean_bits) {
 }
 
 /* QuantizePVT.js:421-484.  targ_bits / add_bits are Int32Arrays: every store truncates. */
-static int on_pe(LjEnc* e, double pe[2][2], int* targ_bits, double mean_bits, int gr, int cbr) {
+static double on_pe(LjEnc* e, double pe[2][2], int* targ_bits, double mean_bits, int gr, int cbr) {
   double tbits = 0, bits;
   int add_bits[2] = {0, 0};
   int ch;
@@ -211,7 +211,7 @@ static int on_pe(LjEnc* e, double pe[2][2], int* targ_bits, double mean_bits, in
       targ_bits[ch] = js_toint32((double)targ_bits[ch] / bits);
     }
   }
-  return (int)max_bits;
+  return max_bits;                 /* a JS number: fractional when the reservoir build-up rule took a tenth of mean_bits */
 }
 
 /* ---------------------------------------------------------------- xmin / noise */
@@ -1305,13 +1305,50 @@ static void iteration_finish_one(LjEnc* e, int gr, int ch) {
   e->ResvSize -= cod_info->part2_3_length + cod_info->part2_length; /* ResvAdjust */
 }
 
-void lj_iteration_loop(LjEnc* e, double pe[2][2], PsyRatio ratio[2][2]) {
+/* Quantize.js:76-83 */
+static void ms_convert(LjEnc* e, int gr) {
+  for (int i = 0; i < 576; ++i) {
+    double l = e->tt[gr][0].xr[i], r = e->tt[gr][1].xr[i];
+    e->tt[gr][0].xr[i] = (l + r) * (LJ_SQRT2 * 0.5);
+    e->tt[gr][1].xr[i] = (l - r) * (LJ_SQRT2 * 0.5);
+  }
+}
+
+/* QuantizePVT.js:486-534; targ_bits is an Int32Array: every store truncates */
+static void reduce_side(int* targ_bits, double ms_ener_ratio, double mean_bits, double max_bits) {
+  double fac = .33 * (.5 - ms_ener_ratio) / .5;
+  if (fac < 0) fac = 0;
+  if (fac > .5) fac = .5;
+  int move_bits = js_toint32(fac * .5 * (targ_bits[0] + targ_bits[1]));
+  if (move_bits > MAX_BITS_PER_CHANNEL - targ_bits[0]) move_bits = MAX_BITS_PER_CHANNEL - targ_bits[0];
+  if (move_bits < 0) move_bits = 0;
+  if (targ_bits[1] >= 125) {
+    if (targ_bits[1] - move_bits > 125) {
+      if (targ_bits[0] < mean_bits) targ_bits[0] += move_bits;
+      targ_bits[1] -= move_bits;
+    } else {
+      targ_bits[0] += targ_bits[1] - 125;
+      targ_bits[1] = 125;
+    }
+  }
+  move_bits = targ_bits[0] + targ_bits[1];
+  if (move_bits > max_bits) {
+    targ_bits[0] = js_toint32((max_bits * targ_bits[0]) / move_bits);
+    targ_bits[1] = js_toint32((max_bits * targ_bits[1]) / move_bits);
+  }
+}
+
+void lj_iteration_loop(LjEnc* e, double pe[2][2], const double* ms_ener_ratio, PsyRatio ratio[2][2]) {
   F32 l3_xmin[SFBMAX];
   F32 xrpow[576];
   int targ_bits[2] = {0, 0};
   double mean_bits = ResvFrameBegin(e);
   for (int gr = 0; gr < e->mode_gr; gr++) {
-    on_pe(e, pe, targ_bits, mean_bits, gr, gr);
+    double max_bits = on_pe(e, pe, targ_bits, mean_bits, gr, gr);
+    if (e->mode_ext == 2) {                    /* MPG_MD_MS_LR (CBRNewIterationLoop.js:46-50) */
+      ms_convert(e, gr);
+      reduce_side(targ_bits, ms_ener_ratio[gr], mean_bits, max_bits);
+    }
     for (int ch = 0; ch < e->channels_out; ch++) {
       double masking_lower_db;
       GrInfo* cod_info = &e->tt[gr][ch];

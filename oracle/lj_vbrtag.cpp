@@ -122,7 +122,7 @@ static void setLameTagFrameHeader(const LjEnc* e, uint8_t* buffer) {
   buffer[2] = (uint8_t)shiftInBitsValue(buffer[2], 2, e->samplerate_index);
   buffer[2] = (uint8_t)shiftInBitsValue(buffer[2], 1, 0);
   buffer[2] = (uint8_t)shiftInBitsValue(buffer[2], 1, 0);                 /* gfp.extension */
-  buffer[3] = (uint8_t)shiftInBitsValue(buffer[3], 2, e->mode_mono ? 3 : 0);   /* gfp.mode.ordinal(): STEREO 0, MONO 3 */
+  buffer[3] = (uint8_t)shiftInBitsValue(buffer[3], 2, e->mode_mono ? 3 : (e->mode_joint ? 1 : 0));   /* gfp.mode.ordinal(): STEREO 0, JOINT_STEREO 1, MONO 3 */
   buffer[3] = (uint8_t)shiftInBitsValue(buffer[3], 2, e->mode_ext);
   buffer[3] = (uint8_t)shiftInBitsValue(buffer[3], 1, 0);                 /* copyright */
   buffer[3] = (uint8_t)shiftInBitsValue(buffer[3], 1, 1);                 /* original */
@@ -199,13 +199,13 @@ static int putLameVBR(const LjEnc* e, int musicLength, uint8_t* streamBuffer, in
   /* nogap_total == nogap_current == 0 (LameInternalFlags.js:335-336): neither flag */
   const int flags = athType + ((expNPsyTune ? 1 : 0) << 4) + ((safeJoint ? 1 : 0) << 5);
   if (quality < 0) quality = 0;
-  stereoMode = e->mode_mono ? 0 : 1;                                       /* MONO 0, STEREO 1 */
+  stereoMode = e->mode_mono ? 0 : (e->mode_joint ? 3 : 1);                 /* MONO 0, STEREO 1, JOINT_STEREO 3 (force_ms off) */
   if (e->in_samplerate <= 32000) sourceFreq = 0x00;
   else if (e->in_samplerate == 48000) sourceFreq = 0x02;
   else if (e->in_samplerate > 48000) sourceFreq = 0x03;
   else sourceFreq = 0x01;
   /* disable_reservoir (index.js:108) && brate < 320, or a source rate <= 32 kHz */
-  if (e->brate < 320 || athType == 0 || e->in_samplerate <= 32000) nonOptimal = 1;
+  if ((e->disable_reservoir && e->brate < 320) || athType == 0 || e->in_samplerate <= 32000) nonOptimal = 1;
   const int misc = noiseShaping + (stereoMode << 2) + (nonOptimal << 5) + (sourceFreq << 6);
   const int musicCRC = e->nMusicCRC;
 

@@ -74,6 +74,7 @@ def lib():
         L.lj_query_out_samplerate.argtypes = [ctypes.c_int] * 3
         L.lj_enable_vbr_tag.argtypes = [ctypes.c_void_p]
         L.lj_enable_reservoir.argtypes = [ctypes.c_void_p]
+        L.lj_enable_joint_stereo.argtypes = [ctypes.c_void_p]
         L.lj_music_crc.argtypes = [ctypes.c_void_p]
         L.lj_bytes_written.argtypes = [ctypes.c_void_p]
         L.lj_bytes_written.restype = ctypes.c_longlong
@@ -95,12 +96,14 @@ def out_samplerate(channels, samplerate, kbps):
 class OracleEncoder:
     """Mirror of lamejs.Mp3Encoder (src/js/index.js:66-136) backed by the C++ restatement."""
 
-    def __init__(self, channels, samplerate, kbps, trace_frames=0, write_vbr_tag=False, reservoir=False):
+    def __init__(self, channels, samplerate, kbps, trace_frames=0, write_vbr_tag=False, reservoir=False, joint_stereo=False):
         self.L = lib()
         self.h = self.L.lj_create(channels, samplerate, kbps)
         if not self.h:
             raise ValueError("unsupported configuration")
         self.channels = channels
+        if joint_stereo:                   # gfp.mode = JOINT_STEREO (SURVEY 8(f2); Mp3Encoder uses STEREO)
+            assert self.L.lj_enable_joint_stereo(self.h) == 0
         if reservoir:                      # gfp.disable_reservoir = false (SURVEY 8(f2); Mp3Encoder never does this)
             assert self.L.lj_enable_reservoir(self.h) == 0
         self.tag_on = bool(write_vbr_tag) and self.L.lj_enable_vbr_tag(self.h) == 1   # gfp.bWriteVbrTag (InitVbrTag may refuse)
