@@ -161,3 +161,23 @@ def test_crc16_combine(oracle):
     for p in parts:
         c = M.crc16_combine(c, oracle.crc16(p), len(p))
     assert c == oracle.crc16(a)
+
+
+def test_entry_points_reject_bad_arguments_without_a_device():
+    """the host-only entry points of this row validate their inputs and never need CUDA"""
+    import ctypes
+    L = M.lib()
+    L.mp3b200_lametag_build.argtypes = [ctypes.c_int] * 3 + [ctypes.c_int64] * 2 + [ctypes.c_int] * 2 + [ctypes.c_void_p, ctypes.c_int]
+    buf = np.zeros(2880, dtype=np.uint8)
+    assert L.mp3b200_lametag_size(2, 44100, 64) < 0 and L.mp3b200_lametag_size(3, 44100, 128) < 0      # lamejs would resample / bad channels
+    assert L.mp3b200_lametag_build(2, 44100, 64, 10, 1000, 0, 576, buf.ctypes.data, 2880) < 0
+    assert L.mp3b200_lametag_build(2, 44100, 128, 0, 0, 0, 576, buf.ctypes.data, 2880) == 0            # no frame counted: no tag
+    assert L.mp3b200_lametag_build(2, 44100, 128, 10, 4170, 0, 576, None, 0) == 417                    # size query
+    assert L.mp3b200_lametag_build(2, 44100, 128, 10, 4170, 0, 576, buf.ctypes.data, 100) == 417 and not buf.any()
+    assert L.mp3b200_wav_read_header(None, 0, None) < 0 and L.mp3b200_get_vbr_tag(None, 10, None) < 0
+    L.mp3b200_crc16_combine.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64]
+    assert L.mp3b200_crc16_combine(1, 2, -1) < 0 and L.mp3b200_crc16_combine(0x1234, 0, 0) == 0x1234
+    # handle entry points with a NULL handle
+    L.mp3b200_put_vbr_tag.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    assert L.mp3b200_set_write_vbr_tag(None, 1) == -3 and L.mp3b200_get_lametag_frame(None, None, 0) == -3 and L.mp3b200_put_vbr_tag(None, None, 0) == -3
+    assert L.mp3b200_music_crc(None) == -1 and L.mp3b200_bytes_written(None) == -1
