@@ -107,6 +107,7 @@ struct LjEnc {
   int vbr_bag[400];
   /* modes Mp3Encoder does not reach: gfp.disable_reservoir (index.js:108 sets it), gfp.mode == JOINT_STEREO */
   int disable_reservoir, mode_joint;
+  int java_int_div;                /* test switch: integer byte counts where Java (and LAME) divide integers, see lj_quant.cpp ResvFrameEnd */
   int encoder_padding;             /* gfp.encoder_padding, set by lame_encode_flush (Lame.js:1412) */
   double lowpass_final;            /* gfp.lowpassfreq after lame_init_params (Lame.js:884-896) */
 };

@@ -629,6 +629,16 @@ int lj_enable_reservoir(LjEnc* e) {
   e->disable_reservoir = 0;
   return 0;
 }
+/* NOT lamejs: the reservoir with Java's integer division at Reservoir.js:283 (`Math.min(...) / 8`).  In JavaScript that
+ * quotient has eighths, the sub-byte remainder of the stuffing is then drained IN FRONT of the next frame's main data and the
+ * header's main_data_begin (truncated) no longer points at it: lamejs's reservoir streams do not decode
+ * (tests/test_modes_oracle.py shows both).  This switch exists so that the reservoir machinery of the oracle can also be
+ * checked by the independent decoder. */
+int lj_enable_reservoir_integer_bytes(LjEnc* e) {
+  if (lj_enable_reservoir(e) != 0) return -1;
+  e->java_int_div = 1;
+  return 0;
+}
 void lj_destroy(LjEnc* e) { if (e) { free(e->s3_ll); free(e->s3_ss); free(e->blackfilt); free(e->inb[0]); free(e->inb[1]); free(e); } }
 
 /* index.js:117-130 + Lame.js:1490-1514.  Returns bytes written or a negative lame error. */

@@ -171,6 +171,7 @@ static void ResvFrameEnd(LjEnc* e, double mean_bits) {
   {
     /* Math.min(...) / 8 on JS numbers: not an integer division (Java's is), so main_data_begin can hold eighths */
     double mdb_bytes = js_min(e->main_data_begin * 8, stuffingBits) / 8;
+    if (e->java_int_div) mdb_bytes = floor(mdb_bytes);     /* Reservoir.java: `int mdb_bytes = Math.min(...) / 8` */
     e->resvDrain_pre += 8 * mdb_bytes;
     stuffingBits -= 8 * mdb_bytes;
     e->ResvSize -= 8 * mdb_bytes;

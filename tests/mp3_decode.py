@@ -2,7 +2,7 @@
 the four block-type windows, frequency inversion, polyphase synthesis) on top of the bitstream parser in mp3_parse.py.
 Independent of the encoder under test: it shares no code and no derivation with lamejs, the oracle or the CUDA kernels
 (the synthesis prototype window comes from the decoder table in the reference's Java tree, see
-tools/gen_decoder_window.py).  Stereo modes: plain L/R only (lamejs' Mp3Encoder never sets mode_ext).  numpy, slow,
+tools/gen_decoder_window.py).  Stereo modes: L/R and M/S (lamejs' Mp3Encoder never sets mode_ext; the oracle's joint-stereo mode does).  numpy, slow,
 meant for a few dozen frames in tests: decoding the oracle's output back to the input is a derived known-answer pin."""
 import json
 import os
@@ -113,17 +113,24 @@ class Decoder:
 
     def decode_frame(self, f):
         out = np.zeros((self.nch, 1152))
+        ms = self.nch == 2 and f["mode"] == 1 and (f["mode_ext"] & 2) != 0     # joint stereo, M/S on (ISO 11172-3 2.4.3.4.9.3)
         for gr in range(2):
+            rq = [self._requantize(f["gi"][gr][ch]) for ch in range(self.nch)]
+            if ms:
+                # both channels carry the same block type in an M/S granule: L = (M + S) / sqrt 2, R = (M - S) / sqrt 2
+                k = 0 if rq[0][0] is not None else 1
+                m, s_ = rq[0][k], rq[1][k]
+                lr = ((m + s_) / np.sqrt(2.0), (m - s_) / np.sqrt(2.0))
+                rq = [(lr[c], None) if k == 0 else (None, lr[c]) for c in range(2)]
             for ch in range(self.nch):
                 g = f["gi"][gr][ch]
-                xr, pw = self._requantize(g)
-                out[ch, 576 * gr:576 * gr + 576] = self._polyphase(ch, self._hybrid(ch, g, xr, pw))
+                out[ch, 576 * gr:576 * gr + 576] = self._polyphase(ch, self._hybrid(ch, g, rq[ch][0], rq[ch][1]))
         return out
 
 
-def decode(data, books, max_frames=None):
+def decode(data, books, max_frames=None, reservoir=False):
     """bytes -> float array [nch][frames * 1152] (full scale = 32768, like the encoder's Int16 input)."""
-    frames = mp3_parse.parse_stream(data, books)
+    frames = mp3_parse.parse_stream_reservoir(data, books) if reservoir else mp3_parse.parse_stream(data, books)
     if max_frames:
         frames = frames[:max_frames]
     dec = Decoder(frames[0]["nch"], frames[0]["sr"])

@@ -89,43 +89,8 @@ class BitReader:
         return v
 
 
-def parse_frame(data, off, books):
-    """Parse one frame starting at byte `off`.  Returns dict with header, side info, per granule/channel
-    quantised lines `ix` (signed), scalefactors, bit accounting and frame length."""
-    br = BitReader(data, off * 8)
-    assert br.get(12) == 0xFFF, "sync"
-    assert br.get(1) == 1 and br.get(2) == 1, "MPEG-1 layer III"
-    prot = br.get(1)
-    bri, sri, pad = br.get(4), br.get(2), br.get(1)
-    br.get(1)
-    mode, mode_ext = br.get(2), br.get(2)
-    br.get(4)
-    sr = _SRATES[sri]
-    nch = 1 if mode == 3 else 2
-    flen = 144000 * _BITRATES[bri] // sr + pad
-    mdb = br.get(9)
-    br.get(5 if nch == 1 else 3)
-    scfsi = [[br.get(1) for _ in range(4)] for _ in range(nch)]
-    gi = [[None] * nch for _ in range(2)]
-    for gr in range(2):
-        for ch in range(nch):
-            g = {"part2_3_length": br.get(12), "big_values": br.get(9) * 2, "global_gain": br.get(8),
-                 "scalefac_compress": br.get(4), "window_switching": br.get(1)}
-            if g["window_switching"]:
-                g["block_type"], g["mixed"] = br.get(2), br.get(1)
-                g["table_select"] = [br.get(5), br.get(5), 0]
-                g["subblock_gain"] = [br.get(3), br.get(3), br.get(3)]
-                g["region0"], g["region1"] = (8 if g["block_type"] == 2 else 7), 36
-            else:
-                g["block_type"], g["mixed"] = 0, 0
-                g["table_select"] = [br.get(5), br.get(5), br.get(5)]
-                g["subblock_gain"] = [0, 0, 0]
-                g["region0"], g["region1"] = br.get(4), br.get(3)
-            g["preflag"], g["scalefac_scale"], g["count1table"] = br.get(1), br.get(1), br.get(1)
-            gi[gr][ch] = g
-    side_end = br.p
-    assert side_end == (off + 4 + (17 if nch == 1 else 32)) * 8
-    assert mdb == 0, "bit reservoir not expected"
+def _parse_main(br, gi, scfsi, nch, sr, books):
+    """scalefactors and Huffman data of one frame's granules from `br` (positioned at the frame's main data)"""
     sfl, sfs = _SFB_L[sr], _SFB_S[sr]
     for gr in range(2):
         for ch in range(nch):
@@ -187,14 +152,77 @@ def parse_frame(data, off, books):
                 i += 4
             assert br.p == end, ("part2_3_length mismatch", gr, ch, br.p - end)
             g["ix"], g["count1_end"] = ix, i
+
+
+def parse_frame(data, off, books, main=None):
+    """Parse one frame starting at byte `off`.  Returns dict with header, side info, per granule/channel
+    quantised lines `ix` (signed), scalefactors, bit accounting and frame length."""
+    br = BitReader(data, off * 8)
+    assert br.get(12) == 0xFFF, "sync"
+    assert br.get(1) == 1 and br.get(2) == 1, "MPEG-1 layer III"
+    prot = br.get(1)
+    bri, sri, pad = br.get(4), br.get(2), br.get(1)
+    br.get(1)
+    mode, mode_ext = br.get(2), br.get(2)
+    br.get(4)
+    sr = _SRATES[sri]
+    nch = 1 if mode == 3 else 2
+    flen = 144000 * _BITRATES[bri] // sr + pad
+    mdb = br.get(9)
+    br.get(5 if nch == 1 else 3)
+    scfsi = [[br.get(1) for _ in range(4)] for _ in range(nch)]
+    gi = [[None] * nch for _ in range(2)]
+    for gr in range(2):
+        for ch in range(nch):
+            g = {"part2_3_length": br.get(12), "big_values": br.get(9) * 2, "global_gain": br.get(8),
+                 "scalefac_compress": br.get(4), "window_switching": br.get(1)}
+            if g["window_switching"]:
+                g["block_type"], g["mixed"] = br.get(2), br.get(1)
+                g["table_select"] = [br.get(5), br.get(5), 0]
+                g["subblock_gain"] = [br.get(3), br.get(3), br.get(3)]
+                g["region0"], g["region1"] = (8 if g["block_type"] == 2 else 7), 36
+            else:
+                g["block_type"], g["mixed"] = 0, 0
+                g["table_select"] = [br.get(5), br.get(5), br.get(5)]
+                g["subblock_gain"] = [0, 0, 0]
+                g["region0"], g["region1"] = br.get(4), br.get(3)
+            g["preflag"], g["scalefac_scale"], g["count1table"] = br.get(1), br.get(1), br.get(1)
+            gi[gr][ch] = g
+    side_end = br.p
+    assert side_end == (off + 4 + (17 if nch == 1 else 32)) * 8
+    if main is None:
+        assert mdb == 0, "bit reservoir not expected"
+        _parse_main(br, gi, scfsi, nch, sr, books)
+        main_end = br.p - off * 8
+    else:
+        # bit reservoir: this frame's main data starts `mdb` bytes before the end of what earlier frames carried
+        start = len(main) - mdb
+        assert start >= 0, "main_data_begin points before the stream"
+        main += data[off + 4 + (17 if nch == 1 else 32):off + flen]
+        mbr = BitReader(main, start * 8)
+        _parse_main(mbr, gi, scfsi, nch, sr, books)
+        assert mbr.p <= len(main) * 8, "main data runs past this frame"
+        main_end = None
     return {"nch": nch, "sr": sr, "kbps": _BITRATES[bri], "padding": pad, "frame_len": flen, "mode": mode,
-            "mode_ext": mode_ext, "scfsi": scfsi, "gi": gi, "main_end_bit": br.p - off * 8}
+            "mode_ext": mode_ext, "scfsi": scfsi, "gi": gi, "main_end_bit": main_end, "main_data_begin": mdb}
 
 
 def parse_stream(data, books):
     off, frames = 0, []
     while off + 4 <= len(data):
         f = parse_frame(data, off, books)
+        frames.append(f)
+        off += f["frame_len"]
+    assert off == len(data), "trailing bytes"
+    return frames
+
+
+def parse_stream_reservoir(data, books):
+    """Like parse_stream for streams written with the bit reservoir: frames sit on the fixed grid, each frame's main data
+    starts main_data_begin bytes before its own side info ends (ISO 11172-3 2.4.2.7), gathered here in one byte string."""
+    off, frames, main = 0, [], bytearray()
+    while off + 4 <= len(data):
+        f = parse_frame(data, off, books, main)
         frames.append(f)
         off += f["frame_len"]
     assert off == len(data), "trailing bytes"

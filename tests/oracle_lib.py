@@ -75,6 +75,7 @@ def lib():
         L.lj_enable_vbr_tag.argtypes = [ctypes.c_void_p]
         L.lj_enable_reservoir.argtypes = [ctypes.c_void_p]
         L.lj_enable_joint_stereo.argtypes = [ctypes.c_void_p]
+        L.lj_enable_reservoir_integer_bytes.argtypes = [ctypes.c_void_p]
         L.lj_music_crc.argtypes = [ctypes.c_void_p]
         L.lj_bytes_written.argtypes = [ctypes.c_void_p]
         L.lj_bytes_written.restype = ctypes.c_longlong
@@ -104,7 +105,9 @@ class OracleEncoder:
         self.channels = channels
         if joint_stereo:                   # gfp.mode = JOINT_STEREO (Mp3Encoder uses STEREO)
             assert self.L.lj_enable_joint_stereo(self.h) == 0
-        if reservoir:                      # gfp.disable_reservoir = false (Mp3Encoder never does this)
+        if reservoir == "java":            # NOT lamejs: integer byte counts as in Reservoir.java (decodable streams)
+            assert self.L.lj_enable_reservoir_integer_bytes(self.h) == 0
+        elif reservoir:                    # gfp.disable_reservoir = false (Mp3Encoder never does this)
             assert self.L.lj_enable_reservoir(self.h) == 0
         self.tag_on = bool(write_vbr_tag) and self.L.lj_enable_vbr_tag(self.h) == 1   # gfp.bWriteVbrTag (InitVbrTag may refuse)
         self.trace = None

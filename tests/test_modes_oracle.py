@@ -71,3 +71,58 @@ def test_the_fixtures_exercise_the_modes(oracle):
     c = GOLD["stereo_resv_noise_2_44100_128_1152_corr"]
     fr = _frames(_encode(oracle, c, *stereo_signal(c))[0])
     assert all(m == 0 and x == 0 for m, x, _ in fr) and max(b for _, _, b in fr) > 0
+
+
+DELAY = 1105
+
+
+def _snr_gain(y, x, n=30000):
+    seg, ref = y[DELAY:DELAY + n], x[:n].astype(np.float64)
+    g = float(np.dot(seg, ref) / np.dot(ref, ref))
+    return 10 * np.log10(np.dot(ref, ref) / np.sum((seg / g - ref) ** 2)), g * 32768.0
+
+
+def _joint_signal():
+    from synth import make_signal
+    l, r0 = make_signal("sweep", 40 * 1152, 44100, seed=3)
+    return l, ((l.astype(np.int32) * 3 + r0.astype(np.int32)) // 4).astype(np.int16)
+
+
+def test_joint_stereo_stream_decodes_to_the_input(oracle, books):
+    """independent of lamejs: an ISO 11172-3 decoder (tests/mp3_decode.py, M/S matrixing added) gets both channels back from an
+    all-M/S stream at LAME's 1105-sample delay with the preset's 0.95 gain"""
+    import mp3_decode
+    import mp3_parse
+    l, r = _joint_signal()
+    enc = oracle.OracleEncoder(2, 44100, 128, joint_stereo=True)
+    data = enc.encode_buffer(l, r) + enc.flush()
+    frames = mp3_parse.parse_stream(data, books)
+    assert all(f["mode"] == 1 for f in frames) and sum(f["mode_ext"] == 2 for f in frames) > 30
+    y = mp3_decode.decode(data, books)
+    for c, x in enumerate((l, r)):
+        snr, gain = _snr_gain(y[c], x)
+        assert snr > 60 and abs(gain - 0.95) < 0.005, (c, snr, gain)
+
+
+def test_lamejs_reservoir_streams_do_not_decode_and_why(oracle, books):
+    """A finding, not a feature.  Reservoir.js:283 computes `Math.min(main_data_begin * 8, stuffingBits) / 8` as a JavaScript
+    number; Java (and LAME) divide integers.  With eighths of a byte in mdb_bytes the sub-byte remainder of the stuffing is
+    drained in FRONT of the next frame's main data while the header carries the truncated main_data_begin, so a decoder starts
+    reading a few bits off.  The oracle reproduces lamejs's bytes (27 fixtures above); the independent parser rejects them at
+    the first back-pointer; with the integer quotient (a test switch of the oracle, not lamejs) the same machinery produces
+    streams that decode to the input, back-pointers up to the 9-bit maximum included."""
+    import mp3_decode
+    import mp3_parse
+    l, r = _joint_signal()
+    js = oracle.OracleEncoder(2, 44100, 128, joint_stereo=True, reservoir=True)
+    data = js.encode_buffer(l, r) + js.flush()
+    with pytest.raises(AssertionError, match="part2_3_length mismatch"):
+        mp3_parse.parse_stream_reservoir(data, books)
+    jv = oracle.OracleEncoder(2, 44100, 128, joint_stereo=True, reservoir="java")
+    data = jv.encode_buffer(l, r) + jv.flush()
+    frames = mp3_parse.parse_stream_reservoir(data, books)
+    assert max(f["main_data_begin"] for f in frames) > 400 and frames[0]["main_data_begin"] == 0
+    y = mp3_decode.decode(data, books, reservoir=True)
+    for c, x in enumerate((l, r)):
+        snr, gain = _snr_gain(y[c], x)
+        assert snr > 60 and abs(gain - 0.95) < 0.005, (c, snr, gain)
