@@ -8,8 +8,8 @@
  *   const tail = enc.flush();
  *
  * Same constructor / encodeBuffer / flush surface and return types as zhuker/lamejs src/js/index.js:66-136.
- * Binding: ffi-napi over the C ABI declared in include/mp3b200.h.  NOT EXECUTABLE in the build image (no node);
- * shipped as the reference-side binding a maintainer would use.
+ * Binding: ffi-napi over the C ABI declared in include/mp3b200.h.  No node in the build image: the file is exercised there under
+ * Qt's JavaScript engine with a stubbed ffi (tests/test_js_shim.py: syntax, exports, call order and arity), not against the GPU.
  */
 const ffi = require('ffi-napi');
 const ref = require('ref-napi');
