@@ -181,3 +181,19 @@ def test_entry_points_reject_bad_arguments_without_a_device():
     L.mp3b200_put_vbr_tag.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
     assert L.mp3b200_set_write_vbr_tag(None, 1) == -3 and L.mp3b200_get_lametag_frame(None, None, 0) == -3 and L.mp3b200_put_vbr_tag(None, None, 0) == -3
     assert L.mp3b200_music_crc(None) == -1 and L.mp3b200_bytes_written(None) == -1
+
+
+@pytest.mark.parametrize("ch,sr,kbps", [(2, 44100, 130), (2, 44100, 120), (1, 44100, 100), (2, 48000, 300), (1, 32000, 70), (2, 24000, 50), (1, 16000, 60), (2, 48000, 1000)])
+def test_tag_frame_with_bitrates_off_the_ladder(oracle, ch, sr, kbps):
+    """kbps is snapped like FindNearestBitrate, but the low-pass (a tag field) comes from the rate as given (Lame.js:838-885 runs
+    before :1053): the tag must follow both"""
+    if oracle.out_samplerate(ch, sr, kbps) != sr:
+        assert M.lib().mp3b200_lametag_size(ch, sr, kbps) < 0
+        return
+    info = _oracle_tag(oracle, ch, sr, kbps, 4, 5)
+    size = M.lib().mp3b200_lametag_size(ch, sr, kbps)
+    if not info["tag_on"]:
+        assert size == 0
+        return
+    assert size == len(info["tag"])
+    assert M.lametag_build(ch, sr, kbps, info["frames"], info["bytes_written"], info["music_crc"], info["encoder_padding"]) == info["tag"]
