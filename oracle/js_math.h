@@ -9,9 +9,13 @@
  * /root/reference and is not pinned by package.json.  We assume V8 (node /
  * Chrome), whose base/ieee754 functions are ports of Sun's fdlibm 5.3
  * (e_log.c, e_log10.c, e_exp.c, e_pow.c), and restate that published
- * algorithm here.  PARITY UNPINNED at this boundary: no JS engine exists in the
- * build image, so these could only be cross-checked against glibc (agreement
- * within 1 ulp on 10^7 random arguments, see tests/test_js_math.py).
+ * algorithm here.  How it is pinned: (1) the build image's JavaScript engine (Qt QV4) computes these with
+ * the C library, and the oracle -- computing with THIS header -- reproduces its bytes on every committed
+ * fixture; (2) tools/jsrun/fdlibm.js is the same algorithm in JavaScript, installed over Math.*, and lamejs
+ * run with it (i.e. as under V8) produces the same bytes again (tools/jsrun/fdlibm_check.py); (3)
+ * tests/test_js_math.py checks fdlibm.js against this header bit for bit and both against glibc (< 1 ulp,
+ * log10 2).  So the bytes do not depend on which of the two libms the engine uses: the float32 store points
+ * absorb the last-ulp differences wherever they were exercised.
  *
  * All arithmetic is plain IEEE double, evaluated left to right, and MUST be
  * compiled without FMA contraction (-ffp-contract=off).
