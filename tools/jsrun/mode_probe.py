@@ -13,8 +13,8 @@ _DRIVER = (T._TAG_DRIVER
            .replace("gfp.bWriteVbrTag=true; gfp.disable_reservoir=true;", "gfp.bWriteVbrTag=false; gfp.disable_reservoir=__NORES;"))
 
 
-def encode(channels, samplerate, kbps, left, right=None, chunk=None, mode="STEREO", disable_reservoir=True):
-    """Returns (bytes, per-call sizes, info dict)."""
+def encode(channels, samplerate, kbps, left, right=None, chunk=None, mode="STEREO", disable_reservoir=True, fdlibm=False):
+    """Returns (bytes, per-call sizes, info dict).  fdlibm: load fdlibm.js first (Math.log / log10 / exp / pow as under V8)."""
     if right is None:
         right = left
     with tempfile.TemporaryDirectory() as td:
@@ -26,6 +26,6 @@ def encode(channels, samplerate, kbps, left, right=None, chunk=None, mode="STERE
                     % (R._hex16(left), R._hex16(right), channels, samplerate, kbps, chunk or 0))
             f.write("var __MODE_NAME='%s'; var __NORES=%s;\n" % (mode, "true" if disable_reservoir else "false"))
             f.write(_DRIVER)
-        o = json.loads(R.run_js([p, d]))
+        o = json.loads(R.run_js(([os.path.join(os.path.dirname(os.path.abspath(__file__)), "fdlibm.js")] if fdlibm else []) + [p, d]))
     data = bytes.fromhex(o.pop("hex"))
     return data, o["sizes"], o
